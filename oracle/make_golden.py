@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""ORACLE / TEST INFRASTRUCTURE — generates tests/golden/refshim_*.npz.
+
+Executes the UNMODIFIED reference sources under /root/reference (read-only) with
+`mlx.core` resolved to oracle/mlx_shim (a NumPy float32 stand-in; MLX itself is not
+installable in this image) and stores inputs + outputs as small fixtures.  The fixtures
+travel with the repo; /root/reference does not exist on the GPU box, so this script is
+only ever run in the build container:
+
+    python oracle/make_golden.py            # writes tests/golden/refshim_*.npz
+
+Reference files executed (whole file or AST-extracted definitions, never copied):
+  mlx_audio/dsp.py                                   (whole module)
+  mlx_audio/stt/models/whisper/audio.py              (whole module)
+  mlx_audio/stt/models/parakeet/audio.py             (whole module)
+  mlx_audio/stt/models/voxtral_realtime/audio.py     (whole module)
+  mlx_audio/codec/models/vocos/mel.py                (whole module)
+  mlx_audio/codec/models/s3tokenizer/utils.py        (whole module)
+  mlx_audio/codec/models/vocos/vocos.py              (class ISTFTHead)
+  mlx_audio/tts/models/kokoro/istftnet.py            (mlx_angle, mlx_unwrap, MLXSTFT)
+  mlx_audio/tts/models/qwen3_tts/qwen3_tts.py        (mel_spectrogram)
+  mlx_audio/vad/models/sortformer/sortformer.py      (preemphasis_filter, extract_mel_features)
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("B2A_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _load_reference():
+    sys.path.insert(0, os.path.join(HERE, "mlx_shim"))
+    import mlx.core as mx  # the shim
+    import mlx.nn as nn
+
+    def pkg(name):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    for p in ("mlx_audio", "mlx_audio.stt", "mlx_audio.stt.models", "mlx_audio.codec",
+              "mlx_audio.codec.models"):
+        pkg(p)
+    dsp = load("mlx_audio.dsp", "mlx_audio/dsp.py")
+    # mlx_audio/utils.py:29-38 re-exports these names from dsp; the real utils.py drags in model
+    # loading (huggingface_hub, mlx.nn ...), so a module carrying only the re-export is used.
+    utils = types.ModuleType("mlx_audio.utils")
+    for n in ("STR_TO_WINDOW_FN", "bartlett", "blackman", "hamming", "hanning", "istft",
+              "mel_filters", "stft"):
+        setattr(utils, n, getattr(dsp, n))
+    sys.modules["mlx_audio.utils"] = utils
+    stt_utils = types.ModuleType("mlx_audio.stt.utils")
+    stt_utils.load_audio = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no file IO in goldens"))
+    sys.modules["mlx_audio.stt.utils"] = stt_utils
+
+    mods = {
+        "dsp": dsp,
+        "whisper": load("mlx_audio.stt.models.whisper_audio", "mlx_audio/stt/models/whisper/audio.py"),
+        "parakeet": load("mlx_audio.stt.models.parakeet_audio", "mlx_audio/stt/models/parakeet/audio.py"),
+        "voxtral": load("mlx_audio.stt.models.voxtral_rt_audio", "mlx_audio/stt/models/voxtral_realtime/audio.py"),
+        "vocos_mel": load("mlx_audio.codec.models.vocos_mel", "mlx_audio/codec/models/vocos/mel.py"),
+        "s3tok": load("mlx_audio.codec.models.s3tok_utils", "mlx_audio/codec/models/s3tokenizer/utils.py"),
+    }
+
+    def extract(rel, names, extra=None):
+        """exec selected top-level definitions of a reference file (verbatim AST nodes)."""
+        src = open(os.path.join(REF, rel)).read()
+        tree = ast.parse(src)
+        keep = [n for n in tree.body
+                if (isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names)
+                or (isinstance(n, ast.Assign) and any(isinstance(t, ast.Name) and t.id in names for t in n.targets))]
+        ns = {"mx": mx, "nn": nn, "np": np, "math": math, "stft": dsp.stft, "istft": dsp.istft,
+              "hanning": dsp.hanning, "mel_filters": dsp.mel_filters}
+        ns.update(extra or {})
+        exec(compile(ast.Module(body=keep, type_ignores=[]), rel, "exec"), ns)
+        return types.SimpleNamespace(**{n: ns[n] for n in names})
+
+    mods["vocos"] = extract("mlx_audio/codec/models/vocos/vocos.py", ["ISTFTHead"])
+    mods["kokoro"] = extract("mlx_audio/tts/models/kokoro/istftnet.py", ["mlx_angle", "mlx_unwrap", "MLXSTFT"])
+    mods["qwen3"] = extract("mlx_audio/tts/models/qwen3_tts/qwen3_tts.py", ["mel_spectrogram"])
+    mods["sortformer"] = extract("mlx_audio/vad/models/sortformer/sortformer.py",
+                                 ["_LOG_GUARD", "_NORM_CONSTANT", "preemphasis_filter", "extract_mel_features"])
+    return mx, mods
+
+
+def synth(seed, n, sr=16000):
+    """The §8(d) synthetic: 0.1*N(0,1) + 0.2*(sin 440 Hz + sin 3 kHz)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    x = 0.1 * rng.standard_normal(n) + 0.2 * (np.sin(2 * np.pi * 440 * t) + np.sin(2 * np.pi * 3000 * t))
+    return x.astype(np.float32)
+
+
+def main():
+    mx, R = _load_reference()
+    dsp = R["dsp"]
+    os.makedirs(OUT, exist_ok=True)
+    A = lambda v: np.asarray(v)
+
+    # ---- windows + filterbanks ---------------------------------------------------------
+    g = {}
+    for kind in ("hanning", "hamming", "blackman", "bartlett"):
+        for size in (16, 20, 21, 400, 401, 1024):
+            for per in (False, True):
+                g[f"win|{kind}|{size}|{int(per)}"] = A(getattr(dsp, kind)(size, per))
+    fb_cases = {
+        "whisper80": (16000, 400, 80, 0, None, "slaney", None),
+        "whisper128": (16000, 400, 128, 0, None, "slaney", None),
+        "parakeet80": (16000, 512, 80, 0, None, "per_feature", None),
+        "vocos100": (24000, 1024, 100, 0, None, None, "htk"),
+        "qwen3tts128": (24000, 1024, 128, 0.0, 12000.0, "slaney", "slaney"),
+        "voxtral128": (16000, 400, 128, 0, 8000, "slaney", "slaney"),
+        "funasr80": (16000, 400, 80, 0, None, "slaney", "htk"),
+        "s3gen80": (24000, 1920, 80, 0, 8000, "slaney", "slaney"),
+        "spark128": (16000, 1024, 128, 10, 8000, "slaney", "slaney"),
+    }
+    for k, a in fb_cases.items():
+        g[f"fb|{k}"] = A(dsp.mel_filters(*a))
+    np.savez_compressed(os.path.join(OUT, "refshim_tables.npz"), **g)
+
+    # ---- stft --------------------------------------------------------------------------
+    g = {}
+    stft_cases = [
+        # name, L, n_fft, hop, win, window(str|("arr",fn,size,periodic)), center, pad_mode
+        ("w400", 4000, 400, 160, None, ("arr", "hanning", 400, False), True, "reflect"),
+        ("p512", 4000, 512, 160, 400, "hann", True, "reflect"),
+        ("v1024", 6000, 1024, None, 256, ("arr", "hanning", 1024, False), True, "reflect"),
+        ("k20", 600, 20, 5, 20, "hann", True, "reflect"),
+        ("h16", 333, 16, 4, 16, ("arr", "hanning", 17, False, -1), True, "reflect"),
+        ("nc1920", 9600, 1920, 384, 1920, ("arr", "hamming", 1920, False), False, "reflect"),
+        ("const512", 3000, 512, 160, 400, "hamming", True, "constant"),
+        ("def800", 5000, 800, None, None, "hann", True, "reflect"),
+        ("black300", 2000, 300, 75, 200, "blackman", True, "reflect"),
+        ("bart64", 999, 64, 16, 64, "bartlett", True, "constant"),
+        ("edge201", 201, 400, 160, None, "hann", True, "reflect"),
+        ("edge_nc", 400, 400, 160, None, "hann", False, "reflect"),
+        ("odd_hop", 3001, 400, 161, None, "hann", True, "reflect"),
+    ]
+
+    def mkwin(spec):
+        if isinstance(spec, str):
+            return spec
+        fn = getattr(dsp, spec[1])
+        w = fn(spec[2], spec[3])
+        if len(spec) > 4:
+            w = w[: spec[4]]
+        return w
+
+    for i, (name, L, n_fft, hop, win, wspec, center, pad_mode) in enumerate(stft_cases):
+        x = synth(100 + i, L)
+        y = dsp.stft(mx.array(x), n_fft, hop, win, mkwin(wspec), center, pad_mode)
+        g[f"stft|{name}|x"] = x
+        g[f"stft|{name}|y"] = A(y).astype(np.complex64)
+    np.savez_compressed(os.path.join(OUT, "refshim_stft.npz"), **g)
+
+    # ---- istft -------------------------------------------------------------------------
+    g = {}
+    rng = np.random.default_rng(7)
+
+    def rspec(F, T):
+        return (rng.standard_normal((F, T)) + 1j * rng.standard_normal((F, T))).astype(np.complex64)
+
+    istft_cases = [
+        # name, F, T, hop, win, window, center, length, normalized
+        ("k20", 11, 200, 5, 20, "hann", True, None, False),
+        ("h16n", 9, 150, 4, 16, "hann", True, None, True),
+        ("v1024", 513, 24, 256, 1024, ("arr", "hanning", 1024, False), True, None, False),
+        ("s2048", 1025, 7, 512, 2048, ("arr", "hanning", 2048, False), True, None, False),
+        ("e1280", 641, 9, 320, 1280, ("arr", "hanning", 1280, False), True, None, False),
+        ("nc_norm", 33, 40, 16, 64, "hamming", False, None, True),
+        ("len", 33, 40, 16, 64, "hann", True, 500, False),
+        ("odd21", 11, 50, 5, 21, ("arr", "hanning", 21, False), True, None, False),
+        ("short_w", 33, 30, 16, 64, ("arr", "hanning", 48, False), True, None, False),
+        ("black", 51, 33, 25, 100, "blackman", True, None, False),
+    ]
+    for name, F, T, hop, win, wspec, center, length, normalized in istft_cases:
+        s = rspec(F, T)
+        if name == "odd21":
+            # irfft of 11 bins gives 20 samples; a 21-tap window cannot broadcast — the reference
+            # raises a shape error here.  Record that instead of values.
+            try:
+                dsp.istft(mx.array(s), hop, win, mkwin(wspec), center, length, normalized)
+                g["istft|odd21|raises"] = np.array(0)
+            except Exception:
+                g["istft|odd21|raises"] = np.array(1)
+            continue
+        y = dsp.istft(mx.array(s), hop, win, mkwin(wspec), center, length, normalized)
+        g[f"istft|{name}|x"] = s
+        g[f"istft|{name}|y"] = A(y).astype(np.float32)
+
+    cache = dsp.ISTFTCache()
+    for name, B, n_fft, hop, T, wkind, center, alen in [
+        ("c64", 3, 64, 16, 50, "hamming", True, 700),
+        ("c1920", 2, 1920, 384, 6, "hamming", True, None),
+        ("c20nc", 4, 20, 5, 120, "hanning", False, None),
+    ]:
+        F = n_fft // 2 + 1
+        re = rng.standard_normal((B, F, T)).astype(np.float32)
+        im = rng.standard_normal((B, F, T)).astype(np.float32)
+        w = getattr(dsp, wkind)(n_fft, False)
+        y = cache.istft(mx.array(re), mx.array(im), n_fft, hop, n_fft, w, center, alen)
+        g[f"icache|{name}|re"], g[f"icache|{name}|im"], g[f"icache|{name}|y"] = re, im, A(y).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "refshim_istft.npz"), **g)
+
+    # ---- model front-ends --------------------------------------------------------------
+    g = {}
+    x = synth(200, 16000)
+    g["whisper|x"] = x
+    g["whisper|80"] = A(R["whisper"].log_mel_spectrogram(x, n_mels=80))
+    g["whisper|128"] = A(R["whisper"].log_mel_spectrogram(mx.array(x), n_mels=128))
+    g["whisper|80pad"] = A(R["whisper"].log_mel_spectrogram(x, n_mels=80, padding=8000))
+    xs = x.copy()
+    xs[5000:] = 0.0  # long digital silence -> the max-8 clamp is active
+    g["whisper|sil|x"] = xs
+    g["whisper|sil|80"] = A(R["whisper"].log_mel_spectrogram(xs, n_mels=80))
+
+    PA = R["parakeet"].PreprocessArgs
+    pa = PA(sample_rate=16000, normalize="per_feature", window_size=0.025, window_stride=0.01,
+            window="hann", features=80, n_fft=512, dither=1e-5)
+    x = synth(201, 24000)
+    g["parakeet|x"] = x
+    g["parakeet|pf"] = A(R["parakeet"].log_mel_spectrogram(mx.array(x), pa))
+    pa2 = PA(sample_rate=16000, normalize="all_features", window_size=0.025, window_stride=0.01,
+             window="hamming", features=64, n_fft=512, dither=0.0, pad_to=30000, pad_value=0.0, preemph=0.0)
+    g["parakeet|global"] = A(R["parakeet"].log_mel_spectrogram(mx.array(x), pa2))
+
+    x = synth(202, 12000)
+    fbv = R["voxtral"].compute_mel_filters()
+    g["voxtral|x"] = x
+    g["voxtral|y"] = A(R["voxtral"].compute_mel_spectrogram(mx.array(x), mx.array(fbv)))
+
+    x = synth(203, 12000, sr=24000)
+    g["vocos|x"] = x
+    g["vocos|mel"] = A(R["vocos_mel"].log_mel_spectrogram(mx.array(x)))
+    head = R["vocos"].ISTFTHead(8, 1024, 256)
+    lin = (0.5 * np.random.default_rng(5).standard_normal((1, 20, 1026))).astype(np.float32)
+    g["vocos|head_in"] = lin
+    g["vocos|head_out"] = A(head(mx.array(lin)))
+    z = np.zeros(120000, np.float32)
+    mel0 = A(R["vocos_mel"].log_mel_spectrogram(mx.array(z)))
+    g["vocos|zeros_mel_shape"] = np.array(mel0.shape)
+    head_z = R["vocos"].ISTFTHead(8, 1024, 256)
+    g["vocos|zeros_audio_len"] = np.array(A(head_z(mx.array(np.zeros((1, mel0.shape[1], 1026), np.float32)))).shape)
+
+    K = R["kokoro"].MLXSTFT(filter_length=20, hop_length=5, win_length=20)
+    x = np.stack([synth(204, 1500, 24000), synth(205, 1500, 24000)])
+    mag, ph = K.transform(mx.array(x))
+    g["kokoro|x"], g["kokoro|mag"], g["kokoro|phase"] = x, A(mag), A(ph)
+    rng2 = np.random.default_rng(9)
+    m2 = np.minimum(np.exp(0.5 * rng2.standard_normal((2, 11, 301))), 1e2).astype(np.float32)
+    p2 = np.sin(rng2.standard_normal((2, 11, 301))).astype(np.float32)
+    g["kokoro|inv_mag"], g["kokoro|inv_phase"] = m2, p2
+    g["kokoro|inv_y"] = A(K.inverse(mx.array(m2), mx.array(p2)))
+    p3 = rng2.uniform(-math.pi, math.pi, (1, 11, 301)).astype(np.float32)
+    g["kokoro|inv_phase_wrapped"] = p3
+    g["kokoro|inv_y_wrapped"] = A(K.inverse(mx.array(m2[:1]), mx.array(p3)))
+    g["kokoro|unwrap"] = A(R["kokoro"].mlx_unwrap(mx.array(p3[0]), axis=1))
+
+    np.random.seed(42)  # the reference test's own input: tts/tests/test_qwen3_tts.py:164-167
+    xq = np.random.randn(12000).astype(np.float32)
+    g["qwen3|y"] = A(R["qwen3"].mel_spectrogram(mx.array(xq)))
+    t = np.arange(12000, dtype=np.float32) / 24000.0
+    g["qwen3|sine_y"] = A(R["qwen3"].mel_spectrogram(mx.array(np.sin(2 * np.pi * 1000 * t).astype(np.float32))))
+
+    x = synth(206, 8000)
+    g["s3|x"] = x
+    g["s3|y"] = A(R["s3tok"].log_mel_spectrogram(mx.array(x)))
+    xb = np.stack([synth(207, 8000), 0.05 * synth(208, 8000)])
+    g["s3|xb"] = xb
+    g["s3|compat"] = A(R["s3tok"].log_mel_spectrogram_compat(mx.array(xb), n_mels=80))
+
+    x = np.stack([synth(209, 9000), synth(210, 9000)])
+    g["sortformer|x"] = x
+    g["sortformer|y"] = A(R["sortformer"].extract_mel_features(mx.array(x)))
+    np.savez_compressed(os.path.join(OUT, "refshim_models.npz"), **g)
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

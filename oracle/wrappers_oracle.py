@@ -1,0 +1,252 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (see dsp_oracle.py header).
+
+NumPy float32 restatement of the per-model feature front-ends / iSTFT heads that sit on
+the hot path.  Each function cites the reference lines it
+follows.  All of them are compositions of dsp_oracle.{stft, istft, mel_filters}.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import dsp_oracle as D
+
+F32 = np.float32
+
+
+def _rpad(x, n, value=0.0):
+    x = np.asarray(x, dtype=F32)
+    return np.concatenate([x, np.full(n, value, dtype=F32)]) if n > 0 else x
+
+
+# -- Whisper: stt/models/whisper/audio.py:44-85 -------------------------------------------
+def whisper_log_mel(audio, n_mels=80, padding=0):
+    x = _rpad(audio, padding)  # :73-74
+    spec = D.stft(x, window=D.hanning(400), n_fft=400, hop_length=160)  # :75-76
+    power = np.square(np.abs(spec[:-1, :])).astype(F32)  # :77 drop last frame; abs() then square()
+    fb = D.mel_filters(16000, 400, n_mels, norm="slaney", mel_scale=None)  # :79
+    mel = power @ fb.T  # :80
+    y = np.log10(np.maximum(mel, F32(1e-10)))  # :82
+    y = np.maximum(y, y.max() - F32(8.0))  # :83 one max over the whole input
+    return ((y + F32(4.0)) / F32(4.0)).astype(F32)  # :84  -> (T, n_mels)
+
+
+def whisper_pad_or_trim(a, length=480000, axis=-1):  # whisper/audio.py:27-41
+    a = np.asarray(a)
+    if a.shape[axis] > length:
+        a = np.take(a, np.arange(length), axis=axis)
+    if a.shape[axis] < length:
+        pw = [(0, 0)] * a.ndim
+        pw[axis] = (0, length - a.shape[axis])
+        a = np.pad(a, pw)
+    return a
+
+
+# -- Parakeet / NeMo: stt/models/parakeet/audio.py:16-78 ----------------------------------
+@dataclass
+class PreprocessArgs:  # parakeet/audio.py:16-36
+    sample_rate: int
+    normalize: str
+    window_size: float
+    window_stride: float
+    window: str
+    features: int
+    n_fft: int
+    dither: float
+    pad_to: int = 0
+    pad_value: float = 0
+    preemph: float = 0.97
+
+    @property
+    def win_length(self):
+        return int(self.window_size * self.sample_rate)
+
+    @property
+    def hop_length(self):
+        return int(self.window_stride * self.sample_rate)
+
+
+def parakeet_log_mel(x, args: PreprocessArgs):
+    x = np.asarray(x, dtype=F32)
+    if args.pad_to > 0 and x.shape[-1] < args.pad_to:  # :42-45
+        x = _rpad(x, args.pad_to - x.shape[-1], args.pad_value)
+    fn = D.STR_TO_WINDOW_FN.get(args.window, None)  # :47-48 (no .lower() here)
+    w = fn(args.win_length) if fn else D.hanning(args.win_length)
+    if args.preemph > 0:  # :53-55
+        x = np.concatenate([x[:1], x[1:] - F32(args.preemph) * x[:-1]]).astype(F32)
+    spec = D.stft(x, args.n_fft, args.hop_length, args.win_length, w)  # :57
+    power = np.square(np.abs(spec)).astype(F32)  # :58
+    fb = D.mel_filters(args.sample_rate, args.n_fft, args.features, norm=args.normalize,
+                       mel_scale=None)  # :59-61 — norm="per_feature" => NO slaney normalisation
+    m = fb @ power.T  # :62  (M, T)
+    m = np.log(m + F32(1e-5))  # :64
+    if args.normalize == "per_feature":  # :66-69, std with ddof=0
+        mean = m.mean(axis=1, keepdims=True, dtype=F32)
+        std = m.std(axis=1, keepdims=True, dtype=F32)
+    else:  # :70-73
+        mean = m.mean(dtype=F32)
+        std = m.std(dtype=F32)
+    out = (m - mean) / (std + F32(1e-5))
+    return out.T[None].astype(F32)  # :75-78 -> (1, T, M)
+
+
+# -- Voxtral-Realtime: stt/models/voxtral_realtime/audio.py:19-96 ------------------------
+def voxtral_rt_mel_filters(num_mel_bins=128, window_size=400, sample_rate=16000):  # :19-38
+    fb = D.mel_filters(sample_rate, window_size, num_mel_bins, 0, 8000, "slaney", "slaney")
+    return np.array(fb).T  # (F, M)
+
+
+def voxtral_rt_mel(audio, mel_filters_fm, window_size=400, hop_length=160, global_log_mel_max=1.5):
+    n = np.arange(window_size, dtype=F32)  # :60-61 periodic Hann evaluated in float32
+    w = (F32(0.5) * (F32(1.0) - np.cos(F32(2.0 * math.pi) * n / F32(window_size)))).astype(F32)
+    p = window_size // 2
+    xp = np.pad(np.asarray(audio, dtype=F32), (p, p), mode="reflect")  # :64-67
+    T = 1 + (xp.shape[0] - window_size) // hop_length  # :70-71
+    idx = np.arange(window_size)[None, :] + (np.arange(T) * hop_length)[:, None]  # :74-77
+    spec = np.fft.rfft(xp[idx] * w[None, :], n=window_size, axis=-1).astype(np.complex64)  # :80
+    mags = (np.abs(spec) ** 2).astype(F32)[:-1, :].T  # :83-84 (F, T-1)
+    mel = np.asarray(mel_filters_fm, F32).T @ mags  # :87
+    y = np.log10(np.maximum(mel, F32(1e-10)))  # :90
+    y = np.maximum(y, F32(global_log_mel_max - 8.0))  # :91-92 fixed floor
+    return ((y + F32(4.0)) / F32(4.0)).astype(F32)  # :93 -> (M, T-1)
+
+
+# -- Vocos: codec/models/vocos/mel.py:8-33 and vocos.py:126-140 --------------------------
+def vocos_log_mel(audio, sample_rate=24000, n_mels=100, n_fft=1024, hop_length=256, padding=0):
+    x = _rpad(audio, padding)
+    # NB hop_length is NOT forwarded: win_length=hop_length is ignored for an array window and
+    # hop defaults to n_fft//4 (mel.py:22)
+    spec = D.stft(x, window=D.hanning(n_fft), n_fft=n_fft, win_length=hop_length)
+    mag = np.abs(spec[:-1, :]).astype(F32)  # :23 magnitude, last frame dropped
+    fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=n_mels, norm=None, mel_scale="htk")
+    mel = mag @ fb.T
+    return np.log(np.maximum(mel, F32(1e-5)))[None].astype(F32)  # :31-33 -> (1, T, M)
+
+
+def vocos_istft_head(x_lin, n_fft, hop_length):
+    """x_lin: output of the head's linear layer, shape (1, T, n_fft+2) (vocos.py:127).
+    Returns the waveform; follows vocos.py:127-140."""
+    x = np.swapaxes(np.asarray(x_lin, F32), 1, 2)  # (1, n_fft+2, T)
+    mag, p = np.split(x, 2, axis=1)
+    mag = np.minimum(np.exp(mag), F32(1e2))  # :129-130
+    S = (mag * (np.cos(p) + 1j * np.sin(p))).astype(np.complex64)  # :131-133
+    return D.istft(S[0], window=D.hanning(n_fft), hop_length=hop_length, win_length=n_fft)  # :134-139
+
+
+# -- Kokoro iSTFTNet: tts/models/kokoro/istftnet.py:399-528 ------------------------------
+def kokoro_unwrap(p, axis=-1, period=2 * math.pi):  # mlx_unwrap :418-452 (discont=None)
+    p = np.asarray(p, F32)
+    discont = period / 2
+    dd = np.diff(p, axis=axis).astype(F32)
+    hi = period / 2
+    lo = -hi
+    ddmod = (dd - F32(period) * np.floor((dd - F32(lo)) / F32(period))).astype(F32)
+    ddmod = np.where((np.abs(dd - F32(hi)) < 1e-10) & (dd > 0), F32(hi), ddmod)
+    corr = (ddmod - dd).astype(F32)
+    corr = np.where(np.abs(dd) < discont, F32(0), corr)
+    shape = list(corr.shape)
+    shape[axis] = 1
+    corr = np.concatenate([np.zeros(shape, F32), corr], axis=axis)
+    return (p + np.cumsum(corr, axis=axis, dtype=F32)).astype(F32)
+
+
+def kokoro_transform(x, n_fft=20, hop=5, win=20, window="hann"):  # MLXSTFT.transform :464-495
+    x = np.asarray(x, F32)
+    if x.ndim == 1:
+        x = x[None, :]
+    mags, phases = [], []
+    for row in x:
+        s = D.stft(row, n_fft=n_fft, hop_length=hop, win_length=win, window=window, center=True,
+                   pad_mode="reflect").T  # (F, T)
+        mags.append(np.abs(s).astype(F32))
+        phases.append(np.arctan2(s.imag, s.real).astype(F32))  # mlx_angle :399-415
+    return np.stack(mags), np.stack(phases)
+
+
+def kokoro_inverse(magnitude, phase, hop=5, win=20, window="hann"):  # MLXSTFT.inverse :497-523
+    outs = []
+    for m, ph in zip(np.asarray(magnitude, F32), np.asarray(phase, F32)):
+        pc = kokoro_unwrap(ph, axis=1)
+        spec = (m * np.cos(pc) + 1j * (m * np.sin(pc))).astype(np.complex64)
+        outs.append(D.istft(spec, hop_length=hop, win_length=win, window=window, center=True, length=None))
+    return np.stack(outs)[:, None, :]
+
+
+# -- Qwen3-TTS mel (the golden-tested wrapper): tts/models/qwen3_tts/qwen3_tts.py:33-90 ---
+def qwen3_tts_mel(audio, n_fft=1024, num_mels=128, sample_rate=24000, hop_size=256, win_size=1024,
+                  fmin=0.0, fmax=12000.0):
+    a = np.asarray(audio, F32)
+    if a.ndim == 1:
+        a = a[None, :]
+    fb = D.mel_filters(sample_rate, n_fft, num_mels, fmin, fmax, "slaney", "slaney")
+    pad = (n_fft - hop_size) // 2
+    out = []
+    for s in a:
+        s = np.concatenate([s[1 : pad + 1][::-1], s, s[-(pad + 1) : -1][::-1]])  # :71-73
+        spec = D.stft(s, n_fft=n_fft, hop_length=hop_size, win_length=win_size, window="hann",
+                      center=False, pad_mode="reflect")
+        mag = np.sqrt(np.abs(spec) ** 2 + F32(1e-9)).astype(F32)  # :85
+        mel = mag @ fb.T
+        out.append(np.log(np.clip(mel, F32(1e-5), None)).astype(F32))  # :89
+    return np.stack(out)  # (B, T, M)
+
+
+# -- S3Tokenizer: codec/models/s3tokenizer/utils.py:13-135 -------------------------------
+def s3tokenizer_log_mel(audio, sample_rate=16000, n_mels=128, n_fft=400, hop_length=160, padding=0):
+    x = _rpad(audio, padding)
+    w = D.hanning(n_fft + 1)[:-1]  # :46 periodic via N+1 trick
+    spec = D.stft(x, window=w, n_fft=n_fft, hop_length=hop_length, win_length=n_fft).swapaxes(0, 1)
+    power = (np.abs(spec) ** 2).astype(F32)  # (F, T) — no frame drop
+    fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=n_mels, norm="slaney", mel_scale="slaney")
+    mel = fb @ power
+    y = np.log10(np.maximum(mel, F32(1e-10)))
+    y = np.maximum(y, y.max() - F32(8.0))
+    return ((y + F32(4.0)) / F32(4.0)).astype(F32)  # (M, T)
+
+
+def s3tokenizer_log_mel_compat(audio, n_mels=128, padding=0):  # :68-135
+    a = np.asarray(audio, F32)
+    was_1d = a.ndim == 1
+    if was_1d:
+        a = a[None]
+    if padding > 0:
+        a = np.pad(a, [(0, 0), (0, padding)])
+    spec = np.stack([D.stft(r, window="hann", n_fft=400, hop_length=160, win_length=400) for r in a])
+    power = (np.abs(spec[:, :-1, :]) ** 2).astype(F32)
+    fb = D.mel_filters(sample_rate=16000, n_fft=400, n_mels=n_mels, norm="slaney", mel_scale="slaney")
+    mel = np.transpose(power @ fb.T, [0, 2, 1])  # (B, M, T)
+    y = np.log10(np.maximum(mel, F32(1e-10)))
+    y = np.maximum(y, y.max() - F32(8.0))  # ONE max over the whole batch
+    y = ((y + F32(4.0)) / F32(4.0)).astype(F32)
+    return y[0] if was_1d else y
+
+
+# -- Sortformer / NeMo (constant pad, centred window, Bessel std): vad/models/sortformer/sortformer.py:36-120
+def sortformer_mel(waveform, sample_rate=16000, n_fft=512, hop_length=160, win_length=400, n_mels=80,
+                   preemphasis_coeff=0.97, normalize="per_feature", pad_to=16):
+    wv = np.asarray(waveform, F32)
+    if wv.ndim == 1:
+        wv = wv[None, :]
+    wv = np.concatenate([wv[..., :1], wv[..., 1:] - F32(preemphasis_coeff) * wv[..., :-1]], axis=-1).astype(F32)
+    fb = D.mel_filters(sample_rate, n_fft, n_mels, 0, None, "slaney", "slaney")
+    w = D.hanning(win_length)
+    if win_length < n_fft:  # caller-side CENTRE padding of the window (:78-83)
+        left = (n_fft - win_length) // 2
+        w = np.concatenate([np.zeros(left, F32), w, np.zeros(n_fft - win_length - left, F32)])
+    feats = []
+    for row in wv:
+        spec = D.stft(row, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=w,
+                      center=True, pad_mode="constant")
+        power = (np.abs(spec) ** 2).astype(F32)
+        feats.append(np.log(power @ fb.T + F32(2.0**-24)).T.astype(F32))  # _LOG_GUARD = 2**-24
+    f = np.stack(feats)  # (B, M, T)
+    if normalize == "per_feature":
+        mean = f.mean(axis=2, keepdims=True, dtype=F32)
+        var = ((f - mean) ** 2).sum(axis=2, keepdims=True, dtype=F32) / F32(f.shape[2] - 1)
+        f = (f - mean) / (np.sqrt(var) + F32(1e-5))
+    if pad_to > 0 and f.shape[2] % pad_to:
+        f = np.pad(f, [(0, 0), (0, 0), (0, pad_to - f.shape[2] % pad_to)])
+    return f.astype(F32)
