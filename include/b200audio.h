@@ -1,0 +1,216 @@
+/*
+ * b200audio — C ABI of the B200-native STFT / log-mel / iSTFT hot path.
+ *
+ * This is the drop-in boundary.  The reference (mlx-audio-plus 0.1.8) has no FFI:
+ * its seam is the Python module mlx_audio/dsp.py plus each model's log_mel_spectrogram.  Our Python
+ * package mirrors that module API and binds THIS header through ctypes
+ * (mlx_audio_plus_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All `d_*` pointers are device pointers in the
+ *     CURRENT CUDA context (one plan per GPU); `h_*` are host pointers.
+ *   - every entry point returns a b2a_status (0 = ok, negative = error); b2a_last_error() returns a
+ *     thread-local message.  The three Python ValueErrors of the reference map to
+ *     B2A_ERR_UNKNOWN_WINDOW (dsp.py:109,175), B2A_ERR_PAD_MODE (dsp.py:126), B2A_ERR_TOO_SHORT
+ *     (dsp.py:132-136); broadcast failures (window longer than n_fft, dsp.py:141/197) -> B2A_ERR_SHAPE.
+ *   - launches are stream-ordered on the given cudaStream_t (passed as void*), no hidden syncs;
+ *     the caller owns every buffer, the library owns only the plan (twiddles, window, filterbank).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     B2A_ERR_CUDA.
+ */
+#ifndef B200AUDIO_H
+#define B200AUDIO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_VERSION 100 /* 0.1.0 */
+
+typedef enum b2a_status {
+  B2A_OK = 0,
+  B2A_ERR_INVALID_ARG = -1,
+  B2A_ERR_UNKNOWN_WINDOW = -2, /* ValueError("Unknown window function")  dsp.py:109,175 */
+  B2A_ERR_PAD_MODE = -3,       /* ValueError("Invalid pad_mode")         dsp.py:126 */
+  B2A_ERR_TOO_SHORT = -4,      /* ValueError("Input is too short")       dsp.py:132-136 */
+  B2A_ERR_SHAPE = -5,          /* broadcast / shape mismatch (MLX shape error in the reference) */
+  B2A_ERR_CUDA = -6,
+  B2A_ERR_UNSUPPORTED = -7,
+  B2A_ERR_NOMEM = -8
+} b2a_status;
+
+/* ---- enumerations ------------------------------------------------------------------------------ */
+enum { B2A_WIN_HANN = 0, B2A_WIN_HAMMING = 1, B2A_WIN_BLACKMAN = 2, B2A_WIN_BARTLETT = 3 };
+enum { B2A_PAD_REFLECT = 0, B2A_PAD_CONSTANT = 1 };
+enum { /* what is taken from each STFT bin */
+  B2A_SPEC_COMPLEX = 0,   /* X (complex64)                      dsp.stft */
+  B2A_SPEC_POWER = 1,     /* |X|^2        whisper/audio.py:77, parakeet/audio.py:58 */
+  B2A_SPEC_MAGNITUDE = 2, /* |X|          vocos/mel.py:23 */
+  B2A_SPEC_SQRT_POWER_EPS = 3 /* sqrt(|X|^2 + eps)  qwen3_tts.py:85 */
+};
+enum { B2A_LOG_NONE = 0, B2A_LOG_LOG10 = 1, B2A_LOG_LN = 2 };
+enum { B2A_GUARD_NONE = 0, B2A_GUARD_MAX = 1 /* max(x,eps) */, B2A_GUARD_ADD = 2 /* x+eps */ };
+enum {
+  B2A_CLAMP_NONE = 0,
+  B2A_CLAMP_CLIP_MAX = 1,  /* max(y, max_over_clip(y) - v)     whisper/audio.py:83 */
+  B2A_CLAMP_BATCH_MAX = 2, /* max(y, max_over_batch(y) - v)    s3tokenizer/utils.py:131 */
+  B2A_CLAMP_FIXED = 3      /* max(y, v)                        voxtral_realtime/audio.py:91-92 */
+};
+enum {
+  B2A_NORM_NONE = 0,
+  B2A_NORM_PER_FEATURE = 1, /* (y-mean_t)/(std_t+eps) per mel   parakeet/audio.py:66-69 */
+  B2A_NORM_GLOBAL = 2       /* one mean/std per clip            parakeet/audio.py:70-73 */
+};
+enum { B2A_LAYOUT_TM = 0 /* (T, M) */, B2A_LAYOUT_MT = 1 /* (M, T) */ };
+enum { B2A_ISTFT_NORM_WINDOW = 0 /* sum w  dsp.py:199 normalized=False */,
+       B2A_ISTFT_NORM_WINDOW_SQ = 1 /* sum w^2 */ };
+enum { /* how istft treats the envelope: */
+  B2A_ISTFT_DIV_WHERE = 0, /* num/den where den>1e-10 else num     dsp.py:207-209 */
+  B2A_ISTFT_DIV_CLAMP = 1  /* num/max(den,1e-10)                   dsp.py:344,407 (ISTFTCache) */
+};
+
+/* ---- front-end (forward) plan -------------------------------------------------------------------
+ * One descriptor expresses every row of SURVEY.md Appendix A "wrapper parameter matrix":
+ *   x -> [right pad to `length` with pad_value] -> [preemphasis] -> centre pad (reflect|constant)
+ *     -> frames (hop) * window -> rFFT(n_fft) -> spec_kind -> [mel filterbank] -> [guard,log]
+ *     -> [clamp] -> [affine (y+add)/div] -> [normalise] -> layout
+ * n_mels == 0 means "no mel projection": the output is the (T, n_fft/2+1) spectrum itself
+ * (complex64 for B2A_SPEC_COMPLEX == dsp.stft, dsp.py:92-141; float32 otherwise). */
+typedef struct b2a_frontend_desc {
+  int32_t n_fft;
+  int32_t hop;
+  int32_t center;   /* dsp.py:128 */
+  int32_t pad_mode; /* B2A_PAD_*  dsp.py:118-126 */
+  int32_t window_len; /* taps in `window` passed to create (<= n_fft; zero-extended on the RIGHT, dsp.py:114-116) */
+  float preemph;      /* 0 = off; y[0]=x[0], y[n]=x[n]-a*x[n-1]  parakeet/audio.py:53-55 */
+  int32_t drop_last;  /* drop the final frame  whisper/audio.py:77 */
+  int32_t spec_kind;  /* B2A_SPEC_* */
+  float spec_eps;
+  int32_t n_mels;     /* 0 = spectrum output */
+  int32_t log_kind;   /* B2A_LOG_* */
+  int32_t guard_kind; /* B2A_GUARD_* */
+  float guard_eps;
+  int32_t clamp_kind; /* B2A_CLAMP_* */
+  float clamp_value;
+  float affine_add; /* applied iff affine_div != 0: (y + add) / div   whisper/audio.py:84 */
+  float affine_div;
+  int32_t norm_kind; /* B2A_NORM_* */
+  int32_t norm_ddof; /* 0 (mx.std) or 1 (sortformer.py:105-108) */
+  float norm_eps;
+  int32_t out_layout; /* B2A_LAYOUT_* */
+  int32_t reserved[4];
+} b2a_frontend_desc;
+
+/* Arguments of one forward launch over `batch` equal-length clips.
+ * Long-form frame-range sharding: a rank that owns frames [frame_begin, frame_begin+frame_count)
+ * of a signal of GLOBAL length `length` passes a slice whose first element is global sample
+ * `sample_offset`; the slice must cover the samples those frames touch (halo of n_fft-hop, +1 with
+ * preemphasis); padding applies at the global ends only. */
+typedef struct b2a_forward_args {
+  const float* audio;    /* device (or host for *_host) pointer to clip 0 */
+  int64_t clip_stride;   /* elements between consecutive clips */
+  int64_t length;        /* global signal length per clip INCLUDING virtual right padding */
+  int64_t valid_length;  /* samples really present (global index < valid_length), rest reads pad_value */
+  float pad_value;       /* parakeet pad_to / whisper `padding` (0) */
+  int32_t batch;
+  int64_t sample_offset; /* global index of audio[0] (0 when not sharded) */
+  int64_t frame_begin;   /* first frame to compute */
+  int64_t frame_count;   /* number of frames to compute, -1 = all (after drop_last) */
+  void* out;             /* features (float32) or spectrum (complex64 / float32), local frames only */
+  int64_t out_clip_stride; /* elements (float32, or complex64 for SPEC_COMPLEX) between clips; 0 = dense */
+  float* clip_max;       /* optional [batch] float: running max of y before clamp (device); NULL = internal */
+  double* feat_sums;     /* optional [batch][2*n_mels] double: sum, sum of squares per mel (device) */
+  void* workspace;       /* device scratch of b2a_frontend_workspace_bytes() or NULL to let the plan own it */
+  size_t workspace_bytes;
+} b2a_forward_args;
+
+typedef struct b2a_plan b2a_plan;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int b2a_version(void);
+const char* b2a_last_error(void);
+int b2a_device_count(void); /* 0 when no CUDA device / driver: compute calls will fail loudly */
+
+/* ---- host-side tables (no GPU needed) ------------------------------------------------------------
+ * b2a_window: dsp.py:33-79 — float64 cosine evaluated per tap, rounded to float32.
+ * b2a_mel_filters: dsp.py:223-296 — float32 arithmetic in the reference's order; `out` is
+ *   row-major (n_mels, n_fft/2+1).  f_max <= 0 means sample_rate/2 (dsp.py:264). */
+int b2a_window(int kind, int size, int periodic, float* h_out);
+int b2a_mel_filters(int sample_rate, int n_fft, int n_mels, double f_min, double f_max,
+                    int norm_slaney, int scale_htk, float* h_out);
+
+/* ---- geometry (pure integer arithmetic, no GPU needed) -------------------------------------------
+ * b2a_stft_geometry: dsp.py:118-136.  Returns B2A_ERR_TOO_SHORT exactly when the reference raises.
+ * b2a_frame_source_index: the bit-exact framing contract — source sample index of tap k of frame t
+ *   (-1 = literal zero from constant padding). */
+int b2a_stft_geometry(int64_t length, int n_fft, int hop, int center, int pad_mode,
+                      int64_t* padded_len, int64_t* num_frames);
+int64_t b2a_frame_source_index(int64_t length, int n_fft, int hop, int center, int pad_mode,
+                               int64_t t, int k);
+int b2a_istft_geometry(int64_t num_frames, int n_fft, int hop, int center, int64_t length /* -1 = None */,
+                       int64_t* ola_len, int64_t* out_start, int64_t* out_len);
+
+/* ---- forward: STFT / spectrogram / log-mel front-ends --------------------------------------------
+ * h_window: window_len taps; h_filterbank: (n_mels, n_fft/2+1) row-major or NULL when n_mels == 0. */
+int b2a_frontend_create(const b2a_frontend_desc* desc, const float* h_window,
+                        const float* h_filterbank, b2a_plan** plan);
+int b2a_plan_destroy(b2a_plan* plan);
+int b2a_frontend_out_frames(const b2a_plan* plan, int64_t length, int64_t* frames /* after drop_last */);
+size_t b2a_frontend_workspace_bytes(const b2a_plan* plan, int32_t batch);
+/* forward = partial + finalize (clamp / normalise) in one stream-ordered call */
+int b2a_frontend_forward(b2a_plan* plan, const b2a_forward_args* args, void* stream);
+/* split form for frame-range sharding: partial() leaves un-clamped / un-normalised values in `out`
+ * and the statistics in args->clip_max / args->feat_sums; the caller reduces those across ranks
+ * (max / sum) and calls finalize() with the GLOBAL frame count. */
+int b2a_frontend_partial(b2a_plan* plan, const b2a_forward_args* args, void* stream);
+int b2a_frontend_finalize(b2a_plan* plan, const b2a_forward_args* args, int64_t global_frames, void* stream);
+/* host-buffer entry (what a NumPy caller hits): H2D, compute, D2H pipelined on internal streams over
+ * chunks of clips; synchronous on return.  `args->audio` and `args->out` are HOST pointers here. */
+int b2a_frontend_forward_host(b2a_plan* plan, const b2a_forward_args* args);
+/* debug / parity: dump the windowed-or-raw frame matrix (T, n_fft) float32 for the bit-exact framing test */
+int b2a_frontend_dump_frames(b2a_plan* plan, const b2a_forward_args* args, int apply_window, void* stream);
+/* which kernel family a plan dispatches to: "fast400", "fast512", "generic", "small", ... */
+const char* b2a_plan_kernel_name(const b2a_plan* plan);
+
+/* ---- inverse: iSTFT with windowed overlap-add -----------------------------------------------------
+ * dsp.istft (dsp.py:144-217) and ISTFTCache.istft (dsp.py:350-417). */
+typedef struct b2a_istft_desc {
+  int32_t n_fft;      /* == win_length at every reference call site */
+  int32_t hop;
+  int32_t window_len; /* <= n_fft, zero-extended on the right (dsp.py:180-181) */
+  int32_t center;
+  int32_t norm_kind;  /* B2A_ISTFT_NORM_* */
+  int32_t div_kind;   /* B2A_ISTFT_DIV_* */
+  int32_t trim_tail;  /* 1: strip n_fft/2 from BOTH ends when center && length<0 (dsp.py:211-212);
+                         0: strip only the front (ISTFTCache, dsp.py:410-412) */
+  int32_t reserved[4];
+} b2a_istft_desc;
+
+typedef struct b2a_inverse_args {
+  const void* spec;     /* interleaved complex64 (batch, F, T) — or real plane when spec_imag != NULL */
+  const void* spec_imag; /* NULL, or imag plane float32 (batch, F, T) (ISTFTCache real/imag form) */
+  int64_t clip_stride;  /* elements (complex64 or float32) between clips; 0 = dense F*T */
+  int64_t num_frames;   /* T */
+  int32_t batch;
+  int64_t length;       /* -1 = None; else out = full[:length] (istft) / [:, :audio_length] (cache) */
+  float* out;           /* (batch, out_len) */
+  int64_t out_clip_stride; /* 0 = dense */
+} b2a_inverse_args;
+
+int b2a_istft_create(const b2a_istft_desc* desc, const float* h_window, b2a_plan** plan);
+int b2a_istft_out_len(const b2a_plan* plan, int64_t num_frames, int64_t length, int64_t* out_len);
+int b2a_istft_inverse(b2a_plan* plan, const b2a_inverse_args* args, void* stream);
+int b2a_istft_inverse_host(b2a_plan* plan, const b2a_inverse_args* args);
+
+/* ---- microbenchmarks used by bench.py for roofline denominators -----------------------------------
+ * FP32 FFMA peak of the current device (TFLOP/s) and a plain device copy bandwidth (GB/s). */
+int b2a_measure_fp32_tflops(double* tflops, void* stream);
+int b2a_measure_copy_gbs(double* gbs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AUDIO_H */

@@ -1,0 +1,121 @@
+// b200audio — shared declarations for the CUDA sources (internal; the public surface is include/b200audio.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200audio.h"
+
+namespace b2a {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B2A_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return b2a::cuda_fail(_e, #call);  \
+  } while (0)
+
+constexpr int kMaxStages = 12;
+constexpr int kMaxGenericRadix = 32;
+
+enum PlanKind { PLAN_FRONTEND = 0, PLAN_ISTFT = 1 };
+enum KernelFamily { KF_GENERIC = 0, KF_FAST = 1, KF_SMALL = 2 };
+
+// Framing geometry shared by host and device (dsp.py:118-136 incl. the short-input slice quirk).
+struct Geometry {
+  int64_t length;      // global signal length
+  int64_t pad_left;    // samples of centre padding actually produced on the left
+  int64_t pad_right;
+  int64_t padded_len;
+  int64_t num_frames;  // T (before drop_last)
+};
+
+__host__ __device__ inline Geometry make_geometry(int64_t length, int n_fft, int hop, int center, int pad_mode) {
+  Geometry g;
+  g.length = length;
+  int64_t p = center ? n_fft / 2 : 0;
+  if (center && pad_mode == B2A_PAD_REFLECT) {
+    // x[1:p+1][::-1] and x[-(p+1):-1][::-1] silently truncate to length-1 samples when length <= p
+    int64_t lim = length > 0 ? length - 1 : 0;
+    g.pad_left = p < lim ? p : lim;
+    g.pad_right = g.pad_left;
+  } else {
+    g.pad_left = p;
+    g.pad_right = p;
+  }
+  g.padded_len = length + g.pad_left + g.pad_right;
+  g.num_frames = g.padded_len >= n_fft ? 1 + (g.padded_len - n_fft) / hop : 0;
+  return g;
+}
+
+// padded position -> source index; -1 = literal zero
+__host__ __device__ inline int64_t source_index(const Geometry& g, int pad_mode, int64_t q) {
+  int64_t s = q - g.pad_left;
+  if (s < 0) return pad_mode == B2A_PAD_REFLECT ? -s : -1;
+  if (s >= g.length) return pad_mode == B2A_PAD_REFLECT ? 2 * g.length - 2 - s : -1;
+  return s;
+}
+
+struct MelCsr {  // filterbank rows as contiguous runs of non-zero taps
+  int* d_start = nullptr;  // [M] first bin
+  int* d_len = nullptr;    // [M] number of taps
+  int* d_off = nullptr;    // [M] offset into d_w
+  float* d_w = nullptr;    // [nnz_total]
+  int nnz = 0;
+  int max_len = 0;
+};
+
+}  // namespace b2a
+
+struct b2a_plan {
+  int kind;
+  int family;
+  const char* kernel_name;
+  b2a_frontend_desc fd;
+  b2a_istft_desc id;
+  int n_fft, hop, n_freqs;
+  int device, sm_count;
+  // device tables
+  float2* d_twiddle;  // W_N^k = exp(-2 pi i k / N), k = 0..N-1 (computed in double)
+  float* d_window;    // n_fft taps, zero-extended on the right
+  std::vector<float> h_window;
+  b2a::MelCsr mel;
+  float* d_fb_dense;  // (M, F) dense copy (used by the fast kernels' own packing)
+  std::vector<float> h_fb;
+  int nstages;
+  int radix[b2a::kMaxStages];
+  // plan-owned scratch (stats etc.), grown on demand
+  void* d_ws;
+  size_t ws_bytes;
+  // host-entry staging
+  void* d_stage_in[2];
+  void* d_stage_out[2];
+  size_t stage_in_bytes, stage_out_bytes;
+  cudaStream_t host_streams[2];
+  cudaEvent_t host_events[2];
+  void* fast;  // family-specific state
+};
+
+namespace b2a {
+// generic (any n_fft) kernels — generic.cu
+int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+                             double* feat_sums, cudaStream_t st);
+int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st);
+int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cudaStream_t st);
+int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, const float* clip_max,
+                      const float* clip_min, const double* feat_sums, cudaStream_t st);
+int init_stats(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_mels, cudaStream_t st);
+size_t generic_smem_limit(const b2a_plan* plan);
+// fast (specialised two-stage register FFT) kernels — fast_fwd.cu
+bool fast_frontend_supported(const b2a_plan* plan);
+int fast_frontend_init(b2a_plan* plan);
+void fast_frontend_destroy(b2a_plan* plan);
+int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+                          double* feat_sums, cudaStream_t st);
+}  // namespace b2a

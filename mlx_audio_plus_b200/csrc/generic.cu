@@ -1,0 +1,788 @@
+// b200audio — generic kernels: correct for ANY n_fft whose prime factors are <= 31.
+//
+// Forward (replaces the MLX op chain of dsp.py:118-141 + each wrapper's epilogue): one CTA owns a tile of
+// consecutive frames of one clip.  The tile's contiguous sample span is staged ONCE in shared memory
+// (padding, virtual right-pad and pre-emphasis are resolved on the way in), so overlapping frames re-read
+// smem, not HBM.  Two real frames are packed as one complex sequence and transformed by a mixed-radix
+// Stockham FFT in shared memory; the spectra are separated by Hermitian symmetry, reduced to
+// power / magnitude, projected through the (banded, CSR) mel filterbank, logged, staged and written with
+// coalesced stores.  Per-clip max/min and per-mel sums are reduced per tile and merged with atomics.
+//
+// Inverse (dsp.py:183-217 / 350-417): gather-form overlap-add.  A CTA owns a contiguous range of OUTPUT
+// samples, inverse-transforms exactly the frames that touch it (two Hermitian spectra packed per complex
+// FFT), windows them into shared memory, and each output sample sums its <= ceil(N/hop) frames in frame
+// order (the order the reference's sequential scatter-add uses), divides by the window envelope computed
+// the same way, and is written once.  No atomics, no materialised index arrays.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b2a {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct FftDesc {
+  int n;
+  int nstages;
+  int radix[kMaxStages];
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// One Stockham pass of radix R over `count` independent length-n sequences laid out back to back.
+// src/dst: [count][n] float2.  tw: W_n^k table.  Ns = product of the radices already applied.
+template <int R>
+__device__ __forceinline__ void butterfly(float2* v);
+
+template <>
+__device__ __forceinline__ void butterfly<2>(float2* v) {
+  float2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void butterfly<3>(float2* v) {
+  const float s = 0.86602540378443864676f;
+  float2 t1 = cadd(v[1], v[2]);
+  float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+  float2 d = csub(v[1], v[2]);
+  float2 t3 = make_float2(s * d.y, -s * d.x);  // -i * s * d
+  v[0] = cadd(v[0], t1);
+  v[1] = cadd(t2, t3);
+  v[2] = csub(t2, t3);
+}
+template <>
+__device__ __forceinline__ void butterfly<4>(float2* v) {
+  float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+  float2 c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+  float2 md = make_float2(d.y, -d.x);  // -i * d
+  v[0] = cadd(a, c);
+  v[2] = csub(a, c);
+  v[1] = cadd(b, md);
+  v[3] = csub(b, md);
+}
+template <>
+__device__ __forceinline__ void butterfly<5>(float2* v) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+  float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+  float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+  float2 x0 = v[0];
+  v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+  float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+  float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+  // -i * (s1 b1 + s2 b2),  -i * (s2 b1 - s1 b2)
+  float2 q1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
+  float2 q2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
+  v[1] = cadd(p1, q1);
+  v[4] = csub(p1, q1);
+  v[2] = cadd(p2, q2);
+  v[3] = csub(p2, q2);
+}
+
+template <int R>
+__device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                    const float2* __restrict__ tw, int n, int Ns, int count) {
+  const int nb = n / R;            // butterflies per sequence
+  const int tstep = n / (Ns * R);  // twiddle index stride
+  for (int idx = threadIdx.x; idx < count * nb; idx += blockDim.x) {
+    const int seq = idx / nb, j = idx - seq * nb;
+    const int k = j % Ns;
+    const float2* s = src + (size_t)seq * n;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 x = s[j + r * nb];
+      if (r > 0) x = cmul(x, tw[k * r * tstep]);  // k*r < Ns*R  =>  index < n
+      v[r] = x;
+    }
+    butterfly<R>(v);
+    float2* d = dst + (size_t)seq * n + (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[r * Ns] = v[r];
+  }
+}
+
+// arbitrary (prime) radix: O(R^2) per butterfly, twiddles from the same table
+__device__ __forceinline__ void stockham_pass_any(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                  const float2* __restrict__ tw, int n, int Ns, int count, int R) {
+  const int nb = n / R;
+  const int tstep = n / (Ns * R);
+  const int rstep = n / R;
+  for (int idx = threadIdx.x; idx < count * nb; idx += blockDim.x) {
+    const int seq = idx / nb, j = idx - seq * nb;
+    const int k = j % Ns;
+    const float2* s = src + (size_t)seq * n;
+    float2 v[kMaxGenericRadix];
+    for (int r = 0; r < R; ++r) {
+      float2 x = s[j + r * nb];
+      if (r > 0) x = cmul(x, tw[k * r * tstep]);  // k*r < Ns*R  =>  index < n
+      v[r] = x;
+    }
+    float2* d = dst + (size_t)seq * n + (j - k) * R + k;
+    for (int q = 0; q < R; ++q) {
+      float2 acc = v[0];
+      for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(v[r], tw[((q * r) % R) * rstep]));
+      d[q * Ns] = acc;
+    }
+  }
+}
+
+// Runs all passes; returns the buffer holding the result.  All threads must call.
+__device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2* tw, int count) {
+  int Ns = 1;
+  float2 *src = a, *dst = b;
+  for (int s = 0; s < fd.nstages; ++s) {
+    const int R = fd.radix[s];
+    switch (R) {
+      case 2: stockham_pass_fixed<2>(src, dst, tw, fd.n, Ns, count); break;
+      case 3: stockham_pass_fixed<3>(src, dst, tw, fd.n, Ns, count); break;
+      case 4: stockham_pass_fixed<4>(src, dst, tw, fd.n, Ns, count); break;
+      case 5: stockham_pass_fixed<5>(src, dst, tw, fd.n, Ns, count); break;
+      default: stockham_pass_any(src, dst, tw, fd.n, Ns, count, R); break;
+    }
+    __syncthreads();
+    Ns *= R;
+    float2* t = src;
+    src = dst;
+    dst = t;
+  }
+  return src;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (v > __int_as_float(old)) {
+    int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (v < __int_as_float(old)) {
+    int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
+struct FwdParams {
+  const float* audio;
+  int64_t clip_stride, valid_length, sample_offset, frame_begin, frame_count;
+  float pad_value;
+  int batch;
+  Geometry geo;
+  int n_fft, hop, n_freqs, pad_mode;
+  float preemph;
+  int spec_kind;
+  float spec_eps;
+  int n_mels, log_kind, guard_kind;
+  float guard_eps;
+  int apply_affine;
+  float affine_add, affine_div;
+  int out_layout;
+  void* out;
+  int64_t out_clip_stride;
+  float *clip_max, *clip_min;
+  double* feat_sums;
+  const float2* tw;
+  const float* window;
+  const int *mel_start, *mel_len, *mel_off;
+  const float* mel_w;
+  FftDesc fft;
+  int frames_per_tile, tiles_per_clip;
+  int dump_frames, dump_windowed;
+};
+
+// global sample (after right-pad + preemphasis) at source index s >= 0
+__device__ __forceinline__ float fetch_sample(const FwdParams& p, const float* clip, int64_t s) {
+  float x = s < p.valid_length ? __ldg(clip + (s - p.sample_offset)) : p.pad_value;
+  if (p.preemph != 0.0f && s > 0) {
+    const int64_t sm = s - 1;
+    const float xm = sm < p.valid_length ? __ldg(clip + (sm - p.sample_offset)) : p.pad_value;
+    x = x - p.preemph * xm;
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.n_fft, hop = p.hop, F = p.n_freqs, FT = p.frames_per_tile, PAIRS = FT / 2;
+  const int span = (FT - 1) * hop + N;
+  float2* bufA = reinterpret_cast<float2*>(smem_raw);
+  float2* bufB = bufA + (size_t)PAIRS * N;
+  float* xs = reinterpret_cast<float*>(bufB + (size_t)PAIRS * N);
+  __shared__ float red_max[kThreads / 32], red_min[kThreads / 32];
+
+  const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int clip_i = (int)(tile / p.tiles_per_clip);
+    const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
+    const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
+    const int64_t lt0 = (int64_t)tile_i * FT;  // local frame index of the tile's first frame
+    const int64_t t0 = p.frame_begin + lt0;    // global frame index
+    const int nf = (int)min((int64_t)FT, p.frame_count - lt0);  // valid frames in this tile
+
+    // ---- stage the sample span (padding / right-pad / pre-emphasis resolved here) -------------------
+    const int64_t q0 = t0 * hop;
+    const int need = (nf - 1) * hop + N;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+      float v = 0.0f;
+      if (i < need) {
+        const int64_t s = source_index(p.geo, p.pad_mode, q0 + i);
+        if (s >= 0) v = fetch_sample(p, clip, s);
+      }
+      xs[i] = v;
+    }
+    __syncthreads();
+
+    if (p.dump_frames) {  // parity hook: the framed (optionally windowed) matrix itself
+      float* o = reinterpret_cast<float*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * N;
+      for (int i = threadIdx.x; i < nf * N; i += blockDim.x) {
+        const int f = i / N, k = i - f * N;
+        float v = xs[f * hop + k];
+        if (p.dump_windowed) v *= p.window[k];
+        o[i] = v;
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- window + pack two real frames per complex sequence ------------------------------------------
+    for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
+      const int pr = i / N, k = i - pr * N;
+      const float w = p.window[k];
+      const int fa = 2 * pr, fb = 2 * pr + 1;
+      const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
+      const float b = fb < nf ? xs[fb * hop + k] * w : 0.0f;
+      bufA[i] = make_float2(a, b);
+    }
+    __syncthreads();
+    float2* Z = run_fft(p.fft, bufA, bufB, p.tw, PAIRS);
+    float2* other = (Z == bufA) ? bufB : bufA;
+
+    // ---- Hermitian separation ------------------------------------------------------------------------
+    if (p.n_mels == 0 && p.spec_kind == B2A_SPEC_COMPLEX) {
+      float2* o = reinterpret_cast<float2*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * F;
+      for (int i = threadIdx.x; i < nf * F; i += blockDim.x) {
+        const int f = i / F, k = i - f * F;
+        const float2* z = Z + (size_t)(f >> 1) * N;
+        const float2 zk = z[k], zm = z[k == 0 ? 0 : N - k];
+        float2 X;
+        if ((f & 1) == 0) X = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        else X = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+        o[i] = X;
+      }
+      __syncthreads();
+      continue;
+    }
+    float* P = reinterpret_cast<float*>(other);  // [FT][F]
+    for (int i = threadIdx.x; i < FT * F; i += blockDim.x) {
+      const int f = i / F, k = i - f * F;
+      float v = 0.0f;
+      if (f < nf) {
+        const float2* z = Z + (size_t)(f >> 1) * N;
+        const float2 zk = z[k], zm = z[k == 0 ? 0 : N - k];
+        float re, im;
+        if ((f & 1) == 0) { re = 0.5f * (zk.x + zm.x); im = 0.5f * (zk.y - zm.y); }
+        else { re = 0.5f * (zk.y + zm.y); im = 0.5f * (zm.x - zk.x); }
+        const float pw = re * re + im * im;
+        switch (p.spec_kind) {
+          case B2A_SPEC_POWER: v = pw; break;
+          case B2A_SPEC_MAGNITUDE: v = sqrtf(pw); break;
+          default: v = sqrtf(pw + p.spec_eps); break;
+        }
+      }
+      P[i] = v;
+    }
+    __syncthreads();
+
+    // ---- mel projection (banded), guard, log, affine; staged in smem ---------------------------------
+    const int M = p.n_mels > 0 ? p.n_mels : F;
+    float* Y = reinterpret_cast<float*>(Z);  // [FT][M]   (M <= F <= N)
+    float lmax = -INFINITY, lmin = INFINITY;
+    for (int i = threadIdx.x; i < nf * M; i += blockDim.x) {
+      const int f = i / M, m = i - f * M;
+      float acc;
+      if (p.n_mels > 0) {
+        const float* row = P + (size_t)f * F + p.mel_start[m];
+        const float* w = p.mel_w + p.mel_off[m];
+        const int len = p.mel_len[m];
+        acc = 0.0f;
+        for (int j = 0; j < len; ++j) acc = fmaf(row[j], __ldg(w + j), acc);
+      } else {
+        acc = P[(size_t)f * F + m];
+      }
+      if (p.guard_kind == B2A_GUARD_MAX) acc = fmaxf(acc, p.guard_eps);
+      else if (p.guard_kind == B2A_GUARD_ADD) acc = acc + p.guard_eps;
+      if (p.log_kind == B2A_LOG_LOG10) acc = log10f(acc);
+      else if (p.log_kind == B2A_LOG_LN) acc = logf(acc);
+      lmax = fmaxf(lmax, acc);
+      lmin = fminf(lmin, acc);
+      if (p.apply_affine) acc = (acc + p.affine_add) / p.affine_div;
+      Y[i] = acc;
+    }
+    if (p.clip_max) {
+      for (int o = 16; o > 0; o >>= 1) {
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      }
+      if ((threadIdx.x & 31) == 0) { red_max[threadIdx.x >> 5] = lmax; red_min[threadIdx.x >> 5] = lmin; }
+    }
+    __syncthreads();
+    if (p.clip_max && threadIdx.x == 0) {
+      float a = red_max[0], b = red_min[0];
+      for (int w = 1; w < kThreads / 32; ++w) { a = fmaxf(a, red_max[w]); b = fminf(b, red_min[w]); }
+      atomic_max_float(p.clip_max + clip_i, a);
+      atomic_min_float(p.clip_min + clip_i, b);
+    }
+    if (p.feat_sums) {
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int f = 0; f < nf; ++f) { const double y = Y[f * M + m]; s1 += y; s2 += y * y; }
+        atomicAdd(p.feat_sums + ((int64_t)clip_i * M + m) * 2 + 0, s1);
+        atomicAdd(p.feat_sums + ((int64_t)clip_i * M + m) * 2 + 1, s2);
+      }
+    }
+    // ---- coalesced write-out ---------------------------------------------------------------------------
+    float* o = reinterpret_cast<float*>(p.out) + (int64_t)clip_i * p.out_clip_stride;
+    if (p.out_layout == B2A_LAYOUT_TM) {
+      float* ot = o + lt0 * M;
+      for (int i = threadIdx.x; i < nf * M; i += blockDim.x) ot[i] = Y[i];
+    } else {
+      for (int i = threadIdx.x; i < nf * M; i += blockDim.x) {
+        const int m = i / nf, f = i - m * nf;
+        o[(int64_t)m * p.frame_count + lt0 + f] = Y[f * M + m];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- finalize: clamp / normalise in place --------------------------------------------------------------
+struct FinParams {
+  float* out;
+  int64_t out_clip_stride;
+  int batch, n_mels, out_layout;
+  int64_t frames;         // local frames held in out
+  int64_t global_frames;  // frames the statistics cover
+  int clamp_kind;
+  float clamp_value;
+  int apply_affine;
+  float affine_add, affine_div;
+  int norm_kind, norm_ddof;
+  float norm_eps;
+  const float *clip_max, *clip_min;
+  const double* feat_sums;
+};
+
+__global__ void __launch_bounds__(256) frontend_finalize_kernel(const FinParams p) {
+  const int clip_i = blockIdx.y;
+  const int M = p.n_mels;
+  float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
+  const int64_t total = p.frames * M;
+  if (p.clamp_kind != B2A_CLAMP_NONE) {
+    float floor_v;
+    bool active = true;
+    if (p.clamp_kind == B2A_CLAMP_FIXED) {
+      floor_v = p.clamp_value;
+      active = p.clip_min[clip_i] < floor_v;
+    } else {
+      float mx = p.clip_max[clip_i];
+      if (p.clamp_kind == B2A_CLAMP_BATCH_MAX)
+        for (int b = 0; b < p.batch; ++b) mx = fmaxf(mx, p.clip_max[b]);
+      floor_v = mx - p.clamp_value;
+      active = p.clip_min[clip_i] < floor_v;
+    }
+    if (!active) return;  // nothing below the floor in this clip: the values written by partial() are final
+    if (p.apply_affine) floor_v = (floor_v + p.affine_add) / p.affine_div;  // monotone => commutes with max
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const float v = o[i];
+      if (v < floor_v) o[i] = floor_v;
+    }
+    return;
+  }
+  if (p.norm_kind != B2A_NORM_NONE) {
+    const double n = (double)p.global_frames;
+    const double* S = p.feat_sums + (int64_t)clip_i * M * 2;
+    float g_mean = 0.f, g_den = 1.f;
+    if (p.norm_kind == B2A_NORM_GLOBAL) {
+      double s1 = 0, s2 = 0;
+      for (int m = 0; m < M; ++m) { s1 += S[2 * m]; s2 += S[2 * m + 1]; }
+      const double cnt = n * M, mean = s1 / cnt;
+      double var = (s2 - cnt * mean * mean) / (cnt - p.norm_ddof);
+      if (var < 0) var = 0;
+      g_mean = (float)mean;
+      g_den = (float)sqrt(var) + p.norm_eps;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int m = p.out_layout == B2A_LAYOUT_TM ? (int)(i % M) : (int)(i / p.frames);
+      float mean = g_mean, den = g_den;
+      if (p.norm_kind == B2A_NORM_PER_FEATURE) {
+        const double mu = S[2 * m] / n;
+        double var = (S[2 * m + 1] - n * mu * mu) / (n - p.norm_ddof);
+        if (var < 0) var = 0;
+        mean = (float)mu;
+        den = (float)sqrt(var) + p.norm_eps;
+      }
+      o[i] = (o[i] - mean) / den;
+    }
+  }
+}
+
+__global__ void init_stats_kernel(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) {
+    if (clip_max) clip_max[i] = -INFINITY;
+    if (clip_min) clip_min[i] = INFINITY;
+  }
+  if (feat_sums && i < n_sums) feat_sums[i] = 0.0;
+}
+
+// ---- inverse ---------------------------------------------------------------------------------------------
+struct InvParams {
+  const float2* spec;     // interleaved, or nullptr
+  const float* spec_re;   // planar form
+  const float* spec_im;
+  int64_t clip_stride, T;
+  int batch;
+  int n_fft, hop, n_freqs;
+  int norm_sq, div_clamp;
+  int64_t out_start, out_len, out_clip_stride;
+  float* out;
+  const float2* tw;
+  const float* window;
+  FftDesc fft;
+  int frames_adv;       // frames advanced per tile (tile covers frames_adv*hop output samples)
+  int frames_cap;       // max frames resident per tile
+  int pairs_chunk;      // pairs transformed per FFT round
+  int tiles_per_clip;
+};
+
+__global__ void __launch_bounds__(kThreads) istft_generic_kernel(const InvParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.n_fft, hop = p.hop, F = p.n_freqs;
+  float2* bufA = reinterpret_cast<float2*>(smem_raw);
+  float2* bufB = bufA + (size_t)p.pairs_chunk * N;
+  float* Y = reinterpret_cast<float*>(bufB + (size_t)p.pairs_chunk * N);  // [frames_cap][N] windowed frames
+  const float invN = 1.0f / (float)N;
+  const int64_t S = (int64_t)p.frames_adv * hop;
+
+  const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int clip_i = (int)(tile / p.tiles_per_clip);
+    const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
+    const int64_t j0 = (int64_t)tile_i * S;                   // first output index of this tile
+    const int64_t j1 = min(j0 + S, p.out_len);
+    const int64_t n0 = p.out_start + j0, n1 = p.out_start + j1;  // OLA coordinates [n0, n1)
+    // frames touching [n0, n1): t*hop <= n1-1  and  t*hop + N - 1 >= n0
+    int64_t t_lo = n0 - N + 1 <= 0 ? 0 : (n0 - N + 1 + hop - 1) / hop;
+    int64_t t_hi = (n1 - 1) / hop;
+    if (t_hi > p.T - 1) t_hi = p.T - 1;
+    const int nfr = (int)(t_hi - t_lo + 1);
+
+    for (int c0 = 0; c0 < nfr; c0 += 2 * p.pairs_chunk) {
+      const int cf = min(2 * p.pairs_chunk, nfr - c0);  // frames in this round
+      const int cp = (cf + 1) / 2;
+      // load + pack: Z[k] = conj(Xa[k] + i Xb[k]) over the full Hermitian-extended spectrum, so that
+      // FFT(Z) = conj(N * (xa + i xb))
+      for (int i = threadIdx.x; i < cp * N; i += blockDim.x) {
+        const int pr = i / N, k = i - pr * N;
+        const int kk = k < F ? k : N - k;  // source bin (N even or odd: bins > N/2 mirror)
+        const bool mir = k >= F;
+        float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
+        const int fa = c0 + 2 * pr, fb = fa + 1;
+        const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo;
+        if (fa < c0 + cf) xa = p.spec ? p.spec[base + fa] : make_float2(p.spec_re[base + fa], p.spec_im[base + fa]);
+        if (fb < c0 + cf) xb = p.spec ? p.spec[base + fb] : make_float2(p.spec_re[base + fb], p.spec_im[base + fb]);
+        // irfft ignores Im(DC) and, for even N, Im(Nyquist)
+        if (kk == 0 || (2 * kk == N)) { xa.y = 0.f; xb.y = 0.f; }
+        if (mir) { xa.y = -xa.y; xb.y = -xb.y; }
+        // z = xa + i xb ; store conj(z)
+        bufA[i] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
+      }
+      __syncthreads();
+      float2* Z = run_fft(p.fft, bufA, bufB, p.tw, cp);
+      for (int i = threadIdx.x; i < cf * N; i += blockDim.x) {
+        const int f = i / N, k = i - f * N;
+        const float2 z = Z[(size_t)(f >> 1) * N + k];
+        const float v = ((f & 1) == 0 ? z.x : -z.y) * invN;
+        Y[(size_t)(c0 + f) * N + k] = v * p.window[k];
+      }
+      __syncthreads();
+    }
+    // gather overlap-add, ascending frame order
+    float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+      const int64_t n = p.out_start + j;
+      int64_t ta = n - N + 1 <= 0 ? 0 : (n - N + 1 + hop - 1) / hop;
+      int64_t tb = n / hop;
+      if (tb > p.T - 1) tb = p.T - 1;
+      float num = 0.f, den = 0.f;
+      for (int64_t t = ta; t <= tb; ++t) {
+        const int k = (int)(n - t * hop);
+        num += Y[(size_t)(t - t_lo) * N + k];
+        const float w = p.window[k];
+        den += p.norm_sq ? w * w : w;
+      }
+      float r;
+      if (p.div_clamp) r = num / fmaxf(den, 1e-10f);
+      else r = den > 1e-10f ? num / den : num;
+      o[j] = r;
+    }
+    __syncthreads();
+  }
+}
+
+static FftDesc make_fft_desc(const b2a_plan* plan) {
+  FftDesc d;
+  d.n = plan->n_fft;
+  d.nstages = plan->nstages;
+  for (int i = 0; i < kMaxStages; ++i) d.radix[i] = plan->radix[i];
+  return d;
+}
+
+}  // namespace
+
+size_t generic_smem_limit(const b2a_plan* plan) {
+  (void)plan;
+  return 200 * 1024;
+}
+
+static int choose_frames_per_tile(int N, int hop, size_t budget, int max_ft) {
+  int best = 0;
+  for (int ft = 2; ft <= max_ft; ft += 2) {
+    size_t bytes = (size_t)4 * ((size_t)(ft - 1) * hop + N) + (size_t)16 * (ft / 2) * N;
+    if (bytes <= budget) best = ft;
+  }
+  return best;
+}
+
+int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+                             double* feat_sums, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.audio = a->audio;
+  p.clip_stride = a->clip_stride;
+  p.valid_length = a->valid_length;
+  p.sample_offset = a->sample_offset;
+  p.frame_begin = a->frame_begin;
+  p.frame_count = a->frame_count;
+  p.pad_value = a->pad_value;
+  p.batch = a->batch;
+  p.geo = make_geometry(a->length, d.n_fft, d.hop, d.center, d.pad_mode);
+  p.n_fft = d.n_fft;
+  p.hop = d.hop;
+  p.n_freqs = plan->n_freqs;
+  p.pad_mode = d.pad_mode;
+  p.preemph = d.preemph;
+  p.spec_kind = d.spec_kind;
+  p.spec_eps = d.spec_eps;
+  p.n_mels = d.n_mels;
+  p.log_kind = d.log_kind;
+  p.guard_kind = d.guard_kind;
+  p.guard_eps = d.guard_eps;
+  p.apply_affine = d.affine_div != 0.0f;
+  p.affine_add = d.affine_add;
+  p.affine_div = d.affine_div;
+  p.out_layout = d.out_layout;
+  p.out = a->out;
+  const int M = d.n_mels > 0 ? d.n_mels : plan->n_freqs;
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * M;
+  p.clip_max = clip_max;
+  p.clip_min = clip_min;
+  p.feat_sums = feat_sums;
+  p.tw = plan->d_twiddle;
+  p.window = plan->d_window;
+  p.mel_start = plan->mel.d_start;
+  p.mel_len = plan->mel.d_len;
+  p.mel_off = plan->mel.d_off;
+  p.mel_w = plan->mel.d_w;
+  p.fft = make_fft_desc(plan);
+  int ft = choose_frames_per_tile(d.n_fft, d.hop, 96 * 1024, 64);
+  if (ft == 0) ft = choose_frames_per_tile(d.n_fft, d.hop, generic_smem_limit(plan), 2);
+  if (ft == 0) {
+    set_error("n_fft=%d too large for the generic kernel", d.n_fft);
+    return B2A_ERR_UNSUPPORTED;
+  }
+  // small inputs: shrink tiles so that the grid still covers the SMs
+  while (ft > 2 && (int64_t)a->batch * ((a->frame_count + ft - 1) / ft) < 2 * plan->sm_count) ft -= 2;
+  p.frames_per_tile = ft;
+  p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
+  const size_t smem = (size_t)4 * ((size_t)(ft - 1) * d.hop + d.n_fft) + (size_t)16 * (ft / 2) * d.n_fft;
+  B2A_CUDA(cudaFuncSetAttribute(frontend_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
+  if (grid < 1) grid = 1;
+  frontend_generic_kernel<<<grid, kThreads, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.audio = a->audio;
+  p.clip_stride = a->clip_stride;
+  p.valid_length = a->valid_length;
+  p.sample_offset = a->sample_offset;
+  p.frame_begin = a->frame_begin;
+  p.frame_count = a->frame_count;
+  p.pad_value = a->pad_value;
+  p.batch = a->batch;
+  p.geo = make_geometry(a->length, d.n_fft, d.hop, d.center, d.pad_mode);
+  p.n_fft = d.n_fft;
+  p.hop = d.hop;
+  p.n_freqs = plan->n_freqs;
+  p.pad_mode = d.pad_mode;
+  p.preemph = d.preemph;
+  p.out = a->out;
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * d.n_fft;
+  p.window = plan->d_window;
+  p.dump_frames = 1;
+  p.dump_windowed = apply_window;
+  int ft = choose_frames_per_tile(d.n_fft, d.hop, 96 * 1024, 16);
+  if (ft == 0) ft = 2;
+  p.frames_per_tile = ft;
+  p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
+  const size_t smem = (size_t)4 * ((size_t)(ft - 1) * d.hop + d.n_fft) + (size_t)16 * (ft / 2) * d.n_fft;
+  B2A_CUDA(cudaFuncSetAttribute(frontend_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * 2);
+  if (grid < 1) grid = 1;
+  frontend_generic_kernel<<<grid, kThreads, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int init_stats(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_mels, cudaStream_t st) {
+  const int n_sums = feat_sums ? batch * n_mels * 2 : 0;
+  const int n = batch > n_sums ? batch : n_sums;
+  if (n <= 0) return B2A_OK;
+  init_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(clip_max, clip_min, feat_sums, batch, n_sums);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, const float* clip_max,
+                      const float* clip_min, const double* feat_sums, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  if (d.clamp_kind == B2A_CLAMP_NONE && d.norm_kind == B2A_NORM_NONE) return B2A_OK;
+  FinParams p;
+  memset(&p, 0, sizeof(p));
+  const int M = d.n_mels > 0 ? d.n_mels : plan->n_freqs;
+  p.out = reinterpret_cast<float*>(a->out);
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * M;
+  p.batch = a->batch;
+  p.n_mels = M;
+  p.out_layout = d.out_layout;
+  p.frames = a->frame_count;
+  p.global_frames = global_frames;
+  p.clamp_kind = d.clamp_kind;
+  p.clamp_value = d.clamp_value;
+  p.apply_affine = d.affine_div != 0.0f;
+  p.affine_add = d.affine_add;
+  p.affine_div = d.affine_div;
+  p.norm_kind = d.norm_kind;
+  p.norm_ddof = d.norm_ddof;
+  p.norm_eps = d.norm_eps;
+  p.clip_max = clip_max;
+  p.clip_min = clip_min;
+  p.feat_sums = feat_sums;
+  const int64_t total = a->frame_count * M;
+  int gx = (int)std::min<int64_t>((total + 256 * 8 - 1) / (256 * 8), 4 * plan->sm_count);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, a->batch);
+  frontend_finalize_kernel<<<grid, 256, 0, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
+  const b2a_istft_desc& d = plan->id;
+  InvParams p;
+  memset(&p, 0, sizeof(p));
+  const int N = d.n_fft, hop = d.hop, F = plan->n_freqs;
+  if (a->spec_imag) {
+    p.spec = nullptr;
+    p.spec_re = reinterpret_cast<const float*>(a->spec);
+    p.spec_im = reinterpret_cast<const float*>(a->spec_imag);
+  } else {
+    p.spec = reinterpret_cast<const float2*>(a->spec);
+  }
+  p.T = a->num_frames;
+  p.clip_stride = a->clip_stride ? a->clip_stride : (int64_t)F * a->num_frames;
+  p.batch = a->batch;
+  p.n_fft = N;
+  p.hop = hop;
+  p.n_freqs = F;
+  p.norm_sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
+  p.div_clamp = d.div_kind == B2A_ISTFT_DIV_CLAMP;
+  int64_t ola, start, len;
+  int64_t eff_len = a->length;
+  b2a_istft_geometry(a->num_frames, N, hop, d.center, d.trim_tail ? eff_len : -1, &ola, &start, &len);
+  if (!d.trim_tail) {  // ISTFTCache: strip only the front, then [:audio_length]
+    start = d.center ? N / 2 : 0;
+    len = ola - start;
+    if (len < 0) len = 0;
+    if (a->length >= 0 && a->length < len) len = a->length;
+  }
+  p.out_start = start;
+  p.out_len = len;
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : len;
+  p.out = a->out;
+  p.tw = plan->d_twiddle;
+  p.window = plan->d_window;
+  p.fft = make_fft_desc(plan);
+  if (len <= 0) return B2A_OK;
+  const int ov = (N + hop - 1) / hop;  // frames overlapping one sample (upper bound)
+  // pick frames_adv so that Y + FFT buffers fit in ~100 KB (up to the hard limit for huge N)
+  int pairs_chunk = N <= 256 ? 8 : (N <= 1024 ? 2 : 1);
+  size_t fft_bytes = (size_t)16 * pairs_chunk * N;
+  int adv = 0;
+  for (int cand = 1; cand <= 256; cand *= 2) {
+    size_t bytes = fft_bytes + (size_t)4 * N * (cand + ov);
+    if (bytes <= 100 * 1024) adv = cand;
+  }
+  if (adv == 0) {
+    adv = 1;
+    if (fft_bytes + (size_t)4 * N * (adv + ov) > generic_smem_limit(plan)) {
+      set_error("n_fft=%d / hop=%d too large for the generic iSTFT kernel", N, hop);
+      return B2A_ERR_UNSUPPORTED;
+    }
+  }
+  while (adv > 1 && (int64_t)a->batch * ((len + (int64_t)adv * hop - 1) / ((int64_t)adv * hop)) < 2 * plan->sm_count)
+    adv /= 2;
+  p.frames_adv = adv;
+  p.frames_cap = adv + ov;
+  p.pairs_chunk = pairs_chunk;
+  const int64_t S = (int64_t)adv * hop;
+  p.tiles_per_clip = (int)((len + S - 1) / S);
+  const size_t smem = fft_bytes + (size_t)4 * N * p.frames_cap;
+  B2A_CUDA(cudaFuncSetAttribute(istft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
+  if (grid < 1) grid = 1;
+  istft_generic_kernel<<<grid, kThreads, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+}  // namespace b2a

