@@ -209,7 +209,7 @@ __device__ __forceinline__ float fetch_sample(const FwdParams& p, const float* c
   if (p.preemph != 0.0f && s > 0) {
     const int64_t sm = s - 1;
     const float xm = sm < p.valid_length ? __ldg(clip + (sm - p.sample_offset)) : p.pad_value;
-    x = x - p.preemph * xm;
+    x = __fsub_rn(x, __fmul_rn(p.preemph, xm));  // two roundings, as `x[1:] - a*x[:-1]` (no FMA contraction)
   }
   return x;
 }
