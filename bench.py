@@ -265,6 +265,7 @@ def main():
     k1.record(stream)
     torch.cuda.synchronize()
     kms = k0.elapsed_time(k1) / a.steps
+    step()  # leave finalized features in `out` (partial() alone skips the clamp)
     clocks = sampler.stop() if rank == 0 else None
     tms = torch.tensor([ms], device=devt, dtype=torch.float64)
     if world > 1:

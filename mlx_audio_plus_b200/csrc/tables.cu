@@ -110,14 +110,14 @@ int b2a_mel_filters(int sample_rate, int n_fft, int n_mels, double f_min, double
     const float m = grid[j];
     if (scale_htk) {
       volatile float e = m / 2595.0f;
-      volatile float pw = powf(10.0f, e);
+      volatile float pw = (float)pow(10.0, (double)e);  // correctly rounded float32 10**x
       volatile float d = pw - 1.0f;
       f_pts[j] = 700.0f * d;
     } else {
       if (m >= (float)min_log_mel) {
         volatile float d = m - (float)min_log_mel;
         volatile float a = (float)logstep * d;
-        volatile float ex = expf(a);
+        volatile float ex = (float)exp((double)a);  // correctly rounded float32 exp
         f_pts[j] = (float)min_log_hz * ex;
       } else {
         f_pts[j] = (float)f_sp * m;
