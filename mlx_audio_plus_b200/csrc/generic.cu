@@ -383,6 +383,7 @@ struct FinParams {
   float norm_eps;
   const float *clip_max, *clip_min;
   const double* feat_sums;
+  int stats_affine;  // 1: clip_max/min were recorded AFTER the affine map (fast kernels)
 };
 
 __global__ void __launch_bounds__(256) frontend_finalize_kernel(const FinParams p) {
@@ -391,23 +392,31 @@ __global__ void __launch_bounds__(256) frontend_finalize_kernel(const FinParams 
   float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
   const int64_t total = p.frames * M;
   if (p.clamp_kind != B2A_CLAMP_NONE) {
-    float floor_v;
-    bool active = true;
+    // floor in the OUTPUT domain; the affine map is monotone increasing, so it commutes with max()
+    float floor_out;
+    bool active;
+    const float lo = p.clip_min[clip_i];
     if (p.clamp_kind == B2A_CLAMP_FIXED) {
-      floor_v = p.clamp_value;
-      active = p.clip_min[clip_i] < floor_v;
+      const float fl = p.apply_affine ? (p.clamp_value + p.affine_add) / p.affine_div : p.clamp_value;
+      floor_out = fl;
+      active = p.stats_affine ? (lo < fl) : (lo < p.clamp_value);
     } else {
       float mx = p.clip_max[clip_i];
       if (p.clamp_kind == B2A_CLAMP_BATCH_MAX)
         for (int b = 0; b < p.batch; ++b) mx = fmaxf(mx, p.clip_max[b]);
-      floor_v = mx - p.clamp_value;
-      active = p.clip_min[clip_i] < floor_v;
+      if (p.stats_affine) {
+        floor_out = p.apply_affine ? mx - p.clamp_value / p.affine_div : mx - p.clamp_value;
+        active = lo < floor_out;
+      } else {
+        const float fl = mx - p.clamp_value;
+        active = lo < fl;
+        floor_out = p.apply_affine ? (fl + p.affine_add) / p.affine_div : fl;
+      }
     }
     if (!active) return;  // nothing below the floor in this clip: the values written by partial() are final
-    if (p.apply_affine) floor_v = (floor_v + p.affine_add) / p.affine_div;  // monotone => commutes with max
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
       const float v = o[i];
-      if (v < floor_v) o[i] = floor_v;
+      if (v < floor_out) o[i] = floor_out;
     }
     return;
   }
@@ -680,6 +689,7 @@ int init_stats(float* clip_max, float* clip_min, double* feat_sums, int batch, i
 
 int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, const float* clip_max,
                       const float* clip_min, const double* feat_sums, cudaStream_t st) {
+  const int stats_affine = plan->family == KF_FAST ? 1 : 0;
   const b2a_frontend_desc& d = plan->fd;
   if (d.clamp_kind == B2A_CLAMP_NONE && d.norm_kind == B2A_NORM_NONE) return B2A_OK;
   FinParams p;
@@ -703,6 +713,7 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   p.clip_max = clip_max;
   p.clip_min = clip_min;
   p.feat_sums = feat_sums;
+  p.stats_affine = stats_affine;
   const int64_t total = a->frame_count * M;
   int gx = (int)std::min<int64_t>((total + 256 * 8 - 1) / (256 * 8), 4 * plan->sm_count);
   if (gx < 1) gx = 1;
