@@ -73,12 +73,14 @@ struct FastParams {
   int64_t out_clip_stride;
   float *clip_max, *clip_min;  // affine-domain statistics
   double* feat_sums;
-  const float2* win2;   // [NC] (w[2m], w[2m+1]) * 0.5
+  const float2* win2;   // [N2][N1] (w[2m], w[2m+1]) * 0.5 with m = N2*n1 + n2
   const float2* tw1;    // [N2][N1]  W_Nc^(n2*k1)
-  const float2* twp;    // [NC/2+1.. NC] W_N^k, k = 0..NC
-  const int *mel_start, *mel_len, *mel_off;
-  const float* mel_w;
-  int mel_nnz;
+  const float2* twp;    // [N1/2][2*N2] post-twiddles W_N^k in the order stage 2 consumes them (see init)
+  // mel filterbank, lane == mel layout: G = ceil(M/32) groups of 32 consecutive mel rows
+  const int* mel_start;   // [G*32] first bin of each row (0 for rows >= M)
+  const int* mel_ginfo;   // [2*G]  (group max length, offset of the group's weights in floats)
+  const float* mel_wg;    // [sum_g glen[g]*32]  W[g][j][lane], zero padded
+  int mel_groups, mel_wg_count;
   int tiles_per_clip;
 };
 
@@ -119,9 +121,9 @@ __device__ __forceinline__ float fetch_sample_f(const FastParams& p, const float
 }
 
 template <class C>
-__device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, int64_t tile) {
-  const int clip_i = (int)(tile / p.tiles_per_clip);
-  const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
+__device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, unsigned tile) {
+  const int clip_i = (int)(tile / (unsigned)p.tiles_per_clip);
+  const int tile_i = (int)(tile - (unsigned)clip_i * (unsigned)p.tiles_per_clip);
   const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
   const int64_t lt0 = (int64_t)tile_i * C::FT;
   const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
@@ -164,50 +166,67 @@ __device__ __forceinline__ void post_pair(float2 zk, float2 zm, float2 w, float&
 }
 
 template <class C>
+struct Smem {  // section offsets in float4 units from the 16-byte aligned dynamic smem base
+  static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
+  static constexpr int WIN = 0;
+  static constexpr int TW1 = WIN + cdiv4(8 * C::NC);
+  static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
+  static constexpr int EX = TWP + cdiv4(8 * C::NC);
+  static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);
+  static constexpr int XS = PW + cdiv4(4 * C::FT * C::PP);
+  static constexpr int DYN = XS + cdiv4(4 * C::XS_FLOATS);  // then: sums (double), mel weights, starts, group info
+};
+
+template <class C>
 __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // carve
-  float2* s_win2 = reinterpret_cast<float2*>(smem_raw);             // [NC]
-  float2* s_tw1 = s_win2 + NC;                                       // [N2*N1]
-  float2* s_twp = s_tw1 + NC;                                        // [NC+1] (+1 pad)
-  float2* E = s_twp + (NC + 2);                                      // [FT*EP]
-  float* Pw = reinterpret_cast<float*>(E + C::FT * C::EP);           // [FT*PP]
-  float* xs = Pw + C::FT * C::PP + 1;                                // [XS_FLOATS]  (8 B aligned below)
-  xs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xs) + 7) & ~(uintptr_t)7);
-  int* s_mel = reinterpret_cast<int*>(xs + C::XS_FLOATS);            // start[M], len[M], off[M]
+  using S = Smem<C>;
+  extern __shared__ float4 smem4[];
+  float2* const s_win2 = reinterpret_cast<float2*>(smem4 + S::WIN);  // [N2][N1]
+  float2* const s_tw1 = reinterpret_cast<float2*>(smem4 + S::TW1);   // [N2][N1]
+  float2* const s_twp = reinterpret_cast<float2*>(smem4 + S::TWP);   // [N1/2][2*N2]
+  float2* const E = reinterpret_cast<float2*>(smem4 + S::EX);        // [FT][EP]
+  float* const Pw = reinterpret_cast<float*>(smem4 + S::PW);         // [FT][PP]
+  float* const xs = reinterpret_cast<float*>(smem4 + S::XS);         // [ROWS][P]
   const int M = p.n_mels;
-  float* s_melw = reinterpret_cast<float*>(s_mel + 3 * M);           // [nnz]
-  double* s_sums = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_melw + p.mel_nnz) + 7) & ~(uintptr_t)7);  // [2*M]
+  const int G = p.mel_groups;
+  double* const s_sums = reinterpret_cast<double*>(smem4 + S::DYN);   // [2*G*32]
+  float* const s_wg = reinterpret_cast<float*>(s_sums + 2 * G * 32);  // [mel_wg_count]
+  int* const s_start = reinterpret_cast<int*>(s_wg + p.mel_wg_count); // [G*32]
+  int* const s_ginfo = s_start + G * 32;                              // [2*G]
   __shared__ float red_max[C::WARPS], red_min[C::WARPS];
   __shared__ int s_cur_clip;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int YP = M | 1;
-  float* Y = reinterpret_cast<float*>(E);  // [FT*YP], aliases the exchange buffer
+  float* const Y = reinterpret_cast<float*>(E);  // [M][33] staging for the (M, T) layout; aliases the exchange buffer
 
   for (int i = threadIdx.x; i < NC; i += C::THREADS) {
     s_win2[i] = p.win2[i];
     s_tw1[i] = p.tw1[i];
+    s_twp[i] = p.twp[i];
   }
-  for (int i = threadIdx.x; i <= NC; i += C::THREADS) s_twp[i] = p.twp[i];
-  for (int i = threadIdx.x; i < M; i += C::THREADS) {
-    s_mel[i] = p.mel_start[i];
-    s_mel[M + i] = p.mel_len[i];
-    s_mel[2 * M + i] = p.mel_off[i];
-  }
-  for (int i = threadIdx.x; i < p.mel_nnz; i += C::THREADS) s_melw[i] = p.mel_w[i];
-  if (p.feat_sums)
-    for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) s_sums[i] = 0.0;
+  for (int i = threadIdx.x; i < G * 32; i += C::THREADS) s_start[i] = p.mel_start[i];
+  for (int i = threadIdx.x; i < 2 * G; i += C::THREADS) s_ginfo[i] = p.mel_ginfo[i];
+  for (int i = threadIdx.x; i < p.mel_wg_count; i += C::THREADS) s_wg[i] = p.mel_wg[i];
+  const bool want_sums = p.feat_sums != nullptr;
+  const bool want_max = p.clip_max != nullptr;
+  if (want_sums)
+    for (int i = threadIdx.x; i < 2 * G * 32; i += C::THREADS) s_sums[i] = 0.0;
   if (threadIdx.x == 0) s_cur_clip = -1;
 
-  const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
-  int64_t tile = blockIdx.x;
+  const unsigned total_tiles = (unsigned)p.batch * (unsigned)p.tiles_per_clip;
+  const unsigned tpc = (unsigned)p.tiles_per_clip;
+  unsigned tile = blockIdx.x;
   if (tile < total_tiles) fill_tile<C>(p, xs, tile);
 
+  const int guard_kind = p.guard_kind;
+  const float guard_eps = p.guard_eps, log_scale = p.log_scale, aff_mul = p.aff_mul, aff_add = p.aff_add;
+  const bool pw_only = p.spec_kind == B2A_SPEC_POWER;
+  const float spec_eps = p.spec_eps;
+
   for (; tile < total_tiles; tile += gridDim.x) {
-    const int clip_i = (int)(tile / p.tiles_per_clip);
-    const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
+    const int clip_i = (int)(tile / tpc);
+    const int tile_i = (int)(tile - (unsigned)clip_i * tpc);
     const int64_t lt0 = (int64_t)tile_i * C::FT;
     const int64_t frames_left = p.frame_count - lt0;
     const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
@@ -216,7 +235,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     __syncthreads();  // xs ready; previous tile's Y fully written out
 
     // per-CTA running per-mel sums: flush when the clip changes
-    if (p.feat_sums && s_cur_clip != clip_i) {
+    if (want_sums && s_cur_clip != clip_i) {
       const int prev = s_cur_clip;
       __syncthreads();
       if (prev >= 0)
@@ -233,31 +252,38 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     for (int rr = 0; rr < C::RPW; ++rr) {
       const int n2 = warp * C::RPW + rr;
       const float* xb = xs + lane * C::P + 2 * n2;
-      const float2* wb = s_win2 + n2;
+      const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
       float2 v[N1];
-      static_for<0, N1>([&](auto I_) {
-        constexpr int n1 = decltype(I_)::value;
-        constexpr int off = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
-        const float2 x = *reinterpret_cast<const float2*>(xb + off);
-        const float2 w = wb[N2 * n1];
-        v[n1] = make_float2(x.x * w.x, x.y * w.y);
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int n1 = 2 * decltype(I_)::value;
+        constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
+        constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
+        const float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
+        const float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
+        const float4 w = wb4[n1 / 2];
+        v[n1] = make_float2(x0.x * w.x, x0.y * w.y);
+        v[n1 + 1] = make_float2(x1.x * w.z, x1.y * w.w);
       });
       Dft<N1>::run(v);
-      const float2* tb = s_tw1 + n2 * N1;
+      const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
       float2* eb = E + lane * C::EP + n2;
-      static_for<0, N1>([&](auto I_) {
-        constexpr int k1 = decltype(I_)::value;
-        constexpr int slot = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
-        float2 y = v[k1];
-        if constexpr (k1 > 0) y = regs::cmul(y, tb[k1]);
-        eb[slot * N2] = y;
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int k1 = 2 * decltype(I_)::value;
+        constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
+        constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+        const float4 t = tb4[k1 / 2];
+        float2 y0 = v[k1];
+        if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
+        const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
+        eb[slot0 * N2] = y0;
+        eb[slot1 * N2] = y1;
       });
     }
     __syncthreads();  // E complete, xs free
 
     // prefetch the next tile's samples while stage 2 / mel run
     {
-      const int64_t next = tile + gridDim.x;
+      const unsigned next = tile + gridDim.x;
       if (next < total_tiles) fill_tile<C>(p, xs, next);
     }
 
@@ -275,31 +301,33 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
       Dft<N2>::run(A);
       Dft<N2>::run(B);
       float* pr = Pw + lane * C::PP;
-      const bool pw_only = p.spec_kind == B2A_SPEC_POWER;
-      const float eps = p.spec_eps;
-      auto emit = [&](int k, float v) { pr[k] = pw_only ? v : sqrtf(v + eps); };
+      auto emit = [&](int k, float v) { pr[k] = pw_only ? v : sqrtf(v + spec_eps); };
+      const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
       if (u != 0) {
-        const float2* tw = s_twp + u;
-        static_for<0, N2>([&](auto I_) {
-          constexpr int k2 = decltype(I_)::value;
+        static_for<0, N2 / 2>([&](auto I_) {
+          constexpr int k2 = 2 * decltype(I_)::value;
+          const float4 t = tw4[k2 / 2];
           float pk, pm;
-          post_pair(A[k2], B[N2 - 1 - k2], tw[N1 * k2], pk, pm);
-          const int k = u + N1 * k2;
-          emit(k, pk);
-          emit(NC - k, pm);
+          post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
+          emit(u + N1 * k2, pk);
+          emit(NC - (u + N1 * k2), pm);
+          post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
+          emit(u + N1 * (k2 + 1), pk);
+          emit(NC - (u + N1 * (k2 + 1)), pm);
         });
       } else {
+        const float2* tw = s_twp;  // unit 0: [0..N2/2] column 0, [N2 .. N2+N2/2) column N1/2
         static_for<0, N2 / 2 + 1>([&](auto I_) {  // column 0: k = N1*k2 <-> Nc - k = N1*(N2-k2)
           constexpr int k2 = decltype(I_)::value;
           float pk, pm;
-          post_pair(A[k2], A[(N2 - k2) % N2], s_twp[N1 * k2], pk, pm);
+          post_pair(A[k2], A[(N2 - k2) % N2], tw[k2], pk, pm);
           emit(N1 * k2, pk);
           emit(NC - N1 * k2, pm);
         });
         static_for<0, N2 / 2>([&](auto I_) {  // column N1/2: k = N1/2 + N1*k2 <-> N1/2 + N1*(N2-1-k2)
           constexpr int k2 = decltype(I_)::value;
           float pk, pm;
-          post_pair(B[k2], B[N2 - 1 - k2], s_twp[N1 / 2 + N1 * k2], pk, pm);
+          post_pair(B[k2], B[N2 - 1 - k2], tw[N2 + k2], pk, pm);
           emit(N1 / 2 + N1 * k2, pk);
           emit(NC - (N1 / 2 + N1 * k2), pm);
         });
@@ -307,86 +335,88 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     }
     __syncthreads();  // Pw complete, E free (Y aliases E)
 
-    // ---- mel projection + log + affine; lane = frame, warp = mel subset ------------------------------------
+    // ---- mel projection + log + affine: LANE = MEL ROW, warp = a few frames of the tile ---------------------
+    // Each lane owns one row of a group of 32 consecutive mel rows; the banded filterbank is walked for
+    // `glen` taps (zero padded to the group's longest row), weights are lane-contiguous in smem, power
+    // values are gathered from the frame's P row, and the result goes straight to HBM with 128 B coalesced
+    // stores ((T, M) layout) or through a small staging tile ((M, T) layout).
     {
-      const float* pr = Pw + lane * C::PP;
-      float* yr = Y + lane * YP;
+      constexpr int NFW = (C::FT + C::WARPS - 1) / C::WARPS;  // frames per warp
       float lmax = -INFINITY, lmin = INFINITY;
-      const bool valid = lane < nf;
-      for (int m = warp; m < M; m += C::WARPS) {
-        const int start = s_mel[m], len = s_mel[M + m];
-        const float* wt = s_melw + s_mel[2 * M + m];
-        const float* pp = pr + start;
-        float acc = 0.0f;
-        for (int j = 0; j < len; ++j) acc = fmaf(pp[j], wt[j], acc);
-        if (p.guard_kind == B2A_GUARD_MAX) acc = fmaxf(acc, p.guard_eps);
-        else if (p.guard_kind == B2A_GUARD_ADD) acc = acc + p.guard_eps;
-        float y = acc;
-        if (p.log_scale != 0.0f) y = __log2f(acc) * p.log_scale;
-        y = fmaf(y, p.aff_mul, p.aff_add);
-        if (valid) {
-          lmax = fmaxf(lmax, y);
-          lmin = fminf(lmin, y);
-        }
-        yr[m] = y;
-        if (p.feat_sums) {
-          double d1 = valid ? (double)y : 0.0, d2 = d1 * d1;
+      float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
+      const bool layout_tm = p.out_layout == B2A_LAYOUT_TM;
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int m = g * 32 + lane;
+        const int L = s_ginfo[2 * g];
+        const float* wp = s_wg + s_ginfo[2 * g + 1] + lane;
+        const float* pb = Pw + warp * C::PP + s_start[m];
+        float acc[NFW];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        for (int i = 0; i < NFW; ++i) acc[i] = 0.0f;
+#pragma unroll 2
+        for (int j = 0; j < L; ++j) {
+          const float w = wp[j * 32];
+#pragma unroll
+          for (int i = 0; i < NFW; ++i) {
+            if (warp + i * C::WARPS < C::FT) acc[i] = fmaf(pb[i * C::WARPS * C::PP + j], w, acc[i]);
           }
-          if (lane == 0) {
-            s_sums[2 * m] += d1;
-            s_sums[2 * m + 1] += d2;
+        }
+        double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NFW; ++i) {
+          const int fr = warp + i * C::WARPS;
+          float a = acc[i];
+          if (guard_kind == B2A_GUARD_MAX) a = fmaxf(a, guard_eps);
+          else if (guard_kind == B2A_GUARD_ADD) a = a + guard_eps;
+          float y = a;
+          if (log_scale != 0.0f) y = __log2f(a) * log_scale;
+          y = fmaf(y, aff_mul, aff_add);
+          const bool ok = fr < nf && m < M;
+          if (ok) {
+            lmax = fmaxf(lmax, y);
+            lmin = fminf(lmin, y);
+            if (layout_tm) o[(lt0 + fr) * M + m] = y;
+            else Y[m * 33 + fr] = y;
+            if (want_sums) {
+              d1 += (double)y;
+              d2 += (double)y * (double)y;
+            }
           }
+        }
+        if (want_sums && m < M) {
+          atomicAdd(&s_sums[2 * m], d1);
+          atomicAdd(&s_sums[2 * m + 1], d2);
         }
       }
-      if (p.clip_max) {
+      if (want_max) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-          lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o2));
+          lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o2));
         }
         if (lane == 0) {
           red_max[warp] = lmax;
           red_min[warp] = lmin;
         }
       }
-    }
-    __syncthreads();
-    if (p.clip_max && threadIdx.x == 0) {
-      float a = red_max[0], b = red_min[0];
+      if (want_max || !layout_tm) __syncthreads();
+      if (want_max && threadIdx.x == 0) {
+        float a = red_max[0], b = red_min[0];
 #pragma unroll
-      for (int w = 1; w < C::WARPS; ++w) {
-        a = fmaxf(a, red_max[w]);
-        b = fminf(b, red_min[w]);
-      }
-      atomic_max_f(p.clip_max + clip_i, a);
-      atomic_min_f(p.clip_min + clip_i, b);
-    }
-    // ---- coalesced store ----------------------------------------------------------------------------------
-    {
-      float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
-      if (p.out_layout == B2A_LAYOUT_TM) {
-        float* ot = o + lt0 * M;
-        int f = 0, m = threadIdx.x;
-        while (m >= M) { m -= M; ++f; }
-        while (f < nf) {
-          ot[f * M + m] = Y[f * YP + m];
-          m += C::THREADS;
-          while (m >= M) { m -= M; ++f; }
+        for (int w = 1; w < C::WARPS; ++w) {
+          a = fmaxf(a, red_max[w]);
+          b = fminf(b, red_min[w]);
         }
-      } else {
-        for (int i = threadIdx.x; i < M * 32; i += C::THREADS) {
-          const int m = i >> 5, f = i & 31;
-          if (f < nf) o[(int64_t)m * p.frame_count + lt0 + f] = Y[f * YP + m];
-        }
+        atomic_max_f(p.clip_max + clip_i, a);
+        atomic_min_f(p.clip_min + clip_i, b);
       }
+      if (!layout_tm && lane < nf)
+        for (int m = warp; m < M; m += C::WARPS) o[(int64_t)m * p.frame_count + lt0 + lane] = Y[m * 33 + lane];
     }
   }
   cp_async_wait_all();
-  if (p.feat_sums) {
+  if (want_sums) {
     __syncthreads();
     const int prev = s_cur_clip;
     if (prev >= 0)
@@ -395,27 +425,24 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
 }
 
 template <class C>
-size_t smem_bytes(int M, int nnz) {
-  size_t b = 0;
-  b += sizeof(float2) * (C::NC + C::NC + C::NC + 2);
-  b += sizeof(float2) * C::FT * C::EP;
-  b += sizeof(float) * (C::FT * C::PP + 1) + 8;
-  b += sizeof(float) * C::XS_FLOATS;
-  b += sizeof(int) * 3 * M + sizeof(float) * nnz + 8;
-  b += sizeof(double) * 2 * M;
-  return b + 16;
+size_t smem_bytes(int G, int wg_count) {
+  return (size_t)16 * Smem<C>::DYN + sizeof(double) * 2 * G * 32 + sizeof(float) * wg_count + sizeof(int) * (G * 32 + 2 * G) + 16;
 }
 
 struct FastState {
   float2* d_win2 = nullptr;
   float2* d_tw1 = nullptr;
   float2* d_twp = nullptr;
+  int* d_start = nullptr;
+  int* d_ginfo = nullptr;
+  float* d_wg = nullptr;
+  int groups = 0, wg_count = 0;
   int variant = 0;  // 1: 400/160, 2: 512/160, 3: 1024/256
 };
 
 template <class C>
 int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
-  const size_t smem = smem_bytes<C>(p.n_mels, p.mel_nnz);
+  const size_t smem = smem_bytes<C>(p.mel_groups, p.mel_wg_count);
   static size_t attr_smem = 0;
   if (smem > attr_smem && smem <= 226 * 1024) {
     B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -426,6 +453,10 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     return B2A_ERR_UNSUPPORTED;
   }
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  if (tiles >= (int64_t)1 << 31) {
+    set_error("fast kernel: %lld tiles in one launch (split the batch)", (long long)tiles);
+    return B2A_ERR_UNSUPPORTED;
+  }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   per_sm = std::max(1, std::min(per_sm, 2));
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
@@ -460,25 +491,75 @@ int fast_frontend_init(b2a_plan* plan) {
   if (d.n_fft == 400) { fs->variant = 1; N1 = 20; N2 = 10; }
   else { fs->variant = 2; N1 = 16; N2 = 16; }
   const int NC = N1 * N2, N = 2 * NC;
-  std::vector<float2> win2(NC), tw1(NC), twp(NC + 2);
-  for (int m = 0; m < NC; ++m)  // 0.5 of the real-FFT post-processing is folded into the window
-    win2[m] = make_float2(0.5f * plan->h_window[2 * m], 0.5f * plan->h_window[2 * m + 1]);
+  std::vector<float2> win2(NC), tw1(NC), twp(NC);
+  for (int n2 = 0; n2 < N2; ++n2)
+    for (int n1 = 0; n1 < N1; ++n1) {  // 0.5 of the real-FFT post-processing is folded into the window
+      const int m = N2 * n1 + n2;
+      win2[n2 * N1 + n1] = make_float2(0.5f * plan->h_window[2 * m], 0.5f * plan->h_window[2 * m + 1]);
+    }
   for (int n2 = 0; n2 < N2; ++n2)
     for (int k1 = 0; k1 < N1; ++k1) {
       const double a = -2.0 * M_PI * (double)((n2 * k1) % NC) / (double)NC;
       tw1[n2 * N1 + k1] = make_float2((float)cos(a), (float)sin(a));
     }
-  for (int k = 0; k <= NC; ++k) {
+  auto wn = [&](int k) {
     const double a = -2.0 * M_PI * (double)k / (double)N;
-    twp[k] = make_float2((float)cos(a), (float)sin(a));
+    return make_float2((float)cos(a), (float)sin(a));
+  };
+  for (int i = 0; i < NC; ++i) twp[i] = make_float2(0.f, 0.f);
+  for (int u = 1; u < N1 / 2; ++u)  // unit u: W_N^(u + N1*k2), k2 = 0..N2-1
+    for (int k2 = 0; k2 < N2; ++k2) twp[u * 2 * N2 + k2] = wn(u + N1 * k2);
+  for (int k2 = 0; k2 <= N2 / 2; ++k2) twp[k2] = wn(N1 * k2);                    // unit 0, column 0
+  for (int k2 = 0; k2 < N2 / 2; ++k2) twp[N2 + k2] = wn(N1 / 2 + N1 * k2);        // unit 0, column N1/2
+  // mel filterbank in lane == mel form
+  const int M = d.n_mels, F = plan->n_freqs;
+  const int G = (M + 31) / 32;
+  std::vector<int> start(G * 32, 0), len(G * 32, 0), ginfo(2 * G, 0);
+  for (int m = 0; m < M; ++m) {
+    int lo = -1, hi = -1;
+    for (int f = 0; f < F; ++f)
+      if (plan->h_fb[(size_t)m * F + f] != 0.0f) {
+        if (lo < 0) lo = f;
+        hi = f;
+      }
+    start[m] = lo < 0 ? 0 : lo;
+    len[m] = lo < 0 ? 0 : hi - lo + 1;
   }
-  twp[NC + 1] = make_float2(0.f, 0.f);
+  std::vector<float> wg;
+  for (int g = 0; g < G; ++g) {
+    int L = 0;
+    for (int l = 0; l < 32; ++l) L = std::max(L, len[g * 32 + l]);
+    // rows shorter than L read (zero weighted) bins past their end: keep those reads inside the P row
+    for (int l = 0; l < 32; ++l)
+      if (start[g * 32 + l] + L > F) start[g * 32 + l] = std::max(0, F - L);
+    ginfo[2 * g] = L;
+    ginfo[2 * g + 1] = (int)wg.size();
+    for (int j = 0; j < L; ++j)
+      for (int l = 0; l < 32; ++l) {
+        const int m = g * 32 + l;
+        float w = 0.0f;
+        if (m < M) {
+          // start may have been shifted left to stay in range: index the dense filterbank directly
+          const int f = start[m] + j;
+          if (f < F) w = plan->h_fb[(size_t)m * F + f];
+        }
+        wg.push_back(w);
+      }
+  }
+  fs->groups = G;
+  fs->wg_count = (int)wg.size();
   B2A_CUDA(cudaMalloc(&fs->d_win2, sizeof(float2) * NC));
   B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float2) * NC));
-  B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * (NC + 2)));
+  B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * NC));
+  B2A_CUDA(cudaMalloc(&fs->d_start, sizeof(int) * G * 32));
+  B2A_CUDA(cudaMalloc(&fs->d_ginfo, sizeof(int) * 2 * G));
+  B2A_CUDA(cudaMalloc(&fs->d_wg, sizeof(float) * std::max<size_t>(wg.size(), 1)));
   B2A_CUDA(cudaMemcpy(fs->d_win2, win2.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_tw1, tw1.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
-  B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float2) * (NC + 2), cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 32, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
   plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : "fast_logmel_512x160";
   return B2A_OK;
 }
@@ -489,6 +570,9 @@ void fast_frontend_destroy(b2a_plan* plan) {
   cudaFree(fs->d_win2);
   cudaFree(fs->d_tw1);
   cudaFree(fs->d_twp);
+  cudaFree(fs->d_start);
+  cudaFree(fs->d_ginfo);
+  cudaFree(fs->d_wg);
   delete fs;
   plan->fast = nullptr;
 }
@@ -534,11 +618,11 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.win2 = fs->d_win2;
   p.tw1 = fs->d_tw1;
   p.twp = fs->d_twp;
-  p.mel_start = plan->mel.d_start;
-  p.mel_len = plan->mel.d_len;
-  p.mel_off = plan->mel.d_off;
-  p.mel_w = plan->mel.d_w;
-  p.mel_nnz = plan->mel.nnz;
+  p.mel_start = fs->d_start;
+  p.mel_ginfo = fs->d_ginfo;
+  p.mel_wg = fs->d_wg;
+  p.mel_groups = fs->groups;
+  p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
   if (fs->variant == 1) return launch<Cfg400>(plan, fs, p, st);
   return launch<Cfg512>(plan, fs, p, st);
