@@ -108,6 +108,16 @@ int ensure_ws(b2a_plan* p, size_t bytes) {
   return B2A_OK;
 }
 
+int ensure_tilemin(b2a_plan* p, int slot, size_t count) {
+  if (p->tilemin_count[slot] >= count) return B2A_OK;
+  if (p->d_tilemin[slot]) cudaFree(p->d_tilemin[slot]);
+  p->d_tilemin[slot] = nullptr;
+  p->tilemin_count[slot] = 0;
+  B2A_CUDA(cudaMalloc(&p->d_tilemin[slot], count * sizeof(float)));
+  p->tilemin_count[slot] = count;
+  return B2A_OK;
+}
+
 size_t stats_bytes(const b2a_plan* p, int batch) {
   const int M = p->fd.n_mels > 0 ? p->fd.n_mels : p->n_freqs;
   size_t b = (size_t)batch * 2 * sizeof(float);
@@ -118,7 +128,8 @@ size_t stats_bytes(const b2a_plan* p, int batch) {
 
 struct StatPtrs {
   float* clip_max;
-  float* clip_min;
+  float* tile_min;
+  int tile_frames;
   double* feat_sums;
 };
 
@@ -144,12 +155,14 @@ int resolve_args(const b2a_plan* p, const b2a_forward_args* in, b2a_forward_args
   return B2A_OK;
 }
 
-int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s) {
+int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s, int slot = 0) {
   const b2a_frontend_desc& d = p->fd;
   const bool need_max = d.clamp_kind != B2A_CLAMP_NONE;
   const bool need_sums = d.norm_kind != B2A_NORM_NONE;
-  s->clip_max = s->clip_min = nullptr;
+  s->clip_max = s->tile_min = nullptr;
   s->feat_sums = nullptr;
+  s->tile_frames = p->family == KF_FAST ? 32 : generic_tile_frames(p, a);
+  if (s->tile_frames <= 0) s->tile_frames = 2;
   if (!need_max && !need_sums && !a->clip_max && !a->feat_sums) return B2A_OK;
   char* base;
   const size_t need = stats_bytes(p, a->batch);
@@ -161,7 +174,12 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s) {
     base = (char*)p->d_ws;
   }
   s->clip_max = (float*)base;
-  s->clip_min = s->clip_max + a->batch;
+  {
+    const size_t tiles = (size_t)a->batch * (size_t)((a->frame_count + s->tile_frames - 1) / s->tile_frames);
+    int rc = ensure_tilemin(p, slot, tiles > 0 ? tiles : 1);
+    if (rc) return rc;
+    s->tile_min = p->d_tilemin[slot];
+  }
   size_t off = ((size_t)a->batch * 2 * sizeof(float) + 15) & ~(size_t)15;
   s->feat_sums = (double*)(base + off);
   if (a->clip_max) s->clip_max = a->clip_max;  // caller-visible (sharded) statistics
@@ -173,12 +191,12 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s) {
 int partial_impl(b2a_plan* p, const b2a_forward_args* a, const StatPtrs& s, cudaStream_t st, bool init) {
   const int M = p->fd.n_mels > 0 ? p->fd.n_mels : p->n_freqs;
   if (init) {
-    int rc = init_stats(s.clip_max, s.clip_min, s.feat_sums, a->batch, M, st);
+    int rc = init_stats(s.clip_max, s.feat_sums, a->batch, M, st);
     if (rc) return rc;
   }
   if (a->frame_count == 0) return B2A_OK;
-  if (p->family == KF_FAST) return fast_frontend_partial(p, a, s.clip_max, s.clip_min, s.feat_sums, st);
-  return generic_frontend_partial(p, a, s.clip_max, s.clip_min, s.feat_sums, st);
+  if (p->family == KF_FAST) return fast_frontend_partial(p, a, s.clip_max, s.tile_min, s.feat_sums, st);
+  return generic_frontend_partial(p, a, s.clip_max, s.tile_min, s.feat_sums, st);
 }
 
 }  // namespace
@@ -274,6 +292,7 @@ int b2a_plan_destroy(b2a_plan* p) {
   cudaFree(p->d_fb_dense);
   cudaFree(p->d_ws);
   for (int i = 0; i < 2; ++i) {
+    cudaFree(p->d_tilemin[i]);
     cudaFree(p->d_stage_in[i]);
     cudaFree(p->d_stage_out[i]);
     if (p->host_streams[i]) cudaStreamDestroy(p->host_streams[i]);
@@ -317,7 +336,7 @@ int b2a_frontend_finalize(b2a_plan* p, const b2a_forward_args* in, int64_t globa
   StatPtrs s;
   if ((rc = locate_stats(p, &a, &s))) return rc;
   if (a.frame_count == 0) return B2A_OK;
-  return frontend_finalize(p, &a, global_frames, s.clip_max, s.clip_min, s.feat_sums, (cudaStream_t)stream);
+  return frontend_finalize(p, &a, global_frames, s.clip_max, s.tile_min, s.tile_frames, s.feat_sums, (cudaStream_t)stream);
 }
 
 int b2a_frontend_forward(b2a_plan* p, const b2a_forward_args* in, void* stream) {
@@ -329,7 +348,7 @@ int b2a_frontend_forward(b2a_plan* p, const b2a_forward_args* in, void* stream) 
   if ((rc = locate_stats(p, &a, &s))) return rc;
   if ((rc = partial_impl(p, &a, s, (cudaStream_t)stream, true))) return rc;
   if (a.frame_count == 0) return B2A_OK;
-  return frontend_finalize(p, &a, a.frame_count, s.clip_max, s.clip_min, s.feat_sums, (cudaStream_t)stream);
+  return frontend_finalize(p, &a, a.frame_count, s.clip_max, s.tile_min, s.tile_frames, s.feat_sums, (cudaStream_t)stream);
 }
 
 int b2a_frontend_dump_frames(b2a_plan* p, const b2a_forward_args* in, int apply_window, void* stream) {
@@ -407,10 +426,10 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
     c.workspace = (char*)p->d_ws + s * sb;
     c.workspace_bytes = sb;
     StatPtrs sp;
-    if ((rc = locate_stats(p, &c, &sp))) return rc;
+    if ((rc = locate_stats(p, &c, &sp, s))) return rc;
     if ((rc = partial_impl(p, &c, sp, st, true))) return rc;
     if (c.frame_count > 0 &&
-        (rc = frontend_finalize(p, &c, c.frame_count, sp.clip_max, sp.clip_min, sp.feat_sums, st)))
+        (rc = frontend_finalize(p, &c, c.frame_count, sp.clip_max, sp.tile_min, sp.tile_frames, sp.feat_sums, st)))
       return rc;
     char* hdst = (char*)a.out + (size_t)c0 * out_stride * out_elem;
     if (out_stride == out_per_clip) {

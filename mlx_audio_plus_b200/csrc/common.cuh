@@ -100,22 +100,25 @@ struct b2a_plan {
   cudaStream_t host_streams[2];
   cudaEvent_t host_events[2];
   void* fast;  // family-specific state
+  float* d_tilemin[2];  // per-tile minima (clamp fix-up skips tiles with nothing below the floor)
+  size_t tilemin_count[2];
 };
 
 namespace b2a {
 // generic (any n_fft) kernels — generic.cu
-int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+int generic_tile_frames(const b2a_plan* plan, const b2a_forward_args* a);
+int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                              double* feat_sums, cudaStream_t st);
 int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st);
 int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cudaStream_t st);
-int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, const float* clip_max,
-                      const float* clip_min, const double* feat_sums, cudaStream_t st);
-int init_stats(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_mels, cudaStream_t st);
+int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, float* clip_max,
+                      const float* tile_min, int tile_frames, const double* feat_sums, cudaStream_t st);
+int init_stats(float* clip_max, double* feat_sums, int batch, int n_mels, cudaStream_t st);
 size_t generic_smem_limit(const b2a_plan* plan);
 // fast (specialised two-stage register FFT) kernels — fast_fwd.cu
 bool fast_frontend_supported(const b2a_plan* plan);
 int fast_frontend_init(b2a_plan* plan);
 void fast_frontend_destroy(b2a_plan* plan);
-int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);
 }  // namespace b2a

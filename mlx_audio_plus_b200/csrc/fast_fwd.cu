@@ -64,14 +64,14 @@ struct FastParams {
   int fast_fill_ok;  // alignment preconditions for the cp.async path
   int spec_kind;
   float spec_eps;
-  int n_mels, guard_kind;
-  float guard_eps;
-  float log_scale;   // 0 = no log; else y = log2(x) * log_scale  (ln2 or log10(2)), then affine
-  float aff_mul, aff_add;  // y' = y * aff_mul + aff_add   (aff_mul = 1/div, aff_add = add/div)
+  int n_mels;
+  float guard_add, guard_floor;  // a = max(a + guard_add, guard_floor)   (ADD: (eps, -inf); MAX: (0, eps))
+  int use_log;                   // y = log2(a) if use_log else a
+  float y_mul, y_add;            // y' = y * y_mul + y_add   (log base change and the affine map folded together)
   int out_layout;
   float* out;
   int64_t out_clip_stride;
-  float *clip_max, *clip_min;  // affine-domain statistics
+  float *clip_max, *tile_min;  // affine-domain statistics (per clip max, per tile min)
   double* feat_sums;
   const float2* win2;   // [N2][N1] (w[2m], w[2m+1]) * 0.5 with m = N2*n1 + n2
   const float2* tw1;    // [N2][N1]  W_Nc^(n2*k1)
@@ -87,6 +87,11 @@ struct FastParams {
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -130,11 +135,21 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, unsign
   const int64_t s0 = q0 - p.geo.pad_left;             // source coordinate
   const bool interior = p.fast_fill_ok && s0 >= 0 && (s0 + C::SPAN) <= p.valid_length && s0 >= p.sample_offset;
   if (interior) {
-    const float* src = clip + (s0 - p.sample_offset);
-    for (int j = threadIdx.x; j < C::SPAN / 2; j += C::THREADS) {
-      const int s = 2 * j;
-      const int row = s / C::HOP, col = s - row * C::HOP;
-      cp_async8(xs + row * C::P + col, src + s);
+    // thread t copies the 8-byte pair (row r0 + RPI*i, column 2*c): both addresses are linear in i
+    constexpr int PPR = C::HOP / 2;             // pairs per row
+    constexpr int RPI = C::THREADS / PPR;       // rows per iteration
+    constexpr int TOTAL_ROWS = (C::SPAN + C::HOP - 1) / C::HOP;
+    constexpr int TAIL = C::SPAN - (TOTAL_ROWS - 1) * C::HOP;  // samples in the last (partial) row
+    const int r0 = threadIdx.x / PPR, c = threadIdx.x - r0 * PPR;
+    if (r0 < RPI) {
+      const float* src = clip + (s0 - p.sample_offset) + r0 * C::HOP + 2 * c;
+      float* dst = xs + r0 * C::P + 2 * c;
+#pragma unroll
+      for (int i = 0; i < (TOTAL_ROWS + RPI - 1) / RPI; ++i) {
+        const int row = r0 + RPI * i;
+        if (row < TOTAL_ROWS - 1 || (row == TOTAL_ROWS - 1 && 2 * c < TAIL))
+          cp_async8(dst + i * RPI * C::P, src + i * RPI * C::HOP);
+      }
     }
   } else {
     const int64_t frames_left = p.frame_count - lt0;
@@ -177,7 +192,7 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
   static constexpr int DYN = XS + cdiv4(4 * C::XS_FLOATS);  // then: sums (double), mel weights, starts, group info
 };
 
-template <class C>
+template <class C, bool LAYOUT_TM, bool WANT_SUMS>
 __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   using S = Smem<C>;
@@ -208,7 +223,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
   for (int i = threadIdx.x; i < G * 32; i += C::THREADS) s_start[i] = p.mel_start[i];
   for (int i = threadIdx.x; i < 2 * G; i += C::THREADS) s_ginfo[i] = p.mel_ginfo[i];
   for (int i = threadIdx.x; i < p.mel_wg_count; i += C::THREADS) s_wg[i] = p.mel_wg[i];
-  const bool want_sums = p.feat_sums != nullptr;
+  constexpr bool want_sums = WANT_SUMS;
   const bool want_max = p.clip_max != nullptr;
   if (want_sums)
     for (int i = threadIdx.x; i < 2 * G * 32; i += C::THREADS) s_sums[i] = 0.0;
@@ -219,8 +234,8 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
   unsigned tile = blockIdx.x;
   if (tile < total_tiles) fill_tile<C>(p, xs, tile);
 
-  const int guard_kind = p.guard_kind;
-  const float guard_eps = p.guard_eps, log_scale = p.log_scale, aff_mul = p.aff_mul, aff_add = p.aff_add;
+  const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
+  const bool use_log = p.use_log != 0;
   const bool pw_only = p.spec_kind == B2A_SPEC_POWER;
   const float spec_eps = p.spec_eps;
 
@@ -344,49 +359,55 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
       constexpr int NFW = (C::FT + C::WARPS - 1) / C::WARPS;  // frames per warp
       float lmax = -INFINITY, lmin = INFINITY;
       float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
-      const bool layout_tm = p.out_layout == B2A_LAYOUT_TM;
+      const float* prow[NFW];
+      float* orow[NFW];
+      bool fok[NFW];
+#pragma unroll
+      for (int i = 0; i < NFW; ++i) {
+        const int fr = warp + i * C::WARPS;
+        const int frc = fr < C::FT ? fr : C::FT - 1;  // clamp: surplus slots recompute a valid row, never stored
+        prow[i] = Pw + frc * C::PP;
+        fok[i] = fr < nf;
+        orow[i] = LAYOUT_TM ? (o + (lt0 + frc) * M + lane) : (Y + lane * 33 + frc);
+      }
+      const int2* ginfo2 = reinterpret_cast<const int2*>(s_ginfo);
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
-        const int m = g * 32 + lane;
-        const int L = s_ginfo[2 * g];
-        const float* wp = s_wg + s_ginfo[2 * g + 1] + lane;
-        const float* pb = Pw + warp * C::PP + s_start[m];
+        const int2 gi = ginfo2[g];  // (group length, weight offset)
+        const int st = s_start[g * 32 + lane];
+        const bool mok = g * 32 + lane < M;
+        const float* wp = s_wg + gi.y + lane;
         float acc[NFW];
 #pragma unroll
         for (int i = 0; i < NFW; ++i) acc[i] = 0.0f;
-#pragma unroll 2
-        for (int j = 0; j < L; ++j) {
+#pragma unroll 1
+        for (int j = 0; j < gi.x; ++j) {
           const float w = wp[j * 32];
 #pragma unroll
-          for (int i = 0; i < NFW; ++i) {
-            if (warp + i * C::WARPS < C::FT) acc[i] = fmaf(pb[i * C::WARPS * C::PP + j], w, acc[i]);
-          }
+          for (int i = 0; i < NFW; ++i) acc[i] = fmaf(prow[i][st + j], w, acc[i]);
         }
         double d1 = 0.0, d2 = 0.0;
 #pragma unroll
         for (int i = 0; i < NFW; ++i) {
-          const int fr = warp + i * C::WARPS;
-          float a = acc[i];
-          if (guard_kind == B2A_GUARD_MAX) a = fmaxf(a, guard_eps);
-          else if (guard_kind == B2A_GUARD_ADD) a = a + guard_eps;
-          float y = a;
-          if (log_scale != 0.0f) y = __log2f(a) * log_scale;
-          y = fmaf(y, aff_mul, aff_add);
-          const bool ok = fr < nf && m < M;
+          const float a = fmaxf(acc[i] + guard_add, guard_floor);
+          float y = use_log ? lg2_approx(a) : a;
+          y = fmaf(y, y_mul, y_add);
+          const bool ok = fok[i] && mok;
+          const float yv = ok ? y : __int_as_float(0x7fc00000);  // NaN is ignored by fmaxf / fminf
+          lmax = fmaxf(lmax, yv);
+          lmin = fminf(lmin, yv);
           if (ok) {
-            lmax = fmaxf(lmax, y);
-            lmin = fminf(lmin, y);
-            if (layout_tm) o[(lt0 + fr) * M + m] = y;
-            else Y[m * 33 + fr] = y;
-            if (want_sums) {
+            if (LAYOUT_TM) orow[i][g * 32] = y;
+            else orow[i][g * 32 * 33] = y;
+            if (WANT_SUMS) {
               d1 += (double)y;
               d2 += (double)y * (double)y;
             }
           }
         }
-        if (want_sums && m < M) {
-          atomicAdd(&s_sums[2 * m], d1);
-          atomicAdd(&s_sums[2 * m + 1], d2);
+        if (WANT_SUMS && mok) {
+          atomicAdd(&s_sums[2 * (g * 32 + lane)], d1);
+          atomicAdd(&s_sums[2 * (g * 32 + lane) + 1], d2);
         }
       }
       if (want_max) {
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
           red_min[warp] = lmin;
         }
       }
-      if (want_max || !layout_tm) __syncthreads();
+      if (want_max || !LAYOUT_TM) __syncthreads();
       if (want_max && threadIdx.x == 0) {
         float a = red_max[0], b = red_min[0];
 #pragma unroll
@@ -409,9 +430,9 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
           b = fminf(b, red_min[w]);
         }
         atomic_max_f(p.clip_max + clip_i, a);
-        atomic_min_f(p.clip_min + clip_i, b);
+        p.tile_min[(int64_t)clip_i * tpc + tile_i] = b;
       }
-      if (!layout_tm && lane < nf)
+      if (!LAYOUT_TM && lane < nf)
         for (int m = warp; m < M; m += C::WARPS) o[(int64_t)m * p.frame_count + lt0 + lane] = Y[m * 33 + lane];
     }
   }
@@ -440,14 +461,21 @@ struct FastState {
   int variant = 0;  // 1: 400/160, 2: 512/160, 3: 1024/256
 };
 
+template <class C, bool TM, bool SUMS>
+int launch_variant(b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  fast_logmel_kernel<C, TM, SUMS><<<grid, C::THREADS, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
 template <class C>
 int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
   const size_t smem = smem_bytes<C>(p.mel_groups, p.mel_wg_count);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem && smem <= 226 * 1024) {
-    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
   if (smem > 226 * 1024) {
     set_error("fast kernel: %zu bytes of shared memory needed", smem);
     return B2A_ERR_UNSUPPORTED;
@@ -461,9 +489,11 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
   per_sm = std::max(1, std::min(per_sm, 2));
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
-  fast_logmel_kernel<C><<<grid, C::THREADS, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
-  return B2A_OK;
+  const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
+  if (tm && !sums) return launch_variant<C, true, false>(plan, p, smem, grid, st);
+  if (tm && sums) return launch_variant<C, true, true>(plan, p, smem, grid, st);
+  if (!tm && !sums) return launch_variant<C, false, false>(plan, p, smem, grid, st);
+  return launch_variant<C, false, true>(plan, p, smem, grid, st);
 }
 
 using Cfg400 = Cfg<20, 10, 160>;
@@ -577,7 +607,7 @@ void fast_frontend_destroy(b2a_plan* plan) {
   plan->fast = nullptr;
 }
 
-int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st) {
   const b2a_frontend_desc& d = plan->fd;
   FastState* fs = reinterpret_cast<FastState*>(plan->fast);
@@ -599,21 +629,22 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.spec_kind = d.spec_kind;
   p.spec_eps = d.spec_kind == B2A_SPEC_SQRT_POWER_EPS ? d.spec_eps : 0.0f;
   p.n_mels = d.n_mels;
-  p.guard_kind = d.guard_kind;
-  p.guard_eps = d.guard_eps;
-  p.log_scale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521f : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942f : 0.0f);
-  if (d.affine_div != 0.0f) {
-    p.aff_mul = 1.0f / d.affine_div;
-    p.aff_add = d.affine_add / d.affine_div;
+  p.guard_add = d.guard_kind == B2A_GUARD_ADD ? d.guard_eps : 0.0f;
+  p.guard_floor = d.guard_kind == B2A_GUARD_MAX ? d.guard_eps : -INFINITY;
+  p.use_log = d.log_kind != B2A_LOG_NONE;
+  const double lscale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521 : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942 : 1.0);
+  if (d.affine_div != 0.0f) {  // ((log2(a) * lscale) + add) / div
+    p.y_mul = (float)(lscale / (double)d.affine_div);
+    p.y_add = (float)((double)d.affine_add / (double)d.affine_div);
   } else {
-    p.aff_mul = 1.0f;
-    p.aff_add = 0.0f;
+    p.y_mul = (float)lscale;
+    p.y_add = 0.0f;
   }
   p.out_layout = d.out_layout;
   p.out = reinterpret_cast<float*>(a->out);
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * d.n_mels;
   p.clip_max = clip_max;
-  p.clip_min = clip_min;
+  p.tile_min = tile_min;
   p.feat_sums = feat_sums;
   p.win2 = fs->d_win2;
   p.tw1 = fs->d_tw1;

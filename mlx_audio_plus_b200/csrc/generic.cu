@@ -192,7 +192,7 @@ struct FwdParams {
   int out_layout;
   void* out;
   int64_t out_clip_stride;
-  float *clip_max, *clip_min;
+  float *clip_max, *tile_min;
   double* feat_sums;
   const float2* tw;
   const float* window;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
       float a = red_max[0], b = red_min[0];
       for (int w = 1; w < kThreads / 32; ++w) { a = fmaxf(a, red_max[w]); b = fminf(b, red_min[w]); }
       atomic_max_float(p.clip_max + clip_i, a);
-      atomic_min_float(p.clip_min + clip_i, b);
+      p.tile_min[(int64_t)clip_i * p.tiles_per_clip + tile_i] = b;
     }
     if (p.feat_sums) {
       for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -381,78 +381,106 @@ struct FinParams {
   float affine_add, affine_div;
   int norm_kind, norm_ddof;
   float norm_eps;
-  const float *clip_max, *clip_min;
+  float* clip_max;
+  const float* tile_min;
+  int tile_frames, tiles_per_clip;
   const double* feat_sums;
-  int stats_affine;  // 1: clip_max/min were recorded AFTER the affine map (fast kernels)
+  int stats_affine;  // 1: clip_max / tile_min were recorded AFTER the affine map (fast kernels)
 };
 
-__global__ void __launch_bounds__(256) frontend_finalize_kernel(const FinParams p) {
-  const int clip_i = blockIdx.y;
-  const int M = p.n_mels;
-  float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
-  const int64_t total = p.frames * M;
-  if (p.clamp_kind != B2A_CLAMP_NONE) {
-    // floor in the OUTPUT domain; the affine map is monotone increasing, so it commutes with max()
-    float floor_out;
-    bool active;
-    const float lo = p.clip_min[clip_i];
-    if (p.clamp_kind == B2A_CLAMP_FIXED) {
-      const float fl = p.apply_affine ? (p.clamp_value + p.affine_add) / p.affine_div : p.clamp_value;
-      floor_out = fl;
-      active = p.stats_affine ? (lo < fl) : (lo < p.clamp_value);
-    } else {
-      float mx = p.clip_max[clip_i];
-      if (p.clamp_kind == B2A_CLAMP_BATCH_MAX)
-        for (int b = 0; b < p.batch; ++b) mx = fmaxf(mx, p.clip_max[b]);
-      if (p.stats_affine) {
-        floor_out = p.apply_affine ? mx - p.clamp_value / p.affine_div : mx - p.clamp_value;
-        active = lo < floor_out;
-      } else {
-        const float fl = mx - p.clamp_value;
-        active = lo < fl;
-        floor_out = p.apply_affine ? (fl + p.affine_add) / p.affine_div : fl;
-      }
-    }
-    if (!active) return;  // nothing below the floor in this clip: the values written by partial() are final
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const float v = o[i];
-      if (v < floor_out) o[i] = floor_out;
-    }
-    return;
+// B2A_CLAMP_BATCH_MAX: one max over the whole batch (s3tokenizer/utils.py:131) -> broadcast into clip_max
+__global__ void batch_max_kernel(float* clip_max, int batch) {
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) m = fmaxf(m, clip_max[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    red[0] = m;
   }
-  if (p.norm_kind != B2A_NORM_NONE) {
-    const double n = (double)p.global_frames;
-    const double* S = p.feat_sums + (int64_t)clip_i * M * 2;
-    float g_mean = 0.f, g_den = 1.f;
-    if (p.norm_kind == B2A_NORM_GLOBAL) {
-      double s1 = 0, s2 = 0;
-      for (int m = 0; m < M; ++m) { s1 += S[2 * m]; s2 += S[2 * m + 1]; }
-      const double cnt = n * M, mean = s1 / cnt;
-      double var = (s2 - cnt * mean * mean) / (cnt - p.norm_ddof);
-      if (var < 0) var = 0;
-      g_mean = (float)mean;
-      g_den = (float)sqrt(var) + p.norm_eps;
+  __syncthreads();
+  m = red[0];
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) clip_max[i] = m;
+}
+
+// Clamp fix-up: one WARP per tile; a tile whose recorded minimum is not below the floor is already final
+// (the affine map is monotone increasing, so it commutes with max()) and costs one 4-byte read.
+__global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
+  const int clip_i = blockIdx.y;
+  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= p.tiles_per_clip) return;
+  float floor_out, floor_cmp;
+  if (p.clamp_kind == B2A_CLAMP_FIXED) {
+    floor_out = p.apply_affine ? (p.clamp_value + p.affine_add) / p.affine_div : p.clamp_value;
+    floor_cmp = p.stats_affine ? floor_out : p.clamp_value;
+  } else {
+    const float mx = p.clip_max[clip_i];
+    if (p.stats_affine) {
+      floor_out = p.apply_affine ? mx - p.clamp_value / p.affine_div : mx - p.clamp_value;
+      floor_cmp = floor_out;
+    } else {
+      floor_cmp = mx - p.clamp_value;
+      floor_out = p.apply_affine ? (floor_cmp + p.affine_add) / p.affine_div : floor_cmp;
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const int m = p.out_layout == B2A_LAYOUT_TM ? (int)(i % M) : (int)(i / p.frames);
-      float mean = g_mean, den = g_den;
-      if (p.norm_kind == B2A_NORM_PER_FEATURE) {
-        const double mu = S[2 * m] / n;
-        double var = (S[2 * m + 1] - n * mu * mu) / (n - p.norm_ddof);
-        if (var < 0) var = 0;
-        mean = (float)mu;
-        den = (float)sqrt(var) + p.norm_eps;
-      }
-      o[i] = (o[i] - mean) / den;
+  }
+  if (!(p.tile_min[(int64_t)clip_i * p.tiles_per_clip + tile] < floor_cmp)) return;
+  float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
+  const int M = p.n_mels;
+  const int64_t f0 = (int64_t)tile * p.tile_frames;
+  const int nf = (int)min((int64_t)p.tile_frames, p.frames - f0);
+  if (p.out_layout == B2A_LAYOUT_TM) {
+    float* t = o + f0 * M;
+    for (int i = lane; i < nf * M; i += 32) {
+      const float v = t[i];
+      if (v < floor_out) t[i] = floor_out;
+    }
+  } else {
+    for (int i = lane; i < nf * M; i += 32) {
+      const int m = i / nf, f = i - m * nf;
+      float* q = o + (int64_t)m * p.frames + f0 + f;
+      if (*q < floor_out) *q = floor_out;
     }
   }
 }
 
-__global__ void init_stats_kernel(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_sums) {
+__global__ void __launch_bounds__(256) normalise_kernel(const FinParams p) {
+  const int clip_i = blockIdx.y;
+  const int M = p.n_mels;
+  float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
+  const int64_t total = p.frames * M;
+  const double n = (double)p.global_frames;
+  const double* S = p.feat_sums + (int64_t)clip_i * M * 2;
+  float g_mean = 0.f, g_den = 1.f;
+  if (p.norm_kind == B2A_NORM_GLOBAL) {
+    double s1 = 0, s2 = 0;
+    for (int m = 0; m < M; ++m) { s1 += S[2 * m]; s2 += S[2 * m + 1]; }
+    const double cnt = n * M, mean = s1 / cnt;
+    double var = (s2 - cnt * mean * mean) / (cnt - p.norm_ddof);
+    if (var < 0) var = 0;
+    g_mean = (float)mean;
+    g_den = (float)sqrt(var) + p.norm_eps;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = p.out_layout == B2A_LAYOUT_TM ? (int)(i % M) : (int)(i / p.frames);
+    float mean = g_mean, den = g_den;
+    if (p.norm_kind == B2A_NORM_PER_FEATURE) {
+      const double mu = S[2 * m] / n;
+      double var = (S[2 * m + 1] - n * mu * mu) / (n - p.norm_ddof);
+      if (var < 0) var = 0;
+      mean = (float)mu;
+      den = (float)sqrt(var) + p.norm_eps;
+    }
+    o[i] = (o[i] - mean) / den;
+  }
+}
+
+__global__ void init_stats_kernel(float* clip_max, double* feat_sums, int batch, int n_sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) {
     if (clip_max) clip_max[i] = -INFINITY;
-    if (clip_min) clip_min[i] = INFINITY;
   }
   if (feat_sums && i < n_sums) feat_sums[i] = 0.0;
 }
@@ -576,7 +604,17 @@ static int choose_frames_per_tile(int N, int hop, size_t budget, int max_ft) {
   return best;
 }
 
-int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* clip_min,
+int generic_tile_frames(const b2a_plan* plan, const b2a_forward_args* a) {
+  const b2a_frontend_desc& d = plan->fd;
+  int ft = choose_frames_per_tile(d.n_fft, d.hop, 96 * 1024, 64);
+  if (ft == 0) ft = choose_frames_per_tile(d.n_fft, d.hop, generic_smem_limit(plan), 2);
+  if (ft == 0) return 0;
+  // small inputs: shrink tiles so that the grid still covers the SMs
+  while (ft > 2 && (int64_t)a->batch * ((a->frame_count + ft - 1) / ft) < 2 * plan->sm_count) ft -= 2;
+  return ft;
+}
+
+int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                              double* feat_sums, cudaStream_t st) {
   const b2a_frontend_desc& d = plan->fd;
   FwdParams p;
@@ -609,7 +647,7 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   const int M = d.n_mels > 0 ? d.n_mels : plan->n_freqs;
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * M;
   p.clip_max = clip_max;
-  p.clip_min = clip_min;
+  p.tile_min = tile_min;
   p.feat_sums = feat_sums;
   p.tw = plan->d_twiddle;
   p.window = plan->d_window;
@@ -618,14 +656,11 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   p.mel_off = plan->mel.d_off;
   p.mel_w = plan->mel.d_w;
   p.fft = make_fft_desc(plan);
-  int ft = choose_frames_per_tile(d.n_fft, d.hop, 96 * 1024, 64);
-  if (ft == 0) ft = choose_frames_per_tile(d.n_fft, d.hop, generic_smem_limit(plan), 2);
+  const int ft = generic_tile_frames(plan, a);
   if (ft == 0) {
     set_error("n_fft=%d too large for the generic kernel", d.n_fft);
     return B2A_ERR_UNSUPPORTED;
   }
-  // small inputs: shrink tiles so that the grid still covers the SMs
-  while (ft > 2 && (int64_t)a->batch * ((a->frame_count + ft - 1) / ft) < 2 * plan->sm_count) ft -= 2;
   p.frames_per_tile = ft;
   p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
   const size_t smem = (size_t)4 * ((size_t)(ft - 1) * d.hop + d.n_fft) + (size_t)16 * (ft / 2) * d.n_fft;
@@ -678,18 +713,17 @@ int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cud
   return B2A_OK;
 }
 
-int init_stats(float* clip_max, float* clip_min, double* feat_sums, int batch, int n_mels, cudaStream_t st) {
+int init_stats(float* clip_max, double* feat_sums, int batch, int n_mels, cudaStream_t st) {
   const int n_sums = feat_sums ? batch * n_mels * 2 : 0;
   const int n = batch > n_sums ? batch : n_sums;
   if (n <= 0) return B2A_OK;
-  init_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(clip_max, clip_min, feat_sums, batch, n_sums);
+  init_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(clip_max, feat_sums, batch, n_sums);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
 
-int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, const float* clip_max,
-                      const float* clip_min, const double* feat_sums, cudaStream_t st) {
-  const int stats_affine = plan->family == KF_FAST ? 1 : 0;
+int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, float* clip_max,
+                      const float* tile_min, int tile_frames, const double* feat_sums, cudaStream_t st) {
   const b2a_frontend_desc& d = plan->fd;
   if (d.clamp_kind == B2A_CLAMP_NONE && d.norm_kind == B2A_NORM_NONE) return B2A_OK;
   FinParams p;
@@ -711,14 +745,26 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   p.norm_ddof = d.norm_ddof;
   p.norm_eps = d.norm_eps;
   p.clip_max = clip_max;
-  p.clip_min = clip_min;
+  p.tile_min = tile_min;
+  p.tile_frames = tile_frames;
+  p.tiles_per_clip = (int)((a->frame_count + tile_frames - 1) / tile_frames);
   p.feat_sums = feat_sums;
-  p.stats_affine = stats_affine;
+  p.stats_affine = plan->family == KF_FAST ? 1 : 0;
+  if (d.clamp_kind != B2A_CLAMP_NONE) {
+    if (d.clamp_kind == B2A_CLAMP_BATCH_MAX) {
+      batch_max_kernel<<<1, 256, 0, st>>>(clip_max, a->batch);
+      B2A_CUDA(cudaGetLastError());
+    }
+    dim3 grid((p.tiles_per_clip + 7) / 8, a->batch);
+    clamp_fixup_kernel<<<grid, 256, 0, st>>>(p);
+    B2A_CUDA(cudaGetLastError());
+    return B2A_OK;
+  }
   const int64_t total = a->frame_count * M;
   int gx = (int)std::min<int64_t>((total + 256 * 8 - 1) / (256 * 8), 4 * plan->sm_count);
   if (gx < 1) gx = 1;
   dim3 grid(gx, a->batch);
-  frontend_finalize_kernel<<<grid, 256, 0, st>>>(p);
+  normalise_kernel<<<grid, 256, 0, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
