@@ -306,7 +306,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(plan.kernel_name, {}).get("dram_bytes_per_launch")
+                per_clip = json.load(open(tp)).get(plan.kernel_name.replace("fast_logmel_", "fast_logmel_"), {}).get("dram_bytes_per_clip")
+                traffic = per_clip * B if per_clip else None  # ncu --set full capture, scaled per launch
             except Exception:
                 traffic = None
         line = {

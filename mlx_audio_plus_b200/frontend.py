@@ -122,6 +122,41 @@ class FrontendPlan(_PlanBase):
         L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
         return out
 
+    # -- split form for frame-range sharding ------------------------------------------------
+    def stats_tensors(self, batch, device):
+        """(clip_max float32 [B], feat_sums float64 [B, n_out, 2]) — the buffers ranks all-reduce."""
+        import torch
+
+        return (torch.full((batch,), float("-inf"), dtype=torch.float32, device=device),
+                torch.zeros((batch, self.n_out, 2), dtype=torch.float64, device=device))
+
+    def partial(self, x_cuda, out, clip_max, feat_sums, *, length, sample_offset, frame_begin, frame_count,
+                valid_length=None, pad_value=0.0):
+        """Un-clamped / un-normalised features of frames [frame_begin, +frame_count) of a signal of GLOBAL
+        `length`, from a slice whose first element is global sample `sample_offset`.  Statistics land in
+        clip_max / feat_sums for the caller to reduce across ranks."""
+        import torch
+
+        B = int(x_cuda.shape[0])
+        valid = length if valid_length is None else valid_length
+        a = self._args(x_cuda.data_ptr(), int(x_cuda.shape[1]), int(length), int(valid), B, out.data_ptr(),
+                       pad_value=pad_value, sample_offset=int(sample_offset), frame_begin=int(frame_begin),
+                       frame_count=int(frame_count), clip_max=clip_max.data_ptr(), feat_sums=feat_sums.data_ptr())
+        st = torch.cuda.current_stream(x_cuda.device).cuda_stream
+        L.check(L.lib.b2a_frontend_partial(self._h, C.byref(a), C.c_void_p(st)))
+        self._last_partial = a
+        return out
+
+    def finalize(self, out, clip_max, feat_sums, *, global_frames):
+        """Clamp / normalise `out` in place with the (all-reduced) statistics."""
+        import torch
+
+        a = self._last_partial
+        a.out, a.clip_max, a.feat_sums = out.data_ptr(), clip_max.data_ptr(), feat_sums.data_ptr()
+        st = torch.cuda.current_stream(out.device).cuda_stream
+        L.check(L.lib.b2a_frontend_finalize(self._h, C.byref(a), int(global_frames), C.c_void_p(st)))
+        return out
+
     def dump_frames(self, x_cuda, apply_window=False, length=None):
         """Parity hook (bit-exact framing test): (B, L) torch CUDA float32 -> (B, T, n_fft) frames.
         Only meaningful on plans created with drop_last=False."""
