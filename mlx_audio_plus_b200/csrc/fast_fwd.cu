@@ -357,34 +357,38 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     // stores ((T, M) layout) or through a small staging tile ((M, T) layout).
     {
       constexpr int NFW = (C::FT + C::WARPS - 1) / C::WARPS;  // frames per warp
+      constexpr int ROWSTEP = C::WARPS * C::PP;                // P rows of consecutive slots are this far apart
+      // Slots whose frame index is >= FT read past the P tile into the (allocated) sample buffer: the values
+      // are garbage but never stored and never enter the statistics (ok == false).
+      static_assert((NFW * C::WARPS - C::FT) * C::PP <= C::XS_FLOATS, "overshoot must stay inside smem");
       float lmax = -INFINITY, lmin = INFINITY;
       float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
-      const float* prow[NFW];
-      float* orow[NFW];
+      const float* const prow0 = Pw + warp * C::PP;
+      // (T, M): row (lt0 + warp + i*WARPS), column g*32 + lane; (M, T) staging: Y[(g*32+lane)*33 + frame]
+      float* op = LAYOUT_TM ? (o + (lt0 + warp) * M + lane) : (Y + lane * 33 + warp);
+      const int ostep = LAYOUT_TM ? C::WARPS * M : C::WARPS;      // between this warp's consecutive frames
+      const int gstep = LAYOUT_TM ? 32 : 32 * 33;                  // between consecutive mel groups
       bool fok[NFW];
 #pragma unroll
-      for (int i = 0; i < NFW; ++i) {
-        const int fr = warp + i * C::WARPS;
-        const int frc = fr < C::FT ? fr : C::FT - 1;  // clamp: surplus slots recompute a valid row, never stored
-        prow[i] = Pw + frc * C::PP;
-        fok[i] = fr < nf;
-        orow[i] = LAYOUT_TM ? (o + (lt0 + frc) * M + lane) : (Y + lane * 33 + frc);
-      }
+      for (int i = 0; i < NFW; ++i) fok[i] = warp + i * C::WARPS < nf;
       const int2* ginfo2 = reinterpret_cast<const int2*>(s_ginfo);
+      const int* stp = s_start + lane;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
         const int2 gi = ginfo2[g];  // (group length, weight offset)
-        const int st = s_start[g * 32 + lane];
         const bool mok = g * 32 + lane < M;
         const float* wp = s_wg + gi.y + lane;
+        const float* pq = prow0 + stp[g * 32];
         float acc[NFW];
 #pragma unroll
         for (int i = 0; i < NFW; ++i) acc[i] = 0.0f;
 #pragma unroll 1
         for (int j = 0; j < gi.x; ++j) {
-          const float w = wp[j * 32];
+          const float w = *wp;
 #pragma unroll
-          for (int i = 0; i < NFW; ++i) acc[i] = fmaf(prow[i][st + j], w, acc[i]);
+          for (int i = 0; i < NFW; ++i) acc[i] = fmaf(pq[i * ROWSTEP], w, acc[i]);
+          wp += 32;
+          pq += 1;
         }
         double d1 = 0.0, d2 = 0.0;
 #pragma unroll
@@ -397,14 +401,14 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
           lmax = fmaxf(lmax, yv);
           lmin = fminf(lmin, yv);
           if (ok) {
-            if (LAYOUT_TM) orow[i][g * 32] = y;
-            else orow[i][g * 32 * 33] = y;
+            op[i * ostep] = y;
             if (WANT_SUMS) {
               d1 += (double)y;
               d2 += (double)y * (double)y;
             }
           }
         }
+        op += gstep;
         if (WANT_SUMS && mok) {
           atomicAdd(&s_sums[2 * (g * 32 + lane)], d1);
           atomicAdd(&s_sums[2 * (g * 32 + lane) + 1], d2);
