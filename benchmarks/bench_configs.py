@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Per-config measurements for BASELINE.json configs C1, C3, C4, C5 (C2 is bench.py's headline).
+
+For every config: device-resident synthetic input, >= 3 warm-ups, CUDA-event timing on the
+launch stream, audio-hours/s, and achieved algorithmic HBM GB/s as a fraction of MEASURED_PEAKS.json.
+Prints one JSON line per config and writes them to the path given by --out."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mlx_audio_plus_b200 import _lib as L  # noqa: E402
+from mlx_audio_plus_b200._arrays import Ingested  # noqa: E402
+from mlx_audio_plus_b200.dsp import hanning, mel_filters  # noqa: E402
+from mlx_audio_plus_b200.frontend import FrontendPlan, IstftPlan  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def synth(B, n, sr, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.arange(n, device="cuda", dtype=torch.float64) / sr
+    tone = (0.2 * (torch.sin(2 * np.pi * 440 * t) + torch.sin(2 * np.pi * 3000 * t))).float()
+    x = torch.empty((B, n), dtype=torch.float32, device="cuda")
+    for c0 in range(0, B, 64):
+        c1 = min(B, c0 + 64)
+        scale = (0.5 + (torch.arange(c0, c1, device="cuda") % 7).float() / 7)[:, None]
+        x[c0:c1] = (0.1 * torch.randn((c1 - c0, n), generator=g, device="cuda") + tone[None]) * scale
+    return x
+
+
+def fwd_case(name, plan, x, sr, steps, length=None):
+    B, n = x.shape
+    ing = Ingested("torch", True, x, None, x.device)
+    out = plan.run(ing, length=length)
+    ms = timeit(lambda: plan.run(ing, length=length), steps)
+    by = x.numel() * 4 + out.numel() * out.element_size()
+    hours = B * n / sr / 3600.0
+    return {"config": name, "kernel": plan.kernel_name, "batch": B, "samples": n, "ms": ms,
+            "audio_hours_per_s": hours / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)}
+
+
+def inv_case(name, plan, spec, sr, steps):
+    B, F, T = spec.shape
+    ing = Ingested("torch", True, spec, None, spec.device)
+    out = plan.run(ing)
+    ms = timeit(lambda: plan.run(ing), steps)
+    by = spec.numel() * 8 + out.numel() * 4
+    hours = out.numel() / sr / 3600.0
+    return {"config": name, "kernel": plan.kernel_name, "batch": B, "frames": T, "ms": ms,
+            "audio_hours_per_s": hours / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    res = []
+
+    def want(k):
+        return not a.only or k in a.only.split(",")
+
+    whisper = dict(n_fft=400, hop=160, window=np.asarray(hanning(400)), drop_last=True, spec_kind=L.SPEC_POWER,
+                   log_kind=L.LOG_LOG10, guard_kind=L.GUARD_MAX, guard_eps=1e-10, clamp_kind=L.CLAMP_CLIP_MAX,
+                   clamp_value=8.0, affine_add=4.0, affine_div=4.0)
+    if want("C1"):
+        plan = FrontendPlan(filterbank=np.asarray(mel_filters(16000, 400, 80, norm="slaney", mel_scale=None)), **whisper)
+        res.append(fwd_case("C1 whisper-80, one 30 s clip (latency)", plan, synth(1, 480000, 16000, 1234), 16000, 50))
+    if want("C3"):
+        plan = FrontendPlan(n_fft=512, hop=160, window=np.asarray(hanning(400)), preemph=0.97, spec_kind=L.SPEC_POWER,
+                            filterbank=np.asarray(mel_filters(16000, 512, 80, norm="per_feature", mel_scale=None)),
+                            log_kind=L.LOG_LN, guard_kind=L.GUARD_ADD, guard_eps=1e-5, norm_kind=L.NORM_PER_FEATURE,
+                            norm_ddof=0, norm_eps=1e-5)
+        res.append(fwd_case("C3 parakeet, one 1-hour file", plan, synth(1, 57_600_000, 16000, 1236), 16000, a.steps))
+        res.append(fwd_case("C3 parakeet, 16 x 1-hour files", plan, synth(16, 57_600_000, 16000, 1236), 16000, 3))
+    if want("C5"):
+        plan = FrontendPlan(n_fft=1024, hop=256, window=np.asarray(hanning(1024)), drop_last=True, spec_kind=L.SPEC_MAGNITUDE,
+                            filterbank=np.asarray(mel_filters(24000, 1024, 100, norm=None, mel_scale="htk")),
+                            log_kind=L.LOG_LN, guard_kind=L.GUARD_MAX, guard_eps=1e-5)
+        for B in (1, 64, 1024, 8192):
+            res.append(fwd_case(f"C5 vocos mel forward, B={B} x 5 s", plan, synth(B, 120000, 24000, 1238), 24000, a.steps))
+        iplan = IstftPlan(n_fft=1024, hop=256, window=np.asarray(hanning(1024)), center=True)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(7)
+        for B in (1, 64, 1024):
+            mag = torch.exp(0.5 * torch.randn((B, 513, 468), generator=g, device="cuda")).clamp(max=1e2)
+            ph = torch.randn((B, 513, 468), generator=g, device="cuda")
+            spec = torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)).contiguous()
+            res.append(inv_case(f"C5 vocos istft head, B={B} x (513,468)", iplan, spec, 24000, a.steps))
+    if want("C4"):
+        iplan = IstftPlan(n_fft=20, hop=5, window=np.asarray(hanning(21)[:-1]), center=True)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(9)
+        for B in (1, 64, 1024):
+            mag = torch.exp(0.5 * torch.randn((B, 11, 24001), generator=g, device="cuda")).clamp(max=1e2)
+            ph = torch.sin(torch.randn((B, 11, 24001), generator=g, device="cuda"))
+            spec = torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)).contiguous()
+            res.append(inv_case(f"C4 kokoro istft, B={B} x (11,24001)", iplan, spec, 24000, a.steps))
+    for r in res:
+        print(json.dumps(r), flush=True)
+    if a.out:
+        json.dump(res, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

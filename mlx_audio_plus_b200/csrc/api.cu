@@ -196,6 +196,7 @@ int partial_impl(b2a_plan* p, const b2a_forward_args* a, const StatPtrs& s, cuda
   }
   if (a->frame_count == 0) return B2A_OK;
   if (p->family == KF_FAST) return fast_frontend_partial(p, a, s.clip_max, s.tile_min, s.feat_sums, st);
+  if (p->family == KF_SMALL) return small_stft(p, a, st);
   return generic_frontend_partial(p, a, s.clip_max, s.tile_min, s.feat_sums, st);
 }
 
@@ -243,6 +244,9 @@ int b2a_frontend_create(const b2a_frontend_desc* d, const float* h_window, const
   if (rc == B2A_OK && fast_frontend_supported(p)) {
     rc = fast_frontend_init(p);
     if (rc == B2A_OK) p->family = KF_FAST;
+  } else if (rc == B2A_OK && small_stft_supported(p)) {
+    p->family = KF_SMALL;
+    p->kernel_name = "stft_small";
   }
   if (rc != B2A_OK) {
     b2a_plan_destroy(p);
@@ -272,6 +276,10 @@ int b2a_istft_create(const b2a_istft_desc* d, const float* h_window, b2a_plan** 
   p->family = KF_GENERIC;
   p->kernel_name = "generic_istft";
   int rc = plan_common_init(p, d->n_fft, d->hop, h_window, d->window_len);
+  if (rc == B2A_OK && small_istft_supported(p)) {
+    p->family = KF_SMALL;
+    p->kernel_name = "istft_small";
+  }
   if (rc != B2A_OK) {
     b2a_plan_destroy(p);
     return rc;
@@ -465,6 +473,7 @@ int b2a_istft_inverse(b2a_plan* p, const b2a_inverse_args* a, void* stream) {
     set_error("istft_inverse: invalid argument");
     return B2A_ERR_INVALID_ARG;
   }
+  if (p->family == KF_SMALL) return small_istft(p, a, (cudaStream_t)stream);
   return generic_istft(p, a, (cudaStream_t)stream);
 }
 
@@ -511,7 +520,7 @@ int b2a_istft_inverse_host(b2a_plan* p, const b2a_inverse_args* in) {
     c.batch = nb;
     c.out = (float*)p->d_stage_out[s];
     c.out_clip_stride = out_len;
-    if ((rc = generic_istft(p, &c, st))) return rc;
+    if ((rc = (p->family == KF_SMALL ? small_istft(p, &c, st) : generic_istft(p, &c, st)))) return rc;
     if (out_len > 0)
       B2A_CUDA(cudaMemcpy2DAsync((char*)in->out + (size_t)c0 * out_stride * 4, (size_t)out_stride * 4, p->d_stage_out[s],
                                  (size_t)out_len * 4, (size_t)out_len * 4, nb, cudaMemcpyDeviceToHost, st));

@@ -33,9 +33,13 @@ namespace {
 using regs::Dft;
 using regs::static_for;
 
-template <int N1_, int N2_, int HOP_>
+template <int N1_, int N2_, int HOP_, bool ALIAS_, int MIN_BLOCKS_>
 struct Cfg {
   static constexpr int N1 = N1_, N2 = N2_, HOP = HOP_;
+  // ALIAS: the power tile P reuses the sample tile's shared memory (no prefetch of the next tile) so that the
+  // CTA fits the occupancy target; otherwise the next tile's samples are prefetched during stage 2 / mel.
+  static constexpr bool ALIAS = ALIAS_;
+  static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
   static constexpr int NC = N1 * N2, N = 2 * NC, F = NC + 1;
   static constexpr int WARPS = N1 / 2;
   static constexpr int THREADS = WARPS * 32;
@@ -96,23 +100,11 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
+// non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
 __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v > __int_as_float(old)) {
-    const int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v < __int_as_float(old)) {
-    const int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 
 __device__ __forceinline__ float fetch_sample_f(const FastParams& p, const float* clip, int64_t s) {
@@ -134,7 +126,20 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, unsign
   const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
   const int64_t s0 = q0 - p.geo.pad_left;             // source coordinate
   const bool interior = p.fast_fill_ok && s0 >= 0 && (s0 + C::SPAN) <= p.valid_length && s0 >= p.sample_offset;
-  if (interior) {
+  if (interior && p.preemph != 0.0f && s0 > p.sample_offset) {
+    // pre-emphasis on the way in: y[n] = x[n] - a*x[n-1] with separately rounded multiply and subtract
+    // (bit-exact vs the reference's `x[1:] - a*x[:-1]`); vectorised, coalesced direct loads
+    const float* src = clip + (s0 - p.sample_offset);
+    const float a = p.preemph;
+    for (int j = threadIdx.x; j < C::SPAN / 2; j += C::THREADS) {
+      const int s = 2 * j;
+      const float2 x = __ldg(reinterpret_cast<const float2*>(src + s));
+      const float xm = __ldg(src + s - 1);
+      const int row = s / C::HOP, col = s - row * C::HOP;
+      *reinterpret_cast<float2*>(xs + row * C::P + col) =
+          make_float2(__fsub_rn(x.x, __fmul_rn(a, xm)), __fsub_rn(x.y, __fmul_rn(a, x.x)));
+    }
+  } else if (interior && p.preemph == 0.0f) {
     // thread t copies the 8-byte pair (row r0 + RPI*i, column 2*c): both addresses are linear in i
     constexpr int PPR = C::HOP / 2;             // pairs per row
     constexpr int RPI = C::THREADS / PPR;       // rows per iteration
@@ -188,12 +193,15 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
   static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
   static constexpr int EX = TWP + cdiv4(8 * C::NC);
   static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);
-  static constexpr int XS = PW + cdiv4(4 * C::FT * C::PP);
-  static constexpr int DYN = XS + cdiv4(4 * C::XS_FLOATS);  // then: sums (double), mel weights, starts, group info
+  static constexpr int XS = C::ALIAS ? PW : PW + cdiv4(4 * C::FT * C::PP);
+  static constexpr int PX_END = C::ALIAS ? PW + (cdiv4(4 * C::FT * C::PP) > cdiv4(4 * C::XS_FLOATS) ? cdiv4(4 * C::FT * C::PP)
+                                                                                                  : cdiv4(4 * C::XS_FLOATS))
+                                         : XS + cdiv4(4 * C::XS_FLOATS);
+  static constexpr int DYN = PX_END;  // then: sums (double), mel weights, starts, group info
 };
 
 template <class C, bool LAYOUT_TM, bool WANT_SUMS>
-__global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastParams p) {
+__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   using S = Smem<C>;
   extern __shared__ float4 smem4[];
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
   const unsigned total_tiles = (unsigned)p.batch * (unsigned)p.tiles_per_clip;
   const unsigned tpc = (unsigned)p.tiles_per_clip;
   unsigned tile = blockIdx.x;
-  if (tile < total_tiles) fill_tile<C>(p, xs, tile);
+  if (!C::ALIAS && tile < total_tiles) fill_tile<C>(p, xs, tile);
 
   const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
   const bool use_log = p.use_log != 0;
@@ -246,6 +254,10 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     const int64_t frames_left = p.frame_count - lt0;
     const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
 
+    if (C::ALIAS) {
+      __syncthreads();  // previous tile's mel phase has finished reading P (which shares xs' memory)
+      fill_tile<C>(p, xs, tile);
+    }
     cp_async_wait_all();
     __syncthreads();  // xs ready; previous tile's Y fully written out
 
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
     // prefetch the next tile's samples while stage 2 / mel run
     {
       const unsigned next = tile + gridDim.x;
-      if (next < total_tiles) fill_tile<C>(p, xs, next);
+      if (!C::ALIAS && next < total_tiles) fill_tile<C>(p, xs, next);
     }
 
     // ---- stage 2 ----------------------------------------------------------------------------------------
@@ -360,7 +372,8 @@ __global__ void __launch_bounds__(C::THREADS, 2) fast_logmel_kernel(const FastPa
       constexpr int ROWSTEP = C::WARPS * C::PP;                // P rows of consecutive slots are this far apart
       // Slots whose frame index is >= FT read past the P tile into the (allocated) sample buffer: the values
       // are garbage but never stored and never enter the statistics (ok == false).
-      static_assert((NFW * C::WARPS - C::FT) * C::PP <= C::XS_FLOATS, "overshoot must stay inside smem");
+      static_assert(C::ALIAS ? (NFW * C::WARPS == C::FT) : ((NFW * C::WARPS - C::FT) * C::PP <= C::XS_FLOATS),
+                    "overshoot must stay inside smem");
       float lmax = -INFINITY, lmin = INFINITY;
       float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
       const float* const prow0 = Pw + warp * C::PP;
@@ -490,7 +503,7 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     return B2A_ERR_UNSUPPORTED;
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = std::max(1, std::min(per_sm, 2));
+  per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
   const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
@@ -500,8 +513,9 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
   return launch_variant<C, false, true>(plan, p, smem, grid, st);
 }
 
-using Cfg400 = Cfg<20, 10, 160>;
-using Cfg512 = Cfg<16, 16, 160>;
+using Cfg400 = Cfg<20, 10, 160, false, 2>;   // Whisper / Voxtral-RT / S3Tokenizer: 320 threads, 2 CTAs / SM
+using Cfg512 = Cfg<16, 16, 160, true, 2>;    // Parakeet / Sortformer: 256 threads, 2 CTAs / SM
+using Cfg1024 = Cfg<32, 16, 256, true, 1>;   // Vocos / Qwen3-TTS mel: 512 threads, 1 CTA / SM
 
 }  // namespace
 
@@ -512,7 +526,8 @@ bool fast_frontend_supported(const b2a_plan* plan) {
   if (d.affine_div < 0.0f) return false;
   const bool v400 = d.n_fft == 400 && d.hop == 160;
   const bool v512 = d.n_fft == 512 && d.hop == 160;
-  if (!(v400 || v512)) return false;
+  const bool v1024 = d.n_fft == 1024 && d.hop == 256;
+  if (!(v400 || v512 || v1024)) return false;
   if (d.n_mels > 256) return false;
   return true;
 }
@@ -523,7 +538,8 @@ int fast_frontend_init(b2a_plan* plan) {
   plan->fast = fs;
   int N1, N2;
   if (d.n_fft == 400) { fs->variant = 1; N1 = 20; N2 = 10; }
-  else { fs->variant = 2; N1 = 16; N2 = 16; }
+  else if (d.n_fft == 512) { fs->variant = 2; N1 = 16; N2 = 16; }
+  else { fs->variant = 3; N1 = 32; N2 = 16; }
   const int NC = N1 * N2, N = 2 * NC;
   std::vector<float2> win2(NC), tw1(NC), twp(NC);
   for (int n2 = 0; n2 < N2; ++n2)
@@ -594,7 +610,7 @@ int fast_frontend_init(b2a_plan* plan) {
   B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 32, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
-  plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : "fast_logmel_512x160";
+  plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : (fs->variant == 2 ? "fast_logmel_512x160" : "fast_logmel_1024x256");
   return B2A_OK;
 }
 
@@ -628,7 +644,7 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.geo = make_geometry(a->length, d.n_fft, d.hop, d.center, d.pad_mode);
   p.pad_mode = d.pad_mode;
   p.preemph = d.preemph;
-  p.fast_fill_ok = d.preemph == 0.0f && (reinterpret_cast<uintptr_t>(a->audio) % 8 == 0) && (a->clip_stride % 2 == 0) &&
+  p.fast_fill_ok = (reinterpret_cast<uintptr_t>(a->audio) % 8 == 0) && (a->clip_stride % 2 == 0) &&
                    (p.geo.pad_left % 2 == 0) && (a->sample_offset % 2 == 0);
   p.spec_kind = d.spec_kind;
   p.spec_eps = d.spec_kind == B2A_SPEC_SQRT_POWER_EPS ? d.spec_eps : 0.0f;
@@ -660,7 +676,8 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
   if (fs->variant == 1) return launch<Cfg400>(plan, fs, p, st);
-  return launch<Cfg512>(plan, fs, p, st);
+  if (fs->variant == 2) return launch<Cfg512>(plan, fs, p, st);
+  return launch<Cfg1024>(plan, fs, p, st);
 }
 
 }  // namespace b2a

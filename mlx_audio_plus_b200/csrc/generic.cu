@@ -156,23 +156,11 @@ __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2
   return src;
 }
 
+// Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
+// non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v > __int_as_float(old)) {
-    int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v < __int_as_float(old)) {
-    int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 
 struct FwdParams {
