@@ -50,7 +50,9 @@ struct Cfg {
   static constexpr int SPAN = (FT - 1) * HOP + N;
   static constexpr int XS_FLOATS = ROWS * P;
   static constexpr int EP = NC + 1;          // exchange pitch per frame (float2), odd
-  static constexpr int PP = (F % 2) ? F : F + 1;  // power pitch per frame (floats), odd
+  // power pitch per frame (floats): odd (stage-2 lane==frame stores are conflict free) and == 9 (mod 32) so that
+  // the mel phase's (4 frames x 8 mel rows) gathers land in distinct banks
+  static constexpr int PP = F + ((9 - F % 32 + 32) % 32);
   static constexpr int K = HOP / (2 * N2);   // taps pairs per row per role step
   static_assert(N1 % 2 == 0 && N2 % WARPS == 0, "role split");
   static_assert(HOP % (2 * N2) == 0, "hop must be a multiple of 2*N2");
@@ -66,6 +68,7 @@ struct FastParams {
   int pad_mode;
   float preemph;
   int fast_fill_ok;  // alignment preconditions for the cp.async path
+  int debug_skip;    // profiling aid (B2A_SKIP bitmask): 1 stage1, 2 stage2, 4 mel, 16 output stores only
   int spec_kind;
   float spec_eps;
   int n_mels;
@@ -185,6 +188,27 @@ __device__ __forceinline__ void post_pair(float2 zk, float2 zm, float2 w, float&
   pm = br * br + bi * bi;
 }
 
+// L taps of one mel group for NFW frames with every load issued before the first FMA (one shared-memory
+// latency per <= 8 taps instead of one per tap: the mel phase is latency-, not throughput-bound)
+template <int L, int NFW, int ROWSTEP, int WSTR>
+__device__ __forceinline__ void mel_group_taps(const float* wp, const float* pq, float (&acc)[NFW]) {
+  static_for<0, (L + 7) / 8>([&](auto C_) {
+    constexpr int c0 = decltype(C_)::value * 8;
+    constexpr int CL = (L - c0) < 8 ? (L - c0) : 8;
+    float w[CL], pv[NFW][CL];
+#pragma unroll
+    for (int j = 0; j < CL; ++j) w[j] = wp[(c0 + j) * WSTR];
+#pragma unroll
+    for (int i = 0; i < NFW; ++i)
+#pragma unroll
+      for (int j = 0; j < CL; ++j) pv[i][j] = pq[i * ROWSTEP + c0 + j];
+#pragma unroll
+    for (int j = 0; j < CL; ++j)
+#pragma unroll
+      for (int i = 0; i < NFW; ++i) acc[i] = fmaf(pv[i][j], w[j], acc[i]);
+  });
+}
+
 template <class C>
 struct Smem {  // section offsets in float4 units from the 16-byte aligned dynamic smem base
   static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
@@ -213,10 +237,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   float* const xs = reinterpret_cast<float*>(smem4 + S::XS);         // [ROWS][P]
   const int M = p.n_mels;
   const int G = p.mel_groups;
-  double* const s_sums = reinterpret_cast<double*>(smem4 + S::DYN);   // [2*G*32]
-  float* const s_wg = reinterpret_cast<float*>(s_sums + 2 * G * 32);  // [mel_wg_count]
-  int* const s_start = reinterpret_cast<int*>(s_wg + p.mel_wg_count); // [G*32]
-  int* const s_ginfo = s_start + G * 32;                              // [2*G]
+  double* const s_sums = reinterpret_cast<double*>(smem4 + S::DYN);   // [2*G*8]
+  float* const s_wg = reinterpret_cast<float*>(s_sums + 2 * G * 8);   // [mel_wg_count]
+  int* const s_start = reinterpret_cast<int*>(s_wg + p.mel_wg_count); // [G*8]
+  int* const s_ginfo = s_start + G * 8 + ((G * 8) & 1);               // [2*G], 8-byte aligned
   __shared__ float red_max[C::WARPS], red_min[C::WARPS];
   __shared__ int s_cur_clip;
 
@@ -228,13 +252,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     s_tw1[i] = p.tw1[i];
     s_twp[i] = p.twp[i];
   }
-  for (int i = threadIdx.x; i < G * 32; i += C::THREADS) s_start[i] = p.mel_start[i];
+  for (int i = threadIdx.x; i < G * 8; i += C::THREADS) s_start[i] = p.mel_start[i];
   for (int i = threadIdx.x; i < 2 * G; i += C::THREADS) s_ginfo[i] = p.mel_ginfo[i];
   for (int i = threadIdx.x; i < p.mel_wg_count; i += C::THREADS) s_wg[i] = p.mel_wg[i];
   constexpr bool want_sums = WANT_SUMS;
   const bool want_max = p.clip_max != nullptr;
   if (want_sums)
-    for (int i = threadIdx.x; i < 2 * G * 32; i += C::THREADS) s_sums[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * G * 8; i += C::THREADS) s_sums[i] = 0.0;
   if (threadIdx.x == 0) s_cur_clip = -1;
 
   const unsigned total_tiles = (unsigned)p.batch * (unsigned)p.tiles_per_clip;
@@ -275,8 +299,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
 
     // ---- stage 1 ----------------------------------------------------------------------------------------
+    const int dbg = p.debug_skip;
 #pragma unroll 1
-    for (int rr = 0; rr < C::RPW; ++rr) {
+    for (int rr = 0; rr < ((dbg & 1) ? 0 : C::RPW); ++rr) {
       const int n2 = warp * C::RPW + rr;
       const float* xb = xs + lane * C::P + 2 * n2;
       const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
@@ -315,7 +340,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
 
     // ---- stage 2 ----------------------------------------------------------------------------------------
-    {
+    if (!(dbg & 2)) {
       const int u = warp;  // column pair (u, N1-u); u == 0 owns columns 0 and N1/2
       float2 A[N2], B[N2];
       const float2* ea = E + lane * C::EP + u * N2;
@@ -362,70 +387,99 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
     __syncthreads();  // Pw complete, E free (Y aliases E)
 
-    // ---- mel projection + log + affine: LANE = MEL ROW, warp = a few frames of the tile ---------------------
-    // Each lane owns one row of a group of 32 consecutive mel rows; the banded filterbank is walked for
-    // `glen` taps (zero padded to the group's longest row), weights are lane-contiguous in smem, power
-    // values are gathered from the frame's P row, and the result goes straight to HBM with 128 B coalesced
-    // stores ((T, M) layout) or through a small staging tile ((M, T) layout).
+    if (!(dbg & 4))
+    // ---- mel projection + log + affine: LANE = (4 frames) x (8 consecutive mel rows) -----------------------------
+    // The filterbank is banded (<= 2 non-zeros per bin): a mel row is a short run of taps.  A warp-instruction
+    // covers 8 consecutive rows for 4 frames, so (a) the P gathers touch ~32 distinct banks (row pitch == 9 mod 32,
+    // neighbouring rows start a few bins apart), (b) rows are zero-padded only to the longest of 8 neighbours,
+    // (c) each store instruction writes four fully used 32-byte sectors of the (T, M) output.  A work item is
+    // (octet of rows, half of the tile's frames): 4 independent accumulators per lane share one weight load.
     {
-      constexpr int NFW = (C::FT + C::WARPS - 1) / C::WARPS;  // frames per warp
-      constexpr int ROWSTEP = C::WARPS * C::PP;                // P rows of consecutive slots are this far apart
-      // Slots whose frame index is >= FT read past the P tile into the (allocated) sample buffer: the values
-      // are garbage but never stored and never enter the statistics (ok == false).
-      static_assert(C::ALIAS ? (NFW * C::WARPS == C::FT) : ((NFW * C::WARPS - C::FT) * C::PP <= C::XS_FLOATS),
-                    "overshoot must stay inside smem");
+      constexpr int NQ = 4;                       // frame quads per item
+      constexpr int ROWSTEP = 4 * C::PP;          // P rows of consecutive quads
+      const int ms = lane & 7, fs = lane >> 3;
       float lmax = -INFINITY, lmin = INFINITY;
       float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
-      const float* const prow0 = Pw + warp * C::PP;
-      // (T, M): row (lt0 + warp + i*WARPS), column g*32 + lane; (M, T) staging: Y[(g*32+lane)*33 + frame]
-      float* op = LAYOUT_TM ? (o + (lt0 + warp) * M + lane) : (Y + lane * 33 + warp);
-      const int ostep = LAYOUT_TM ? C::WARPS * M : C::WARPS;      // between this warp's consecutive frames
-      const int gstep = LAYOUT_TM ? 32 : 32 * 33;                  // between consecutive mel groups
-      bool fok[NFW];
-#pragma unroll
-      for (int i = 0; i < NFW; ++i) fok[i] = warp + i * C::WARPS < nf;
       const int2* ginfo2 = reinterpret_cast<const int2*>(s_ginfo);
-      const int* stp = s_start + lane;
-#pragma unroll 1
-      for (int g = 0; g < G; ++g) {
-        const int2 gi = ginfo2[g];  // (group length, weight offset)
-        const bool mok = g * 32 + lane < M;
-        const float* wp = s_wg + gi.y + lane;
-        const float* pq = prow0 + stp[g * 32];
-        float acc[NFW];
+      // output addressing: 32-bit element offsets from a per-tile base; (T, M): (f0 + 4q)*M + m, (M, T) staging:
+      // m*33 + f0 + 4q
+      float* const obase = LAYOUT_TM ? (o + lt0 * M) : Y;
+      const int qstep = LAYOUT_TM ? 4 * M : 4;
+      const int fstep = LAYOUT_TM ? M : 1, mstep = LAYOUT_TM ? 1 : 33;
+      const bool full = nf == C::FT && (M & 7) == 0 && !(dbg & 16);  // every slot valid: no per-output predicates
+      auto item = [&](auto FULL_, int it) {
+        constexpr bool FULL = decltype(FULL_)::value;
+        const int oct = it >> 1, half = it & 1;
+        const int m = oct * 8 + ms;
+        const int f0 = half * 16 + fs;            // this lane's frames: f0 + 4q
+        const int2 gi = ginfo2[oct];              // (octet length, weight offset)
+        const float* wp = s_wg + gi.y + ms;
+        const float* pq = Pw + f0 * C::PP + s_start[m];
+        float acc[NQ];
 #pragma unroll
-        for (int i = 0; i < NFW; ++i) acc[i] = 0.0f;
+        for (int i = 0; i < NQ; ++i) acc[i] = 0.0f;
+        switch (gi.x) {  // one dispatch per item, taps fully unrolled with all loads issued up front
+          case 0: break;
+#define B2A_MEL_CASE(LL) case LL: mel_group_taps<LL, NQ, ROWSTEP, 8>(wp, pq, acc); break;
+          B2A_MEL_CASE(1) B2A_MEL_CASE(2) B2A_MEL_CASE(3) B2A_MEL_CASE(4) B2A_MEL_CASE(5) B2A_MEL_CASE(6)
+          B2A_MEL_CASE(7) B2A_MEL_CASE(8) B2A_MEL_CASE(9) B2A_MEL_CASE(10) B2A_MEL_CASE(11) B2A_MEL_CASE(12)
+          B2A_MEL_CASE(13) B2A_MEL_CASE(14) B2A_MEL_CASE(15) B2A_MEL_CASE(16)
+#undef B2A_MEL_CASE
+          default:
 #pragma unroll 1
-        for (int j = 0; j < gi.x; ++j) {
-          const float w = *wp;
+            for (int j = 0; j < gi.x; ++j) {
+              const float w = wp[j * 8];
 #pragma unroll
-          for (int i = 0; i < NFW; ++i) acc[i] = fmaf(pq[i * ROWSTEP], w, acc[i]);
-          wp += 32;
-          pq += 1;
+              for (int i = 0; i < NQ; ++i) acc[i] = fmaf(pq[i * ROWSTEP + j], w, acc[i]);
+            }
         }
+        float* const op = obase + (f0 * fstep + m * mstep);
+        const bool mok = m < M;
         double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < NFW; ++i) {
+        for (int i = 0; i < NQ; ++i) {
           const float a = fmaxf(acc[i] + guard_add, guard_floor);
           float y = use_log ? lg2_approx(a) : a;
           y = fmaf(y, y_mul, y_add);
-          const bool ok = fok[i] && mok;
-          const float yv = ok ? y : __int_as_float(0x7fc00000);  // NaN is ignored by fmaxf / fminf
-          lmax = fmaxf(lmax, yv);
-          lmin = fminf(lmin, yv);
-          if (ok) {
-            op[i * ostep] = y;
+          if (FULL) {
+            lmax = fmaxf(lmax, y);
+            lmin = fminf(lmin, y);
+            op[i * qstep] = y;
             if (WANT_SUMS) {
               d1 += (double)y;
               d2 += (double)y * (double)y;
             }
+          } else {
+            const bool ok = mok && (f0 + 4 * i < nf);
+            const float yv = ok ? y : __int_as_float(0x7fc00000);  // NaN is ignored by fmaxf / fminf
+            lmax = fmaxf(lmax, yv);
+            lmin = fminf(lmin, yv);
+            if (ok && (!(dbg & 16) || y == 1234.5678f)) {
+              op[i * qstep] = y;
+              if (WANT_SUMS) {
+                d1 += (double)y;
+                d2 += (double)y * (double)y;
+              }
+            }
           }
         }
-        op += gstep;
-        if (WANT_SUMS && mok) {
-          atomicAdd(&s_sums[2 * (g * 32 + lane)], d1);
-          atomicAdd(&s_sums[2 * (g * 32 + lane) + 1], d2);
+        if (WANT_SUMS) {  // fold the 4 frame-sub lanes of each mel row, then one shared-memory atomic per row
+          d1 += __shfl_xor_sync(0xffffffffu, d1, 8);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, 8);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, 16);
+          if (fs == 0 && mok) {
+            atomicAdd(&s_sums[2 * m], d1);
+            atomicAdd(&s_sums[2 * m + 1], d2);
+          }
         }
+      };
+      if (full) {
+#pragma unroll 1
+        for (int it = warp; it < 2 * G; it += C::WARPS) item(std::true_type{}, it);
+      } else {
+#pragma unroll 1
+        for (int it = warp; it < 2 * G; it += C::WARPS) item(std::false_type{}, it);
       }
       if (want_max) {
 #pragma unroll
@@ -464,7 +518,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
 
 template <class C>
 size_t smem_bytes(int G, int wg_count) {
-  return (size_t)16 * Smem<C>::DYN + sizeof(double) * 2 * G * 32 + sizeof(float) * wg_count + sizeof(int) * (G * 32 + 2 * G) + 16;
+  return (size_t)16 * Smem<C>::DYN + sizeof(double) * 2 * G * 8 + sizeof(float) * (wg_count + (wg_count & 1)) + sizeof(int) * (G * 8 + 2 * G + 2) + 16;
 }
 
 struct FastState {
@@ -561,10 +615,10 @@ int fast_frontend_init(b2a_plan* plan) {
     for (int k2 = 0; k2 < N2; ++k2) twp[u * 2 * N2 + k2] = wn(u + N1 * k2);
   for (int k2 = 0; k2 <= N2 / 2; ++k2) twp[k2] = wn(N1 * k2);                    // unit 0, column 0
   for (int k2 = 0; k2 < N2 / 2; ++k2) twp[N2 + k2] = wn(N1 / 2 + N1 * k2);        // unit 0, column N1/2
-  // mel filterbank in lane == mel form
+  // mel filterbank in (8 rows per octet) form: per octet the longest row length L and the weights W[j][row]
   const int M = d.n_mels, F = plan->n_freqs;
-  const int G = (M + 31) / 32;
-  std::vector<int> start(G * 32, 0), len(G * 32, 0), ginfo(2 * G, 0);
+  const int G = (M + 7) / 8;
+  std::vector<int> start(G * 8, 0), len(G * 8, 0), ginfo(2 * G, 0);
   for (int m = 0; m < M; ++m) {
     int lo = -1, hi = -1;
     for (int f = 0; f < F; ++f)
@@ -578,19 +632,18 @@ int fast_frontend_init(b2a_plan* plan) {
   std::vector<float> wg;
   for (int g = 0; g < G; ++g) {
     int L = 0;
-    for (int l = 0; l < 32; ++l) L = std::max(L, len[g * 32 + l]);
+    for (int l = 0; l < 8; ++l) L = std::max(L, len[g * 8 + l]);
     // rows shorter than L read (zero weighted) bins past their end: keep those reads inside the P row
-    for (int l = 0; l < 32; ++l)
-      if (start[g * 32 + l] + L > F) start[g * 32 + l] = std::max(0, F - L);
+    for (int l = 0; l < 8; ++l)
+      if (start[g * 8 + l] + L > F) start[g * 8 + l] = std::max(0, F - L);
     ginfo[2 * g] = L;
     ginfo[2 * g + 1] = (int)wg.size();
     for (int j = 0; j < L; ++j)
-      for (int l = 0; l < 32; ++l) {
-        const int m = g * 32 + l;
+      for (int l = 0; l < 8; ++l) {
+        const int m = g * 8 + l;
         float w = 0.0f;
         if (m < M) {
-          // start may have been shifted left to stay in range: index the dense filterbank directly
-          const int f = start[m] + j;
+          const int f = start[m] + j;  // start may have been shifted left: index the dense filterbank directly
           if (f < F) w = plan->h_fb[(size_t)m * F + f];
         }
         wg.push_back(w);
@@ -601,13 +654,13 @@ int fast_frontend_init(b2a_plan* plan) {
   B2A_CUDA(cudaMalloc(&fs->d_win2, sizeof(float2) * NC));
   B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float2) * NC));
   B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * NC));
-  B2A_CUDA(cudaMalloc(&fs->d_start, sizeof(int) * G * 32));
+  B2A_CUDA(cudaMalloc(&fs->d_start, sizeof(int) * G * 8));
   B2A_CUDA(cudaMalloc(&fs->d_ginfo, sizeof(int) * 2 * G));
   B2A_CUDA(cudaMalloc(&fs->d_wg, sizeof(float) * std::max<size_t>(wg.size(), 1)));
   B2A_CUDA(cudaMemcpy(fs->d_win2, win2.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_tw1, tw1.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
-  B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 32, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 8, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
   plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : (fs->variant == 2 ? "fast_logmel_512x160" : "fast_logmel_1024x256");
@@ -646,6 +699,7 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.preemph = d.preemph;
   p.fast_fill_ok = (reinterpret_cast<uintptr_t>(a->audio) % 8 == 0) && (a->clip_stride % 2 == 0) &&
                    (p.geo.pad_left % 2 == 0) && (a->sample_offset % 2 == 0);
+  p.debug_skip = getenv("B2A_SKIP") ? atoi(getenv("B2A_SKIP")) : 0;
   p.spec_kind = d.spec_kind;
   p.spec_eps = d.spec_kind == B2A_SPEC_SQRT_POWER_EPS ? d.spec_eps : 0.0f;
   p.n_mels = d.n_mels;
