@@ -5,6 +5,12 @@
 // natural order in and out.  R in {2,3,4,5} are hand-written butterflies; composite sizes are assembled at
 // compile time by Cooley-Tukey (twiddles folded to immediates) or, for coprime factors, by the Good-Thomas
 // prime-factor map (no twiddles at all): 8=2x4, 16=4x4, 32=4x8, 10=2x5 (PFA), 20=4x5 (PFA), 25=5x5.
+//
+// On the device every complex value is one packed f32x2 register pair and the butterflies are written with
+// Blackwell's packed FP32 instructions (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, sm_100+):
+// a complex add is ONE instruction, multiplication by +-i is folded into an FFMA2 with a (+-1, -+1) constant on
+// the half-swapped operand (the swap is an operand swizzle, not a MOV).  DFT-20 = 112 instructions instead of
+// 224 scalar ones.  The host path (unit test) uses the same formulas in plain C++.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -75,9 +81,57 @@ B2A_HD void static_for(F&& f) {
   }
 }
 
-B2A_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-B2A_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-B2A_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// ---- packed complex primitives -------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pk2(float2 a) {
+  u64_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 up2(u64_t r) {
+  float2 a;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ float2 padd(float2 a, float2 b) {
+  u64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 psub(float2 a, float2 b) {
+  u64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {
+  u64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+  u64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return up2(r);
+}
+#else
+inline float2 padd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 psub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+inline float2 pmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 pfma(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+B2A_HD float2 pswap(float2 a) { return make_float2(a.y, a.x); }
+B2A_HD float2 pbc(float c) { return make_float2(c, c); }
+
+B2A_HD float2 cadd(float2 a, float2 b) { return padd(a, b); }
+B2A_HD float2 csub(float2 a, float2 b) { return psub(a, b); }
+// a * b with b given as (re, im): 2 packed instructions
+B2A_HD float2 cmul(float2 a, float2 b) { return pfma(pswap(a), make_float2(-b.y, b.y), pmul(a, pbc(b.x))); }
+// a * w with the twiddle pre-expanded as (wr, wr, -wi, wi): no negation / broadcast needed at run time
+B2A_HD float2 cmul_x(float2 a, float4 w) { return pfma(pswap(a), make_float2(w.z, w.w), pmul(a, make_float2(w.x, w.y))); }
+// a * (-i) and a * (+i)
+B2A_HD float2 mul_mi(float2 a) { return pmul(pswap(a), make_float2(1.0f, -1.0f)); }
+B2A_HD float2 mul_pi(float2 a) { return pmul(pswap(a), make_float2(-1.0f, 1.0f)); }
 
 // v * exp(-2*pi*i*NUM/DEN) with the trivial rotations resolved at compile time
 template <int NUM, int DEN>
@@ -86,15 +140,15 @@ B2A_HD float2 twiddle(float2 v) {
   if constexpr (n == 0) {
     return v;
   } else if constexpr (4 * n == DEN) {  // -i
-    return make_float2(v.y, -v.x);
+    return mul_mi(v);
   } else if constexpr (2 * n == DEN) {  // -1
-    return make_float2(-v.x, -v.y);
+    return pmul(v, pbc(-1.0f));
   } else if constexpr (4 * n == 3 * DEN) {  // +i
-    return make_float2(-v.y, v.x);
+    return mul_pi(v);
   } else {
     constexpr cplx_d w = unit_root(-n, DEN);
     constexpr float wr = (float)w.re, wi = (float)w.im;
-    return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+    return pfma(pswap(v), make_float2(-wi, wi), pmul(v, make_float2(wr, wr)));
   }
 }
 
@@ -109,33 +163,32 @@ template <>
 struct Dft<2> {
   static B2A_HD void run(float2 (&v)[2]) {
     const float2 a = v[0], b = v[1];
-    v[0] = cadd(a, b);
-    v[1] = csub(a, b);
+    v[0] = padd(a, b);
+    v[1] = psub(a, b);
   }
 };
 template <>
 struct Dft<3> {
   static B2A_HD void run(float2 (&v)[3]) {
     constexpr float s = 0.86602540378443864676f;
-    const float2 t1 = cadd(v[1], v[2]);
-    const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
-    const float2 d = csub(v[1], v[2]);
-    const float2 t3 = make_float2(s * d.y, -s * d.x);
-    v[0] = cadd(v[0], t1);
-    v[1] = cadd(t2, t3);
-    v[2] = csub(t2, t3);
+    const float2 t1 = padd(v[1], v[2]);
+    const float2 t2 = pfma(t1, pbc(-0.5f), v[0]);
+    const float2 ds = pswap(psub(v[1], v[2]));
+    const float2 t3 = pmul(ds, make_float2(s, -s));  // -i * s * d
+    v[0] = padd(v[0], t1);
+    v[1] = padd(t2, t3);
+    v[2] = psub(t2, t3);
   }
 };
 template <>
 struct Dft<4> {
   static B2A_HD void run(float2 (&v)[4]) {
-    const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
-    const float2 c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
-    const float2 md = make_float2(d.y, -d.x);  // -i*d
-    v[0] = cadd(a, c);
-    v[2] = csub(a, c);
-    v[1] = cadd(b, md);
-    v[3] = csub(b, md);
+    const float2 a = padd(v[0], v[2]), b = psub(v[0], v[2]);
+    const float2 c = padd(v[1], v[3]), ds = pswap(psub(v[1], v[3]));
+    v[0] = padd(a, c);
+    v[2] = psub(a, c);
+    v[1] = pfma(ds, make_float2(1.0f, -1.0f), b);   // b - i*d
+    v[3] = pfma(ds, make_float2(-1.0f, 1.0f), b);   // b + i*d
   }
 };
 template <>
@@ -143,18 +196,19 @@ struct Dft<5> {
   static B2A_HD void run(float2 (&v)[5]) {
     constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    const float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
-    const float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+    const float2 a1 = padd(v[1], v[4]), b1s = pswap(psub(v[1], v[4]));
+    const float2 a2 = padd(v[2], v[3]), b2s = pswap(psub(v[2], v[3]));
     const float2 x0 = v[0];
-    v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
-    const float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
-    const float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
-    const float2 q1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
-    const float2 q2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
-    v[1] = cadd(p1, q1);
-    v[4] = csub(p1, q1);
-    v[2] = cadd(p2, q2);
-    v[3] = csub(p2, q2);
+    v[0] = padd(padd(x0, a1), a2);
+    const float2 p1 = pfma(a2, pbc(c2), pfma(a1, pbc(c1), x0));
+    const float2 p2 = pfma(a2, pbc(c1), pfma(a1, pbc(c2), x0));
+    // q1 = -i*(s1 b1 + s2 b2), q2 = -i*(s2 b1 - s1 b2) on the half-swapped differences
+    const float2 q1 = pfma(b2s, make_float2(s2, -s2), pmul(b1s, make_float2(s1, -s1)));
+    const float2 q2 = pfma(b2s, make_float2(-s1, s1), pmul(b1s, make_float2(s2, -s2)));
+    v[1] = padd(p1, q1);
+    v[4] = psub(p1, q1);
+    v[2] = padd(p2, q2);
+    v[3] = psub(p2, q2);
   }
 };
 
