@@ -81,8 +81,8 @@ struct FastParams {
   float *clip_max, *tile_min;  // affine-domain statistics (per clip max, per tile min)
   double* feat_sums;
   const float2* win2;   // [N2][N1] (w[2m], w[2m+1]) * 0.5 with m = N2*n1 + n2
-  const float4* tw1;    // [N2][N1]  W_Nc^(n2*k1) expanded as (wr, wr, -wi, wi) for the packed complex multiply
-  const float4* twp;    // [N1/2][2*N2] post-twiddles W_N^k (same expansion) in the order stage 2 consumes them
+  const float2* tw1;    // [N2][N1]  W_Nc^(n2*k1) as (wr, wi); two per LDS.128 broadcast
+  const float2* twp;    // [N1/2][2*N2] post-twiddles W_N^k in the order stage 2 consumes them
   // mel filterbank, lane == mel layout: G = ceil(M/32) groups of 32 consecutive mel rows
   const int* mel_start;   // [G*32] first bin of each row (0 for rows >= M)
   const int* mel_ginfo;   // [2*G]  (group max length, offset of the group's weights in floats)
@@ -178,11 +178,11 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, unsign
 
 // real-FFT post-twiddle for one bin pair (k, Nc-k); Zk = Z[k], Zm = Z[Nc-k]; w = W_N^k; all scaled by the
 // 0.5 folded into the window.  Returns |X[k]|^2 and |X[Nc-k]|^2.
-__device__ __forceinline__ void post_pair(float2 zk, float2 zm, float4 w, float& pk, float& pm) {
+__device__ __forceinline__ void post_pair(float2 zk, float2 zm, float2 w, float& pk, float& pm) {
   using namespace regs;
   const float2 e = pfma(zm, make_float2(1.0f, -1.0f), zk);                 // (zk.x + zm.x, zk.y - zm.y)
   const float2 o = pfma(pswap(zk), make_float2(1.0f, -1.0f), pswap(zm));   // (zk.y + zm.y, zm.x - zk.x)
-  const float2 t = cmul_x(o, w);
+  const float2 t = cmul(o, w);
   const float2 a = padd(e, t), b = psub(e, t);
   pk = fmaf(a.y, a.y, a.x * a.x);
   pm = fmaf(b.y, b.y, b.x * b.x);
@@ -214,8 +214,8 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
   static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
   static constexpr int WIN = 0;
   static constexpr int TW1 = WIN + cdiv4(8 * C::NC);
-  static constexpr int TWP = TW1 + cdiv4(16 * C::NC);
-  static constexpr int EX = TWP + cdiv4(16 * C::NC);
+  static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
+  static constexpr int EX = TWP + cdiv4(8 * C::NC);
   static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);
   static constexpr int XS = C::ALIAS ? PW : PW + cdiv4(4 * C::FT * C::PP);
   static constexpr int PX_END = C::ALIAS ? PW + (cdiv4(4 * C::FT * C::PP) > cdiv4(4 * C::XS_FLOATS) ? cdiv4(4 * C::FT * C::PP)
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   using S = Smem<C>;
   extern __shared__ float4 smem4[];
   float2* const s_win2 = reinterpret_cast<float2*>(smem4 + S::WIN);  // [N2][N1]
-  float4* const s_tw1 = smem4 + S::TW1;                              // [N2][N1] expanded twiddles
-  float4* const s_twp = smem4 + S::TWP;                              // [N1/2][2*N2] expanded post-twiddles
+  float2* const s_tw1 = reinterpret_cast<float2*>(smem4 + S::TW1);   // [N2][N1]
+  float2* const s_twp = reinterpret_cast<float2*>(smem4 + S::TWP);   // [N1/2][2*N2]
   float2* const E = reinterpret_cast<float2*>(smem4 + S::EX);        // [FT][EP]
   float* const Pw = reinterpret_cast<float*>(smem4 + S::PW);         // [FT][PP]
   float* const xs = reinterpret_cast<float*>(smem4 + S::XS);         // [ROWS][P]
@@ -317,14 +317,18 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
       });
       Dft<N1>::run(v);
-      const float4* tb = s_tw1 + n2 * N1;
+      const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
       float2* eb = E + lane * C::EP + n2;
-      static_for<0, N1>([&](auto I_) {
-        constexpr int k1 = decltype(I_)::value;
-        constexpr int slot = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
-        float2 y = v[k1];
-        if constexpr (k1 > 0) y = regs::cmul_x(y, tb[k1]);
-        eb[slot * N2] = y;
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int k1 = 2 * decltype(I_)::value;
+        constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
+        constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+        const float4 t = tb4[k1 / 2];
+        float2 y0 = v[k1];
+        if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
+        const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
+        eb[slot0 * N2] = y0;
+        eb[slot1 * N2] = y1;
       });
     }
     __syncthreads();  // E complete, xs free
@@ -350,14 +354,19 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       Dft<N2>::run(B);
       float* pr = Pw + lane * C::PP;
       auto emit = [&](int k, float v) { pr[k] = pw_only ? v : sqrtf(v + spec_eps); };
-      const float4* tw = s_twp + u * 2 * N2;
+      const float2* tw = s_twp + u * 2 * N2;
       if (u != 0) {
-        static_for<0, N2>([&](auto I_) {
-          constexpr int k2 = decltype(I_)::value;
+        const float4* tw4 = reinterpret_cast<const float4*>(tw);
+        static_for<0, N2 / 2>([&](auto I_) {
+          constexpr int k2 = 2 * decltype(I_)::value;
+          const float4 t = tw4[k2 / 2];
           float pk, pm;
-          post_pair(A[k2], B[N2 - 1 - k2], tw[k2], pk, pm);
+          post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
           emit(u + N1 * k2, pk);
           emit(NC - (u + N1 * k2), pm);
+          post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
+          emit(u + N1 * (k2 + 1), pk);
+          emit(NC - (u + N1 * (k2 + 1)), pm);
         });
       } else {  // unit 0: [0..N2/2] column 0, [N2 .. N2+N2/2) column N1/2
         static_for<0, N2 / 2 + 1>([&](auto I_) {  // column 0: k = N1*k2 <-> Nc - k = N1*(N2-k2)
@@ -514,8 +523,8 @@ size_t smem_bytes(int G, int wg_count) {
 
 struct FastState {
   float2* d_win2 = nullptr;
-  float4* d_tw1 = nullptr;
-  float4* d_twp = nullptr;
+  float2* d_tw1 = nullptr;
+  float2* d_twp = nullptr;
   int* d_start = nullptr;
   int* d_ginfo = nullptr;
   float* d_wg = nullptr;
@@ -587,20 +596,17 @@ int fast_frontend_init(b2a_plan* plan) {
   else { fs->variant = 3; N1 = 32; N2 = 16; }
   const int NC = N1 * N2, N = 2 * NC;
   std::vector<float2> win2(NC);
-  std::vector<float4> tw1(NC), twp(NC);
+  std::vector<float2> tw1(NC), twp(NC);
   for (int n2 = 0; n2 < N2; ++n2)
     for (int n1 = 0; n1 < N1; ++n1) {  // 0.5 of the real-FFT post-processing is folded into the window
       const int m = N2 * n1 + n2;
       win2[n2 * N1 + n1] = make_float2(0.5f * plan->h_window[2 * m], 0.5f * plan->h_window[2 * m + 1]);
     }
-  auto expand = [](double a) {  // (wr, wr, -wi, wi): operands of the two packed FMAs of a complex multiply
-    const float wr = (float)cos(a), wi = (float)sin(a);
-    return make_float4(wr, wr, -wi, wi);
-  };
+  auto expand = [](double a) { return make_float2((float)cos(a), (float)sin(a)); };
   for (int n2 = 0; n2 < N2; ++n2)
     for (int k1 = 0; k1 < N1; ++k1) tw1[n2 * N1 + k1] = expand(-2.0 * M_PI * (double)((n2 * k1) % NC) / (double)NC);
   auto wn = [&](int k) { return expand(-2.0 * M_PI * (double)k / (double)N); };
-  for (int i = 0; i < NC; ++i) twp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NC; ++i) twp[i] = make_float2(0.f, 0.f);
   for (int u = 1; u < N1 / 2; ++u)  // unit u: W_N^(u + N1*k2), k2 = 0..N2-1
     for (int k2 = 0; k2 < N2; ++k2) twp[u * 2 * N2 + k2] = wn(u + N1 * k2);
   for (int k2 = 0; k2 <= N2 / 2; ++k2) twp[k2] = wn(N1 * k2);                    // unit 0, column 0
@@ -642,14 +648,14 @@ int fast_frontend_init(b2a_plan* plan) {
   fs->groups = G;
   fs->wg_count = (int)wg.size();
   B2A_CUDA(cudaMalloc(&fs->d_win2, sizeof(float2) * NC));
-  B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float4) * NC));
-  B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float4) * NC));
+  B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float2) * NC));
+  B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * NC));
   B2A_CUDA(cudaMalloc(&fs->d_start, sizeof(int) * G * 8));
   B2A_CUDA(cudaMalloc(&fs->d_ginfo, sizeof(int) * 2 * G));
   B2A_CUDA(cudaMalloc(&fs->d_wg, sizeof(float) * std::max<size_t>(wg.size(), 1)));
   B2A_CUDA(cudaMemcpy(fs->d_win2, win2.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
-  B2A_CUDA(cudaMemcpy(fs->d_tw1, tw1.data(), sizeof(float4) * NC, cudaMemcpyHostToDevice));
-  B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float4) * NC, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_tw1, tw1.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float2) * NC, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 8, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
