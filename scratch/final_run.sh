@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+python -m pytest tests -q -m gpu 2>&1 | tail -2
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py > gpurun_out/bench_r01_final.json 2> gpurun_out/bench_r01_final.err; tail -c 300 gpurun_out/bench_r01_final.err
+python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_r01_reference.json 2> gpurun_out/bench_r01_reference.err
+python benchmarks/bench_configs.py --out gpurun_out/configs_r01.json > /dev/null 2>&1
+CMD="python bench.py --clips 512 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv $CMD > gpurun_out/ncu_l.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:fast_logmel -s 2 -c 1 -o gpurun_out/prof_r01_fast_logmel $CMD > gpurun_out/ncu.log 2>&1
+tail -1 gpurun_out/ncu.log
+cat gpurun_out/bench_r01_final.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['cpu_baseline']['value'], d['clocks'])"
+cat gpurun_out/bench_r01_reference.json | cut -c1-300
