@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libb200audio.so")
-SOURCES = ["tables.cu", "generic.cu", "fast_fwd.cu", "small.cu", "api.cu"]
+SOURCES = ["tables.cu", "generic.cu", "fast_fwd.cu", "fast_400.cu", "fast_512.cu", "fast_1024.cu", "small.cu", "api.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static",
@@ -33,15 +33,45 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    # straight-line mel code for the named filterbanks, generated from the product's own b2a_mel_filters
+    gen = os.path.join(HERE, "mel_gen.cuh")
+    if force or not os.path.exists(gen) or os.path.getmtime(gen) < max(
+            os.path.getmtime(os.path.join(HERE, "tables.cu")), os.path.getmtime(os.path.join(HERE, "gen_mel.py"))):
+        sys.path.insert(0, HERE)
+        try:
+            import gen_mel
+            gen_mel.generate(gen)
+        finally:
+            sys.path.pop(0)
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    flags = [f for f in FLAGS if f != "--use_fast_math=false"]
+    cflags = [f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")]
     if verbose:
-        flags += ["-Xptxas", "-v"]
-    cmd = [nvcc()] + flags + ["-o", LIB] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        cflags += ["-Xptxas", "-v"]
+    if os.environ.get("B2A_DEV_400_ONLY"):
+        cflags += ["-DB2A_DEV_400_ONLY"]
+    # one nvcc per translation unit, in parallel; then one link
+    obj_dir = os.path.join(HERE, "_obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        return obj, subprocess.run([nvcc()] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        results = list(ex.map(compile_one, srcs))
+    log = ""
+    for obj, r in results:
+        log += r.stdout + r.stderr
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building libb200audio.so")
+    r = subprocess.run([nvcc(), "-shared", "-cudart", "static", "-o", LIB] + [o for o, _ in results],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libb200audio.so")
+        raise RuntimeError("nvcc failed linking libb200audio.so")
+    r.stderr = log + r.stderr
     if verbose:
         print(r.stderr)
     return LIB

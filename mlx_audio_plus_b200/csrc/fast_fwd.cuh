@@ -1,0 +1,837 @@
+// b200audio — specialised fused log-mel front-end kernels ("fast" family): shared kernel template, included by the
+// per-variant translation units fast_400.cu / fast_512.cu / fast_1024.cu (compiled in parallel by csrc/build.py).
+//
+// Design: one CTA owns a tile of 32 consecutive frames of one clip; LANE == FRAME,
+// WARP == COLUMN ROLE.  A real frame of n_fft = 2*Nc samples is treated as Nc complex samples
+// z[m] = x[2m] + i x[2m+1] (half-size complex FFT + Hermitian post-twiddle); the Nc-point FFT is split
+// Nc = N1 x N2 and BOTH stages run entirely in registers with compile-time twiddles (fft_regs.cuh):
+//
+//   fill     the tile's contiguous sample span is copied ONCE global->shared with cp.async (8 B / thread,
+//            fully coalesced), in rows of `hop` samples with a padded pitch so that frame-strided reads are
+//            bank-conflict free; the next tile's span is prefetched while stage 2 / mel of this tile run.
+//   stage 1  warp = column n2 (N2 of them): each lane loads its frame's N1 strided complex samples, applies
+//            the window (warp-uniform, broadcast from smem), DFT-N1 in registers, multiplies the inter-stage
+//            twiddle W_Nc^(n2*k1) (warp-uniform) and stores to the exchange buffer E[frame][slot(k1)][n2].
+//   stage 2  warp = column pair (k1, N1-k1): two DFT-N2 in registers give Z[k] and Z[Nc-k] in the SAME
+//            thread, so the real-FFT post-twiddle X[k] = E + W_N^k O, the power / magnitude and the store to
+//            P[frame][k] need no further exchange.
+//   mel      warp = subset of mel rows, lane = frame: the filterbank is a banded CSR (<= 2 non-zeros per
+//            bin); start/len/weights are warp-uniform smem broadcasts; guard, MUFU log2, fused
+//            scale+affine; values staged in smem, per-tile max/min reduced by shuffles, per-mel sums in fp64.
+//   store    coalesced 128 B rows to HBM.
+// Every shared-memory access pattern is lane-strided by an ODD pitch (conflict free) or a broadcast.
+// HBM traffic is the compulsory input-once + output-once.
+#pragma once
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "fft_regs.cuh"
+#include "mel_gen.cuh"
+
+namespace b2a {
+
+struct FastParams {
+  const float* audio;
+  int64_t clip_stride, valid_length, sample_offset, frame_begin, frame_count;
+  float pad_value;
+  int batch;
+  Geometry geo;
+  int pad_mode;
+  float preemph;
+  int fast_fill_ok;  // alignment preconditions for the cp.async path
+  int spec_kind;
+  float spec_eps;
+  int n_mels;
+  float guard_add, guard_floor;  // a = max(a + guard_add, guard_floor)   (ADD: (eps, -inf); MAX: (0, eps))
+  int use_log;                   // y = log2(a) if use_log else a
+  float y_mul, y_add;            // y' = y * y_mul + y_add   (log base change and the affine map folded together)
+  int out_layout;
+  float* out;
+  int64_t out_clip_stride;
+  float *clip_max, *tile_min;  // affine-domain statistics (per clip max, per tile min)
+  double* feat_sums;
+  const float2* win2;   // [N2][N1] (w[2m], w[2m+1]) * 0.5 with m = N2*n1 + n2
+  const float2* tw1;    // [N2][N1]  W_Nc^(n2*k1) as (wr, wi); two per LDS.128 broadcast
+  const float2* twp;    // [N1/2][2*N2] post-twiddles W_N^k in the order stage 2 consumes them
+  // mel filterbank, lane == mel layout: G = ceil(M/32) groups of 32 consecutive mel rows
+  const int* mel_start;   // [G*32] first bin of each row (0 for rows >= M)
+  const int* mel_ginfo;   // [2*G]  (group max length, offset of the group's weights in floats)
+  const float* mel_wg;    // [sum_g glen[g]*32]  W[g][j][lane], zero padded
+  int mel_groups, mel_wg_count;
+  int tiles_per_clip;
+  long long* dbg_clk;  // profiling aid (B2A_CLOCKS=file): per CTA, cycles accumulated per phase [8] (thread 0's view)
+};
+
+struct FastState {
+  float2* d_win2 = nullptr;
+  float2* d_tw1 = nullptr;
+  float2* d_twp = nullptr;
+  int* d_start = nullptr;
+  int* d_ginfo = nullptr;
+  float* d_wg = nullptr;
+  int groups = 0, wg_count = 0;
+  int variant = 0;  // 1: 400/160, 2: 512/160, 3: 1024/256
+  int spec = 0;     // index into the variant's generated mel specs (0: run-time tables)
+  const char* spec_name = nullptr;
+};
+
+// per-variant translation units (fast_400.cu, fast_512.cu, fast_1024.cu): filterbank matching and launch
+int fast_match_400(const b2a_plan* plan, const char** name);
+int fast_match_512(const b2a_plan* plan, const char** name);
+int fast_match_1024(const b2a_plan* plan, const char** name);
+int fast_launch_400(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
+int fast_launch_512(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
+int fast_launch_1024(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
+
+namespace {
+
+using regs::Dft;
+using regs::static_for;
+
+struct NoSpec {  // run-time mel tables (any filterbank); melgen::MelSpec_* bake a named filterbank into code
+  static constexpr int M = 0, NW = 0, F = 0;
+  template <class Emit>
+  static __device__ __forceinline__ void run(int, const float*, Emit&&) {}
+};
+
+template <int N1_, int N2_, int HOP_, bool ALIAS_, int MIN_BLOCKS_>
+struct Cfg {
+  static constexpr int N1 = N1_, N2 = N2_, HOP = HOP_;
+  // ALIAS: the power tile P reuses the sample tile's shared memory (no prefetch of the next tile) so that the
+  // CTA fits the occupancy target; otherwise the next tile's samples are prefetched during stage 2 / mel.
+  static constexpr bool ALIAS = ALIAS_;
+  static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
+  static constexpr int NC = N1 * N2, N = 2 * NC, F = NC + 1;
+  static constexpr int WARPS = N1 / 2;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int RPW = N2 / WARPS;  // stage-1 roles per warp
+  static constexpr int FT = 32;           // frames per tile == warp width
+  static constexpr int P = HOP + (((HOP / 2) % 2 == 0) ? 2 : 0);  // row pitch (floats); P/2 odd
+  static constexpr int ROWS = FT - 1 + (N + HOP - 1) / HOP;
+  static constexpr int SPAN = (FT - 1) * HOP + N;
+  static constexpr int XS_FLOATS = ROWS * P;
+  static constexpr int EP = NC + 1;          // exchange pitch per frame (float2), odd
+  // power pitch per frame (floats): odd (stage-2 lane==frame stores are conflict free) and == 9 (mod 32) so that
+  // the mel phase's (4 frames x 8 mel rows) gathers land in distinct banks
+  static constexpr int PP = F + ((9 - F % 32 + 32) % 32);
+  static constexpr int K = HOP / (2 * N2);   // taps pairs per row per role step
+  static_assert(N1 % 2 == 0 && N2 % WARPS == 0, "role split");
+  static_assert(HOP % (2 * N2) == 0, "hop must be a multiple of 2*N2");
+  static_assert(NC % 2 == 0, "Nc even");
+};
+
+
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gmem));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100+)
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
+// non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ float fetch_sample_f(const FastParams& p, const float* clip, int64_t s) {
+  float x = s < p.valid_length ? __ldg(clip + (s - p.sample_offset)) : p.pad_value;
+  if (p.preemph != 0.0f && s > 0) {
+    const int64_t sm = s - 1;
+    const float xm = sm < p.valid_length ? __ldg(clip + (sm - p.sample_offset)) : p.pad_value;
+    x = __fsub_rn(x, __fmul_rn(p.preemph, xm));
+  }
+  return x;
+}
+
+// Per-thread constants of the interior fill path, computed once per kernel: thread t copies the 8-byte pair
+// (row r0 + RPI*i, column 2*c) for i = 0..ITERS-1; both addresses are linear in i, so every copy is one LDGSTS
+// with immediate offsets and only the last (partial) iteration is predicated.
+template <class C>
+struct FillCtx {
+  static constexpr int PPR = C::HOP / 2;             // pairs per row
+  static constexpr int RPI = C::THREADS / PPR;       // rows per iteration
+  static constexpr int TOTAL_ROWS = (C::SPAN + C::HOP - 1) / C::HOP;
+  static constexpr int TAIL = C::SPAN - (TOTAL_ROWS - 1) * C::HOP;  // samples in the last (partial) row
+  static constexpr int ITERS = (TOTAL_ROWS + RPI - 1) / RPI;
+  static_assert((TOTAL_ROWS - 1) / RPI == ITERS - 1, "exactly the last iteration is partial");
+  int src_off;     // floats from the tile's first sample
+  unsigned dst;    // shared-window byte address
+  bool active, last_ok;
+  __device__ __forceinline__ void init(unsigned xs_sa) {
+    const int r0 = threadIdx.x / PPR, c = threadIdx.x - r0 * PPR;
+    src_off = r0 * C::HOP + 2 * c;
+    dst = xs_sa + 4u * (unsigned)(r0 * C::P + 2 * c);
+    active = r0 < RPI;
+    const int row = r0 + RPI * (ITERS - 1);
+    last_ok = active && (row < TOTAL_ROWS - 1 || (row == TOTAL_ROWS - 1 && 2 * c < TAIL));
+  }
+};
+
+// Copies the tile's sample span into shared memory (rows of HOP samples at pitch P).
+template <class C>
+__device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const FillCtx<C>& fc, int clip_i, int tile_i) {
+  const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
+  const int64_t lt0 = (int64_t)tile_i * C::FT;
+  const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
+  const int64_t s0 = q0 - p.geo.pad_left;             // source coordinate
+  const bool interior = p.fast_fill_ok && s0 >= 0 && (s0 + C::SPAN) <= p.valid_length && s0 >= p.sample_offset;
+  if (interior && p.preemph == 0.0f) {
+    const float* src = clip + (s0 - p.sample_offset) + fc.src_off;
+    if (fc.active) {
+#pragma unroll
+      for (int i = 0; i < FillCtx<C>::ITERS - 1; ++i)
+        cp_async8(fc.dst + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
+    }
+    if (fc.last_ok) {
+      constexpr int i = FillCtx<C>::ITERS - 1;
+      cp_async8(fc.dst + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
+    }
+  } else if (interior && s0 > p.sample_offset) {
+    // pre-emphasis on the way in: y[n] = x[n] - a*x[n-1] with separately rounded multiply and subtract
+    // (bit-exact vs the reference's `x[1:] - a*x[:-1]`); vectorised, coalesced direct loads
+    const float* src = clip + (s0 - p.sample_offset);
+    const float a = p.preemph;
+    for (int j = threadIdx.x; j < C::SPAN / 2; j += C::THREADS) {
+      const int s = 2 * j;
+      const float2 x = __ldg(reinterpret_cast<const float2*>(src + s));
+      const float xm = __ldg(src + s - 1);
+      const int row = s / C::HOP, col = s - row * C::HOP;
+      *reinterpret_cast<float2*>(xs + row * C::P + col) =
+          make_float2(__fsub_rn(x.x, __fmul_rn(a, xm)), __fsub_rn(x.y, __fmul_rn(a, x.x)));
+    }
+  } else {
+    const int64_t frames_left = p.frame_count - lt0;
+    const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
+    const int need = (nf - 1) * C::HOP + C::N;
+    for (int i = threadIdx.x; i < C::SPAN; i += C::THREADS) {
+      float v = 0.0f;
+      if (i < need) {
+        const int64_t s = source_index(p.geo, p.pad_mode, q0 + i);
+        if (s >= 0) v = fetch_sample_f(p, clip, s);
+      }
+      const int row = i / C::HOP, col = i - row * C::HOP;
+      xs[row * C::P + col] = v;
+    }
+  }
+  cp_async_commit();
+}
+
+// real-FFT post-twiddle for one bin pair (k, Nc-k); Zk = Z[k], Zm = Z[Nc-k]; w = W_N^k; all scaled by the
+// 0.5 folded into the window.  Returns |X[k]|^2 and |X[Nc-k]|^2.
+__device__ __forceinline__ void post_pair(float2 zk, float2 zm, float2 w, float& pk, float& pm) {
+  using namespace regs;
+  const float2 e = pfma(zm, make_float2(1.0f, -1.0f), zk);                 // (zk.x + zm.x, zk.y - zm.y)
+  const float2 o = pfma(pswap(zk), make_float2(1.0f, -1.0f), pswap(zm));   // (zk.y + zm.y, zm.x - zk.x)
+  const float2 t = cmul(o, w);
+  const float2 a = padd(e, t), b = psub(e, t);
+  pk = fmaf(a.y, a.y, a.x * a.x);
+  pm = fmaf(b.y, b.y, b.x * b.x);
+}
+
+// L taps of one mel group for NFW frames with every load issued before the first FMA (one shared-memory
+// latency per <= 8 taps instead of one per tap: the mel phase is latency-, not throughput-bound)
+template <int L, int NFW, int ROWSTEP, int WSTR>
+__device__ __forceinline__ void mel_group_taps(const float* wp, const float* pq, float (&acc)[NFW]) {
+  static_for<0, (L + 7) / 8>([&](auto C_) {
+    constexpr int c0 = decltype(C_)::value * 8;
+    constexpr int CL = (L - c0) < 8 ? (L - c0) : 8;
+    float w[CL], pv[NFW][CL];
+#pragma unroll
+    for (int j = 0; j < CL; ++j) w[j] = wp[(c0 + j) * WSTR];
+#pragma unroll
+    for (int i = 0; i < NFW; ++i)
+#pragma unroll
+      for (int j = 0; j < CL; ++j) pv[i][j] = pq[i * ROWSTEP + c0 + j];
+#pragma unroll
+    for (int j = 0; j < CL; ++j)
+#pragma unroll
+      for (int i = 0; i < NFW; ++i) acc[i] = fmaf(pv[i][j], w[j], acc[i]);
+  });
+}
+
+template <class C>
+struct Smem {  // section offsets in float4 units from the 16-byte aligned dynamic smem base
+  static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
+  static constexpr int WIN = 0;
+  static constexpr int TW1 = WIN + cdiv4(8 * C::NC);
+  static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
+  static constexpr int EX = TWP + cdiv4(8 * C::NC);
+  static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);
+  static constexpr int XS = C::ALIAS ? PW : PW + cdiv4(4 * C::FT * C::PP);
+  static constexpr int PX_END = C::ALIAS ? PW + (cdiv4(4 * C::FT * C::PP) > cdiv4(4 * C::XS_FLOATS) ? cdiv4(4 * C::FT * C::PP)
+                                                                                                  : cdiv4(4 * C::XS_FLOATS))
+                                         : XS + cdiv4(4 * C::XS_FLOATS);
+  static constexpr int DYN = PX_END;  // then: sums (double), mel weights, starts, group info
+};
+
+// ---- run-time-table mel phase (any filterbank, both layouts): LANE = (4 frames) x (8 consecutive mel rows) ------
+// The filterbank is banded (<= 2 non-zeros per bin): a mel row is a short run of taps.  A warp-instruction
+// covers 8 consecutive rows for 4 frames, so (a) the P gathers touch ~32 distinct banks (row pitch == 9 mod 32,
+// neighbouring rows start a few bins apart), (b) rows are zero-padded only to the longest of 8 neighbours,
+// (c) each store instruction writes four fully used 32-byte sectors of the (T, M) output.  A work item is
+// (octet of rows, half of the tile's frames): 4 independent accumulators per lane share one weight load.
+template <class C, bool LAYOUT_TM, bool WANT_SUMS>
+__device__ __forceinline__ void mel_runtime_tables(const FastParams& p, const float* Pw, float* Y, const float* s_wg,
+                                                   const int* s_start, const int* s_ginfo, double* s_sums, float* o,
+                                                   int64_t lt0, int nf, int warp, int lane, float& lmax, float& lmin) {
+  constexpr int NQ = 4;                       // frame quads per item
+  constexpr int ROWSTEP = 4 * C::PP;          // P rows of consecutive quads
+  const int M = p.n_mels, G = p.mel_groups;
+  const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
+  const bool use_log = p.use_log != 0;
+  const int ms = lane & 7, fs = lane >> 3;
+  const int2* ginfo2 = reinterpret_cast<const int2*>(s_ginfo);
+  // output addressing: 32-bit element offsets from a per-tile base; (T, M): (f0 + 4q)*M + m, (M, T) staging:
+  // m*33 + f0 + 4q
+  float* const obase = LAYOUT_TM ? (o + lt0 * M) : Y;
+  const int qstep = LAYOUT_TM ? 4 * M : 4;
+  const int fstep = LAYOUT_TM ? M : 1, mstep = LAYOUT_TM ? 1 : 33;
+  const bool full = nf == C::FT && (M & 7) == 0;  // every slot valid: no per-output predicates
+  auto item = [&](auto FULL_, int it) {
+    constexpr bool FULL = decltype(FULL_)::value;
+    const int oct = it >> 1, half = it & 1;
+    const int m = oct * 8 + ms;
+    const int f0 = half * 16 + fs;            // this lane's frames: f0 + 4q
+    const int2 gi = ginfo2[oct];              // (octet length, weight offset)
+    const float* wp = s_wg + gi.y + ms;
+    const float* pq = Pw + f0 * C::PP + s_start[m];
+    float acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = 0.0f;
+    switch (gi.x) {  // one dispatch per item, taps fully unrolled with all loads issued up front
+      case 0: break;
+#define B2A_MEL_CASE(LL) case LL: mel_group_taps<LL, NQ, ROWSTEP, 8>(wp, pq, acc); break;
+      B2A_MEL_CASE(1) B2A_MEL_CASE(2) B2A_MEL_CASE(3) B2A_MEL_CASE(4) B2A_MEL_CASE(5) B2A_MEL_CASE(6)
+      B2A_MEL_CASE(7) B2A_MEL_CASE(8) B2A_MEL_CASE(9) B2A_MEL_CASE(10) B2A_MEL_CASE(11) B2A_MEL_CASE(12)
+      B2A_MEL_CASE(13) B2A_MEL_CASE(14) B2A_MEL_CASE(15) B2A_MEL_CASE(16)
+#undef B2A_MEL_CASE
+      default:
+#pragma unroll 1
+        for (int j = 0; j < gi.x; ++j) {
+          const float w = wp[j * 8];
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) acc[i] = fmaf(pq[i * ROWSTEP + j], w, acc[i]);
+        }
+    }
+    float* const op = obase + (f0 * fstep + m * mstep);
+    const bool mok = m < M;
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const float a = fmaxf(acc[i] + guard_add, guard_floor);
+      float y = use_log ? lg2_approx(a) : a;
+      y = fmaf(y, y_mul, y_add);
+      if (FULL) {
+        lmax = fmaxf(lmax, y);
+        lmin = fminf(lmin, y);
+        op[i * qstep] = y;
+        if (WANT_SUMS) {
+          d1 += (double)y;
+          d2 += (double)y * (double)y;
+        }
+      } else {
+        const bool ok = mok && (f0 + 4 * i < nf);
+        const float yv = ok ? y : __int_as_float(0x7fc00000);  // NaN is ignored by fmaxf / fminf
+        lmax = fmaxf(lmax, yv);
+        lmin = fminf(lmin, yv);
+        if (ok) {
+          op[i * qstep] = y;
+          if (WANT_SUMS) {
+            d1 += (double)y;
+            d2 += (double)y * (double)y;
+          }
+        }
+      }
+    }
+    if (WANT_SUMS) {  // fold the 4 frame-sub lanes of each mel row, then one shared-memory atomic per row
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 8);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, 8);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, 16);
+      if (fs == 0 && mok) {
+        atomicAdd(&s_sums[2 * m], d1);
+        atomicAdd(&s_sums[2 * m + 1], d2);
+      }
+    }
+  };
+  if (full) {
+#pragma unroll 1
+    for (int it = warp; it < 2 * G; it += C::WARPS) item(std::true_type{}, it);
+  } else {
+#pragma unroll 1
+    for (int it = warp; it < 2 * G; it += C::WARPS) item(std::false_type{}, it);
+  }
+}
+
+template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS>
+__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
+  constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
+  constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh); requires the (T, M) layout
+  static_assert(!SPEC || (LAYOUT_TM && MS::NW == C::WARPS && MS::F == C::F && MS::M % 4 == 0),
+                "mel spec / kernel variant mismatch");
+  // SPEC path staging tile Y[frame][YP]: YP/4 odd -> the STS.128 of phase A and the LDS.128 of phase B are
+  // both bank-conflict free
+  constexpr int YP = SPEC ? (((MS::M / 4) & 1) ? MS::M : MS::M + 4) : 4;
+  constexpr int QL = SPEC ? MS::M / 4 : 1;  // lanes that carry a row quad in phase B
+  static_assert(!SPEC || (size_t)C::FT * YP * 4 <= (size_t)C::FT * C::EP * 8, "Y must fit in the exchange buffer");
+  using S = Smem<C>;
+  extern __shared__ float4 smem4[];
+  float2* const s_win2 = reinterpret_cast<float2*>(smem4 + S::WIN);  // [N2][N1]
+  float2* const s_tw1 = reinterpret_cast<float2*>(smem4 + S::TW1);   // [N2][N1]
+  float2* const s_twp = reinterpret_cast<float2*>(smem4 + S::TWP);   // [N1/2][2*N2]
+  float2* const E = reinterpret_cast<float2*>(smem4 + S::EX);        // [FT][EP]
+  float* const Pw = reinterpret_cast<float*>(smem4 + S::PW);         // [FT][PP]
+  float* const xs = reinterpret_cast<float*>(smem4 + S::XS);         // [ROWS][P]
+  const int M = SPEC ? MS::M : p.n_mels;
+  const int G = p.mel_groups;
+  double* const s_sums = reinterpret_cast<double*>(smem4 + S::DYN);   // [2*G*8]
+  float* const s_wg = reinterpret_cast<float*>(s_sums + 2 * G * 8);   // [mel_wg_count]
+  int* const s_start = reinterpret_cast<int*>(s_wg + p.mel_wg_count); // [G*8]
+  int* const s_ginfo = s_start + G * 8 + ((G * 8) & 1);               // [2*G], 8-byte aligned
+  __shared__ float red_max[C::WARPS], red_min[C::WARPS];
+  __shared__ int s_cur_clip;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* const Y = reinterpret_cast<float*>(E);  // staging tile; aliases the exchange buffer
+  FillCtx<C> fc;
+  fc.init((unsigned)__cvta_generic_to_shared(xs));
+
+  for (int i = threadIdx.x; i < NC; i += C::THREADS) {
+    s_win2[i] = p.win2[i];
+    s_tw1[i] = p.tw1[i];
+    s_twp[i] = p.twp[i];
+  }
+  if (!SPEC) {
+    for (int i = threadIdx.x; i < G * 8; i += C::THREADS) s_start[i] = p.mel_start[i];
+    for (int i = threadIdx.x; i < 2 * G; i += C::THREADS) s_ginfo[i] = p.mel_ginfo[i];
+    for (int i = threadIdx.x; i < p.mel_wg_count; i += C::THREADS) s_wg[i] = p.mel_wg[i];
+  }
+  constexpr bool want_sums = WANT_SUMS;
+  const bool want_max = p.clip_max != nullptr;
+  if (want_sums)
+    for (int i = threadIdx.x; i < 2 * G * 8; i += C::THREADS) s_sums[i] = 0.0;
+  if (threadIdx.x == 0) s_cur_clip = -1;
+
+  // tile walk: tile = clip_i * tiles_per_clip + tile_i advances by gridDim.x without a division per tile
+  const int tpc = p.tiles_per_clip;
+  const int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
+  int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
+  if (!C::ALIAS && clip_i < p.batch) fill_tile<C>(p, xs, fc, clip_i, tile_i);
+
+  const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
+  const bool use_log = p.use_log != 0;
+  const bool pw_only = p.spec_kind == B2A_SPEC_POWER;
+  const float spec_eps = p.spec_eps;
+
+  // stage-2 roles: unit u owns the column pair (u, N1-u); unit 0 owns columns 0 and N1/2, whose bins pair up
+  // WITHIN a column.  It runs the same post-processing code after a register permutation (see below); only its
+  // output bins differ: slots [0, N2/2) -> N1*(s+1), slots [N2/2, N2) -> N1/2 + N1*(s - N2/2).
+  const int u = warp;
+  const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
+  const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
+
+  // SPEC path: statistics live in registers across tiles (lane == row quad in the write-out phase)
+  constexpr int NS = (SPEC && WANT_SUMS) ? 4 : 1;
+  double d1[NS], d2[NS];
+  int sum_clip = -1;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) d1[j] = d2[j] = 0.0;
+  int red_clip = -1, red_tile = 0;  // tile whose per-warp max / min wait in red_max / red_min (thread 0 folds them)
+  auto fold_red = [&]() {
+    if (SPEC && want_max && threadIdx.x == 0 && red_clip >= 0) {
+      float a = red_max[0], b = red_min[0];
+#pragma unroll
+      for (int w = 1; w < C::WARPS; ++w) {
+        a = fmaxf(a, red_max[w]);
+        b = fminf(b, red_min[w]);
+      }
+      atomic_max_f(p.clip_max + red_clip, a);
+      p.tile_min[(int64_t)red_clip * tpc + red_tile] = b;
+    }
+  };
+  auto flush_sums = [&]() {  // SPEC path; called by every thread of the CTA (the clip change is CTA-uniform)
+    if (SPEC && WANT_SUMS && sum_clip >= 0) {
+      if (lane < QL) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          atomicAdd(&s_sums[2 * (4 * lane + j)], d1[j]);
+          atomicAdd(&s_sums[2 * (4 * lane + j) + 1], d2[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) d1[j] = d2[j] = 0.0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) {
+        atomicAdd(p.feat_sums + (int64_t)sum_clip * 2 * M + i, s_sums[i]);
+        s_sums[i] = 0.0;
+      }
+      __syncthreads();
+    }
+  };
+
+  long long clk_prev = 0;
+  long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool clk_on = p.dbg_clk != nullptr && threadIdx.x == 0;
+  auto tick = [&](int slot) {
+    if (clk_on) {
+      const long long t = clock64();
+      clk_acc[slot] += t - clk_prev;
+      clk_prev = t;
+    }
+  };
+  if (clk_on) clk_prev = clock64();
+#pragma unroll 1
+  while (clip_i < p.batch) {
+    const int64_t lt0 = (int64_t)tile_i * C::FT;
+    const int64_t frames_left = p.frame_count - lt0;
+    const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
+    int nclip = clip_i + step_c, ntile = tile_i + step_t;  // the tile this CTA processes next
+    if (ntile >= tpc) {
+      ntile -= tpc;
+      ++nclip;
+    }
+
+    if (C::ALIAS) {
+      __syncthreads();  // previous tile's mel phase has finished reading P (which shares xs' memory)
+      fill_tile<C>(p, xs, fc, clip_i, tile_i);
+    }
+    cp_async_wait_all();
+    __syncthreads();  // xs ready; previous tile's Y fully written out
+    tick(0);
+    fold_red();
+
+    // per-CTA running per-mel sums: flush when the clip changes
+    if (!SPEC && want_sums && s_cur_clip != clip_i) {
+      const int prev = s_cur_clip;
+      __syncthreads();
+      if (prev >= 0)
+        for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) {
+          atomicAdd(p.feat_sums + (int64_t)prev * 2 * M + i, s_sums[i]);
+          s_sums[i] = 0.0;
+        }
+      if (threadIdx.x == 0) s_cur_clip = clip_i;
+      __syncthreads();
+    }
+    if (SPEC && want_sums && sum_clip != clip_i) {
+      flush_sums();
+      sum_clip = clip_i;
+    }
+
+    // ---- stage 1 ----------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int rr = 0; rr < C::RPW; ++rr) {
+      const int n2 = warp * C::RPW + rr;
+      const float* xb = xs + lane * C::P + 2 * n2;
+      const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
+      float2 v[N1];
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int n1 = 2 * decltype(I_)::value;
+        constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
+        constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
+        const float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
+        const float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
+        const float4 w = wb4[n1 / 2];
+        v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
+        v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
+      });
+      Dft<N1>::run(v);
+      const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
+      float2* eb = E + lane * C::EP + n2;
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int k1 = 2 * decltype(I_)::value;
+        constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
+        constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+        const float4 t = tb4[k1 / 2];
+        float2 y0 = v[k1];
+        if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
+        const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
+        eb[slot0 * N2] = y0;
+        eb[slot1 * N2] = y1;
+      });
+    }
+    __syncthreads();  // E complete, xs free
+    tick(1);
+
+    // prefetch the next tile's samples while stage 2 / mel run
+    if (!C::ALIAS && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
+
+    // ---- stage 2 ----------------------------------------------------------------------------------------
+    {
+      float2 A[N2], B[N2];
+      const float2* ea = E + lane * C::EP + u * N2;
+      const float2* eb = E + lane * C::EP + (N1 / 2 + u) * N2;
+      static_for<0, N2>([&](auto I_) {
+        constexpr int j = decltype(I_)::value;
+        A[j] = ea[j];
+        B[j] = eb[j];
+      });
+      Dft<N2>::run(A);
+      Dft<N2>::run(B);
+      float* pr = Pw + lane * C::PP;
+      auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
+      if (u == 0) {
+        // unit 0: the DC / Nyquist pair comes from A[0] alone; then permute so that the shared post-processing
+        // below pairs column 0 with itself (slots 0..N2/2-1: A[s+1] with A[N2-1-s]) and column N1/2 with itself
+        // (slots N2/2..N2-1: B[s-N2/2] with B[3N2/2-1-s]).  One code path for every warp keeps the loop body
+        // inside the 32 KB instruction cache.
+        float pk, pm;
+        post_pair(A[0], A[0], make_float2(1.0f, 0.0f), pk, pm);
+        emit(pr, pk);
+        emit(pr + NC, pm);
+        float2 T[N2 / 2];
+        static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = B[N2/2+j] (j < N2/2); stash B's lower half
+          constexpr int j = decltype(I_)::value;
+          T[j] = B[j];
+          B[j] = B[N2 / 2 + j];
+        });
+        static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = A[j] (j >= N2/2)
+          constexpr int j = decltype(I_)::value;
+          B[N2 / 2 + j] = A[N2 / 2 + j];
+        });
+        static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = A[s+1] (s < N2/2); A[N2/2] is still intact in newB
+          constexpr int s = decltype(I_)::value;
+          A[s] = (s + 1 < N2 / 2) ? A[s + 1] : B[N2 / 2];
+        });
+        static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = old B[s-N2/2] (s >= N2/2)
+          constexpr int j = decltype(I_)::value;
+          A[N2 / 2 + j] = T[j];
+        });
+      }
+      const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
+      float* const plo = pr + kb_lo;           // bins kb_lo + N1*s
+      float* const mlo = pr + (NC - kb_lo);    // mirrored bins
+      float* const phi = pr + kb_hi;
+      float* const mhi = pr + (NC - kb_hi);
+      static_for<0, N2 / 2>([&](auto I_) {
+        constexpr int k2 = 2 * decltype(I_)::value;
+        const float4 t = tw4[k2 / 2];
+        float pk, pm;
+        post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
+        emit((k2 < N2 / 2 ? plo : phi) + N1 * k2, pk);
+        emit((k2 < N2 / 2 ? mlo : mhi) - N1 * k2, pm);
+        post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
+        emit((k2 + 1 < N2 / 2 ? plo : phi) + N1 * (k2 + 1), pk);
+        emit((k2 + 1 < N2 / 2 ? mlo : mhi) - N1 * (k2 + 1), pm);
+      });
+    }
+    __syncthreads();  // Pw complete, E free (Y aliases E)
+    tick(2);
+
+    float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
+    if constexpr (SPEC) {
+      // ---- mel, phase A: LANE = FRAME.  The named filterbank is straight-line code (mel_gen.cuh): one
+      // conflict-free LDS per bin (odd row pitch) shared by the two rows it feeds, one FFMA per tap with the weight
+      // as an immediate; four finished rows are parked in Y[frame][m..m+3] with one STS.128.
+      {
+        const float* pr = Pw + lane * C::PP;
+        float4* const yl = reinterpret_cast<float4*>(Y + lane * YP);
+        MS::run(warp, pr, [&](auto M_, float a0, float a1, float a2, float a3) {
+          constexpr int m = decltype(M_)::value;
+          yl[m / 4] = make_float4(a0, a1, a2, a3);
+        });
+      }
+      __syncthreads();  // Y complete
+      tick(3);
+      // ---- mel, phase B: LANE = ROW QUAD (code shared by every warp).  Per frame: one LDS.128, guard + MUFU
+      // log2 + folded base-change / affine FFMA on four values, one coalesced STG.128 into the (T, M) output,
+      // FMNMX3 for the tile max / min; per-feature sums stay in registers across tiles.
+      {
+        float lmax = -INFINITY, lmin = INFINITY;
+        float4* const orow = reinterpret_cast<float4*>(o + lt0 * MS::M) + lane;
+        const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
+        if (lane < QL) {
+#pragma unroll 1
+          for (int f = warp; f < nf; f += C::WARPS) {
+            float4 v = yb[f * (YP / 4)];
+            float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float a = fmaxf(e[c] + guard_add, guard_floor);
+              const float y = use_log ? lg2_approx(a) : a;
+              e[c] = fmaf(y, y_mul, y_add);
+              if (WANT_SUMS) {
+                d1[c % NS] += (double)e[c];
+                d2[c % NS] += (double)e[c] * (double)e[c];
+              }
+            }
+            orow[f * (MS::M / 4)] = v;
+            lmax = fmax3(lmax, v.x, v.y);
+            lmin = fmin3(lmin, v.x, v.y);
+            lmax = fmax3(lmax, v.z, v.w);
+            lmin = fmin3(lmin, v.z, v.w);
+          }
+        }
+        if (want_max) {
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o2));
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o2));
+          }
+          if (lane == 0) {
+            red_max[warp] = lmax;
+            red_min[warp] = lmin;
+          }
+          red_clip = clip_i;   // folded by thread 0 after the next barrier
+          red_tile = tile_i;
+        }
+      }
+    } else {
+      float lmax = -INFINITY, lmin = INFINITY;
+      mel_runtime_tables<C, LAYOUT_TM, WANT_SUMS>(p, Pw, Y, s_wg, s_start, s_ginfo, s_sums, o, lt0, nf, warp, lane, lmax, lmin);
+      if (want_max) {
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o2));
+          lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o2));
+        }
+        if (lane == 0) {
+          red_max[warp] = lmax;
+          red_min[warp] = lmin;
+        }
+      }
+      if (want_max || !LAYOUT_TM) __syncthreads();
+      if (want_max && threadIdx.x == 0) {
+        float a = red_max[0], b = red_min[0];
+#pragma unroll
+        for (int w = 1; w < C::WARPS; ++w) {
+          a = fmaxf(a, red_max[w]);
+          b = fminf(b, red_min[w]);
+        }
+        atomic_max_f(p.clip_max + clip_i, a);
+        p.tile_min[(int64_t)clip_i * tpc + tile_i] = b;
+      }
+      if (!LAYOUT_TM && lane < nf)
+        for (int m = warp; m < M; m += C::WARPS) o[(int64_t)m * p.frame_count + lt0 + lane] = Y[m * 33 + lane];
+    }
+    clip_i = nclip;
+    tile_i = ntile;
+    tick(4);
+    if (clk_on) ++clk_acc[7];
+  }
+  if (clk_on)
+    for (int i = 0; i < 8; ++i) p.dbg_clk[blockIdx.x * 8 + i] = clk_acc[i];
+  cp_async_wait_all();
+  if (SPEC) {
+    __syncthreads();
+    fold_red();
+    if (want_sums) flush_sums();
+  } else if (want_sums) {
+    __syncthreads();
+    const int prev = s_cur_clip;
+    if (prev >= 0)
+      for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) atomicAdd(p.feat_sums + (int64_t)prev * 2 * M + i, s_sums[i]);
+  }
+}
+
+template <class C>
+size_t smem_bytes(int G, int wg_count) {
+  return (size_t)16 * Smem<C>::DYN + sizeof(double) * 2 * G * 8 + sizeof(float) * (wg_count + (wg_count & 1)) + sizeof(int) * (G * 8 + 2 * G + 2) + 16;
+}
+
+
+template <class C, bool TM, bool SUMS, class MS>
+int launch_variant(b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  fast_logmel_kernel<C, TM, SUMS, MS><<<grid, C::THREADS, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+// does the plan's filterbank equal the generated spec bit for bit?
+template <class MS>
+bool spec_matches(const b2a_plan* plan) {
+  if (plan->fd.n_mels != MS::M || plan->n_freqs != MS::F) return false;
+  int t = 0;
+  for (int m = 0; m < MS::M; ++m) {
+    const float* row = plan->h_fb.data() + (size_t)m * MS::F;
+    for (int f = 0; f < MS::F; ++f) {
+      const bool inside = f >= MS::kStart[m] && f < MS::kStart[m] + MS::kLen[m];
+      unsigned bits;
+      memcpy(&bits, row + f, 4);
+      if (inside ? bits != MS::kWBits[t + f - MS::kStart[m]] : (row[f] != 0.0f)) return false;
+    }
+    t += MS::kLen[m];
+  }
+  return true;
+}
+
+// the specs each kernel variant is instantiated for: X(index, spec type, also with per-feature sums)
+#define B2A_SPECS_400(X) X(1, melgen::MelSpec_whisper80, false) X(2, melgen::MelSpec_whisper128, false) X(3, melgen::MelSpec_funasr80, false)
+#define B2A_SPECS_512(X) X(1, melgen::MelSpec_parakeet80, true) X(2, melgen::MelSpec_parakeet128, true) \
+                         X(3, melgen::MelSpec_nemo_slaney80, true) X(4, melgen::MelSpec_nemo_slaney128, true)
+#define B2A_SPECS_1024(X) X(1, melgen::MelSpec_vocos100, false) X(2, melgen::MelSpec_qwen3tts128, false)
+
+template <class C>
+struct SpecList;
+
+#define B2A_MATCH(IDX, MS, SUMS_OK) if (spec_matches<MS>(plan)) { *name = MS::kName; return IDX; }
+#define B2A_LAUNCH(IDX, MS, SUMS_OK)                                                             \
+  case IDX:                                                                                      \
+    if (!sums) return launch_variant<C, true, false, MS>(plan, p, smem, grid, st);               \
+    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS>(plan, p, smem, grid, st);    \
+    break;
+#define B2A_SPECLIST(CFG, LIST)                                                                             \
+  template <>                                                                                               \
+  struct SpecList<CFG> {                                                                                    \
+    using C = CFG;                                                                                          \
+    static int match(const b2a_plan* plan, const char** name) { LIST(B2A_MATCH) return 0; }                 \
+    /* returns B2A_OK after a launch, or 1 when (spec, sums) has no instance and the caller falls back */   \
+    static int launch(int spec, bool sums, b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) { \
+      switch (spec) { LIST(B2A_LAUNCH) default: break; }                                                    \
+      return 1;                                                                                             \
+    }                                                                                                       \
+  };
+
+template <class C>
+int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
+  size_t smem = smem_bytes<C>(p.mel_groups, p.mel_wg_count);
+  if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
+  if (smem > 226 * 1024) {
+    set_error("fast kernel: %zu bytes of shared memory needed", smem);
+    return B2A_ERR_UNSUPPORTED;
+  }
+  const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  if (tiles >= (int64_t)1 << 31) {
+    set_error("fast kernel: %lld tiles in one launch (split the batch)", (long long)tiles);
+    return B2A_ERR_UNSUPPORTED;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
+  if (grid < 1) grid = 1;
+  const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
+  const bool vec_ok = reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0;  // STG.128 rows
+  if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel
+    const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, smem, grid, st);
+    if (rc != 1) return rc;
+  }
+  if (tm && !sums) return launch_variant<C, true, false, NoSpec>(plan, p, smem, grid, st);
+  if (tm && sums) return launch_variant<C, true, true, NoSpec>(plan, p, smem, grid, st);
+  if (!tm && !sums) return launch_variant<C, false, false, NoSpec>(plan, p, smem, grid, st);
+  return launch_variant<C, false, true, NoSpec>(plan, p, smem, grid, st);
+}
+
+
+}  // namespace
+}  // namespace b2a

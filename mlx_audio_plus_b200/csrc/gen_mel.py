@@ -1,0 +1,201 @@
+"""Build-time generator of csrc/mel_gen.cuh: straight-line mel-projection code for the NAMED filterbanks.
+
+A mel filterbank is a banded matrix (a frequency bin feeds at most two adjacent triangles), but its band
+structure is run-time data, and with run-time tables the projection costs ~6 instructions per tap (address
+arithmetic, length dispatch, weight loads).  For the filterbanks the reference's wrappers actually use
+(SURVEY.md App. A "wrapper parameter matrix") this script bakes the structure into code: per warp a straight
+line of `p = P[k]; acc_m = fmaf(p, W, acc_m)` with the bin offset and the weight as immediates — one shared-
+memory load per BIN (shared by the two rows it feeds) and one FFMA per tap.
+
+The filterbank itself is NOT recomputed here: it comes from the product's own host routine `b2a_mel_filters`
+(csrc/tables.cu, compiled on the fly into a scratch shared object), so the generated tables are bit-identical
+to what a plan receives at run time.  At plan creation fast_fwd.cu compares the caller's filterbank with the
+generated one bit for bit; any other filterbank takes the run-time-table path of the same kernel.
+
+Run: python -m mlx_audio_plus_b200.csrc.gen_mel   (also invoked by csrc/build.py when tables.cu changes)
+"""
+import ctypes
+import os
+import shutil
+import struct
+import subprocess
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "mel_gen.cuh")
+
+# name, sample_rate, n_fft, n_mels, f_min, f_max, norm_slaney, scale_htk, warps of the fast kernel variant
+SPECS = [
+    # Whisper / GLM-ASR / Smart-Turn / S3Tokenizer-compat (whisper/audio.py:76; mel_scale=None -> Slaney)
+    ("whisper80", 16000, 400, 80, 0.0, 0.0, 1, 0, 10),
+    # Whisper large-v3 / Voxtral-RT / S3Tokenizer (voxtral_realtime/audio.py:19-33: f_max=8000 == sr/2)
+    ("whisper128", 16000, 400, 128, 0.0, 0.0, 1, 0, 10),
+    # FunASR (funasr/audio.py:32-81: htk scale, slaney norm)
+    ("funasr80", 16000, 400, 80, 0.0, 0.0, 1, 1, 10),
+    # Parakeet / NeMo (parakeet/audio.py:59-61: norm="per_feature" -> no Slaney normalisation)
+    ("parakeet80", 16000, 512, 80, 0.0, 0.0, 0, 0, 8),
+    ("parakeet128", 16000, 512, 128, 0.0, 0.0, 0, 0, 8),
+    # Sortformer / LFM2 style (slaney scale + slaney norm on n_fft=512)
+    ("nemo_slaney80", 16000, 512, 80, 0.0, 0.0, 1, 0, 8),
+    ("nemo_slaney128", 16000, 512, 128, 0.0, 0.0, 1, 0, 8),
+    # Vocos / IndexTTS (vocos/mel.py:26: htk, no norm, 24 kHz)
+    ("vocos100", 24000, 1024, 100, 0.0, 0.0, 0, 1, 16),
+    # Qwen3-TTS speaker mel (qwen3_tts.py:33-90: slaney/slaney, f_max 12000 == sr/2)
+    ("qwen3tts128", 24000, 1024, 128, 0.0, 12000.0, 1, 0, 16),
+]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def _tables_lib(tmp):
+    so = os.path.join(tmp, "libb2a_tables.so")
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", so,
+           os.path.join(HERE, "tables.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on tables.cu:\n" + r.stdout + r.stderr)
+    lib = ctypes.CDLL(so)
+    lib.b2a_mel_filters.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.b2a_mel_filters.restype = ctypes.c_int
+    return lib
+
+
+def _bits(x):
+    return struct.unpack("<I", struct.pack("<f", x))[0]
+
+
+def _hexf(x):
+    # exact C++17 hexadecimal float literal of a float32 value
+    return float(x).hex() + "f"
+
+
+def _filterbank(lib, sr, n_fft, M, fmin, fmax, norm, htk):
+    F = n_fft // 2 + 1
+    buf = (ctypes.c_float * (M * F))()
+    rc = lib.b2a_mel_filters(sr, n_fft, M, fmin, fmax, norm, htk, buf)
+    if rc != 0:
+        raise RuntimeError("b2a_mel_filters failed")
+    return [[buf[m * F + f] for f in range(F)] for m in range(M)], F
+
+
+def _emit_spec(lib, spec):
+    name, sr, n_fft, M, fmin, fmax, norm, htk, NW = spec
+    fb, F = _filterbank(lib, sr, n_fft, M, fmin, fmax, norm, htk)
+    start, length = [], []
+    for m in range(M):
+        nz = [f for f in range(F) if fb[m][f] != 0.0]
+        if nz:
+            start.append(nz[0])
+            length.append(nz[-1] - nz[0] + 1)
+        else:
+            start.append(0)
+            length.append(0)
+    wbits = []
+    for m in range(M):
+        wbits += [_bits(fb[m][start[m] + j]) for j in range(length[m])]
+    nnz = len(wbits)
+    # contiguous blocks of row QUADS per warp (a quad is stored with one STS.128), balanced by tap + load cost
+    assert M % 4 == 0, "the generated path stores rows four at a time"
+    NQ = M // 4
+
+    def quad_cost(q):
+        rows = range(4 * q, 4 * q + 4)
+        live = [m for m in rows if length[m] > 0]
+        if not live:
+            return 1
+        bins = max(start[m] + length[m] for m in live) - min(start[m] for m in live)
+        return sum(length[m] for m in rows) + bins + 1
+
+    cost = [quad_cost(q) for q in range(NQ)]
+    total = sum(cost)
+    # optimal contiguous partition (minimise the heaviest warp): DP over (quads, warps)
+    pre = [0]
+    for c in cost:
+        pre.append(pre[-1] + c)
+    INF = float("inf")
+    best = [[INF] * (NW + 1) for _ in range(NQ + 1)]
+    cut = [[0] * (NW + 1) for _ in range(NQ + 1)]
+    best[0][0] = 0
+    for w in range(1, NW + 1):
+        for q in range(NQ + 1):
+            for j in range(q + 1):
+                v = max(best[j][w - 1], pre[q] - pre[j])
+                if v < best[q][w]:
+                    best[q][w], cut[q][w] = v, j
+    bounds = [NQ]
+    q = NQ
+    for w in range(NW, 0, -1):
+        q = cut[q][w]
+        bounds.append(q)
+    bounds = bounds[::-1]
+    o = []
+    o.append(f"// {name}: sr={sr} n_fft={n_fft} n_mels={M} f_min={fmin} f_max={fmax or sr / 2} "
+             f"norm={'slaney' if norm else 'none'} scale={'htk' if htk else 'slaney'}; {nnz} taps; "
+             f"warp costs {[sum(cost[bounds[w]:bounds[w + 1]]) for w in range(NW)]}")
+    o.append(f"struct MelSpec_{name} {{")
+    o.append(f"  static constexpr int M = {M}, F = {F}, NW = {NW}, NNZ = {nnz}, N_FFT = {n_fft};")
+    o.append(f"  static constexpr const char* kName = \"{name}\";")
+    o.append(f"  static constexpr int kStart[{M}] = {{{', '.join(map(str, start))}}};")
+    o.append(f"  static constexpr int kLen[{M}] = {{{', '.join(map(str, length))}}};")
+    o.append(f"  static constexpr unsigned kWBits[{max(nnz, 1)}] = {{{', '.join('0x%08xu' % b for b in wbits) or '0u'}}};")
+    o.append("  // lane == frame: `pr` is this lane's power-spectrum row; emit4(integral_constant<m0>, a0..a3) per row quad")
+    o.append("  template <class Emit4>")
+    o.append("  static __device__ __forceinline__ void run(int warp, const float* __restrict__ pr, Emit4&& emit4) {")
+    o.append("    switch (warp) {")
+    for w in range(NW):
+        m0, m1 = 4 * bounds[w], 4 * bounds[w + 1]
+        o.append(f"      case {w}: {{  // rows [{m0}, {m1})")
+        if m1 > m0:
+            rows = list(range(m0, m1))
+            o.append("        float " + ", ".join(f"a{m} = 0.0f" for m in rows) + ";")
+            live = [m for m in rows if length[m] > 0]
+            if live:
+                k0 = min(start[m] for m in live)
+                k1 = max(start[m] + length[m] for m in live)
+                for k in range(k0, k1):
+                    users = [m for m in live if start[m] <= k < start[m] + length[m] and fb[m][k] != 0.0]
+                    if not users:
+                        continue
+                    stmts = " ".join(f"a{m} = fmaf(p, {_hexf(fb[m][k])}, a{m});" for m in users)
+                    o.append(f"        {{ const float p = pr[{k}]; {stmts} }}")
+            for m in range(m0, m1, 4):
+                o.append(f"        emit4(std::integral_constant<int, {m}>{{}}, a{m}, a{m + 1}, a{m + 2}, a{m + 3});")
+        o.append("      } break;")
+    o.append("      default: break;")
+    o.append("    }")
+    o.append("  }")
+    o.append("};")
+    return "\n".join(o)
+
+
+def generate(path=OUT):
+    with tempfile.TemporaryDirectory() as tmp:
+        lib = _tables_lib(tmp)
+        parts = [
+            "// GENERATED by csrc/gen_mel.py from b2a_mel_filters (csrc/tables.cu) — do not edit.",
+            "// Straight-line mel projections for the named filterbanks; see gen_mel.py for the why and the how.",
+            "#pragma once",
+            "#include <type_traits>",
+            "",
+            "namespace b2a {",
+            "namespace melgen {",
+            "",
+        ]
+        for s in SPECS:
+            parts.append(_emit_spec(lib, s))
+            parts.append("")
+        parts.append("#define B2A_MEL_SPECS(X) " + " ".join(f"X(MelSpec_{s[0]})" for s in SPECS))
+        parts += ["", "}  // namespace melgen", "}  // namespace b2a", ""]
+    text = "\n".join(parts)
+    if os.path.exists(path) and open(path).read() == text:
+        return path
+    with open(path, "w") as f:
+        f.write(text)
+    return path
+
+
+if __name__ == "__main__":
+    print(generate())
