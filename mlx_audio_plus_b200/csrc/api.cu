@@ -279,6 +279,9 @@ int b2a_istft_create(const b2a_istft_desc* d, const float* h_window, b2a_plan** 
   if (rc == B2A_OK && small_istft_supported(p)) {
     p->family = KF_SMALL;
     p->kernel_name = "istft_small";
+  } else if (rc == B2A_OK && fast_istft_supported(p)) {
+    rc = fast_istft_init(p);
+    if (rc == B2A_OK) p->family = KF_FAST;
   }
   if (rc != B2A_OK) {
     b2a_plan_destroy(p);
@@ -290,6 +293,7 @@ int b2a_istft_create(const b2a_istft_desc* d, const float* h_window, b2a_plan** 
 
 int b2a_plan_destroy(b2a_plan* p) {
   if (!p) return B2A_OK;
+  if (p->fast && p->kind == PLAN_ISTFT) fast_istft_destroy(p);
   if (p->fast) fast_frontend_destroy(p);
   cudaFree(p->d_twiddle);
   cudaFree(p->d_window);
@@ -474,6 +478,7 @@ int b2a_istft_inverse(b2a_plan* p, const b2a_inverse_args* a, void* stream) {
     return B2A_ERR_INVALID_ARG;
   }
   if (p->family == KF_SMALL) return small_istft(p, a, (cudaStream_t)stream);
+  if (p->family == KF_FAST) return fast_istft(p, a, (cudaStream_t)stream);
   return generic_istft(p, a, (cudaStream_t)stream);
 }
 
@@ -520,7 +525,9 @@ int b2a_istft_inverse_host(b2a_plan* p, const b2a_inverse_args* in) {
     c.batch = nb;
     c.out = (float*)p->d_stage_out[s];
     c.out_clip_stride = out_len;
-    if ((rc = (p->family == KF_SMALL ? small_istft(p, &c, st) : generic_istft(p, &c, st)))) return rc;
+    if ((rc = (p->family == KF_SMALL ? small_istft(p, &c, st)
+                                     : (p->family == KF_FAST ? fast_istft(p, &c, st) : generic_istft(p, &c, st)))))
+      return rc;
     if (out_len > 0)
       B2A_CUDA(cudaMemcpy2DAsync((char*)in->out + (size_t)c0 * out_stride * 4, (size_t)out_stride * 4, p->d_stage_out[s],
                                  (size_t)out_len * 4, (size_t)out_len * 4, nb, cudaMemcpyDeviceToHost, st));

@@ -121,6 +121,11 @@ int fast_frontend_init(b2a_plan* plan);
 void fast_frontend_destroy(b2a_plan* plan);
 int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);
+// fused iSTFT for n_fft = 4*hop vocoder heads (1024/256) — fast_inv.cu
+bool fast_istft_supported(const b2a_plan* plan);
+int fast_istft_init(b2a_plan* plan);
+void fast_istft_destroy(b2a_plan* plan);
+int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st);
 // small-n (n_fft 16 / 20) thread-per-frame kernels — small.cu
 bool small_istft_supported(const b2a_plan* plan);
 int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st);

@@ -161,7 +161,11 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.mel_groups = fs->groups;
   p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
+#ifdef B2A_PHASE_CLOCKS
   const char* clk_path = getenv("B2A_CLOCKS");
+#else
+  const char* clk_path = nullptr;
+#endif
   if (clk_path) {
     const int maxg = plan->sm_count * 4;
     B2A_CUDA(cudaMalloc(&p.dbg_clk, sizeof(long long) * 8 * maxg));

@@ -135,6 +135,12 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+// order-preserving float <-> signed-int key (an involution): lets REDUX.MIN/MAX.S32 reduce floats across a warp
+__device__ __forceinline__ int float_key(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -380,7 +386,8 @@ __device__ __forceinline__ void mel_runtime_tables(const FastParams& p, const fl
   }
 }
 
-template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS>
+// SPECK: spectrum kind fixed at compile time (B2A_SPEC_POWER / MAGNITUDE / SQRT_POWER_EPS), or -1 = run-time
+template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh); requires the (T, M) layout
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
 
   const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
   const bool use_log = p.use_log != 0;
-  const bool pw_only = p.spec_kind == B2A_SPEC_POWER;
+  const bool pw_only = SPECK >= 0 ? SPECK == B2A_SPEC_POWER : p.spec_kind == B2A_SPEC_POWER;
   const float spec_eps = p.spec_eps;
 
   // stage-2 roles: unit u owns the column pair (u, N1-u); unit 0 owns columns 0 and N1/2, whose bins pair up
@@ -486,6 +493,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
   };
 
+#ifdef B2A_PHASE_CLOCKS  // development builds: per-phase cycle counters (thread 0's view), dumped by B2A_CLOCKS=file
   long long clk_prev = 0;
   long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool clk_on = p.dbg_clk != nullptr && threadIdx.x == 0;
@@ -497,6 +505,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
   };
   if (clk_on) clk_prev = clock64();
+#else
+  auto tick = [](int) {};
+#endif
 #pragma unroll 1
   while (clip_i < p.batch) {
     const int64_t lt0 = (int64_t)tile_i * C::FT;
@@ -678,15 +689,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
             lmin = fmin3(lmin, v.z, v.w);
           }
         }
-        if (want_max) {
-#pragma unroll
-          for (int o2 = 16; o2 > 0; o2 >>= 1) {
-            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o2));
-            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o2));
-          }
+        if (want_max) {  // one REDUX each on order-preserving integer keys instead of ten dependent shuffles
+          const int kmax = __reduce_max_sync(0xffffffffu, float_key(lmax));
+          const int kmin = __reduce_min_sync(0xffffffffu, float_key(lmin));
           if (lane == 0) {
-            red_max[warp] = lmax;
-            red_min[warp] = lmin;
+            red_max[warp] = key_float(kmax);
+            red_min[warp] = key_float(kmin);
           }
           red_clip = clip_i;   // folded by thread 0 after the next barrier
           red_tile = tile_i;
@@ -723,10 +731,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     clip_i = nclip;
     tile_i = ntile;
     tick(4);
+#ifdef B2A_PHASE_CLOCKS
     if (clk_on) ++clk_acc[7];
+#endif
   }
+#ifdef B2A_PHASE_CLOCKS
   if (clk_on)
     for (int i = 0; i < 8; ++i) p.dbg_clk[blockIdx.x * 8 + i] = clk_acc[i];
+#endif
   cp_async_wait_all();
   if (SPEC) {
     __syncthreads();
@@ -746,14 +758,14 @@ size_t smem_bytes(int G, int wg_count) {
 }
 
 
-template <class C, bool TM, bool SUMS, class MS>
+template <class C, bool TM, bool SUMS, class MS, int SPECK = -1>
 int launch_variant(b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  fast_logmel_kernel<C, TM, SUMS, MS><<<grid, C::THREADS, smem, st>>>(p);
+  fast_logmel_kernel<C, TM, SUMS, MS, SPECK><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
@@ -776,20 +788,26 @@ bool spec_matches(const b2a_plan* plan) {
   return true;
 }
 
-// the specs each kernel variant is instantiated for: X(index, spec type, also with per-feature sums)
-#define B2A_SPECS_400(X) X(1, melgen::MelSpec_whisper80, false) X(2, melgen::MelSpec_whisper128, false) X(3, melgen::MelSpec_funasr80, false)
-#define B2A_SPECS_512(X) X(1, melgen::MelSpec_parakeet80, true) X(2, melgen::MelSpec_parakeet128, true) \
-                         X(3, melgen::MelSpec_nemo_slaney80, true) X(4, melgen::MelSpec_nemo_slaney128, true)
-#define B2A_SPECS_1024(X) X(1, melgen::MelSpec_vocos100, false) X(2, melgen::MelSpec_qwen3tts128, false)
+// the specs each kernel variant is instantiated for: X(index, spec type, also with per-feature sums, spectrum kind
+// of the wrapper that uses it — any other combination takes the run-time-table kernel)
+#define B2A_SPECS_400(X)                                                                                    \
+  X(1, melgen::MelSpec_whisper80, false, B2A_SPEC_POWER) X(2, melgen::MelSpec_whisper128, false, B2A_SPEC_POWER) \
+  X(3, melgen::MelSpec_funasr80, false, B2A_SPEC_POWER)
+#define B2A_SPECS_512(X)                                                                                     \
+  X(1, melgen::MelSpec_parakeet80, true, B2A_SPEC_POWER) X(2, melgen::MelSpec_parakeet128, true, B2A_SPEC_POWER) \
+  X(3, melgen::MelSpec_nemo_slaney80, true, B2A_SPEC_POWER) X(4, melgen::MelSpec_nemo_slaney128, true, B2A_SPEC_POWER)
+#define B2A_SPECS_1024(X) \
+  X(1, melgen::MelSpec_vocos100, false, B2A_SPEC_MAGNITUDE) X(2, melgen::MelSpec_qwen3tts128, false, B2A_SPEC_SQRT_POWER_EPS)
 
 template <class C>
 struct SpecList;
 
-#define B2A_MATCH(IDX, MS, SUMS_OK) if (spec_matches<MS>(plan)) { *name = MS::kName; return IDX; }
-#define B2A_LAUNCH(IDX, MS, SUMS_OK)                                                             \
-  case IDX:                                                                                      \
-    if (!sums) return launch_variant<C, true, false, MS>(plan, p, smem, grid, st);               \
-    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS>(plan, p, smem, grid, st);    \
+#define B2A_MATCH(IDX, MS, SUMS_OK, SPECK) if (spec_matches<MS>(plan)) { *name = MS::kName; return IDX; }
+#define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK)                                                              \
+  case IDX:                                                                                              \
+    if (p.spec_kind != SPECK) break;                                                                     \
+    if (!sums) return launch_variant<C, true, false, MS, SPECK>(plan, p, smem, grid, st);               \
+    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK>(plan, p, smem, grid, st);    \
     break;
 #define B2A_SPECLIST(CFG, LIST)                                                                             \
   template <>                                                                                               \

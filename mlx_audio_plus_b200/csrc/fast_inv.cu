@@ -1,0 +1,381 @@
+// b200audio — fused iSTFT ("fast inverse") for n_fft = 4*hop vocoder heads: Vocos 1024/256, Vocos-Encodec 1280/320
+// (dsp.py:144-217 istft, dsp.py:350-417 ISTFTCache.istft).
+//
+// Mirror image of the forward fast kernel: LANE == FRAME, WARP == COLUMN ROLE, everything between the (B, F, T)
+// spectrum in HBM and the waveform in HBM lives in registers and ONE shared-memory buffer.
+//
+//   tile     32 consecutive frames (lane l <-> frame t0 - 4 + l); the tile owns the FA = 28 * hop output samples all
+//            of whose (up to 4) contributing frames are inside it; the 3-frame halo is recomputed by the neighbour
+//            (12.5 % redundant work, but no atomics, no cross-CTA ordering, loads start on a 32-byte sector).
+//   step 1   warp = unit u (bin columns u and N1-u): each lane reads its frame's X[k], X[Nc-k] (the (B, F, T) layout
+//            makes every load a coalesced 256-byte row across the warp), undoes the Hermitian packing
+//            (Z = E + iO: the half-size complex spectrum of z[m] = x[2m] + i x[2m+1]; Im(DC), Im(Nyquist) ignored as
+//            irfft does), inverse DFT-N2 in registers, inter-stage twiddle, store to E[frame][k1][n2].
+//            The inverse transform runs in the "swapped domain" (re <-> im): it is then the FORWARD codelets with
+//            the FORWARD twiddles.
+//   step 2   warp = residue n2: DFT-N1 in registers, window (1/N folded in), and the time samples go back IN PLACE:
+//            row `frame` of E becomes the windowed frame in natural sample order.
+//   step 3   gather-form overlap-add: a thread owns two adjacent output samples, sums its <= 4 frames in ascending
+//            frame order (the order of the reference's sequential scatter-add), divides by the window envelope
+//            (period-hop table when all four frames exist, summed on the fly at the clip's edges) and stores
+//            coalesced float2.  No T x n_fft intermediate, no index arrays, no atomics in HBM.
+// Algorithmic bytes: F*8 in + hop*4 out per frame (5128 B for Vocos).
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "fft_regs.cuh"
+
+namespace b2a {
+
+namespace {
+
+using regs::Dft;
+using regs::static_for;
+
+template <int N1_, int N2_>
+struct ICfg {
+  static constexpr int N1 = N1_, N2 = N2_;
+  static constexpr int NC = N1 * N2, N = 2 * NC, F = NC + 1, HOP = N / 4;
+  static constexpr int WARPS = N1 / 2, THREADS = WARPS * 32;
+  static constexpr int FT = 32, HALO = 4, FA = FT - HALO;   // frames per tile, halo lanes (3 needed, 4 keeps alignment)
+  static constexpr int EP = NC + 1;                         // row pitch in float2 (odd: lane-strided access conflict free)
+  static constexpr int S = FA * HOP;                        // output samples owned by a tile
+  static_assert(N2 == WARPS, "one step-2 residue per warp");
+  static_assert(N2 % 2 == 0 && N1 % 2 == 0, "even factors");
+  static_assert((S / 2) % THREADS == 0, "whole sample pairs per thread");
+};
+
+struct InvFastParams {
+  const float2* spec;    // interleaved (B, F, T), or nullptr
+  const float* spec_re;  // planar
+  const float* spec_im;
+  int64_t clip_stride, T;
+  int batch, tiles_per_clip;
+  int norm_sq, div_clamp, vec_ok;
+  int64_t out_start, out_len, out_clip_stride;
+  float* out;
+  const float2* twp;   // [WARPS][N2]   pre-twiddles conj(W_N^k) per unit slot
+  const float2* tw1;   // [WARPS][2][N2] inter-stage twiddles W_Nc^(n2*k1) for the unit's two columns
+  const float2* win2;  // [N2][N1]      (w[2m], w[2m+1]) / N with m = N2*n1 + n2
+  const float* wenv;   // [N]           w or w^2 (envelope taps)
+  const float* den;    // [HOP]         full-overlap envelope, summed in ascending frame order
+};
+
+struct InvFastState {
+  float2 *d_twp = nullptr, *d_tw1 = nullptr, *d_win2 = nullptr;
+  float *d_wenv = nullptr, *d_den = nullptr;
+  int variant = 0;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFastParams p) {
+  constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, HOP = C::HOP;
+  extern __shared__ float4 smem4[];
+  float2* const E = reinterpret_cast<float2*>(smem4);                   // [FT][EP]
+  float2* const s_twp = E + C::FT * C::EP;                              // [WARPS][N2] (FT*EP is even: 16-byte aligned)
+  float2* const s_tw1 = s_twp + C::WARPS * N2;                          // [WARPS][2][N2]
+  float2* const s_win2 = s_tw1 + C::WARPS * 2 * N2;                     // [N2][N1]
+  float* const s_wenv = reinterpret_cast<float*>(s_win2 + N2 * N1);     // [N]
+  float* const s_den = s_wenv + C::N;                                   // [HOP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < C::WARPS * N2; i += C::THREADS) s_twp[i] = p.twp[i];
+  for (int i = threadIdx.x; i < C::WARPS * 2 * N2; i += C::THREADS) s_tw1[i] = p.tw1[i];
+  for (int i = threadIdx.x; i < NC; i += C::THREADS) s_win2[i] = p.win2[i];
+  for (int i = threadIdx.x; i < C::N; i += C::THREADS) s_wenv[i] = p.wenv[i];
+  for (int i = threadIdx.x; i < HOP; i += C::THREADS) s_den[i] = p.den[i];
+
+  const int u = warp;
+  const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
+  const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
+  const int rowA = u, rowB = u != 0 ? N1 - u : N1 / 2;    // E rows (k1) of the unit's two columns
+  const int tpc = p.tiles_per_clip;
+  const int64_t T = p.T;
+  const bool planar = p.spec == nullptr;
+
+#pragma unroll 1
+  for (int64_t tile = blockIdx.x; tile < (int64_t)p.batch * tpc; tile += gridDim.x) {
+    const int clip_i = (int)(tile / tpc);
+    const int tile_i = (int)(tile - (int64_t)clip_i * tpc);
+    const int64_t t_first = (int64_t)tile_i * C::FA - C::HALO;  // frame of lane 0
+    const int64_t t = t_first + lane;
+    const bool live = t >= 0 && t < T;
+    __syncthreads();  // previous tile's overlap-add has finished reading E
+
+    // ---- step 1 ---------------------------------------------------------------------------------------
+    {
+      float2 A[N2], B[N2];  // slot order first; swapped domain (x = Im, y = Re)
+      const int64_t cbase = (int64_t)clip_i * p.clip_stride + t;
+      auto load_bin = [&](int k) -> float2 {
+        if (!live) return make_float2(0.0f, 0.0f);
+        const int64_t i = cbase + (int64_t)k * T;
+        return planar ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
+      };
+      float2 xa[N2], xb[N2];
+      static_for<0, N2>([&](auto S_) {
+        constexpr int s = decltype(S_)::value;
+        const int k = (s < N2 / 2 ? kb_lo : kb_hi) + N1 * s;
+        xa[s] = load_bin(k);
+        xb[s] = load_bin(NC - k);
+      });
+      float2 dc = make_float2(0.0f, 0.0f);
+      if (u == 0) dc = make_float2(load_bin(0).x, load_bin(NC).x);  // Im(DC), Im(Nyquist) are ignored (irfft)
+      const float4* tp4 = reinterpret_cast<const float4*>(s_twp + u * N2);
+      static_for<0, N2 / 2>([&](auto S_) {
+        constexpr int s0 = 2 * decltype(S_)::value;
+        const float4 w2 = tp4[s0 / 2];  // (c, s) of slots s0, s0+1: conj(W_N^k) = (cos, sin)(2 pi k / N)
+        static_for<0, 2>([&](auto J_) {
+          constexpr int s = s0 + decltype(J_)::value;
+          const float2 w = decltype(J_)::value == 0 ? make_float2(w2.x, w2.y) : make_float2(w2.z, w2.w);
+          const float2 a = xa[s], b = xb[s];
+          const float2 e2 = regs::pfma(b, make_float2(1.0f, -1.0f), a);   // a + conj(b)
+          const float2 d = regs::pfma(b, make_float2(-1.0f, 1.0f), a);    // a - conj(b)
+          const float2 o2 = regs::cmul(d, w);                             // (a - conj b) * conj(W_N^k)
+          // Z[k] = E + iO, Z[Nc-k] = conj(E) + i conj(O); stored swapped (im, re)
+          A[s] = regs::pfma(o2, make_float2(1.0f, -1.0f), regs::pswap(e2));            // (e_i + o_r, e_r - o_i)
+          B[N2 - 1 - s] = regs::pfma(regs::pswap(e2), make_float2(-1.0f, 1.0f), o2);   // (o_r - e_i, o_i + e_r)
+        });
+      });
+      if (u == 0) {
+        // unit 0 owns columns 0 and N1/2, whose bins pair up within a column: undo the slot order
+        // col0[0] = DC, col0[j] = slotA[j-1] (j < N2/2), col0[j] = slotB[j] (j >= N2/2);
+        // colH[j] = slotA[N2/2+j] (j < N2/2), colH[j] = slotB[j-N2/2] (j >= N2/2)
+        float2 c0[N2], cH[N2];
+        c0[0] = make_float2(dc.x - dc.y, dc.x + dc.y);  // Z[0] = (X0 + XN) + i (X0 - XN), swapped
+        static_for<1, N2 / 2>([&](auto J_) { constexpr int j = decltype(J_)::value; c0[j] = A[j - 1]; });
+        static_for<N2 / 2, N2>([&](auto J_) { constexpr int j = decltype(J_)::value; c0[j] = B[j]; });
+        static_for<0, N2 / 2>([&](auto J_) { constexpr int j = decltype(J_)::value; cH[j] = A[N2 / 2 + j]; });
+        static_for<N2 / 2, N2>([&](auto J_) { constexpr int j = decltype(J_)::value; cH[j] = B[j - N2 / 2]; });
+        static_for<0, N2>([&](auto J_) {
+          constexpr int j = decltype(J_)::value;
+          A[j] = c0[j];
+          B[j] = cH[j];
+        });
+      }
+      Dft<N2>::run(A);
+      Dft<N2>::run(B);
+      const float4* t4a = reinterpret_cast<const float4*>(s_tw1 + (u * 2 + 0) * N2);
+      const float4* t4b = reinterpret_cast<const float4*>(s_tw1 + (u * 2 + 1) * N2);
+      float2* ea = E + lane * C::EP + rowA * N2;
+      float2* eb = E + lane * C::EP + rowB * N2;
+      static_for<0, N2 / 2>([&](auto I_) {
+        constexpr int n2 = 2 * decltype(I_)::value;
+        const float4 ta = t4a[n2 / 2], tb = t4b[n2 / 2];
+        ea[n2] = n2 == 0 ? A[0] : regs::cmul(A[n2], make_float2(ta.x, ta.y));
+        ea[n2 + 1] = regs::cmul(A[n2 + 1], make_float2(ta.z, ta.w));
+        eb[n2] = n2 == 0 ? B[0] : regs::cmul(B[n2], make_float2(tb.x, tb.y));
+        eb[n2 + 1] = regs::cmul(B[n2 + 1], make_float2(tb.z, tb.w));
+      });
+    }
+    __syncthreads();  // E[frame][k1][n2] complete
+
+    // ---- step 2 ---------------------------------------------------------------------------------------
+    {
+      const int n2 = warp;
+      float2 v[N1];
+      float2* er = E + lane * C::EP + n2;
+      static_for<0, N1>([&](auto K_) {
+        constexpr int k1 = decltype(K_)::value;
+        v[k1] = er[k1 * N2];
+      });
+      Dft<N1>::run(v);
+      const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int n1 = 2 * decltype(I_)::value;
+        const float4 w = wb4[n1 / 2];
+        // swapped domain: v = (Im z, Re z); sample pair (x[2m], x[2m+1]) = (Re z, Im z) * (w[2m], w[2m+1]) / N
+        er[n1 * N2] = regs::pmul(regs::pswap(v[n1]), make_float2(w.x, w.y));
+        er[(n1 + 1) * N2] = regs::pmul(regs::pswap(v[n1 + 1]), make_float2(w.z, w.w));
+      });
+    }
+    __syncthreads();  // rows of E are now windowed frames in natural sample order
+
+    // ---- step 3: overlap-add -------------------------------------------------------------------------
+    {
+      const float* Yf = reinterpret_cast<const float*>(E);
+      float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
+      const int64_t n_base = (int64_t)tile_i * C::S;
+      const int64_t t_q0 = (int64_t)tile_i * C::FA;  // frame index of q = 0
+#pragma unroll
+      for (int it = 0; it < (C::S / 2) / C::THREADS; ++it) {
+        const int nl = 2 * (it * C::THREADS + threadIdx.x);  // local sample index (even)
+        const int q = nl / HOP, r = nl - q * HOP;
+        // contributing frames: lanes q+1 .. q+4 (frames t_q0 + q - 3 .. t_q0 + q), sample offsets r + 3*HOP .. r
+        const float* y = Yf + (q + 1) * (2 * C::EP) + r + 3 * HOP;
+        float2 num = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 yv = *reinterpret_cast<const float2*>(y + j * (2 * C::EP - HOP));
+          num.x += yv.x;
+          num.y += yv.y;
+        }
+        const int64_t ta = t_q0 + q - 3, tb = t_q0 + q;
+        float2 den;
+        if (ta >= 0 && tb < T) {
+          den = *reinterpret_cast<const float2*>(s_den + r);
+        } else {
+          den = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t tt = ta + j;
+            if (tt >= 0 && tt < T) {
+              const float2 wv = *reinterpret_cast<const float2*>(s_wenv + r + (3 - j) * HOP);
+              den.x += wv.x;
+              den.y += wv.y;
+            }
+          }
+        }
+        float2 res;
+        if (p.div_clamp) {
+          res.x = __fdiv_rn(num.x, fmaxf(den.x, 1e-10f));
+          res.y = __fdiv_rn(num.y, fmaxf(den.y, 1e-10f));
+        } else {
+          res.x = den.x > 1e-10f ? __fdiv_rn(num.x, den.x) : num.x;
+          res.y = den.y > 1e-10f ? __fdiv_rn(num.y, den.y) : num.y;
+        }
+        const int64_t j0 = n_base + nl - p.out_start;
+        if (p.vec_ok && j0 >= 0 && j0 + 1 < p.out_len) {
+          *reinterpret_cast<float2*>(o + j0) = res;
+        } else {
+          if (j0 >= 0 && j0 < p.out_len) o[j0] = res.x;
+          if (j0 + 1 >= 0 && j0 + 1 < p.out_len) o[j0 + 1] = res.y;
+        }
+      }
+    }
+  }
+}
+
+template <class C>
+size_t inv_smem_bytes() {
+  return sizeof(float2) * ((size_t)C::FT * C::EP + C::WARPS * C::N2 * 3 + C::NC) + sizeof(float) * (C::N + C::HOP) + 16;
+}
+
+template <class C>
+int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
+  const size_t smem = inv_smem_bytes<C>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, plan->sm_count));
+  fast_istft_kernel<C><<<grid, C::THREADS, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+using ICfg1024 = ICfg<32, 16>;  // Vocos / Vocos-mel heads: n_fft 1024, hop 256; 512 threads, 1 CTA / SM
+
+}  // namespace
+
+bool fast_istft_supported(const b2a_plan* plan) {
+  const b2a_istft_desc& d = plan->id;
+  if (getenv("B2A_FORCE_GENERIC")) return false;
+  return d.n_fft == 1024 && d.hop == 256;
+}
+
+int fast_istft_init(b2a_plan* plan) {
+  using C = ICfg1024;
+  const b2a_istft_desc& d = plan->id;
+  InvFastState* fs = new InvFastState();
+  plan->fast = fs;
+  fs->variant = 1;
+  constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, N = C::N, HOP = C::HOP;
+  auto expand = [](double a) { return make_float2((float)cos(a), (float)sin(a)); };
+  std::vector<float2> twp(C::WARPS * N2), tw1(C::WARPS * 2 * N2), win2(NC);
+  std::vector<float> wenv(N), den(HOP);
+  for (int u = 0; u < C::WARPS; ++u) {
+    const int kb_lo = u != 0 ? u : N1, kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;
+    for (int s = 0; s < N2; ++s) {
+      const int k = (s < N2 / 2 ? kb_lo : kb_hi) + N1 * s;
+      twp[u * N2 + s] = expand(2.0 * M_PI * (double)k / (double)N);  // conj(W_N^k)
+    }
+    const int rowA = u, rowB = u != 0 ? N1 - u : N1 / 2;
+    for (int n2 = 0; n2 < N2; ++n2) {  // forward twiddles W_Nc^(n2*k1) (the inverse runs in the swapped domain)
+      tw1[(u * 2 + 0) * N2 + n2] = expand(-2.0 * M_PI * (double)((n2 * rowA) % NC) / (double)NC);
+      tw1[(u * 2 + 1) * N2 + n2] = expand(-2.0 * M_PI * (double)((n2 * rowB) % NC) / (double)NC);
+    }
+  }
+  const float inv_n = 1.0f / (float)N;  // a power of two for n_fft = 1024: exact, commutes with the window product
+  for (int n2 = 0; n2 < N2; ++n2)
+    for (int n1 = 0; n1 < N1; ++n1) {
+      const int m = N2 * n1 + n2;
+      win2[n2 * N1 + n1] = make_float2(plan->h_window[2 * m] * inv_n, plan->h_window[2 * m + 1] * inv_n);
+    }
+  const bool sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
+  for (int n = 0; n < N; ++n) wenv[n] = sq ? plan->h_window[n] * plan->h_window[n] : plan->h_window[n];
+  for (int r = 0; r < HOP; ++r) {  // ascending frame order: the oldest frame contributes tap r + 3*hop
+    float s = 0.0f;
+    for (int j = 0; j < 4; ++j) s += wenv[r + (3 - j) * HOP];
+    den[r] = s;
+  }
+  B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * twp.size()));
+  B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float2) * tw1.size()));
+  B2A_CUDA(cudaMalloc(&fs->d_win2, sizeof(float2) * win2.size()));
+  B2A_CUDA(cudaMalloc(&fs->d_wenv, sizeof(float) * wenv.size()));
+  B2A_CUDA(cudaMalloc(&fs->d_den, sizeof(float) * den.size()));
+  B2A_CUDA(cudaMemcpy(fs->d_twp, twp.data(), sizeof(float2) * twp.size(), cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_tw1, tw1.data(), sizeof(float2) * tw1.size(), cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_win2, win2.data(), sizeof(float2) * win2.size(), cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_wenv, wenv.data(), sizeof(float) * wenv.size(), cudaMemcpyHostToDevice));
+  B2A_CUDA(cudaMemcpy(fs->d_den, den.data(), sizeof(float) * den.size(), cudaMemcpyHostToDevice));
+  plan->kernel_name = "fast_istft_1024x256";
+  return B2A_OK;
+}
+
+void fast_istft_destroy(b2a_plan* plan) {
+  InvFastState* fs = reinterpret_cast<InvFastState*>(plan->fast);
+  if (!fs) return;
+  cudaFree(fs->d_twp);
+  cudaFree(fs->d_tw1);
+  cudaFree(fs->d_win2);
+  cudaFree(fs->d_wenv);
+  cudaFree(fs->d_den);
+  delete fs;
+  plan->fast = nullptr;
+}
+
+int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
+  using C = ICfg1024;
+  const b2a_istft_desc& d = plan->id;
+  InvFastState* fs = reinterpret_cast<InvFastState*>(plan->fast);
+  InvFastParams p;
+  memset(&p, 0, sizeof(p));
+  const int N = d.n_fft, hop = d.hop, F = plan->n_freqs;
+  if (a->spec_imag) {
+    p.spec_re = reinterpret_cast<const float*>(a->spec);
+    p.spec_im = reinterpret_cast<const float*>(a->spec_imag);
+  } else {
+    p.spec = reinterpret_cast<const float2*>(a->spec);
+  }
+  p.T = a->num_frames;
+  p.clip_stride = a->clip_stride ? a->clip_stride : (int64_t)F * a->num_frames;
+  p.batch = a->batch;
+  p.norm_sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
+  p.div_clamp = d.div_kind == B2A_ISTFT_DIV_CLAMP;
+  int64_t ola, start, len;
+  b2a_istft_geometry(a->num_frames, N, hop, d.center, d.trim_tail ? a->length : -1, &ola, &start, &len);
+  if (!d.trim_tail) {  // ISTFTCache: strip only the front, then [:audio_length]
+    start = d.center ? N / 2 : 0;
+    len = ola - start;
+    if (len < 0) len = 0;
+    if (a->length >= 0 && a->length < len) len = a->length;
+  }
+  if (len <= 0) return B2A_OK;
+  p.out_start = start;
+  p.out_len = len;
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : len;
+  p.out = a->out;
+  p.vec_ok = (reinterpret_cast<uintptr_t>(a->out) % 8 == 0) && (p.out_clip_stride % 2 == 0) && (start % 2 == 0);
+  p.twp = fs->d_twp;
+  p.tw1 = fs->d_tw1;
+  p.win2 = fs->d_win2;
+  p.wenv = fs->d_wenv;
+  p.den = fs->d_den;
+  // tiles cover OLA coordinates [0, start + len)
+  p.tiles_per_clip = (int)((start + len + C::S - 1) / C::S);
+  return launch_inv<C>(plan, p, st);
+}
+
+}  // namespace b2a

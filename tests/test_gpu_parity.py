@@ -42,6 +42,8 @@ def assert_stft_close(y, ref):
 def assert_wave_close(y, ref, tol=1e-5):
     y = host(y)
     assert y.shape == ref.shape
+    if ref.size == 0:
+        return
     fin = np.isfinite(ref)
     assert (np.isfinite(y) == fin).all()
     assert np.abs(y[fin] - ref[fin]).max() <= tol * np.abs(ref[fin]).max()
@@ -161,6 +163,55 @@ def test_istft_batch_and_roundtrip_property():
     y = host(istft(S.swapaxes(1, 2).contiguous(), 256, 1024, window=w, normalized=True))
     n = y.shape[1]
     assert np.abs(y[:, 1024:-1024] - x[:, 1024 : n - 1024]).max() <= 2e-5
+
+
+def _rand_spec(seed, F, T, batch=None):
+    rng = np.random.default_rng(seed)
+    shape = (F, T) if batch is None else (batch, F, T)
+    mag = np.minimum(np.exp(rng.normal(0, 0.5, shape)), 1e2)
+    ph = rng.uniform(-np.pi, np.pi, shape)
+    return (mag * np.exp(1j * ph)).astype(np.complex64)  # Im(DC), Im(Nyquist) non-zero on purpose (App. B.12)
+
+
+@pytest.mark.parametrize("T,window,center,length,normalized", [
+    (468, ("hanning", 1024, False, None), True, None, False),     # Vocos head: symmetric array window, sum-w
+    (37, "hann", True, None, True),                                # periodic string window, sum-w^2, T % 4 != 0
+    (29, "hamming", False, None, False),                           # no centre trim; exactly one tile + 1 frame
+    (5, ("hanning", 1024, False, None), True, 777, False),         # `length` keeps the centre pad, odd length
+    (1, "hann", True, None, False),                                # a single frame: empty after the centre trim
+    (1, "hann", False, None, False),                               # a single frame, untrimmed
+    (3, "blackman", True, None, True),
+    (120, ("hanning", 640, True, None), True, None, False),        # short window, right zero-extended
+])
+def test_fast_istft_1024_parity(T, window, center, length, normalized):
+    """The fused 1024/256 inverse kernel (fast_inv.cu) against the oracle on every option of dsp.istft."""
+    from mlx_audio_plus_b200.dsp import istft
+
+    x = _rand_spec(900 + T, 513, T)
+    w = mkwin(window)
+    ref = O.istft(x, 256, 1024, w, center, length, normalized)
+    y = istft(dev(x), 256, 1024, w, center, length, normalized)
+    assert_wave_close(y, ref)
+
+
+def test_fast_istft_1024_batch_planar_and_kernel_name():
+    """ISTFTCache form (separate real / imag planes, sum-w^2, clamp guard, front-only trim) through the fused
+    kernel, batched; also pins that the fused kernel is the one that ran."""
+    from mlx_audio_plus_b200.dsp import ISTFTCache
+    from mlx_audio_plus_b200 import frontend
+
+    B, T = 5, 61
+    x = _rand_spec(4242, 513, T, batch=B)
+    w = np.asarray(O.hanning(1024, False))
+    oc = O.ISTFTCache()
+    c = ISTFTCache()
+    for alen in (None, 9000):
+        ref = oc.istft(x.real, x.imag, 1024, 256, 1024, w, True, alen)
+        y = c.istft(dev(np.ascontiguousarray(x.real)), dev(np.ascontiguousarray(x.imag)), 1024, 256, 1024, w, True, alen)
+        assert_wave_close(y, ref)
+    names = {pl.kernel_name for pl in list(frontend._CACHE.values())
+             if isinstance(pl, frontend.IstftPlan) and pl.n_fft == 1024 and pl.hop == 256}
+    assert names == {"fast_istft_1024x256"}, names
 
 
 # ---- model front-ends ---------------------------------------------------------------------------------
