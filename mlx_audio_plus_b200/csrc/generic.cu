@@ -434,32 +434,72 @@ __global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
   }
 }
 
+// (x - mean) / (std + eps), in place.  The per-mel (or global) mean and denominator are derived ONCE per block
+// from the float64 sums into shared memory; the sweep itself is float4 loads / stores (HBM bound: it re-reads
+// and re-writes the features, the only part of the path that touches the output twice).
 __global__ void __launch_bounds__(256) normalise_kernel(const FinParams p) {
+  __shared__ float s_mean[256], s_den[256];
   const int clip_i = blockIdx.y;
   const int M = p.n_mels;
   float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
   const int64_t total = p.frames * M;
   const double n = (double)p.global_frames;
   const double* S = p.feat_sums + (int64_t)clip_i * M * 2;
-  float g_mean = 0.f, g_den = 1.f;
   if (p.norm_kind == B2A_NORM_GLOBAL) {
-    double s1 = 0, s2 = 0;
-    for (int m = 0; m < M; ++m) { s1 += S[2 * m]; s2 += S[2 * m + 1]; }
-    const double cnt = n * M, mean = s1 / cnt;
-    double var = (s2 - cnt * mean * mean) / (cnt - p.norm_ddof);
-    if (var < 0) var = 0;
-    g_mean = (float)mean;
-    g_den = (float)sqrt(var) + p.norm_eps;
-  }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int m = p.out_layout == B2A_LAYOUT_TM ? (int)(i % M) : (int)(i / p.frames);
-    float mean = g_mean, den = g_den;
-    if (p.norm_kind == B2A_NORM_PER_FEATURE) {
+    if (threadIdx.x == 0) {
+      double s1 = 0, s2 = 0;
+      for (int m = 0; m < M; ++m) { s1 += S[2 * m]; s2 += S[2 * m + 1]; }
+      const double cnt = n * M, mean = s1 / cnt;
+      double var = (s2 - cnt * mean * mean) / (cnt - p.norm_ddof);
+      if (var < 0) var = 0;
+      s_mean[0] = (float)mean;
+      s_den[0] = (float)sqrt(var) + p.norm_eps;
+    }
+    __syncthreads();
+    const float g_mean = s_mean[0], g_den = s_den[0];
+    __syncthreads();
+    for (int m = threadIdx.x; m < M && m < 256; m += blockDim.x) {
+      s_mean[m] = g_mean;
+      s_den[m] = g_den;
+    }
+  } else {
+    for (int m = threadIdx.x; m < M && m < 256; m += blockDim.x) {
       const double mu = S[2 * m] / n;
       double var = (S[2 * m + 1] - n * mu * mu) / (n - p.norm_ddof);
       if (var < 0) var = 0;
+      s_mean[m] = (float)mu;
+      s_den[m] = (float)sqrt(var) + p.norm_eps;
+    }
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = M <= 256 && (M & 3) == 0 && p.out_layout == B2A_LAYOUT_TM && (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+  if (vec) {
+    float4* o4 = reinterpret_cast<float4*>(o);
+    const int M4 = M >> 2;
+    for (int64_t i = first; i < (total >> 2); i += stride) {
+      const int m = (int)(i % M4) << 2;
+      float4 v = o4[i];
+      v.x = __fdiv_rn(v.x - s_mean[m], s_den[m]);
+      v.y = __fdiv_rn(v.y - s_mean[m + 1], s_den[m + 1]);
+      v.z = __fdiv_rn(v.z - s_mean[m + 2], s_den[m + 2]);
+      v.w = __fdiv_rn(v.w - s_mean[m + 3], s_den[m + 3]);
+      o4[i] = v;
+    }
+    return;
+  }
+  for (int64_t i = first; i < total; i += stride) {
+    const int m = p.out_layout == B2A_LAYOUT_TM ? (int)(i % M) : (int)(i / p.frames);
+    float mean, den;
+    if (m < 256) {
+      mean = s_mean[m];
+      den = s_den[m];
+    } else {  // very wide outputs (n_mels == 0: normalised spectra) — derive per element
+      const double mu = p.norm_kind == B2A_NORM_GLOBAL ? (double)s_mean[0] : S[2 * m] / n;
+      double var = (S[2 * m + 1] - n * mu * mu) / (n - p.norm_ddof);
+      if (var < 0) var = 0;
       mean = (float)mu;
-      den = (float)sqrt(var) + p.norm_eps;
+      den = p.norm_kind == B2A_NORM_GLOBAL ? s_den[0] : (float)sqrt(var) + p.norm_eps;
     }
     o[i] = (o[i] - mean) / den;
   }
@@ -749,7 +789,7 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
     return B2A_OK;
   }
   const int64_t total = a->frame_count * M;
-  int gx = (int)std::min<int64_t>((total + 256 * 8 - 1) / (256 * 8), 4 * plan->sm_count);
+  int gx = (int)std::min<int64_t>((total + 256 * 16 - 1) / (256 * 16), 8 * plan->sm_count);
   if (gx < 1) gx = 1;
   dim3 grid(gx, a->batch);
   normalise_kernel<<<grid, 256, 0, st>>>(p);
