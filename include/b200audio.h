@@ -71,6 +71,10 @@ enum { /* how istft treats the envelope: */
   B2A_ISTFT_DIV_WHERE = 0, /* num/den where den>1e-10 else num     dsp.py:207-209 */
   B2A_ISTFT_DIV_CLAMP = 1  /* num/max(den,1e-10)                   dsp.py:344,407 (ISTFTCache) */
 };
+enum {
+  B2A_ISTFT_INPUT_COMPLEX = 0,
+  B2A_ISTFT_INPUT_POLAR = 1
+};
 
 /* ---- front-end (forward) plan -------------------------------------------------------------------
  * One descriptor expresses every row of SURVEY.md Appendix A "wrapper parameter matrix":
@@ -186,7 +190,13 @@ typedef struct b2a_istft_desc {
   int32_t div_kind;   /* B2A_ISTFT_DIV_* */
   int32_t trim_tail;  /* 1: strip n_fft/2 from BOTH ends when center && length<0 (dsp.py:211-212);
                          0: strip only the front (ISTFTCache, dsp.py:410-412) */
-  int32_t reserved[4];
+  float div_eps;      /* envelope floor of the division guard; 0 = the reference's 1e-10 (dsp.py:207,344).  The
+                         model-local HiFT / CosyVoice iSTFTs use 1e-8 (s3gen/hifigan.py:521, cosyvoice3/hifigan.py:493) */
+  int32_t input_form; /* B2A_ISTFT_INPUT_*: COMPLEX = spec (+ optional spec_imag plane); POLAR = `spec` is the MAGNITUDE
+                         plane and `spec_imag` the PHASE plane: X = clip(mag) * (cos p + i sin p) is formed in the kernel
+                         (kokoro/istftnet.py:500-512, s3gen/hifigan.py:480-485, cosyvoice3/hifigan.py:447-452) */
+  float mag_clip_max; /* POLAR: magnitude is clipped to <= this (1e2 in the HiFT heads); <= 0 = no upper clip */
+  int32_t mag_clip_min_zero; /* POLAR: 1 = clip magnitude to >= 0 (cosyvoice3/hifigan.py:447 a_min=0.0) */
 } b2a_istft_desc;
 
 typedef struct b2a_inverse_args {

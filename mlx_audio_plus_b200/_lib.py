@@ -23,6 +23,7 @@ NORM_NONE, NORM_PER_FEATURE, NORM_GLOBAL = 0, 1, 2
 LAYOUT_TM, LAYOUT_MT = 0, 1
 ISTFT_NORM_WINDOW, ISTFT_NORM_WINDOW_SQ = 0, 1
 ISTFT_DIV_WHERE, ISTFT_DIV_CLAMP = 0, 1
+ISTFT_INPUT_COMPLEX, ISTFT_INPUT_POLAR = 0, 1
 
 OK, ERR_INVALID_ARG, ERR_UNKNOWN_WINDOW, ERR_PAD_MODE, ERR_TOO_SHORT = 0, -1, -2, -3, -4
 ERR_SHAPE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -5, -6, -7, -8
@@ -54,7 +55,7 @@ class IstftDesc(C.Structure):
     _fields_ = [
         ("n_fft", C.c_int32), ("hop", C.c_int32), ("window_len", C.c_int32), ("center", C.c_int32),
         ("norm_kind", C.c_int32), ("div_kind", C.c_int32), ("trim_tail", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("div_eps", C.c_float), ("input_form", C.c_int32), ("mag_clip_max", C.c_float), ("mag_clip_min_zero", C.c_int32),
     ]
 
 

@@ -477,6 +477,10 @@ int b2a_istft_inverse(b2a_plan* p, const b2a_inverse_args* a, void* stream) {
     set_error("istft_inverse: invalid argument");
     return B2A_ERR_INVALID_ARG;
   }
+  if (p->id.input_form == B2A_ISTFT_INPUT_POLAR && !a->spec_imag) {
+    set_error("istft_inverse: the polar input form needs the phase plane in spec_imag");
+    return B2A_ERR_INVALID_ARG;
+  }
   if (p->family == KF_SMALL) return small_istft(p, a, (cudaStream_t)stream);
   if (p->family == KF_FAST) return fast_istft(p, a, (cudaStream_t)stream);
   return generic_istft(p, a, (cudaStream_t)stream);

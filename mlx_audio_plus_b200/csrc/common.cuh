@@ -62,6 +62,32 @@ __host__ __device__ inline int64_t source_index(const Geometry& g, int pad_mode,
   return s;
 }
 
+// iSTFT input forms (b2a_istft_desc.input_form): how a kernel turns the two values it read for a bin into X[k]
+struct PolarSpec {
+  int polar;          // 1: (a, b) = (magnitude, phase) -> clip(a) * (cos b, sin b)
+  float clip_max;     // <= 0: none
+  int clip_min_zero;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 polar_to_complex(const PolarSpec& ps, float2 v) {
+  if (!ps.polar) return v;
+  float m = v.x;
+  if (ps.clip_max > 0.0f) m = fminf(m, ps.clip_max);
+  if (ps.clip_min_zero) m = fmaxf(m, 0.0f);
+  float s, c;
+  sincosf(v.y, &s, &c);  // full-range accurate version (the reference uses libm-grade cos / sin)
+  return make_float2(m * c, m * s);
+}
+#endif
+inline PolarSpec make_polar_spec(const b2a_istft_desc& d) {
+  PolarSpec ps;
+  ps.polar = d.input_form == B2A_ISTFT_INPUT_POLAR;
+  ps.clip_max = d.mag_clip_max;
+  ps.clip_min_zero = d.mag_clip_min_zero;
+  return ps;
+}
+inline float istft_div_eps(const b2a_istft_desc& d) { return d.div_eps > 0.0f ? d.div_eps : 1e-10f; }
+
 struct MelCsr {  // filterbank rows as contiguous runs of non-zero taps
   int* d_start = nullptr;  // [M] first bin
   int* d_len = nullptr;    // [M] number of taps

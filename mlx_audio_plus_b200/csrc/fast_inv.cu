@@ -60,6 +60,8 @@ struct InvFastParams {
   const float2* win2;  // [N2][N1]      (w[2m], w[2m+1]) / N with m = N2*n1 + n2
   const float* wenv;   // [N]           w or w^2 (envelope taps)
   const float* den;    // [HOP]         full-overlap envelope, summed in ascending frame order
+  PolarSpec polar;
+  float div_eps;
 };
 
 struct InvFastState {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
       auto load_bin = [&](int k) -> float2 {
         if (!live) return make_float2(0.0f, 0.0f);
         const int64_t i = cbase + (int64_t)k * T;
-        return planar ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
+        return planar ? polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i))) : __ldg(p.spec + i);
       };
       float2 xa[N2], xb[N2];
       static_for<0, N2>([&](auto S_) {
@@ -227,11 +229,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
         }
         float2 res;
         if (p.div_clamp) {
-          res.x = __fdiv_rn(num.x, fmaxf(den.x, 1e-10f));
-          res.y = __fdiv_rn(num.y, fmaxf(den.y, 1e-10f));
+          res.x = __fdiv_rn(num.x, fmaxf(den.x, p.div_eps));
+          res.y = __fdiv_rn(num.y, fmaxf(den.y, p.div_eps));
         } else {
-          res.x = den.x > 1e-10f ? __fdiv_rn(num.x, den.x) : num.x;
-          res.y = den.y > 1e-10f ? __fdiv_rn(num.y, den.y) : num.y;
+          res.x = den.x > p.div_eps ? __fdiv_rn(num.x, den.x) : num.x;
+          res.y = den.y > p.div_eps ? __fdiv_rn(num.y, den.y) : num.y;
         }
         const int64_t j0 = n_base + nl - p.out_start;
         if (p.vec_ok && j0 >= 0 && j0 + 1 < p.out_len) {
@@ -354,6 +356,8 @@ int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.batch = a->batch;
   p.norm_sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
   p.div_clamp = d.div_kind == B2A_ISTFT_DIV_CLAMP;
+  p.polar = make_polar_spec(d);
+  p.div_eps = istft_div_eps(d);
   int64_t ola, start, len;
   b2a_istft_geometry(a->num_frames, N, hop, d.center, d.trim_tail ? a->length : -1, &ola, &start, &len);
   if (!d.trim_tail) {  // ISTFTCache: strip only the front, then [:audio_length]

@@ -531,6 +531,8 @@ struct InvParams {
   int frames_cap;       // max frames resident per tile
   int pairs_chunk;      // pairs transformed per FFT round
   int tiles_per_clip;
+  PolarSpec polar;
+  float div_eps;
 };
 
 __global__ void __launch_bounds__(kThreads) istft_generic_kernel(const InvParams p) {
@@ -567,8 +569,10 @@ __global__ void __launch_bounds__(kThreads) istft_generic_kernel(const InvParams
         float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
         const int fa = c0 + 2 * pr, fb = fa + 1;
         const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo;
-        if (fa < c0 + cf) xa = p.spec ? p.spec[base + fa] : make_float2(p.spec_re[base + fa], p.spec_im[base + fa]);
-        if (fb < c0 + cf) xb = p.spec ? p.spec[base + fb] : make_float2(p.spec_re[base + fb], p.spec_im[base + fb]);
+        if (fa < c0 + cf)
+          xa = p.spec ? p.spec[base + fa] : polar_to_complex(p.polar, make_float2(p.spec_re[base + fa], p.spec_im[base + fa]));
+        if (fb < c0 + cf)
+          xb = p.spec ? p.spec[base + fb] : polar_to_complex(p.polar, make_float2(p.spec_re[base + fb], p.spec_im[base + fb]));
         // irfft ignores Im(DC) and, for even N, Im(Nyquist)
         if (kk == 0 || (2 * kk == N)) { xa.y = 0.f; xb.y = 0.f; }
         if (mir) { xa.y = -xa.y; xb.y = -xb.y; }
@@ -600,8 +604,8 @@ __global__ void __launch_bounds__(kThreads) istft_generic_kernel(const InvParams
         den += p.norm_sq ? w * w : w;
       }
       float r;
-      if (p.div_clamp) r = num / fmaxf(den, 1e-10f);
-      else r = den > 1e-10f ? num / den : num;
+      if (p.div_clamp) r = num / fmaxf(den, p.div_eps);
+      else r = den > p.div_eps ? num / den : num;
       o[j] = r;
     }
     __syncthreads();
@@ -817,6 +821,8 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.n_freqs = F;
   p.norm_sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
   p.div_clamp = d.div_kind == B2A_ISTFT_DIV_CLAMP;
+  p.polar = make_polar_spec(d);
+  p.div_eps = istft_div_eps(d);
   int64_t ola, start, len;
   int64_t eff_len = a->length;
   b2a_istft_geometry(a->num_frames, N, hop, d.center, d.trim_tail ? eff_len : -1, &ola, &start, &len);

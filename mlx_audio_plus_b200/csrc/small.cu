@@ -31,6 +31,8 @@ struct SmallInvParams {
   float* out;
   float w[32];  // synthesis window (zero extended)
   int warps_per_clip;
+  PolarSpec polar;
+  float div_eps;
 };
 
 template <int N>
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
   } else {
 #pragma unroll
     for (int k = 0; k < F; ++k)
-      X[k] = live ? make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T), __ldg(p.spec_im + base + (int64_t)k * p.T))
+      X[k] = live ? polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T),
+                                                          __ldg(p.spec_im + base + (int64_t)k * p.T)))
                   : make_float2(0.f, 0.f);
   }
   X[0].y = 0.f;   // irfft ignores Im(DC) and Im(Nyquist)
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
     const int64_t jo = n - p.out_start;
     if (jo >= 0 && jo < p.out_len) {
       float r;
-      if (p.div_clamp) r = num[j] / fmaxf(den[j], 1e-10f);
-      else r = den[j] > 1e-10f ? num[j] / den[j] : num[j];
+      if (p.div_clamp) r = num[j] / fmaxf(den[j], p.div_eps);
+      else r = den[j] > p.div_eps ? num[j] / den[j] : num[j];
       o[jo] = r;
     }
   }
@@ -195,6 +198,8 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.hop = d.hop;
   p.norm_sq = d.norm_kind == B2A_ISTFT_NORM_WINDOW_SQ;
   p.div_clamp = d.div_kind == B2A_ISTFT_DIV_CLAMP;
+  p.polar = make_polar_spec(d);
+  p.div_eps = istft_div_eps(d);
   int64_t ola, start, len;
   b2a_istft_geometry(a->num_frames, N, d.hop, d.center, d.trim_tail ? a->length : -1, &ola, &start, &len);
   if (!d.trim_tail) {

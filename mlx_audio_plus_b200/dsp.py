@@ -134,6 +134,27 @@ def istft(x, hop_length=None, win_length=None, window="hann", center=True, lengt
     return emit(ing, out[0] if squeeze else out)
 
 
+def istft_polar(magnitude, phase, n_fft, hop_length, window, *, center=True, normalized=False, div_clamp=False,
+                div_eps=0.0, trim_tail=True, length=None, mag_clip_max=0.0, mag_clip_min_zero=False):
+    """iSTFT of a spectrum given as (magnitude, phase) planes of shape (B, F, T): the fused form of the
+    `mag*cos(phase) + 1j*mag*sin(phase)` -> istft sequences in kokoro/istftnet.py:500-519, s3gen/hifigan.py:480-549
+    and cosyvoice3/hifigan.py:447-499 — clip, cos / sin, inverse FFT, window, overlap-add and envelope division run
+    in ONE kernel; the complex spectrum never exists in HBM.  Not a reference name: the model-local drop-ins call it."""
+    m, ph = ingest(magnitude, "float32"), ingest(phase, "float32")
+    if m.data.ndim != 3 or tuple(m.data.shape) != tuple(ph.data.shape):
+        raise ValueError("istft_polar expects magnitude / phase of identical shape (batch, freq, time)")
+    if m.on_device != ph.on_device:
+        raise ValueError("magnitude and phase must live on the same device")
+    w = host_window(window)
+    if w.shape[0] > n_fft or m.data.shape[1] != n_fft // 2 + 1:
+        raise ValueError("istft_polar: window / spectrum do not match n_fft")
+    plan = cached_plan(IstftPlan, _device_index(m), w, n_fft=int(n_fft), hop=int(hop_length), center=bool(center),
+                       normalized=bool(normalized), div_clamp=bool(div_clamp), trim_tail=bool(trim_tail),
+                       div_eps=float(div_eps), polar=True, mag_clip_max=float(mag_clip_max),
+                       mag_clip_min_zero=bool(mag_clip_min_zero))
+    return emit(m, plan.run(m, imag=ph, length=length))
+
+
 @lru_cache(maxsize=None)
 def mel_filters(
     sample_rate: int,

@@ -173,7 +173,8 @@ class FrontendPlan(_PlanBase):
 
 
 class IstftPlan(_PlanBase):
-    def __init__(self, *, n_fft, hop, window, center=True, normalized=False, div_clamp=False, trim_tail=True):
+    def __init__(self, *, n_fft, hop, window, center=True, normalized=False, div_clamp=False, trim_tail=True,
+                 div_eps=0.0, polar=False, mag_clip_max=0.0, mag_clip_min_zero=False):
         super().__init__()
         window = np.ascontiguousarray(window, dtype=np.float32)
         d = L.IstftDesc()
@@ -181,6 +182,9 @@ class IstftPlan(_PlanBase):
         d.norm_kind = L.ISTFT_NORM_WINDOW_SQ if normalized else L.ISTFT_NORM_WINDOW
         d.div_kind = L.ISTFT_DIV_CLAMP if div_clamp else L.ISTFT_DIV_WHERE
         d.trim_tail = int(bool(trim_tail))
+        d.div_eps = float(div_eps)
+        d.input_form = L.ISTFT_INPUT_POLAR if polar else L.ISTFT_INPUT_COMPLEX
+        d.mag_clip_max, d.mag_clip_min_zero = float(mag_clip_max), int(bool(mag_clip_min_zero))
         self.desc = d
         self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
         L.check(L.lib.b2a_istft_create(C.byref(d), window.ctypes.data_as(C.c_void_p), C.byref(self._h)))

@@ -7,7 +7,7 @@ import math
 
 import numpy as np
 
-from ....dsp import istft, stft
+from ....dsp import _resolve_window, istft_polar, stft
 
 
 def _is_torch(x):
@@ -70,15 +70,11 @@ class MLXSTFT:
 
     def inverse(self, magnitude, phase):
         phase_cont = mlx_unwrap(phase, axis=2)
-        if _is_torch(magnitude):
-            import torch
-
-            spec = torch.complex(magnitude * torch.cos(phase_cont), magnitude * torch.sin(phase_cont))
-        else:
-            m = np.asarray(magnitude, np.float32)
-            spec = (m * np.cos(phase_cont) + 1j * (m * np.sin(phase_cont))).astype(np.complex64)
-        audio = istft(spec, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
-                      center=True, length=None)  # (B, L)
+        # mag * cos / sin of the unwrapped phase (istftnet.py:505-507) is formed inside the iSTFT kernel; string
+        # windows are periodic in istft (dsp.py:172-176), sum-w envelope with the where-guard (dsp.py:199-209)
+        w = _resolve_window(self.window, self.win_length, periodic_trick=True)
+        audio = istft_polar(magnitude, phase_cont, self.filter_length, self.hop_length, w, center=True,
+                            normalized=False, div_clamp=False, trim_tail=True)  # (B, L)
         return audio[:, None, :]
 
     def __call__(self, input_data):

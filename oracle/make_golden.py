@@ -95,6 +95,8 @@ def _load_reference():
     mods["vocos"] = extract("mlx_audio/codec/models/vocos/vocos.py", ["ISTFTHead"])
     mods["kokoro"] = extract("mlx_audio/tts/models/kokoro/istftnet.py", ["mlx_angle", "mlx_unwrap", "MLXSTFT"])
     mods["qwen3"] = extract("mlx_audio/tts/models/qwen3_tts/qwen3_tts.py", ["mel_spectrogram"])
+    mods["hift_s3gen"] = extract("mlx_audio/codec/models/s3gen/hifigan.py", ["stft", "istft"])
+    mods["hift_cosy3"] = extract("mlx_audio/tts/models/cosyvoice3/hifigan.py", ["stft", "istft"], {"Tuple": tuple})
     mods["sortformer"] = extract("mlx_audio/vad/models/sortformer/sortformer.py",
                                  ["_LOG_GUARD", "_NORM_CONSTANT", "preemphasis_filter", "extract_mel_features"])
     return mx, mods
@@ -108,8 +110,30 @@ def synth(seed, n, sr=16000):
     return x.astype(np.float32)
 
 
+def hift_goldens(mx, R):
+    """tests/golden/refshim_hift.npz: the HiFT model-local stft / istft pairs."""
+    A = lambda v: np.asarray(v)
+    g = {}
+    rng = np.random.default_rng(77)
+    for n_fft, hop in ((16, 4), (20, 5)):
+        w = np.asarray(R["dsp"].hanning(n_fft + 1)[:-1])  # periodic Hann, as scipy get_window(fftbins=True)
+        x = np.stack([synth(300 + i, 1203, 24000) * (0.5 + i) for i in range(3)])
+        mag = np.exp(rng.normal(0, 1.5, (3, n_fft // 2 + 1, 151))).astype(np.float32)  # some values beyond the 1e2 clip
+        mag[0, 2, 5], mag[1, 3, 7] = 250.0, -0.5  # exercise both clip bounds
+        ph = rng.uniform(-np.pi, np.pi, mag.shape).astype(np.float32)
+        g[f"n{n_fft}|w"], g[f"n{n_fft}|x"], g[f"n{n_fft}|mag"], g[f"n{n_fft}|phase"] = w, x, mag, ph
+        for name in ("hift_s3gen", "hift_cosy3"):
+            re, im = R[name].stft(mx.array(x), n_fft, hop, mx.array(w))
+            g[f"n{n_fft}|{name}|re"], g[f"n{n_fft}|{name}|im"] = A(re), A(im)
+            g[f"n{n_fft}|{name}|y"] = A(R[name].istft(mx.array(mag), mx.array(ph), n_fft, hop, mx.array(w)))
+    np.savez_compressed(os.path.join(OUT, "refshim_hift.npz"), **g)
+
+
 def main():
     mx, R = _load_reference()
+    if "--hift-only" in sys.argv:
+        hift_goldens(mx, R)
+        return
     dsp = R["dsp"]
     os.makedirs(OUT, exist_ok=True)
     A = lambda v: np.asarray(v)
@@ -290,6 +314,7 @@ def main():
     g["sortformer|x"] = x
     g["sortformer|y"] = A(R["sortformer"].extract_mel_features(mx.array(x)))
     np.savez_compressed(os.path.join(OUT, "refshim_models.npz"), **g)
+    hift_goldens(mx, R)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

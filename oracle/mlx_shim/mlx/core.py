@@ -169,6 +169,18 @@ squeeze = _unary(_np.squeeze)
 swapaxes = _unary(_np.swapaxes)
 
 
+def take(x, indices, axis=None):
+    return _w(_np.take(_np.asarray(x), _np.asarray(indices), axis=axis))
+
+
+def reshape(x, shape):
+    return _w(_np.reshape(x, shape))
+
+
+def repeat(x, repeats, axis=None):
+    return _w(_np.repeat(_np.asarray(x), repeats, axis=axis))
+
+
 def transpose(x, axes=None):
     return _w(_np.transpose(x, axes))
 
@@ -205,6 +217,14 @@ class fft:
     @staticmethod
     def rfft(x, n=None, axis=-1):
         return _np.fft.rfft(_np.asarray(x), n=n, axis=axis).astype(_np.complex64).view(array)
+
+    @staticmethod
+    def fft(x, n=None, axis=-1):
+        return _np.fft.fft(_np.asarray(x).astype(_np.complex64), n=n, axis=axis).astype(_np.complex64).view(array)
+
+    @staticmethod
+    def ifft(x, n=None, axis=-1):
+        return _np.fft.ifft(_np.asarray(x).astype(_np.complex64), n=n, axis=axis).astype(_np.complex64).view(array)
 
     @staticmethod
     def irfft(x, n=None, axis=-1):

@@ -250,3 +250,44 @@ def sortformer_mel(waveform, sample_rate=16000, n_fft=512, hop_length=160, win_l
     if pad_to > 0 and f.shape[2] % pad_to:
         f = np.pad(f, [(0, 0), (0, 0), (0, pad_to - f.shape[2] % pad_to)])
     return f.astype(F32)
+
+
+# -- HiFT vocoder STFT pair (model-local, batched): codec/models/s3gen/hifigan.py:408-549 (reflect pad, clip <= 1e2)
+#    and tts/models/cosyvoice3/hifigan.py:382-499 (zero pad, clip to [0, 1e2]); n_fft=16, hop=4 in HiFTGenerator
+def hift_stft(x, n_fft, hop, window, pad_mode="reflect"):
+    x = np.asarray(x, F32)
+    window = np.asarray(window, F32)
+    p = n_fft // 2
+    if pad_mode == "reflect":  # s3gen/hifigan.py:421-427
+        xp = np.concatenate([x[:, 1 : p + 1][:, ::-1], x, x[:, -(p + 1) : -1][:, ::-1]], axis=1)
+    else:  # cosyvoice3/hifigan.py:399-400
+        xp = np.pad(x, [(0, 0), (p, p)])
+    n_frames = (xp.shape[1] - n_fft) // hop + 1
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    frames = (xp[:, idx] * window).astype(F32)  # (B, frames, n_fft)
+    spec = np.fft.rfft(frames, axis=-1).astype(np.complex64)  # fft[:n_fft//2+1] == rfft (s3gen :449-453)
+    spec = np.swapaxes(spec, 1, 2)
+    return np.ascontiguousarray(spec.real), np.ascontiguousarray(spec.imag)
+
+
+def hift_istft(magnitude, phase, n_fft, hop, window, clip_min_zero=False):
+    m = np.asarray(magnitude, F32)
+    ph = np.asarray(phase, F32)
+    window = np.asarray(window, F32)
+    m = np.clip(m, 0.0 if clip_min_zero else None, F32(1e2))  # s3gen :481 / cosyvoice3 :447
+    re, im = (m * np.cos(ph)).astype(F32), (m * np.sin(ph)).astype(F32)
+    spec = np.swapaxes(re + 1j * im, 1, 2).astype(np.complex64)  # (B, frames, F)
+    # real(ifft(Hermitian-extended spectrum)) == irfft: Im(DC), Im(Nyquist) drop out (s3gen :491-502)
+    frames = (np.fft.irfft(spec, n=n_fft, axis=-1).astype(F32) * window).astype(F32)
+    B, n_frames, _ = frames.shape
+    out_len = n_fft + (n_frames - 1) * hop
+    idx = (np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]).reshape(-1)
+    wsum = np.zeros(out_len, F32)
+    np.add.at(wsum, idx, np.tile((window * window).astype(F32), n_frames))
+    wsum = np.maximum(wsum, F32(1e-8))  # s3gen :521 / cosyvoice3 :493
+    out = np.zeros((B, out_len), F32)
+    for b in range(B):
+        np.add.at(out[b], idx, frames[b].reshape(-1))
+    out = (out / wsum[None, :]).astype(F32)
+    p = n_fft // 2
+    return out[:, p:-p]

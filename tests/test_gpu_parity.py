@@ -214,6 +214,43 @@ def test_fast_istft_1024_batch_planar_and_kernel_name():
     assert names == {"fast_istft_1024x256"}, names
 
 
+# ---- HiFT model-local stft / istft ------------------------------------------------------
+@pytest.mark.parametrize("n_fft,hop", [(16, 4), (20, 5)])
+@pytest.mark.parametrize("name,mod", [("hift_s3gen", "mlx_audio_plus_b200.codec.models.s3gen.hifigan"),
+                                      ("hift_cosy3", "mlx_audio_plus_b200.tts.models.cosyvoice3.hifigan")])
+@pytest.mark.parametrize("where", ["cuda", "numpy"])
+def test_hift_pair_parity(golden, n_fft, hop, name, mod, where):
+    """Batched stft -> (real, imag) and the fused polar istft (clip, cos / sin, irfft, window, overlap-add,
+    max(sum w^2, 1e-8)) against fixtures produced by the reference's own functions."""
+    import importlib
+
+    m = importlib.import_module(mod)
+    g = golden("hift")
+    put = dev if where == "cuda" else (lambda a: a)
+    w, x = g[f"n{n_fft}|w"], g[f"n{n_fft}|x"]
+    re, im = m.stft(put(x), n_fft, hop, w)
+    ref_re, ref_im = g[f"n{n_fft}|{name}|re"], g[f"n{n_fft}|{name}|im"]
+    assert tuple(re.shape) == ref_re.shape
+    assert_stft_close((host(re) + 1j * host(im)).astype(np.complex64), (ref_re + 1j * ref_im).astype(np.complex64))
+    y = m.istft(put(g[f"n{n_fft}|mag"]), put(g[f"n{n_fft}|phase"]), n_fft, hop, w)
+    assert_wave_close(y, g[f"n{n_fft}|{name}|y"])
+
+
+def test_polar_istft_1024_matches_complex_path():
+    """The polar input form on the fused 1024/256 kernel == the complex form fed with clip(mag)*(cos, sin)."""
+    from mlx_audio_plus_b200.dsp import istft, istft_polar
+
+    rng = np.random.default_rng(5)
+    mag = np.exp(rng.normal(0, 2.0, (2, 513, 40))).astype(np.float32)
+    ph = rng.uniform(-20, 20, mag.shape).astype(np.float32)
+    w = np.asarray(O.hanning(1024))
+    mc = np.minimum(mag, np.float32(1e2))
+    spec = (mc * np.cos(ph) + 1j * (mc * np.sin(ph))).astype(np.complex64)
+    ref = np.stack([O.istft(spec[i], 256, 1024, w, True, None, False) for i in range(2)])
+    y = istft_polar(dev(mag), dev(ph), 1024, 256, w, mag_clip_max=1e2)
+    assert_wave_close(y, ref)
+
+
 # ---- model front-ends ---------------------------------------------------------------------------------
 def test_whisper_parity(golden):
     from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
