@@ -59,7 +59,8 @@ struct InvFastParams {
   const float2* tw1;   // [WARPS][2][N2] inter-stage twiddles W_Nc^(n2*k1) for the unit's two columns
   const float2* win2;  // [N2][N1]      (w[2m], w[2m+1]) / N with m = N2*n1 + n2
   const float* wenv;   // [N]           w or w^2 (envelope taps)
-  const float* den;    // [HOP]         full-overlap envelope, summed in ascending frame order
+  const float* den;    // [HOP]         1 / (full-overlap envelope summed in ascending frame order)
+  int rden_ok;         // every entry of the full-overlap envelope is above the division guard
   PolarSpec polar;
   float div_eps;
 };
@@ -67,10 +68,12 @@ struct InvFastParams {
 struct InvFastState {
   float2 *d_twp = nullptr, *d_tw1 = nullptr, *d_win2 = nullptr;
   float *d_wenv = nullptr, *d_den = nullptr;
-  int variant = 0;
+  int variant = 0, rden_ok = 1;
 };
 
-template <class C>
+// POLAR (magnitude / phase planes) is a compile-time variant: the accurate sincosf is ~100 instructions per call
+// site and would otherwise sit, unused, in the instruction stream of the complex-input kernel (32 KB I-cache).
+template <class C, bool POLAR>
 __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, HOP = C::HOP;
   extern __shared__ float4 smem4[];
@@ -79,13 +82,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
   float2* const s_tw1 = s_twp + C::WARPS * N2;                          // [WARPS][2][N2]
   float2* const s_win2 = s_tw1 + C::WARPS * 2 * N2;                     // [N2][N1]
   float* const s_wenv = reinterpret_cast<float*>(s_win2 + N2 * N1);     // [N]
-  float* const s_den = s_wenv + C::N;                                   // [HOP]
+  float* const s_rden = s_wenv + C::N;                                  // [HOP]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < C::WARPS * N2; i += C::THREADS) s_twp[i] = p.twp[i];
   for (int i = threadIdx.x; i < C::WARPS * 2 * N2; i += C::THREADS) s_tw1[i] = p.tw1[i];
   for (int i = threadIdx.x; i < NC; i += C::THREADS) s_win2[i] = p.win2[i];
   for (int i = threadIdx.x; i < C::N; i += C::THREADS) s_wenv[i] = p.wenv[i];
-  for (int i = threadIdx.x; i < HOP; i += C::THREADS) s_den[i] = p.den[i];
+  for (int i = threadIdx.x; i < HOP; i += C::THREADS) s_rden[i] = p.den[i];
 
   const int u = warp;
   const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
@@ -106,53 +109,73 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
 
     // ---- step 1 ---------------------------------------------------------------------------------------
     {
-      float2 A[N2], B[N2];  // slot order first; swapped domain (x = Im, y = Re)
-      const int64_t cbase = (int64_t)clip_i * p.clip_stride + t;
-      auto load_bin = [&](int k) -> float2 {
+      float2 A[N2], B[N2];  // columns (u, N1-u) in k2 order; swapped domain (x = Im, y = Re)
+      // Running element offsets: bin k of slot s is kb + N1*s, its partner Nc - k; consecutive slots are N1*T
+      // elements apart, so every address is one 64-bit add away from the previous one.
+      const int64_t stepT = (int64_t)N1 * T, jumpT = (int64_t)(kb_hi - kb_lo) * T;
+      int64_t oa = (int64_t)clip_i * p.clip_stride + t + (int64_t)kb_lo * T;
+      int64_t ob = (int64_t)clip_i * p.clip_stride + t + (int64_t)(NC - kb_lo) * T;
+      auto load_at = [&](int64_t i) -> float2 {
         if (!live) return make_float2(0.0f, 0.0f);
-        const int64_t i = cbase + (int64_t)k * T;
-        return planar ? polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i))) : __ldg(p.spec + i);
+        if (POLAR) return polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)));
+        return planar ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
       };
       float2 xa[N2], xb[N2];
       static_for<0, N2>([&](auto S_) {
         constexpr int s = decltype(S_)::value;
-        const int k = (s < N2 / 2 ? kb_lo : kb_hi) + N1 * s;
-        xa[s] = load_bin(k);
-        xb[s] = load_bin(NC - k);
+        if (s == N2 / 2) {  // unit 0 switches from column 0 to column N1/2 here (jumpT == 0 for the other units)
+          oa += jumpT;
+          ob -= jumpT;
+        }
+        xa[s] = load_at(oa);
+        xb[s] = load_at(ob);
+        oa += stepT;
+        ob -= stepT;
       });
       float2 dc = make_float2(0.0f, 0.0f);
-      if (u == 0) dc = make_float2(load_bin(0).x, load_bin(NC).x);  // Im(DC), Im(Nyquist) are ignored (irfft)
+      if (u == 0) {  // Im(DC), Im(Nyquist) are ignored (irfft)
+        const int64_t o0 = (int64_t)clip_i * p.clip_stride + t;
+        dc = make_float2(load_at(o0).x, load_at(o0 + (int64_t)NC * T).x);
+      }
       const float4* tp4 = reinterpret_cast<const float4*>(s_twp + u * N2);
-      static_for<0, N2 / 2>([&](auto S_) {
-        constexpr int s0 = 2 * decltype(S_)::value;
-        const float4 w2 = tp4[s0 / 2];  // (c, s) of slots s0, s0+1: conj(W_N^k) = (cos, sin)(2 pi k / N)
-        static_for<0, 2>([&](auto J_) {
-          constexpr int s = s0 + decltype(J_)::value;
-          const float2 w = decltype(J_)::value == 0 ? make_float2(w2.x, w2.y) : make_float2(w2.z, w2.w);
-          const float2 a = xa[s], b = xb[s];
-          const float2 e2 = regs::pfma(b, make_float2(1.0f, -1.0f), a);   // a + conj(b)
-          const float2 d = regs::pfma(b, make_float2(-1.0f, 1.0f), a);    // a - conj(b)
-          const float2 o2 = regs::cmul(d, w);                             // (a - conj b) * conj(W_N^k)
-          // Z[k] = E + iO, Z[Nc-k] = conj(E) + i conj(O); stored swapped (im, re)
-          A[s] = regs::pfma(o2, make_float2(1.0f, -1.0f), regs::pswap(e2));            // (e_i + o_r, e_r - o_i)
-          B[N2 - 1 - s] = regs::pfma(regs::pswap(e2), make_float2(-1.0f, 1.0f), o2);   // (o_r - e_i, o_i + e_r)
+      // Hermitian unpacking of one slot; the two results land in DIFFERENT registers for unit 0 (whose columns 0 and
+      // N1/2 pair up within themselves), so the unpacking is instantiated twice behind a warp-uniform branch rather
+      // than followed by ~50 predicated register moves in every warp:
+      //   general: A[s] = Z'[k], B[N2-1-s] = Z'[Nc-k]
+      //   unit 0 : slots s < N2/2 -> col0[s+1], col0[N2-1-s]; slots s >= N2/2 -> colH[s-N2/2], colH[3N2/2-1-s]
+      auto unpack = [&](auto U0_) {
+        constexpr bool U0 = decltype(U0_)::value;
+        static_for<0, N2 / 2>([&](auto S_) {
+          constexpr int s0 = 2 * decltype(S_)::value;
+          const float4 w2 = tp4[s0 / 2];  // (c, s) of slots s0, s0+1: conj(W_N^k) = (cos, sin)(2 pi k / N)
+          static_for<0, 2>([&](auto J_) {
+            constexpr int s = s0 + decltype(J_)::value;
+            const float2 w = decltype(J_)::value == 0 ? make_float2(w2.x, w2.y) : make_float2(w2.z, w2.w);
+            const float2 a = xa[s], b = xb[s];
+            const float2 e2 = regs::pfma(b, make_float2(1.0f, -1.0f), a);   // a + conj(b)
+            const float2 d = regs::pfma(b, make_float2(-1.0f, 1.0f), a);    // a - conj(b)
+            const float2 o2 = regs::cmul(d, w);                             // (a - conj b) * conj(W_N^k)
+            // Z[k] = E + iO, Z[Nc-k] = conj(E) + i conj(O); stored swapped (im, re)
+            const float2 zk = regs::pfma(o2, make_float2(1.0f, -1.0f), regs::pswap(e2));   // (e_i + o_r, e_r - o_i)
+            const float2 zm = regs::pfma(regs::pswap(e2), make_float2(-1.0f, 1.0f), o2);   // (o_r - e_i, o_i + e_r)
+            if constexpr (!U0) {
+              A[s] = zk;
+              B[N2 - 1 - s] = zm;
+            } else if constexpr (s < N2 / 2) {
+              if constexpr (s + 1 < N2 / 2) A[s + 1] = zk;   // the self-paired bin Nc/2 (s + 1 == N2/2) arrives as zm
+              A[N2 - 1 - s] = zm;
+            } else {
+              B[s - N2 / 2] = zk;
+              B[3 * N2 / 2 - 1 - s] = zm;
+            }
+          });
         });
-      });
+      };
       if (u == 0) {
-        // unit 0 owns columns 0 and N1/2, whose bins pair up within a column: undo the slot order
-        // col0[0] = DC, col0[j] = slotA[j-1] (j < N2/2), col0[j] = slotB[j] (j >= N2/2);
-        // colH[j] = slotA[N2/2+j] (j < N2/2), colH[j] = slotB[j-N2/2] (j >= N2/2)
-        float2 c0[N2], cH[N2];
-        c0[0] = make_float2(dc.x - dc.y, dc.x + dc.y);  // Z[0] = (X0 + XN) + i (X0 - XN), swapped
-        static_for<1, N2 / 2>([&](auto J_) { constexpr int j = decltype(J_)::value; c0[j] = A[j - 1]; });
-        static_for<N2 / 2, N2>([&](auto J_) { constexpr int j = decltype(J_)::value; c0[j] = B[j]; });
-        static_for<0, N2 / 2>([&](auto J_) { constexpr int j = decltype(J_)::value; cH[j] = A[N2 / 2 + j]; });
-        static_for<N2 / 2, N2>([&](auto J_) { constexpr int j = decltype(J_)::value; cH[j] = B[j - N2 / 2]; });
-        static_for<0, N2>([&](auto J_) {
-          constexpr int j = decltype(J_)::value;
-          A[j] = c0[j];
-          B[j] = cH[j];
-        });
+        unpack(std::true_type{});
+        A[0] = make_float2(dc.x - dc.y, dc.x + dc.y);  // Z[0] = (X0 + XN) + i (X0 - XN), swapped
+      } else {
+        unpack(std::false_type{});
       }
       Dft<N2>::run(A);
       Dft<N2>::run(B);
@@ -194,16 +217,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
 
     // ---- step 3: overlap-add -------------------------------------------------------------------------
     {
+      // THREADS * 2 consecutive samples per sweep: a thread keeps its hop-relative offset r and walks 4 hops per
+      // sweep, so every address below advances by a constant
+      constexpr int HPS = 2 * C::THREADS / HOP;            // hops per sweep
+      static_assert((2 * C::THREADS) % HOP == 0, "whole hops per sweep");
       const float* Yf = reinterpret_cast<const float*>(E);
       float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
-      const int64_t n_base = (int64_t)tile_i * C::S;
-      const int64_t t_q0 = (int64_t)tile_i * C::FA;  // frame index of q = 0
-#pragma unroll
-      for (int it = 0; it < (C::S / 2) / C::THREADS; ++it) {
-        const int nl = 2 * (it * C::THREADS + threadIdx.x);  // local sample index (even)
-        const int q = nl / HOP, r = nl - q * HOP;
+      const int q0 = (2 * threadIdx.x) / HOP, r = 2 * threadIdx.x - q0 * HOP;
+      const int t_q0 = tile_i * C::FA;  // frame index of q = 0
+      const int Ti = (int)T;
+      const float* y = Yf + (q0 + 1) * (2 * C::EP) + r + 3 * HOP;
+      int64_t j0 = (int64_t)tile_i * C::S + 2 * threadIdx.x - p.out_start;
+      const float2 rden = *reinterpret_cast<const float2*>(s_rden + r);
+#pragma unroll 1
+      for (int it = 0; it < (C::S / 2) / C::THREADS; ++it, y += HPS * 2 * C::EP, j0 += 2 * C::THREADS) {
+        const int q = q0 + HPS * it;
         // contributing frames: lanes q+1 .. q+4 (frames t_q0 + q - 3 .. t_q0 + q), sample offsets r + 3*HOP .. r
-        const float* y = Yf + (q + 1) * (2 * C::EP) + r + 3 * HOP;
         float2 num = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -211,31 +240,31 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
           num.x += yv.x;
           num.y += yv.y;
         }
-        const int64_t ta = t_q0 + q - 3, tb = t_q0 + q;
-        float2 den;
-        if (ta >= 0 && tb < T) {
-          den = *reinterpret_cast<const float2*>(s_den + r);
+        const int ta = t_q0 + q - 3, tb = t_q0 + q;
+        float2 res;
+        if (ta >= 0 && tb < Ti && p.rden_ok) {
+          // all four frames exist: the envelope is the period-hop table; its reciprocal (rounded once from double)
+          // replaces the division (<= 1 ulp from the quotient)
+          res = make_float2(num.x * rden.x, num.y * rden.y);
         } else {
-          den = make_float2(0.0f, 0.0f);
+          float2 den = make_float2(0.0f, 0.0f);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int64_t tt = ta + j;
-            if (tt >= 0 && tt < T) {
+            const int tt = ta + j;
+            if (tt >= 0 && tt < Ti) {
               const float2 wv = *reinterpret_cast<const float2*>(s_wenv + r + (3 - j) * HOP);
               den.x += wv.x;
               den.y += wv.y;
             }
           }
+          if (p.div_clamp) {
+            res.x = __fdiv_rn(num.x, fmaxf(den.x, p.div_eps));
+            res.y = __fdiv_rn(num.y, fmaxf(den.y, p.div_eps));
+          } else {
+            res.x = den.x > p.div_eps ? __fdiv_rn(num.x, den.x) : num.x;
+            res.y = den.y > p.div_eps ? __fdiv_rn(num.y, den.y) : num.y;
+          }
         }
-        float2 res;
-        if (p.div_clamp) {
-          res.x = __fdiv_rn(num.x, fmaxf(den.x, p.div_eps));
-          res.y = __fdiv_rn(num.y, fmaxf(den.y, p.div_eps));
-        } else {
-          res.x = den.x > p.div_eps ? __fdiv_rn(num.x, den.x) : num.x;
-          res.y = den.y > p.div_eps ? __fdiv_rn(num.y, den.y) : num.y;
-        }
-        const int64_t j0 = n_base + nl - p.out_start;
         if (p.vec_ok && j0 >= 0 && j0 + 1 < p.out_len) {
           *reinterpret_cast<float2*>(o + j0) = res;
         } else {
@@ -252,17 +281,17 @@ size_t inv_smem_bytes() {
   return sizeof(float2) * ((size_t)C::FT * C::EP + C::WARPS * C::N2 * 3 + C::NC) + sizeof(float) * (C::N + C::HOP) + 16;
 }
 
-template <class C>
+template <class C, bool POLAR>
 int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
   const size_t smem = inv_smem_bytes<C>();
   static bool attr_done = false;
   if (!attr_done) {
-    B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C, POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, plan->sm_count));
-  fast_istft_kernel<C><<<grid, C::THREADS, smem, st>>>(p);
+  fast_istft_kernel<C, POLAR><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
@@ -310,7 +339,8 @@ int fast_istft_init(b2a_plan* plan) {
   for (int r = 0; r < HOP; ++r) {  // ascending frame order: the oldest frame contributes tap r + 3*hop
     float s = 0.0f;
     for (int j = 0; j < 4; ++j) s += wenv[r + (3 - j) * HOP];
-    den[r] = s;
+    if (!(s > (d.div_eps > 0.0f ? d.div_eps : 1e-10f))) fs->rden_ok = 0;  // guard active: keep the exact division path
+    den[r] = (float)(1.0 / (double)s);
   }
   B2A_CUDA(cudaMalloc(&fs->d_twp, sizeof(float2) * twp.size()));
   B2A_CUDA(cudaMalloc(&fs->d_tw1, sizeof(float2) * tw1.size()));
@@ -377,9 +407,10 @@ int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.win2 = fs->d_win2;
   p.wenv = fs->d_wenv;
   p.den = fs->d_den;
+  p.rden_ok = fs->rden_ok;
   // tiles cover OLA coordinates [0, start + len)
   p.tiles_per_clip = (int)((start + len + C::S - 1) / C::S);
-  return launch_inv<C>(plan, p, st);
+  return p.polar.polar ? launch_inv<C, true>(plan, p, st) : launch_inv<C, false>(plan, p, st);
 }
 
 }  // namespace b2a

@@ -35,7 +35,7 @@ struct SmallInvParams {
   float div_eps;
 };
 
-template <int N>
+template <int N, bool POLAR>
 __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p) {
   constexpr int NC = N / 2, F = NC + 1, HOP = N / 4;
   const int lane = threadIdx.x & 31;
@@ -53,10 +53,11 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
     for (int k = 0; k < F; ++k) X[k] = live ? __ldg(p.spec + base + (int64_t)k * p.T) : make_float2(0.f, 0.f);
   } else {
 #pragma unroll
-    for (int k = 0; k < F; ++k)
-      X[k] = live ? polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T),
-                                                          __ldg(p.spec_im + base + (int64_t)k * p.T)))
+    for (int k = 0; k < F; ++k) {
+      X[k] = live ? make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T), __ldg(p.spec_im + base + (int64_t)k * p.T))
                   : make_float2(0.f, 0.f);
+      if (POLAR) X[k] = live ? polar_to_complex(p.polar, X[k]) : X[k];
+    }
   }
   X[0].y = 0.f;   // irfft ignores Im(DC) and Im(Nyquist)
   X[NC].y = 0.f;
@@ -216,8 +217,10 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   const int64_t slots = a->num_frames + 3;
   p.warps_per_clip = (int)((slots + 28) / 29);
   dim3 grid((p.warps_per_clip + 7) / 8, a->batch);
-  if (N == 20) istft_small_kernel<20><<<grid, 256, 0, st>>>(p);
-  else istft_small_kernel<16><<<grid, 256, 0, st>>>(p);
+  if (N == 20 && p.polar.polar) istft_small_kernel<20, true><<<grid, 256, 0, st>>>(p);
+  else if (N == 20) istft_small_kernel<20, false><<<grid, 256, 0, st>>>(p);
+  else if (p.polar.polar) istft_small_kernel<16, true><<<grid, 256, 0, st>>>(p);
+  else istft_small_kernel<16, false><<<grid, 256, 0, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
