@@ -334,3 +334,62 @@ def test_kokoro_parity(golden):
     assert_wave_close(y, g["kokoro|inv_y"])
     yw = K.inverse(dev(g["kokoro|inv_mag"][:1]), dev(g["kokoro|inv_phase_wrapped"]))
     assert_wave_close(yw, g["kokoro|inv_y_wrapped"], tol=1e-4)  # fp32 cumsum in unwrap is order dependent
+
+
+# ---- BASELINE.json full sizes: size-independent properties + spot checks against the oracle ---------------------
+def _bench_like_batch(B, n, sr, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.arange(n, device="cuda", dtype=torch.float64) / sr
+    tone = (0.2 * (torch.sin(2 * np.pi * 440 * t) + torch.sin(2 * np.pi * 3000 * t))).float()
+    x = torch.empty((B, n), dtype=torch.float32, device="cuda")
+    for c0 in range(0, B, 256):
+        c1 = min(B, c0 + 256)
+        scale = (0.5 + (torch.arange(c0, c1, device="cuda") % 7).float() / 7)[:, None]
+        x[c0:c1] = (0.1 * torch.randn((c1 - c0, n), generator=g, device="cuda") + tone[None]) * scale
+    return x
+
+
+def test_c2_full_batch_4096x30s_properties():
+    """BASELINE configs[1] at full size (4096 x 30 s, 128 mels): (a) sampled clips equal the oracle within 1e-4,
+    (b) the batched launch is BIT-identical to running a clip alone (clips are independent: per-clip max, no
+    cross-clip state), (c) the per-clip maximum maps to exactly (max+4)/4 and nothing lies below max - 2.0
+    (the max-8 clamp after the /4 affine map)."""
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    free, _ = torch.cuda.mem_get_info()
+    B = 4096 if free > 40e9 else 512
+    x = _bench_like_batch(B, 480000, 16000, 1235)
+    y = log_mel_spectrogram(x, n_mels=128)
+    assert tuple(y.shape) == (B, 3000, 128)
+    picks = [0, 1, 7, B // 2 + 3, B - 1]
+    for i in picks:
+        ref = W.whisper_log_mel(x[i].cpu().numpy(), 128)
+        assert np.abs(y[i].cpu().numpy() - ref).max() <= 1e-4
+        alone = log_mel_spectrogram(x[i : i + 1].clone(), n_mels=128)[0]
+        assert torch.equal(alone, y[i])
+    mx = y.amax(dim=(1, 2))
+    mn = y.amin(dim=(1, 2))
+    assert bool(((mx - mn) <= 2.0 + 1e-6).all())
+    assert bool(torch.isfinite(y).all())
+
+
+def test_c3_one_hour_file_full_size_vs_oracle():
+    """BASELINE configs[2] at full size (one 1-hour file, Parakeet front-end: pre-emphasis, n_fft 512 / win 400 /
+    hop 160, 80 mels, ln(x + 1e-5), per-feature normalisation over all 360 001 frames): the whole output against the
+    oracle (<= 5e-4: the division by the per-mel std amplifies), plus the size-independent property that
+    every mel row has mean 0 and std 1."""
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram
+
+    args = PreprocessArgs(sample_rate=16000, normalize="per_feature", window_size=0.025, window_stride=0.01,
+                          window="hann", features=80, n_fft=512, dither=0.0)
+    x = _bench_like_batch(1, 57_600_000, 16000, 1236)[0]
+    y = log_mel_spectrogram(x, args)
+    assert tuple(y.shape) == (1, 360001, 80)
+    yd = y[0].double()
+    assert float(yd.mean(0).abs().max()) <= 1e-4
+    assert float((yd.std(0, unbiased=False) - 1).abs().max()) <= 1e-3
+    ref = W.parakeet_log_mel(x.cpu().numpy(), W.PreprocessArgs(**{k: getattr(args, k) for k in (
+        "sample_rate", "normalize", "window_size", "window_stride", "window", "features", "n_fft", "dither")}))
+    assert ref.shape == (1, 360001, 80)
+    assert np.abs(y.cpu().numpy() - ref).max() <= 5e-4
