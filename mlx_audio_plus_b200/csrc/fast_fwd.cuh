@@ -91,7 +91,7 @@ using regs::static_for;
 
 struct NoSpec {  // run-time mel tables (any filterbank); melgen::MelSpec_* bake a named filterbank into code
   static constexpr int M = 0, NW = 0, F = 0;
-  template <class Emit>
+  template <class C, class Emit>
   static __device__ __forceinline__ void run(int, const float*, Emit&&) {}
 };
 
@@ -116,6 +116,20 @@ struct Cfg {
   // the mel phase's (4 frames x 8 mel rows) gathers land in distinct banks
   static constexpr int PP = F + ((9 - F % 32 + 32) % 32);
   static constexpr int K = HOP / (2 * N2);   // taps pairs per row per role step
+  // Slot (float2 index within a frame's exchange row) of power bin k when the power tile is written IN PLACE over the
+  // exchange buffer (generated-mel kernels): a stage-2 unit only overwrites slots of the two columns it has just
+  // consumed — unit u: bin u + N1*s -> slot u*N2 + s, its mirror Nc - k -> slot (N1/2 + u)*N2 + s; unit 0 keeps its
+  // slot order (see stage 2), parks DC in the duplicate slot of its self-paired bin Nc/2 and Nyquist in the pad slot.
+  __host__ __device__ static constexpr int sig(int k) {
+    if (k == 0) return (N1 / 2) * N2 + N2 / 2 - 1;
+    if (k == NC) return NC;
+    const int r = k % N1, q = k / N1;
+    if (r == 0) return q <= N2 / 2 ? (q - 1) : (N1 / 2) * N2 + (N2 - 1 - q);
+    if (r == N1 / 2) return q < N2 / 2 ? (N2 / 2 + q) : (N1 / 2) * N2 + (N2 / 2 + (N2 - 1 - q));
+    if (r < N1 / 2) return r * N2 + q;
+    const int u = N1 - r;
+    return (N1 / 2 + u) * N2 + (NC - k - u) / N1;
+  }
   static_assert(N1 % 2 == 0 && N2 % WARPS == 0, "role split");
   static_assert(HOP % (2 * N2) == 0, "hop must be a multiple of 2*N2");
   static_assert(NC % 2 == 0, "Nc even");
@@ -272,18 +286,25 @@ __device__ __forceinline__ void mel_group_taps(const float* wp, const float* pq,
   });
 }
 
-template <class C>
+// YP: pitch (floats) of the generated-mel staging tile Y[frame][YP]; 0 = run-time-table kernel.
+// Generated-mel kernels (YP > 0): the power tile lives IN PLACE in the exchange buffer (Cfg::sig), Y and the sample
+// tile have their own space, and the next tile's samples are always prefetched.  Run-time-table kernels keep a
+// separate power tile (natural bin order), alias Y with the exchange buffer and, for ALIAS configs, the power tile
+// with the sample tile (no prefetch).
+template <class C, int YP>
 struct Smem {  // section offsets in float4 units from the 16-byte aligned dynamic smem base
   static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
+  static constexpr bool PIE = YP > 0;
+  static constexpr bool PREFETCH = PIE || !C::ALIAS;
   static constexpr int WIN = 0;
   static constexpr int TW1 = WIN + cdiv4(8 * C::NC);
   static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
   static constexpr int EX = TWP + cdiv4(8 * C::NC);
-  static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);
-  static constexpr int XS = C::ALIAS ? PW : PW + cdiv4(4 * C::FT * C::PP);
-  static constexpr int PX_END = C::ALIAS ? PW + (cdiv4(4 * C::FT * C::PP) > cdiv4(4 * C::XS_FLOATS) ? cdiv4(4 * C::FT * C::PP)
-                                                                                                  : cdiv4(4 * C::XS_FLOATS))
-                                         : XS + cdiv4(4 * C::XS_FLOATS);
+  static constexpr int PW = EX + cdiv4(8 * C::FT * C::EP);   // PIE: the staging tile Y starts here
+  static constexpr int PW_SIZE = PIE ? cdiv4(4 * C::FT * YP) : cdiv4(4 * C::FT * C::PP);
+  static constexpr int XS = PREFETCH ? PW + PW_SIZE : PW;
+  static constexpr int PX_END = PREFETCH ? XS + cdiv4(4 * C::XS_FLOATS)
+                                         : PW + (PW_SIZE > cdiv4(4 * C::XS_FLOATS) ? PW_SIZE : cdiv4(4 * C::XS_FLOATS));
   static constexpr int DYN = PX_END;  // then: sums (double), mel weights, starts, group info
 };
 
@@ -397,8 +418,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   // both bank-conflict free
   constexpr int YP = SPEC ? (((MS::M / 4) & 1) ? MS::M : MS::M + 4) : 4;
   constexpr int QL = SPEC ? MS::M / 4 : 1;  // lanes that carry a row quad in phase B
-  static_assert(!SPEC || (size_t)C::FT * YP * 4 <= (size_t)C::FT * C::EP * 8, "Y must fit in the exchange buffer");
-  using S = Smem<C>;
+  using S = Smem<C, SPEC ? YP : 0>;
+  constexpr bool PREFETCH = S::PREFETCH;
   extern __shared__ float4 smem4[];
   float2* const s_win2 = reinterpret_cast<float2*>(smem4 + S::WIN);  // [N2][N1]
   float2* const s_tw1 = reinterpret_cast<float2*>(smem4 + S::TW1);   // [N2][N1]
@@ -416,7 +437,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   __shared__ int s_cur_clip;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* const Y = reinterpret_cast<float*>(E);  // staging tile; aliases the exchange buffer
+  // staging tile: own space in the generated-mel kernels (the exchange buffer then holds the power tile), else it
+  // aliases the exchange buffer
+  float* const Y = SPEC ? Pw : reinterpret_cast<float*>(E);
   FillCtx<C> fc;
   fc.init((unsigned)__cvta_generic_to_shared(xs));
 
@@ -440,7 +463,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   const int tpc = p.tiles_per_clip;
   const int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
   int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
-  if (!C::ALIAS && clip_i < p.batch) fill_tile<C>(p, xs, fc, clip_i, tile_i);
+  if (PREFETCH && clip_i < p.batch) fill_tile<C>(p, xs, fc, clip_i, tile_i);
 
   const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
   const bool use_log = p.use_log != 0;
@@ -519,7 +542,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       ++nclip;
     }
 
-    if (C::ALIAS) {
+    if (!PREFETCH) {
       __syncthreads();  // previous tile's mel phase has finished reading P (which shares xs' memory)
       fill_tile<C>(p, xs, fc, clip_i, tile_i);
     }
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     tick(1);
 
     // prefetch the next tile's samples while stage 2 / mel run
-    if (!C::ALIAS && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
+    if (PREFETCH && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
 
     // ---- stage 2 ----------------------------------------------------------------------------------------
     {
@@ -595,17 +618,18 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       });
       Dft<N2>::run(A);
       Dft<N2>::run(B);
-      float* pr = Pw + lane * C::PP;
+      // power tile: separate, natural bin order (run-time-table kernels) — or in place over this frame's exchange row,
+      // one value per float2 slot, in the half selected by lane >> 4 (the row pitch is 2 * odd floats, so lanes l and
+      // l + 16 would otherwise share a bank)
+      float* pr = SPEC ? reinterpret_cast<float*>(E + lane * C::EP) + (lane >> 4) : Pw + lane * C::PP;
       auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
+      float dc_k = 0.0f, dc_m = 0.0f;
       if (u == 0) {
         // unit 0: the DC / Nyquist pair comes from A[0] alone; then permute so that the shared post-processing
         // below pairs column 0 with itself (slots 0..N2/2-1: A[s+1] with A[N2-1-s]) and column N1/2 with itself
         // (slots N2/2..N2-1: B[s-N2/2] with B[3N2/2-1-s]).  One code path for every warp keeps the loop body
         // inside the 32 KB instruction cache.
-        float pk, pm;
-        post_pair(A[0], A[0], make_float2(1.0f, 0.0f), pk, pm);
-        emit(pr, pk);
-        emit(pr + NC, pm);
+        post_pair(A[0], A[0], make_float2(1.0f, 0.0f), dc_k, dc_m);
         float2 T[N2 / 2];
         static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = B[N2/2+j] (j < N2/2); stash B's lower half
           constexpr int j = decltype(I_)::value;
@@ -626,21 +650,27 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         });
       }
       const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
-      float* const plo = pr + kb_lo;           // bins kb_lo + N1*s
-      float* const mlo = pr + (NC - kb_lo);    // mirrored bins
-      float* const phi = pr + kb_hi;
-      float* const mhi = pr + (NC - kb_hi);
+      // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
+      float* const plo = SPEC ? pr + 2 * (u * N2) : pr + kb_lo;
+      float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * N2) : pr + (NC - kb_lo);
+      float* const phi = SPEC ? plo : pr + kb_hi;
+      float* const mhi = SPEC ? mlo : pr + (NC - kb_hi);
+      constexpr int SK = SPEC ? 2 : N1, SM = SPEC ? 2 : -N1;
       static_for<0, N2 / 2>([&](auto I_) {
         constexpr int k2 = 2 * decltype(I_)::value;
         const float4 t = tw4[k2 / 2];
         float pk, pm;
         post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
-        emit((k2 < N2 / 2 ? plo : phi) + N1 * k2, pk);
-        emit((k2 < N2 / 2 ? mlo : mhi) - N1 * k2, pm);
+        emit((k2 < N2 / 2 ? plo : phi) + SK * k2, pk);
+        emit((k2 < N2 / 2 ? mlo : mhi) + SM * k2, pm);
         post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
-        emit((k2 + 1 < N2 / 2 ? plo : phi) + N1 * (k2 + 1), pk);
-        emit((k2 + 1 < N2 / 2 ? mlo : mhi) - N1 * (k2 + 1), pm);
+        emit((k2 + 1 < N2 / 2 ? plo : phi) + SK * (k2 + 1), pk);
+        emit((k2 + 1 < N2 / 2 ? mlo : mhi) + SM * (k2 + 1), pm);
       });
+      if (u == 0) {  // after the loop: in the in-place layout DC reuses the duplicate slot of the self-paired bin Nc/2
+        emit(pr + (SPEC ? 2 * C::sig(0) : 0), dc_k);
+        emit(pr + (SPEC ? 2 * C::sig(NC) : NC), dc_m);
+      }
     }
     __syncthreads();  // Pw complete, E free (Y aliases E)
     tick(2);
@@ -651,9 +681,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       // conflict-free LDS per bin (odd row pitch) shared by the two rows it feeds, one FFMA per tap with the weight
       // as an immediate; four finished rows are parked in Y[frame][m..m+3] with one STS.128.
       {
-        const float* pr = Pw + lane * C::PP;
+        const float* pr = reinterpret_cast<const float*>(E + lane * C::EP) + (lane >> 4);  // in-place power tile
         float4* const yl = reinterpret_cast<float4*>(Y + lane * YP);
-        MS::run(warp, pr, [&](auto M_, float a0, float a1, float a2, float a3) {
+        MS::template run<C>(warp, pr, [&](auto M_, float a0, float a1, float a2, float a3) {
           constexpr int m = decltype(M_)::value;
           yl[m / 4] = make_float4(a0, a1, a2, a3);
         });
@@ -752,14 +782,31 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   }
 }
 
-template <class C>
+template <class C, int YP>
 size_t smem_bytes(int G, int wg_count) {
-  return (size_t)16 * Smem<C>::DYN + sizeof(double) * 2 * G * 8 + sizeof(float) * (wg_count + (wg_count & 1)) + sizeof(int) * (G * 8 + 2 * G + 2) + 16;
+  return (size_t)16 * Smem<C, YP>::DYN + sizeof(double) * 2 * G * 8 + sizeof(float) * (wg_count + (wg_count & 1)) + sizeof(int) * (G * 8 + 2 * G + 2) + 16;
 }
 
 
+// staging pitch of a generated-mel kernel (0 for the run-time-table kernels); must match the kernel's own YP
+template <class MS>
+constexpr int spec_yp() {
+  return MS::M > 0 ? ((((MS::M / 4) & 1) ? MS::M : MS::M + 4)) : 0;
+}
+
 template <class C, bool TM, bool SUMS, class MS, int SPECK = -1>
-int launch_variant(b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) {
+int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
+  size_t smem = smem_bytes<C, spec_yp<MS>()>(p.mel_groups, p.mel_wg_count);
+  if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
+  if (smem > 226 * 1024) {
+    set_error("fast kernel: %zu bytes of shared memory needed", smem);
+    return B2A_ERR_UNSUPPORTED;
+  }
+  const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
+  if (grid < 1) grid = 1;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -806,8 +853,8 @@ struct SpecList;
 #define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK)                                                              \
   case IDX:                                                                                              \
     if (p.spec_kind != SPECK) break;                                                                     \
-    if (!sums) return launch_variant<C, true, false, MS, SPECK>(plan, p, smem, grid, st);               \
-    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK>(plan, p, smem, grid, st);    \
+    if (!sums) return launch_variant<C, true, false, MS, SPECK>(plan, p, st);                           \
+    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK>(plan, p, st);                \
     break;
 #define B2A_SPECLIST(CFG, LIST)                                                                             \
   template <>                                                                                               \
@@ -815,7 +862,7 @@ struct SpecList;
     using C = CFG;                                                                                          \
     static int match(const b2a_plan* plan, const char** name) { LIST(B2A_MATCH) return 0; }                 \
     /* returns B2A_OK after a launch, or 1 when (spec, sums) has no instance and the caller falls back */   \
-    static int launch(int spec, bool sums, b2a_plan* plan, FastParams& p, size_t smem, int grid, cudaStream_t st) { \
+    static int launch(int spec, bool sums, b2a_plan* plan, FastParams& p, cudaStream_t st) {                \
       switch (spec) { LIST(B2A_LAUNCH) default: break; }                                                    \
       return 1;                                                                                             \
     }                                                                                                       \
@@ -823,33 +870,22 @@ struct SpecList;
 
 template <class C>
 int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
-  size_t smem = smem_bytes<C>(p.mel_groups, p.mel_wg_count);
-  if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
-  if (smem > 226 * 1024) {
-    set_error("fast kernel: %zu bytes of shared memory needed", smem);
-    return B2A_ERR_UNSUPPORTED;
-  }
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
   if (tiles >= (int64_t)1 << 31) {
     set_error("fast kernel: %lld tiles in one launch (split the batch)", (long long)tiles);
     return B2A_ERR_UNSUPPORTED;
   }
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
-  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
-  if (grid < 1) grid = 1;
   const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
   const bool vec_ok = reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0;  // STG.128 rows
   if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel
-    const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, smem, grid, st);
+    const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, st);
     if (rc != 1) return rc;
   }
-  if (tm && !sums) return launch_variant<C, true, false, NoSpec>(plan, p, smem, grid, st);
-  if (tm && sums) return launch_variant<C, true, true, NoSpec>(plan, p, smem, grid, st);
-  if (!tm && !sums) return launch_variant<C, false, false, NoSpec>(plan, p, smem, grid, st);
-  return launch_variant<C, false, true, NoSpec>(plan, p, smem, grid, st);
+  if (tm && !sums) return launch_variant<C, true, false, NoSpec>(plan, p, st);
+  if (tm && sums) return launch_variant<C, true, true, NoSpec>(plan, p, st);
+  if (!tm && !sums) return launch_variant<C, false, false, NoSpec>(plan, p, st);
+  return launch_variant<C, false, true, NoSpec>(plan, p, st);
 }
-
 
 }  // namespace
 }  // namespace b2a

@@ -141,8 +141,9 @@ def _emit_spec(lib, spec):
     o.append(f"  static constexpr int kStart[{M}] = {{{', '.join(map(str, start))}}};")
     o.append(f"  static constexpr int kLen[{M}] = {{{', '.join(map(str, length))}}};")
     o.append(f"  static constexpr unsigned kWBits[{max(nnz, 1)}] = {{{', '.join('0x%08xu' % b for b in wbits) or '0u'}}};")
-    o.append("  // lane == frame: `pr` is this lane's power-spectrum row; emit4(integral_constant<m0>, a0..a3) per row quad")
-    o.append("  template <class Emit4>")
+    o.append("  // lane == frame: `pr` is this lane's power row inside the exchange buffer (bin k at float 2 * C::sig(k));")
+    o.append("  // emit4(integral_constant<m0>, a0..a3) per row quad")
+    o.append("  template <class C, class Emit4>")
     o.append("  static __device__ __forceinline__ void run(int warp, const float* __restrict__ pr, Emit4&& emit4) {")
     o.append("    switch (warp) {")
     for w in range(NW):
@@ -160,7 +161,7 @@ def _emit_spec(lib, spec):
                     if not users:
                         continue
                     stmts = " ".join(f"a{m} = fmaf(p, {_hexf(fb[m][k])}, a{m});" for m in users)
-                    o.append(f"        {{ const float p = pr[{k}]; {stmts} }}")
+                    o.append(f"        {{ const float p = pr[2 * C::sig({k})]; {stmts} }}")
             for m in range(m0, m1, 4):
                 o.append(f"        emit4(std::integral_constant<int, {m}>{{}}, a{m}, a{m + 1}, a{m + 2}, a{m + 3});")
         o.append("      } break;")
