@@ -105,7 +105,14 @@ typedef struct b2a_frontend_desc {
   int32_t norm_ddof; /* 0 (mx.std) or 1 (sortformer.py:105-108) */
   float norm_eps;
   int32_t out_layout; /* B2A_LAYOUT_* */
-  int32_t reserved[4];
+  /* Kaldi-style PER-FRAME pre-processing (compute_fbank_kaldi, dsp.py:577-676), applied to the first `frame_len`
+   * samples of every frame before the window; all off when zero.  Served by the generic kernel. */
+  int32_t frame_len;    /* samples of a frame that carry signal (window_size); 0 = n_fft.  Dither, DC removal and
+                           per-frame pre-emphasis act on these; the window zero-extends the rest (dsp.py:652-656) */
+  int32_t frame_dc;     /* 1: subtract the frame's own mean (dsp.py:624-626) */
+  float frame_preemph;  /* y[0]=x[0], y[k]=x[k]-a*x[k-1] WITHIN the frame, after DC removal (dsp.py:628-632) */
+  float dither;         /* add dither * N(0,1), drawn independently per frame element (dsp.py:619-622); the stream
+                           is Philox keyed by b2a_forward_args.seed — reproducible, not MLX's generator */
 } b2a_frontend_desc;
 
 /* Arguments of one forward launch over `batch` equal-length clips.
@@ -129,6 +136,7 @@ typedef struct b2a_forward_args {
   double* feat_sums;     /* optional [batch][2*n_mels] double: sum, sum of squares per mel (device) */
   void* workspace;       /* device scratch of b2a_frontend_workspace_bytes() or NULL to let the plan own it */
   size_t workspace_bytes;
+  uint64_t seed;         /* dither stream (used only when desc.dither != 0) */
 } b2a_forward_args;
 
 typedef struct b2a_plan b2a_plan;
@@ -175,6 +183,9 @@ int b2a_frontend_finalize(b2a_plan* plan, const b2a_forward_args* args, int64_t 
  * chunks of clips; synchronous on return.  `args->audio` and `args->out` are HOST pointers here. */
 int b2a_frontend_forward_host(b2a_plan* plan, const b2a_forward_args* args);
 /* debug / parity: dump the windowed-or-raw frame matrix (T, n_fft) float32 for the bit-exact framing test */
+/* compute_deltas_kaldi (dsp.py:439-483): d[f][t] = sum_{k=-n..n} k * x[f][t+k] / (n(n+1)(2n+1)/3), n = (win_length-1)/2,
+ * over `rows` rows of `cols` samples (device pointers); edge = 1 replicates the end samples, 0 pads with zeros. */
+int b2a_deltas(const float* x, float* out, int64_t rows, int64_t cols, int32_t win_length, int32_t edge, void* stream);
 int b2a_frontend_dump_frames(b2a_plan* plan, const b2a_forward_args* args, int apply_window, void* stream);
 /* which kernel family a plan dispatches to: "fast400", "fast512", "generic", "small", ... */
 const char* b2a_plan_kernel_name(const b2a_plan* plan);

@@ -37,7 +37,8 @@ class FrontendDesc(C.Structure):
         ("log_kind", C.c_int32), ("guard_kind", C.c_int32), ("guard_eps", C.c_float),
         ("clamp_kind", C.c_int32), ("clamp_value", C.c_float), ("affine_add", C.c_float),
         ("affine_div", C.c_float), ("norm_kind", C.c_int32), ("norm_ddof", C.c_int32),
-        ("norm_eps", C.c_float), ("out_layout", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("norm_eps", C.c_float), ("out_layout", C.c_int32),
+        ("frame_len", C.c_int32), ("frame_dc", C.c_int32), ("frame_preemph", C.c_float), ("dither", C.c_float),
     ]
 
 
@@ -47,7 +48,7 @@ class ForwardArgs(C.Structure):
         ("valid_length", C.c_int64), ("pad_value", C.c_float), ("batch", C.c_int32),
         ("sample_offset", C.c_int64), ("frame_begin", C.c_int64), ("frame_count", C.c_int64),
         ("out", C.c_void_p), ("out_clip_stride", C.c_int64), ("clip_max", C.c_void_p),
-        ("feat_sums", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("feat_sums", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("seed", C.c_uint64),
     ]
 
 
@@ -86,6 +87,7 @@ SYMBOLS = {
     "b2a_frontend_finalize": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_int64, C.c_void_p]),
     "b2a_frontend_forward_host": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs)]),
     "b2a_frontend_dump_frames": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_int, C.c_void_p]),
+    "b2a_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "b2a_plan_kernel_name": (C.c_char_p, [C.c_void_p]),
     "b2a_istft_create": (C.c_int, [C.POINTER(IstftDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2a_istft_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),

@@ -229,6 +229,10 @@ int b2a_frontend_create(const b2a_frontend_desc* d, const float* h_window, const
     set_error("frontend_create: mel projection of a complex spectrum is undefined");
     return B2A_ERR_INVALID_ARG;
   }
+  if (d->frame_len < 0 || d->frame_len > d->n_fft) {
+    set_error("frontend_create: frame_len=%d outside [0, n_fft=%d]", d->frame_len, d->n_fft);
+    return B2A_ERR_INVALID_ARG;
+  }
   if (d->clamp_kind != B2A_CLAMP_NONE && d->norm_kind != B2A_NORM_NONE) {
     set_error("frontend_create: clamp and normalise together are not a reference configuration");
     return B2A_ERR_UNSUPPORTED;
@@ -254,6 +258,18 @@ int b2a_frontend_create(const b2a_frontend_desc* d, const float* h_window, const
   }
   *out = p;
   return B2A_OK;
+}
+
+int b2a_deltas(const float* x, float* out, int64_t rows, int64_t cols, int32_t win_length, int32_t edge, void* stream) {
+  if (!x || !out || rows < 0 || cols < 0) {
+    set_error("deltas: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  if (win_length < 3) {  // dsp.py:456-457
+    set_error("win_length should be >= 3, got %d", win_length);
+    return B2A_ERR_INVALID_ARG;
+  }
+  return deltas(x, out, rows, cols, win_length, edge, (cudaStream_t)stream);
 }
 
 int b2a_istft_create(const b2a_istft_desc* d, const float* h_window, b2a_plan** out) {

@@ -140,6 +140,7 @@ int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cud
 int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_frames, float* clip_max,
                       const float* tile_min, int tile_frames, const double* feat_sums, cudaStream_t st);
 int init_stats(float* clip_max, double* feat_sums, int batch, int n_mels, cudaStream_t st);
+int deltas(const float* x, float* out, int64_t rows, int64_t cols, int win_length, int edge, cudaStream_t st);
 size_t generic_smem_limit(const b2a_plan* plan);
 // fast (specialised two-stage register FFT) kernels — fast_fwd.cu
 bool fast_frontend_supported(const b2a_plan* plan);

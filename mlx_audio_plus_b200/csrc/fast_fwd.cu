@@ -11,6 +11,7 @@ bool fast_frontend_supported(const b2a_plan* plan) {
   if (getenv("B2A_FORCE_GENERIC")) return false;
   if (d.n_mels <= 0 || d.spec_kind == B2A_SPEC_COMPLEX) return false;
   if (d.affine_div < 0.0f) return false;
+  if (d.frame_dc || d.frame_preemph != 0.0f || d.dither != 0.0f || d.frame_len != 0) return false;  // Kaldi per-frame steps
   const bool v400 = d.n_fft == 400 && d.hop == 160;
   const bool v512 = d.n_fft == 512 && d.hop == 160;
   const bool v1024 = d.n_fft == 1024 && d.hop == 256;

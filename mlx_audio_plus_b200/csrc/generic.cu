@@ -15,6 +15,8 @@
 // the same way, and is written once.  No atomics, no materialised index arrays.
 #include <algorithm>
 
+#include <curand_kernel.h>
+
 #include "common.cuh"
 
 namespace b2a {
@@ -189,6 +191,10 @@ struct FwdParams {
   FftDesc fft;
   int frames_per_tile, tiles_per_clip;
   int dump_frames, dump_windowed;
+  // Kaldi per-frame pre-processing (compute_fbank_kaldi, dsp.py:619-632)
+  int frame_len, frame_dc;
+  float frame_preemph, dither;
+  unsigned long long seed;
 };
 
 // global sample (after right-pad + preemphasis) at source index s >= 0
@@ -246,16 +252,79 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
     }
 
     // ---- window + pack two real frames per complex sequence ------------------------------------------
-    for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
-      const int pr = i / N, k = i - pr * N;
-      const float w = p.window[k];
-      const int fa = 2 * pr, fb = 2 * pr + 1;
-      const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
-      const float b = fb < nf ? xs[fb * hop + k] * w : 0.0f;
-      bufA[i] = make_float2(a, b);
+    float2* Z;
+    if (p.frame_dc || p.frame_preemph != 0.0f || p.dither != 0.0f) {
+      // Kaldi front-end (dsp.py:619-656): per FRAME, on its first W = frame_len samples: + dither * N(0,1)
+      // (independent per frame element), - the frame's own mean, pre-emphasis within the frame (sample 0 kept),
+      // then the window (zero beyond W).  Raw frames go to bufA, the finished ones to bufB.
+      const int W = p.frame_len > 0 ? p.frame_len : N;
+      for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
+        const int pr = i / N, k = i - pr * N;
+        const int fa = 2 * pr, fb = 2 * pr + 1;
+        float a = (fa < nf && k < W) ? xs[fa * hop + k] : 0.0f;
+        float b = (fb < nf && k < W) ? xs[fb * hop + k] : 0.0f;
+        if (p.dither != 0.0f && k < W) {
+          curandStatePhilox4_32_10_t rs;  // counter-based: (seed, frame pair, sample) -> two normals, O(1) set-up
+          curand_init(p.seed, (unsigned long long)clip_i * (unsigned long long)((p.geo.num_frames + 1) / 2 + 1) +
+                                  (unsigned long long)((t0 >> 1) + pr), (unsigned long long)k, &rs);
+          const float2 g = curand_normal2(&rs);
+          a += p.dither * g.x;
+          b += p.dither * g.y;
+        }
+        bufA[i] = make_float2(a, b);
+      }
+      __syncthreads();
+      float2* means = reinterpret_cast<float2*>(xs);  // the sample span is consumed: reuse it for the frame means
+      if (p.frame_dc) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int pr = warp; pr < PAIRS; pr += nw) {
+          float sa = 0.0f, sb = 0.0f;
+          for (int k = lane; k < W; k += 32) {
+            const float2 v = bufA[(size_t)pr * N + k];
+            sa += v.x;
+            sb += v.y;
+          }
+          for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+          }
+          if (lane == 0) means[pr] = make_float2(sa / (float)W, sb / (float)W);
+        }
+      }
+      __syncthreads();
+      const float pe = p.frame_preemph;
+      for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
+        const int pr = i / N, k = i - pr * N;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (k < W) {
+          const float2 m = p.frame_dc ? means[pr] : make_float2(0.0f, 0.0f);
+          const float2 x = bufA[i];
+          v = make_float2(x.x - m.x, x.y - m.y);
+          if (pe != 0.0f && k > 0) {  // separately rounded multiply and subtract, as the reference's array expression
+            const float2 xp = bufA[i - 1];
+            v.x = __fsub_rn(v.x, __fmul_rn(pe, xp.x - m.x));
+            v.y = __fsub_rn(v.y, __fmul_rn(pe, xp.y - m.y));
+          }
+          const float w = p.window[k];
+          v.x *= w;
+          v.y *= w;
+        }
+        bufB[i] = v;
+      }
+      __syncthreads();
+      Z = run_fft(p.fft, bufB, bufA, p.tw, PAIRS);
+    } else {
+      for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
+        const int pr = i / N, k = i - pr * N;
+        const float w = p.window[k];
+        const int fa = 2 * pr, fb = 2 * pr + 1;
+        const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
+        const float b = fb < nf ? xs[fb * hop + k] * w : 0.0f;
+        bufA[i] = make_float2(a, b);
+      }
+      __syncthreads();
+      Z = run_fft(p.fft, bufA, bufB, p.tw, PAIRS);
     }
-    __syncthreads();
-    float2* Z = run_fft(p.fft, bufA, bufB, p.tw, PAIRS);
     float2* other = (Z == bufA) ? bufB : bufA;
 
     // ---- Hermitian separation ------------------------------------------------------------------------
@@ -505,6 +574,26 @@ __global__ void __launch_bounds__(256) normalise_kernel(const FinParams p) {
   }
 }
 
+// compute_deltas_kaldi (dsp.py:439-483): a (2n+1)-tap antisymmetric FIR along time, edge samples replicated (or zeros)
+__global__ void __launch_bounds__(256) deltas_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows,
+                                                     int64_t cols, int n, float denom, int edge) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, t = i - r * cols;
+    const float* row = x + r * cols;
+    float acc = 0.0f;
+    for (int k = -n; k <= n; ++k) {  // ascending tap order, as mx.sum(window * kernel_weights) over the window axis
+      int64_t j = t + k;
+      float v;
+      if (j < 0) v = edge ? row[0] : 0.0f;
+      else if (j >= cols) v = edge ? row[cols - 1] : 0.0f;
+      else v = row[j];
+      acc += v * (float)k;
+    }
+    out[i] = acc / denom;
+  }
+}
+
 __global__ void init_stats_kernel(float* clip_max, double* feat_sums, int batch, int n_sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) {
@@ -688,6 +777,11 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   p.mel_off = plan->mel.d_off;
   p.mel_w = plan->mel.d_w;
   p.fft = make_fft_desc(plan);
+  p.frame_len = d.frame_len;
+  p.frame_dc = d.frame_dc;
+  p.frame_preemph = d.frame_preemph;
+  p.dither = d.dither;
+  p.seed = a->seed;
   const int ft = generic_tile_frames(plan, a);
   if (ft == 0) {
     set_error("n_fft=%d too large for the generic kernel", d.n_fft);
@@ -741,6 +835,17 @@ int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cud
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * 2);
   if (grid < 1) grid = 1;
   frontend_generic_kernel<<<grid, kThreads, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int deltas(const float* x, float* out, int64_t rows, int64_t cols, int win_length, int edge, cudaStream_t st) {
+  const int n = (win_length - 1) / 2;
+  const float denom = (float)((double)n * (n + 1) * (2 * n + 1) / 3.0);
+  const int64_t total = rows * cols;
+  if (total <= 0) return B2A_OK;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  deltas_kernel<<<grid, 256, 0, st>>>(x, out, rows, cols, n, denom, edge);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }

@@ -228,6 +228,7 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
 bool small_stft_supported(const b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
   if (getenv("B2A_FORCE_GENERIC")) return false;
+  if (d.frame_dc || d.frame_preemph != 0.0f || d.dither != 0.0f || d.frame_len != 0) return false;
   return (d.n_fft == 20 || d.n_fft == 16) && d.n_mels == 0 && d.spec_kind == B2A_SPEC_COMPLEX;
 }
 

@@ -30,6 +30,12 @@ __all__ = [
     "istft",
     "ISTFTCache",
     "mel_filters",
+    # Kaldi-compatible features (reference dsp.py:439-676)
+    "compute_deltas_kaldi",
+    "mel_scale_kaldi",
+    "inverse_mel_scale_kaldi",
+    "get_mel_banks_kaldi",
+    "compute_fbank_kaldi",
 ]
 
 
@@ -231,3 +237,149 @@ class ISTFTCache:
     def cache_info(self):
         nb, pi = len(self.norm_buffer_cache), len(self.position_cache)
         return {"norm_buffers": nb, "position_indices": pi, "total_cached_items": nb + pi}
+
+
+# ---- Kaldi-compatible features: reference dsp.py:439-676 -------------------------------------------------------
+def compute_deltas_kaldi(specgram, win_length: int = 5, mode: str = "edge"):
+    """Delta coefficients along the last axis, d_t = sum_n n (c_{t+n} - c_{t-n}) / (2 sum_n n^2); reference
+    dsp.py:439-483 (a Python loop over time steps there, one launch here)."""
+    if win_length < 3:
+        raise ValueError(f"win_length should be >= 3, got {win_length}")  # dsp.py:456-457
+    ing = ingest(specgram, "float32")
+    shape = tuple(int(v) for v in ing.data.shape)
+    cols = shape[-1]
+    rows = int(np.prod(shape[:-1])) if len(shape) > 1 else 1
+    edge = 1 if mode == "edge" else 0
+    if ing.on_device:
+        import torch
+
+        x = ing.data.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(ing.device):
+            st = torch.cuda.current_stream(ing.device).cuda_stream
+            _L.check(_L.lib.b2a_deltas(x.data_ptr(), out.data_ptr(), rows, cols, int(win_length), edge, _C.c_void_p(st)))
+        return emit(ing, out)
+    import torch
+
+    dev = _device_index(None)
+    with torch.cuda.device(dev):
+        x = torch.from_numpy(np.ascontiguousarray(ing.data)).cuda(dev)
+        out = torch.empty_like(x)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _L.check(_L.lib.b2a_deltas(x.data_ptr(), out.data_ptr(), rows, cols, int(win_length), edge, _C.c_void_p(st)))
+        return emit(ing, out.cpu().numpy())
+
+
+def mel_scale_kaldi(freq):
+    """1127 ln(1 + f/700) in float32 (reference dsp.py:486-488)."""
+    f = np.asarray(freq, dtype=np.float32)
+    return (np.float32(1127.0) * np.log(np.float32(1.0) + f / np.float32(700.0))).astype(np.float32).view(DspArray)
+
+
+def inverse_mel_scale_kaldi(mel_freq):
+    """700 (exp(m/1127) - 1) in float32 (reference dsp.py:491-493)."""
+    m = np.asarray(mel_freq, dtype=np.float32)
+    return (np.float32(700.0) * (np.exp(m / np.float32(1127.0)) - np.float32(1.0))).astype(np.float32).view(DspArray)
+
+
+def _next_power_of_2(x: int) -> int:
+    return 1 if x == 0 else 2 ** (x - 1).bit_length()  # dsp.py:496-498
+
+
+def get_mel_banks_kaldi(num_bins: int, window_length_padded: int, sample_freq: float, low_freq: float,
+                        high_freq: float):
+    """Kaldi mel filterbank (num_bins, n_fft/2) and the centre frequencies; reference dsp.py:526-574 (float32
+    array arithmetic in the reference's order; the band edges are Python floats there)."""
+    assert num_bins > 3, "Must have at least 3 mel bins"
+    assert window_length_padded % 2 == 0
+    f32 = np.float32
+    num_fft_bins = window_length_padded // 2
+    nyquist = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyquist
+    assert (0.0 <= low_freq < nyquist) and (0.0 < high_freq <= nyquist)
+    fft_bin_width = sample_freq / window_length_padded
+    mel_low = float(mel_scale_kaldi(f32(low_freq)))
+    mel_high = float(mel_scale_kaldi(f32(high_freq)))
+    delta = (mel_high - mel_low) / (num_bins + 1)
+    idx = np.arange(num_bins, dtype=np.int32).reshape(-1, 1)
+    left = (f32(mel_low) + idx.astype(f32) * f32(delta)).astype(f32)
+    center = (f32(mel_low) + (idx.astype(f32) + f32(1.0)) * f32(delta)).astype(f32)
+    right = (f32(mel_low) + (idx.astype(f32) + f32(2.0)) * f32(delta)).astype(f32)
+    center_freqs = np.asarray(inverse_mel_scale_kaldi(center))
+    mel = np.asarray(mel_scale_kaldi(f32(fft_bin_width) * np.arange(num_fft_bins, dtype=np.int32).astype(f32))).reshape(1, -1)
+    up = ((mel - left) / (center - left)).astype(f32)
+    down = ((right - mel) / (right - center)).astype(f32)
+    bins = np.maximum(np.zeros(1, f32), np.minimum(up, down)).astype(f32)
+    return bins.view(DspArray), center_freqs.squeeze().view(DspArray)
+
+
+def _kaldi_window(win_type: str, size: int) -> np.ndarray:
+    # float32 array expressions of dsp.py:634-648 (NOT the float64 windows of hanning()/hamming())
+    f32 = np.float32
+    n = np.arange(size, dtype=np.int32).astype(f32)
+    arg = (f32(2.0) * f32(np.pi) * n / f32(size - 1)).astype(f32)
+    if win_type == "hamming":
+        return (f32(0.54) - f32(0.46) * np.cos(arg)).astype(f32)
+    if win_type == "hanning":
+        return (f32(0.5) - f32(0.5) * np.cos(arg)).astype(f32)
+    if win_type == "povey":
+        hann = (f32(0.5) - f32(0.5) * np.cos(arg)).astype(f32)
+        return np.power(hann, f32(0.85)).astype(f32)
+    return np.ones(size, f32)
+
+
+def compute_fbank_kaldi(waveform, sample_rate: int = 48000, win_len: int = 1920, win_inc: int = 384,
+                        num_mels: int = 60, win_type: str = "hamming", preemphasis: float = 0.97, dither: float = 1.0,
+                        snip_edges: bool = True, low_freq: float = 20.0, high_freq: float = 0.0, *, seed: int = 0):
+    """Kaldi-compatible log mel filterbank features (time, num_mels); reference dsp.py:577-676.  Framing, dither,
+    per-frame DC removal, per-frame pre-emphasis, window, zero-extension to the next power of two, real FFT, power,
+    mel projection and ln(max(., 1e-8)) run in ONE kernel.  `dither` != 0 draws N(0,1) per frame element from a
+    Philox stream keyed by `seed` (the reference draws from MLX's global generator: equal in distribution only)."""
+    ing = ingest(waveform, "float32")
+    if ing.data.ndim == 2:
+        ing.data = ing.data[0]  # dsp.py:607-608
+    frame_length_ms = win_len / sample_rate * 1000
+    frame_shift_ms = win_inc / sample_rate * 1000
+    shift = int(sample_rate * frame_shift_ms * 0.001)
+    size = int(sample_rate * frame_length_ms * 0.001)
+    n_fft = _next_power_of_2(size)
+    num_samples = int(ing.data.shape[0])
+    x = ing.data
+    if snip_edges:  # dsp.py:507-510
+        m = 0 if num_samples < size else 1 + (num_samples - size) // shift
+    else:  # dsp.py:511-521: reflect on the left without the edge sample, on the right INCLUDING it
+        m = (num_samples + shift // 2) // shift
+        pad = size // 2 - shift // 2
+        if ing.on_device:
+            import torch
+
+            flip = lambda v: torch.flip(v, dims=(0,))
+            cat = torch.cat
+        else:
+            flip = lambda v: v[::-1]
+            cat = np.concatenate
+        if pad > 0:
+            left = flip(x[1 : pad + 1])
+            right = flip(x[num_samples - pad :]) if pad > 1 else flip(x[1:])
+            x = cat([left, x, right])
+        else:
+            x = cat([x[-pad:], flip(x)])
+    if m <= 0:
+        return emit(ing, np.zeros((0, num_mels), np.float32)) if not ing.on_device else _empty_like_device(ing, num_mels)
+    bins, _ = get_mel_banks_kaldi(num_mels, n_fft, float(sample_rate), low_freq, high_freq)
+    fb = np.pad(np.asarray(bins), [(0, 0), (0, 1)])  # dsp.py:668
+    plan = cached_plan(FrontendPlan, _device_index(ing), _kaldi_window(win_type, size), fb, n_fft=n_fft, hop=shift,
+                       center=False, spec_kind=_L.SPEC_POWER, log_kind=_L.LOG_LN, guard_kind=_L.GUARD_MAX,
+                       guard_eps=1e-8, frame_len=size, frame_dc=True, frame_preemph=float(preemphasis),
+                       dither=float(dither))
+    ing.data = x.reshape(1, -1) if not ing.on_device else x.reshape(1, -1).contiguous()
+    length = int(ing.data.shape[1]) + (n_fft - size)  # the zero extension of the LAST frame is virtual padding
+    out = plan.run(ing, length=length, frame_count=m, seed=seed)
+    return emit(ing, out[0])
+
+
+def _empty_like_device(ing, num_mels):
+    import torch
+
+    return torch.zeros((0, num_mels), dtype=torch.float32, device=ing.device)

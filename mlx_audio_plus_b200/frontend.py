@@ -49,7 +49,7 @@ class FrontendPlan(_PlanBase):
                  spec_kind=L.SPEC_COMPLEX, spec_eps=0.0, filterbank=None, log_kind=L.LOG_NONE,
                  guard_kind=L.GUARD_NONE, guard_eps=0.0, clamp_kind=L.CLAMP_NONE, clamp_value=0.0,
                  affine_add=0.0, affine_div=0.0, norm_kind=L.NORM_NONE, norm_ddof=0, norm_eps=0.0,
-                 out_layout=L.LAYOUT_TM):
+                 out_layout=L.LAYOUT_TM, frame_len=0, frame_dc=False, frame_preemph=0.0, dither=0.0):
         super().__init__()
         window = np.ascontiguousarray(window, dtype=np.float32)
         if center and pad_mode not in ("reflect", "constant"):
@@ -70,6 +70,8 @@ class FrontendPlan(_PlanBase):
         d.affine_add, d.affine_div = float(affine_add), float(affine_div)
         d.norm_kind, d.norm_ddof, d.norm_eps = int(norm_kind), int(norm_ddof), float(norm_eps)
         d.out_layout = int(out_layout)
+        d.frame_len, d.frame_dc = int(frame_len), int(bool(frame_dc))
+        d.frame_preemph, d.dither = float(frame_preemph), float(dither)
         self.desc = d
         self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
         self.n_out = d.n_mels if d.n_mels > 0 else self.n_freqs
@@ -99,13 +101,16 @@ class FrontendPlan(_PlanBase):
         return a
 
     # -- execution --------------------------------------------------------------------------------------
-    def run(self, ing: Ingested, *, length=None, pad_value=0.0):
+    def run(self, ing: Ingested, *, length=None, pad_value=0.0, frame_count=None, seed=0):
         """ing.data: (B, L) float32 (host ndarray or torch CUDA tensor).  `length` > L adds virtual right
-        padding with pad_value (whisper `padding`, parakeet pad_to).  Returns (B, ...) in the same place."""
+        padding with pad_value (whisper `padding`, parakeet pad_to).  `frame_count` keeps only the first frames
+        (Kaldi snip_edges=False framing); `seed` keys the dither stream.  Returns (B, ...) in the same place."""
         x = ing.data
         B, Lx = int(x.shape[0]), int(x.shape[1])
         length = Lx if length is None else int(length)
         T = self.out_frames(length)
+        if frame_count is not None:
+            T = min(T, int(frame_count))
         shape = self.out_shape(B, T)
         if ing.on_device:
             import torch
@@ -113,13 +118,17 @@ class FrontendPlan(_PlanBase):
             with torch.cuda.device(ing.device):
                 out = torch.empty(shape, dtype=torch.complex64 if self.complex_out else torch.float32, device=ing.device)
                 st = torch.cuda.current_stream(ing.device).cuda_stream
-                a = self._args(x.data_ptr(), Lx, length, Lx, B, out.data_ptr(), pad_value=pad_value)
-                L.check(L.lib.b2a_frontend_forward(self._h, C.byref(a), C.c_void_p(st)))
+                a = self._args(x.data_ptr(), Lx, length, Lx, B, out.data_ptr(), pad_value=pad_value, frame_count=T)
+                a.seed = int(seed)
+                if T > 0:
+                    L.check(L.lib.b2a_frontend_forward(self._h, C.byref(a), C.c_void_p(st)))
             return out
         _current_device_and_stream()  # fail loudly without a GPU
         out = np.empty(shape, dtype=np.complex64 if self.complex_out else np.float32)
-        a = self._args(x.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value)
-        L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
+        a = self._args(x.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value, frame_count=T)
+        a.seed = int(seed)
+        if T > 0:
+            L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
         return out
 
     # -- split form for frame-range sharding ------------------------------------------------

@@ -129,10 +129,43 @@ def hift_goldens(mx, R):
     np.savez_compressed(os.path.join(OUT, "refshim_hift.npz"), **g)
 
 
+def kaldi_goldens(mx, R):
+    """tests/golden/refshim_kaldi.npz: the Kaldi-compatible part of mlx_audio/dsp.py (439-676), dither = 0."""
+    A = lambda v: np.asarray(v)
+    dsp = R["dsp"]
+    g = {}
+    x48 = (synth(401, 30000, 48000) * 8000.0).astype(np.float32)  # int16-scale amplitudes, as MossFormer2 feeds
+    x16 = (synth(402, 9000, 16000) * 8000.0 + 37.5).astype(np.float32)  # with a DC offset
+    g["x48"], g["x16"] = x48, x16
+    cases = {
+        "moss": (x48, dict(sample_rate=48000, win_len=1920, win_inc=384, num_mels=60, win_type="hamming", preemphasis=0.97)),
+        "povey16": (x16, dict(sample_rate=16000, win_len=400, win_inc=160, num_mels=80, win_type="povey", preemphasis=0.97)),
+        "hann_nopre": (x16, dict(sample_rate=16000, win_len=400, win_inc=160, num_mels=24, win_type="hanning",
+                                 preemphasis=0.0, low_freq=0.0, high_freq=-400.0)),
+        "rect_noclip": (x16, dict(sample_rate=16000, win_len=512, win_inc=128, num_mels=40, win_type="rectangular",
+                                  preemphasis=0.5, snip_edges=False)),
+        "short": (x16[:300], dict(sample_rate=16000, win_len=400, win_inc=160, num_mels=23)),
+    }
+    for name, (x, kw) in cases.items():
+        g[f"fbank|{name}"] = A(dsp.compute_fbank_kaldi(mx.array(x), dither=0.0, **kw))
+    bins, cf = dsp.get_mel_banks_kaldi(60, 2048, 48000.0, 20.0, 0.0)
+    g["banks|60_2048"], g["banks|60_2048|cf"] = A(bins), A(cf)
+    bins, cf = dsp.get_mel_banks_kaldi(80, 512, 16000.0, 20.0, -400.0)
+    g["banks|80_512"], g["banks|80_512|cf"] = A(bins), A(cf)
+    f = g["fbank|moss"].T.copy()
+    g["deltas|edge5"] = A(dsp.compute_deltas_kaldi(mx.array(f), win_length=5))
+    g["deltas|const9"] = A(dsp.compute_deltas_kaldi(mx.array(f), win_length=9, mode="constant"))
+    g["deltas|3d"] = A(dsp.compute_deltas_kaldi(mx.array(f[:24].reshape(2, 12, -1)), win_length=3))
+    np.savez_compressed(os.path.join(OUT, "refshim_kaldi.npz"), **g)
+
+
 def main():
     mx, R = _load_reference()
     if "--hift-only" in sys.argv:
         hift_goldens(mx, R)
+        return
+    if "--kaldi-only" in sys.argv:
+        kaldi_goldens(mx, R)
         return
     dsp = R["dsp"]
     os.makedirs(OUT, exist_ok=True)
@@ -315,6 +348,7 @@ def main():
     g["sortformer|y"] = A(R["sortformer"].extract_mel_features(mx.array(x)))
     np.savez_compressed(os.path.join(OUT, "refshim_models.npz"), **g)
     hift_goldens(mx, R)
+    kaldi_goldens(mx, R)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

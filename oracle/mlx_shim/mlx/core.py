@@ -46,6 +46,18 @@ class array(_np.ndarray):
                 dtype = a.dtype
         return _np.array(a, dtype=dtype).view(cls)
 
+    # MLX promotes `integer array (op) python float` to float32; NumPy would go to float64.  (Needed by the Kaldi
+    # mel banks, dsp.py:558-560: `mel_low_freq + bin_idx * mel_freq_delta` with an int32 bin_idx.)
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method == "__call__" and any(isinstance(v, float) for v in inputs):
+            inputs = tuple(_np.asarray(v, dtype=_np.float32) if isinstance(v, _np.ndarray) and v.dtype.kind in "iu" else v
+                           for v in inputs)
+        inputs = tuple(_np.asarray(v) if isinstance(v, array) else v for v in inputs)
+        if "out" in kwargs:
+            kwargs["out"] = tuple(_np.asarray(v) if isinstance(v, array) else v for v in kwargs["out"])
+        r = getattr(ufunc, method)(*inputs, **kwargs)
+        return r.view(array) if isinstance(r, _np.ndarray) else r
+
     # mx.array method surface used by the reference
     def abs(self):
         return _np.abs(self).view(array)

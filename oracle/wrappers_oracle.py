@@ -291,3 +291,82 @@ def hift_istft(magnitude, phase, n_fft, hop, window, clip_min_zero=False):
     out = (out / wsum[None, :]).astype(F32)
     p = n_fft // 2
     return out[:, p:-p]
+
+
+# -- Kaldi-compatible features: dsp.py:439-676 (compute_deltas_kaldi, mel banks, compute_fbank_kaldi with dither=0) --
+def kaldi_deltas(specgram, win_length=5, mode="edge"):  # dsp.py:439-483
+    x = np.asarray(specgram, F32)
+    shape = x.shape
+    x = x.reshape(-1, shape[-1])
+    n = (win_length - 1) // 2
+    denom = F32(float(n * (n + 1) * (2 * n + 1)) / 3.0)
+    padded = np.pad(x, [(0, 0), (n, n)], mode="edge" if mode == "edge" else "constant")
+    k = np.arange(-n, n + 1).astype(F32)
+    out = np.zeros_like(x)
+    for i in range(x.shape[1]):
+        out[:, i] = (padded[:, i : i + win_length] * k).sum(axis=1, dtype=F32) / denom
+    return out.reshape(shape)
+
+
+def kaldi_mel_scale(f):  # dsp.py:486-488
+    return (F32(1127.0) * np.log(F32(1.0) + np.asarray(f, F32) / F32(700.0))).astype(F32)
+
+
+def kaldi_inverse_mel_scale(m):  # dsp.py:491-493
+    return (F32(700.0) * (np.exp(np.asarray(m, F32) / F32(1127.0)) - F32(1.0))).astype(F32)
+
+
+def kaldi_mel_banks(num_bins, n_fft, sample_freq, low_freq, high_freq):  # dsp.py:526-574
+    nyq = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyq
+    width = sample_freq / n_fft
+    lo, hi = float(kaldi_mel_scale(low_freq)), float(kaldi_mel_scale(high_freq))
+    d = (hi - lo) / (num_bins + 1)
+    i = np.arange(num_bins).reshape(-1, 1).astype(F32)
+    left, center, right = (F32(lo) + i * F32(d)), (F32(lo) + (i + F32(1)) * F32(d)), (F32(lo) + (i + F32(2)) * F32(d))
+    mel = kaldi_mel_scale(F32(width) * np.arange(n_fft // 2).astype(F32)).reshape(1, -1)
+    up, down = (mel - left) / (center - left), (right - mel) / (right - center)
+    return np.maximum(F32(0), np.minimum(up, down)).astype(F32), kaldi_inverse_mel_scale(center).squeeze()
+
+
+def kaldi_fbank(waveform, sample_rate=48000, win_len=1920, win_inc=384, num_mels=60, win_type="hamming",
+                preemphasis=0.97, snip_edges=True, low_freq=20.0, high_freq=0.0):  # dsp.py:577-676, dither = 0
+    x = np.asarray(waveform, F32)
+    if x.ndim == 2:
+        x = x[0]
+    shift = int(sample_rate * (win_inc / sample_rate * 1000) * 0.001)
+    size = int(sample_rate * (win_len / sample_rate * 1000) * 0.001)
+    n_fft = 1 if size == 0 else 2 ** (size - 1).bit_length()
+    n = x.shape[0]
+    if snip_edges:  # dsp.py:507-510
+        if n < size:
+            return np.zeros((0, num_mels), F32)
+        m = 1 + (n - size) // shift
+    else:  # dsp.py:511-521
+        m = (n + shift // 2) // shift
+        pad = size // 2 - shift // 2
+        if pad > 0:
+            right = x[-1 : -pad - 1 : -1] if pad > 1 else x[-1:0:-1]
+            x = np.concatenate([x[1 : pad + 1][::-1], x, right])
+        else:
+            x = np.concatenate([x[-pad:], x[::-1]])
+    fr = np.lib.stride_tricks.as_strided(x, shape=(m, size), strides=(4 * shift, 4)).astype(F32)
+    fr = fr - fr.mean(axis=1, keepdims=True, dtype=F32)  # dsp.py:624-626
+    if preemphasis != 0.0:  # dsp.py:628-632
+        fr = np.concatenate([fr[:, :1], fr[:, 1:] - F32(preemphasis) * fr[:, :-1]], axis=1).astype(F32)
+    k = np.arange(size).astype(F32)
+    arg = F32(2) * F32(np.pi) * k / F32(size - 1)
+    if win_type == "hamming":
+        w = F32(0.54) - F32(0.46) * np.cos(arg)
+    elif win_type == "hanning":
+        w = F32(0.5) - F32(0.5) * np.cos(arg)
+    elif win_type == "povey":
+        w = np.power(F32(0.5) - F32(0.5) * np.cos(arg), F32(0.85))
+    else:
+        w = np.ones(size, F32)
+    fr = (fr * w.astype(F32)).astype(F32)
+    spec = np.abs(np.fft.rfft(fr, n=n_fft, axis=1).astype(np.complex64)) ** F32(2.0)  # dsp.py:659-660
+    bins, _ = kaldi_mel_banks(num_mels, n_fft, float(sample_rate), low_freq, high_freq)
+    fb = np.pad(bins, [(0, 0), (0, 1)])
+    return np.log(np.maximum(spec.astype(F32) @ fb.T, F32(1e-8))).astype(F32)

@@ -251,6 +251,53 @@ def test_polar_istft_1024_matches_complex_path():
     assert_wave_close(y, ref)
 
 
+# ---- Kaldi-compatible features (dsp.py:439-676) -------------------------------------------------
+@pytest.mark.parametrize("where", ["cuda", "numpy"])
+def test_kaldi_fbank_and_deltas_parity(golden, where):
+    """compute_fbank_kaldi (one fused launch: framing, per-frame DC removal and pre-emphasis, float32 Kaldi window,
+    zero-extension to 2^k, FFT, power, Kaldi mel banks, ln(max(., 1e-8))) and compute_deltas_kaldi against fixtures
+    produced by the reference's own code.  2e-4 absolute on the log energies (values ~ 5..20)."""
+    from mlx_audio_plus_b200 import dsp
+    from test_oracle_golden import KALDI_CASES
+
+    g = golden("kaldi")
+    put = dev if where == "cuda" else (lambda a: a)
+    for name, (xk, kw) in KALDI_CASES.items():
+        y = host(dsp.compute_fbank_kaldi(put(g[xk]), dither=0.0, **kw))
+        ref = g[f"fbank|{name}"]
+        assert y.shape == ref.shape, name
+        assert np.abs(y - ref).max() <= 2e-4, (name, np.abs(y - ref).max())
+    assert tuple(dsp.compute_fbank_kaldi(put(g["x16"][:300]), sample_rate=16000, win_len=400, win_inc=160, num_mels=23,
+                                         dither=0.0).shape) == (0, 23)
+    f = g["fbank|moss"].T.copy()
+    for key, x, kw in (("deltas|edge5", f, dict(win_length=5)), ("deltas|const9", f, dict(win_length=9, mode="constant")),
+                       ("deltas|3d", f[:24].reshape(2, 12, -1), dict(win_length=3))):
+        d = host(dsp.compute_deltas_kaldi(put(x), **kw))
+        assert d.shape == g[key].shape and np.abs(d - g[key]).max() <= 1e-5 * np.abs(g[key]).max()
+
+
+def test_kaldi_dither_is_seeded_noise_of_the_right_size():
+    """dither != 0 cannot match MLX's generator; it must be reproducible per seed, differ across seeds, and perturb
+    the frames like N(0, dither^2): on silence the mean frame energy after the Hamming window is dither^2 * sum(w^2)
+    (minus the removed DC), which the flat part of the mel output reflects."""
+    from mlx_audio_plus_b200 import dsp
+
+    x = dev(np.zeros(48000, np.float32))
+    kw = dict(sample_rate=16000, win_len=400, win_inc=160, num_mels=40, win_type="hamming", preemphasis=0.0)
+    a = host(dsp.compute_fbank_kaldi(x, dither=1.0, seed=11, **kw))
+    b = host(dsp.compute_fbank_kaldi(x, dither=1.0, seed=11, **kw))
+    c = host(dsp.compute_fbank_kaldi(x, dither=1.0, seed=12, **kw))
+    z = host(dsp.compute_fbank_kaldi(x, dither=0.0, **kw))
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.allclose(z, np.log(1e-8))  # silence without dither: the floor everywhere
+    # white noise of variance 1 through window w and a triangular mel filter with weights t_k: E[mel] = sum(w^2) * sum_k t_k
+    w = dsp._kaldi_window("hamming", 400)
+    fb = np.pad(np.asarray(dsp.get_mel_banks_kaldi(40, 512, 16000.0, 20.0, 0.0)[0]), [(0, 0), (0, 1)])
+    expect = np.log((w.astype(np.float64) ** 2).sum() * fb.sum(axis=1))
+    got = np.log(np.exp(a.astype(np.float64)).mean(axis=0))
+    assert np.abs(got[5:] - expect[5:]).max() <= 0.15, np.abs(got - expect).max()  # low bins lose the removed DC
+
+
 # ---- model front-ends ---------------------------------------------------------------------------------
 def test_whisper_parity(golden):
     from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
