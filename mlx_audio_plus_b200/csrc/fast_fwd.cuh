@@ -516,6 +516,55 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
   };
 
+  // ---- mel, phase B of the generated-mel kernels: LANE = ROW QUAD (code shared by every warp).  Per frame: one
+  // LDS.128 from the staging tile, guard + MUFU log2 + folded base-change / affine FFMA on four values, one coalesced
+  // STG.128 into the (T, M) output, FMNMX3 for the tile max / min; per-feature sums stay in registers across tiles.
+  // It runs one barrier interval LATE — together with stage 1 of the NEXT tile (Y has its own space): one barrier
+  // fewer per tile, and its load -> store latency chains overlap the butterflies.
+  auto phase_b = [&](int pclip, int ptile, int pnf) {
+    if (SPEC && want_sums && sum_clip != pclip) {
+      flush_sums();
+      sum_clip = pclip;
+    }
+    float lmax = -INFINITY, lmin = INFINITY;
+    float* const o = p.out + (int64_t)pclip * p.out_clip_stride;
+    float4* const orow = reinterpret_cast<float4*>(o + (int64_t)ptile * C::FT * MS::M) + lane;
+    const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
+    if (lane < QL) {
+#pragma unroll 1
+      for (int f = warp; f < pnf; f += C::WARPS) {
+        float4 v = yb[f * (YP / 4)];
+        float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float a = fmaxf(e[c] + guard_add, guard_floor);
+          const float y = use_log ? lg2_approx(a) : a;
+          e[c] = fmaf(y, y_mul, y_add);
+          if (WANT_SUMS) {
+            d1[c % NS] += (double)e[c];
+            d2[c % NS] += (double)e[c] * (double)e[c];
+          }
+        }
+        orow[f * (MS::M / 4)] = v;
+        lmax = fmax3(lmax, v.x, v.y);
+        lmin = fmin3(lmin, v.x, v.y);
+        lmax = fmax3(lmax, v.z, v.w);
+        lmin = fmin3(lmin, v.z, v.w);
+      }
+    }
+    if (want_max) {  // one REDUX each on order-preserving integer keys instead of ten dependent shuffles
+      const int kmax = __reduce_max_sync(0xffffffffu, float_key(lmax));
+      const int kmin = __reduce_min_sync(0xffffffffu, float_key(lmin));
+      if (lane == 0) {
+        red_max[warp] = key_float(kmax);
+        red_min[warp] = key_float(kmin);
+      }
+      red_clip = pclip;   // folded by thread 0 after the next barrier
+      red_tile = ptile;
+    }
+  };
+  int prev_clip = -1, prev_tile = 0, prev_nf = 0;  // tile whose staged rows wait in Y
+
 #ifdef B2A_PHASE_CLOCKS  // development builds: per-phase cycle counters (thread 0's view), dumped by B2A_CLOCKS=file
   long long clk_prev = 0;
   long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -547,9 +596,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       fill_tile<C>(p, xs, fc, clip_i, tile_i);
     }
     cp_async_wait_all();
-    __syncthreads();  // xs ready; previous tile's Y fully written out
+    __syncthreads();  // xs ready; run-time-table kernels: previous tile's Y written out; generated: Y(prev) complete
     tick(0);
-    fold_red();
+    if (SPEC && prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
 
     // per-CTA running per-mel sums: flush when the clip changes
     if (!SPEC && want_sums && s_cur_clip != clip_i) {
@@ -563,11 +612,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       if (threadIdx.x == 0) s_cur_clip = clip_i;
       __syncthreads();
     }
-    if (SPEC && want_sums && sum_clip != clip_i) {
-      flush_sums();
-      sum_clip = clip_i;
-    }
-
     // ---- stage 1 ----------------------------------------------------------------------------------------
 #pragma unroll 1
     for (int rr = 0; rr < C::RPW; ++rr) {
@@ -602,6 +646,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
     __syncthreads();  // E complete, xs free
     tick(1);
+    fold_red();  // the per-warp max / min of the rows phase B has just written
 
     // prefetch the next tile's samples while stage 2 / mel run
     if (PREFETCH && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
@@ -688,48 +733,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
           yl[m / 4] = make_float4(a0, a1, a2, a3);
         });
       }
-      __syncthreads();  // Y complete
+      prev_clip = clip_i;  // phase B of this tile runs after the next barrier, next to stage 1 of the next tile
+      prev_tile = tile_i;
+      prev_nf = nf;
       tick(3);
-      // ---- mel, phase B: LANE = ROW QUAD (code shared by every warp).  Per frame: one LDS.128, guard + MUFU
-      // log2 + folded base-change / affine FFMA on four values, one coalesced STG.128 into the (T, M) output,
-      // FMNMX3 for the tile max / min; per-feature sums stay in registers across tiles.
-      {
-        float lmax = -INFINITY, lmin = INFINITY;
-        float4* const orow = reinterpret_cast<float4*>(o + lt0 * MS::M) + lane;
-        const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
-        if (lane < QL) {
-#pragma unroll 1
-          for (int f = warp; f < nf; f += C::WARPS) {
-            float4 v = yb[f * (YP / 4)];
-            float* e = reinterpret_cast<float*>(&v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float a = fmaxf(e[c] + guard_add, guard_floor);
-              const float y = use_log ? lg2_approx(a) : a;
-              e[c] = fmaf(y, y_mul, y_add);
-              if (WANT_SUMS) {
-                d1[c % NS] += (double)e[c];
-                d2[c % NS] += (double)e[c] * (double)e[c];
-              }
-            }
-            orow[f * (MS::M / 4)] = v;
-            lmax = fmax3(lmax, v.x, v.y);
-            lmin = fmin3(lmin, v.x, v.y);
-            lmax = fmax3(lmax, v.z, v.w);
-            lmin = fmin3(lmin, v.z, v.w);
-          }
-        }
-        if (want_max) {  // one REDUX each on order-preserving integer keys instead of ten dependent shuffles
-          const int kmax = __reduce_max_sync(0xffffffffu, float_key(lmax));
-          const int kmin = __reduce_min_sync(0xffffffffu, float_key(lmin));
-          if (lane == 0) {
-            red_max[warp] = key_float(kmax);
-            red_min[warp] = key_float(kmin);
-          }
-          red_clip = clip_i;   // folded by thread 0 after the next barrier
-          red_tile = tile_i;
-        }
-      }
     } else {
       float lmax = -INFINITY, lmin = INFINITY;
       mel_runtime_tables<C, LAYOUT_TM, WANT_SUMS>(p, Pw, Y, s_wg, s_start, s_ginfo, s_sums, o, lt0, nf, warp, lane, lmax, lmin);
@@ -771,6 +778,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
 #endif
   cp_async_wait_all();
   if (SPEC) {
+    __syncthreads();
+    if (prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
     __syncthreads();
     fold_red();
     if (want_sums) flush_sums();
