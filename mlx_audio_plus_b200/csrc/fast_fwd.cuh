@@ -308,6 +308,121 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
   static constexpr int DYN = PX_END;  // then: sums (double), mel weights, starts, group info
 };
 
+// ---- stage 1 of one tile: warp = residue n2 (RPW of them per warp), lane = frame -----------------------------------
+template <class C>
+__device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const float2* s_win2, const float2* s_tw1, int warp,
+                                            int lane) {
+  constexpr int N1 = C::N1, N2 = C::N2;
+#pragma unroll 1
+  for (int rr = 0; rr < C::RPW; ++rr) {
+    const int n2 = warp * C::RPW + rr;
+    const float* xb = xs + lane * C::P + 2 * n2;
+    const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
+    float2 v[N1];
+    static_for<0, N1 / 2>([&](auto I_) {
+      constexpr int n1 = 2 * decltype(I_)::value;
+      constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
+      constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
+      const float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
+      const float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
+      const float4 w = wb4[n1 / 2];
+      v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
+      v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
+    });
+    Dft<N1>::run(v);
+    const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
+    float2* eb = E + lane * C::EP + n2;
+    static_for<0, N1 / 2>([&](auto I_) {
+      constexpr int k1 = 2 * decltype(I_)::value;
+      constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
+      constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+      const float4 t = tb4[k1 / 2];
+      float2 y0 = v[k1];
+      if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
+      const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
+      eb[slot0 * N2] = y0;
+      eb[slot1 * N2] = y1;
+    });
+  }
+}
+
+// ---- stage 2 of one tile: warp = unit u, lane = frame.  Unit u owns the column pair (u, N1-u); unit 0 owns columns 0
+// and N1/2, whose bins pair up WITHIN a column: it runs the same post-processing code after a register permutation and
+// only its output bins differ (slots [0, N2/2) -> N1*(s+1), slots [N2/2, N2) -> N1/2 + N1*(s - N2/2)).
+// INPLACE: the power tile overwrites this frame's exchange row (Cfg::sig); otherwise it goes to Pw in natural bin order.
+template <class C, bool INPLACE>
+__device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* s_twp, int warp, int lane, bool pw_only,
+                                            float spec_eps) {
+  constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
+  constexpr bool SPEC = INPLACE;
+  const int u = warp;
+  const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
+  const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
+  float2 A[N2], B[N2];
+  const float2* ea = E + lane * C::EP + u * N2;
+  const float2* eb = E + lane * C::EP + (N1 / 2 + u) * N2;
+  static_for<0, N2>([&](auto I_) {
+    constexpr int j = decltype(I_)::value;
+    A[j] = ea[j];
+    B[j] = eb[j];
+  });
+  Dft<N2>::run(A);
+  Dft<N2>::run(B);
+  // power tile: separate, natural bin order (run-time-table kernels) — or in place over this frame's exchange row,
+  // one value per float2 slot, in the half selected by lane >> 4 (the row pitch is 2 * odd floats, so lanes l and
+  // l + 16 would otherwise share a bank)
+  float* pr = SPEC ? reinterpret_cast<float*>(E + lane * C::EP) + (lane >> 4) : Pw + lane * C::PP;
+  auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
+  float dc_k = 0.0f, dc_m = 0.0f;
+  if (u == 0) {
+    // unit 0: the DC / Nyquist pair comes from A[0] alone; then permute so that the shared post-processing
+    // below pairs column 0 with itself (slots 0..N2/2-1: A[s+1] with A[N2-1-s]) and column N1/2 with itself
+    // (slots N2/2..N2-1: B[s-N2/2] with B[3N2/2-1-s]).  One code path for every warp keeps the loop body
+    // inside the 32 KB instruction cache.
+    post_pair(A[0], A[0], make_float2(1.0f, 0.0f), dc_k, dc_m);
+    float2 T[N2 / 2];
+    static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = B[N2/2+j] (j < N2/2); stash B's lower half
+      constexpr int j = decltype(I_)::value;
+      T[j] = B[j];
+      B[j] = B[N2 / 2 + j];
+    });
+    static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = A[j] (j >= N2/2)
+      constexpr int j = decltype(I_)::value;
+      B[N2 / 2 + j] = A[N2 / 2 + j];
+    });
+    static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = A[s+1] (s < N2/2); A[N2/2] is still intact in newB
+      constexpr int s = decltype(I_)::value;
+      A[s] = (s + 1 < N2 / 2) ? A[s + 1] : B[N2 / 2];
+    });
+    static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = old B[s-N2/2] (s >= N2/2)
+      constexpr int j = decltype(I_)::value;
+      A[N2 / 2 + j] = T[j];
+    });
+  }
+  const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
+  // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
+  float* const plo = SPEC ? pr + 2 * (u * N2) : pr + kb_lo;
+  float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * N2) : pr + (NC - kb_lo);
+  float* const phi = SPEC ? plo : pr + kb_hi;
+  float* const mhi = SPEC ? mlo : pr + (NC - kb_hi);
+  constexpr int SK = SPEC ? 2 : N1, SM = SPEC ? 2 : -N1;
+  static_for<0, N2 / 2>([&](auto I_) {
+    constexpr int k2 = 2 * decltype(I_)::value;
+    const float4 t = tw4[k2 / 2];
+    float pk, pm;
+    post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
+    emit((k2 < N2 / 2 ? plo : phi) + SK * k2, pk);
+    emit((k2 < N2 / 2 ? mlo : mhi) + SM * k2, pm);
+    post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
+    emit((k2 + 1 < N2 / 2 ? plo : phi) + SK * (k2 + 1), pk);
+    emit((k2 + 1 < N2 / 2 ? mlo : mhi) + SM * (k2 + 1), pm);
+  });
+  if (u == 0) {  // after the loop: in the in-place layout DC reuses the duplicate slot of the self-paired bin Nc/2
+    emit(pr + (SPEC ? 2 * C::sig(0) : 0), dc_k);
+    emit(pr + (SPEC ? 2 * C::sig(NC) : NC), dc_m);
+  }
+}
+
 // ---- run-time-table mel phase (any filterbank, both layouts): LANE = (4 frames) x (8 consecutive mel rows) ------
 // The filterbank is banded (<= 2 non-zeros per bin): a mel row is a short run of taps.  A warp-instruction
 // covers 8 consecutive rows for 4 frames, so (a) the P gathers touch ~32 distinct banks (row pitch == 9 mod 32,
@@ -470,13 +585,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   const bool pw_only = SPECK >= 0 ? SPECK == B2A_SPEC_POWER : p.spec_kind == B2A_SPEC_POWER;
   const float spec_eps = p.spec_eps;
 
-  // stage-2 roles: unit u owns the column pair (u, N1-u); unit 0 owns columns 0 and N1/2, whose bins pair up
-  // WITHIN a column.  It runs the same post-processing code after a register permutation (see below); only its
-  // output bins differ: slots [0, N2/2) -> N1*(s+1), slots [N2/2, N2) -> N1/2 + N1*(s - N2/2).
-  const int u = warp;
-  const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
-  const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
-
   // SPEC path: statistics live in registers across tiles (lane == row quad in the write-out phase)
   constexpr int NS = (SPEC && WANT_SUMS) ? 4 : 1;
   double d1[NS], d2[NS];
@@ -613,37 +721,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       __syncthreads();
     }
     // ---- stage 1 ----------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (int rr = 0; rr < C::RPW; ++rr) {
-      const int n2 = warp * C::RPW + rr;
-      const float* xb = xs + lane * C::P + 2 * n2;
-      const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
-      float2 v[N1];
-      static_for<0, N1 / 2>([&](auto I_) {
-        constexpr int n1 = 2 * decltype(I_)::value;
-        constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
-        constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
-        const float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
-        const float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
-        const float4 w = wb4[n1 / 2];
-        v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
-        v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
-      });
-      Dft<N1>::run(v);
-      const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
-      float2* eb = E + lane * C::EP + n2;
-      static_for<0, N1 / 2>([&](auto I_) {
-        constexpr int k1 = 2 * decltype(I_)::value;
-        constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
-        constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
-        const float4 t = tb4[k1 / 2];
-        float2 y0 = v[k1];
-        if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
-        const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
-        eb[slot0 * N2] = y0;
-        eb[slot1 * N2] = y1;
-      });
-    }
+    stage1_tile<C>(xs, E, s_win2, s_tw1, warp, lane);
     __syncthreads();  // E complete, xs free
     tick(1);
     fold_red();  // the per-warp max / min of the rows phase B has just written
@@ -652,71 +730,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     if (PREFETCH && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
 
     // ---- stage 2 ----------------------------------------------------------------------------------------
-    {
-      float2 A[N2], B[N2];
-      const float2* ea = E + lane * C::EP + u * N2;
-      const float2* eb = E + lane * C::EP + (N1 / 2 + u) * N2;
-      static_for<0, N2>([&](auto I_) {
-        constexpr int j = decltype(I_)::value;
-        A[j] = ea[j];
-        B[j] = eb[j];
-      });
-      Dft<N2>::run(A);
-      Dft<N2>::run(B);
-      // power tile: separate, natural bin order (run-time-table kernels) — or in place over this frame's exchange row,
-      // one value per float2 slot, in the half selected by lane >> 4 (the row pitch is 2 * odd floats, so lanes l and
-      // l + 16 would otherwise share a bank)
-      float* pr = SPEC ? reinterpret_cast<float*>(E + lane * C::EP) + (lane >> 4) : Pw + lane * C::PP;
-      auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
-      float dc_k = 0.0f, dc_m = 0.0f;
-      if (u == 0) {
-        // unit 0: the DC / Nyquist pair comes from A[0] alone; then permute so that the shared post-processing
-        // below pairs column 0 with itself (slots 0..N2/2-1: A[s+1] with A[N2-1-s]) and column N1/2 with itself
-        // (slots N2/2..N2-1: B[s-N2/2] with B[3N2/2-1-s]).  One code path for every warp keeps the loop body
-        // inside the 32 KB instruction cache.
-        post_pair(A[0], A[0], make_float2(1.0f, 0.0f), dc_k, dc_m);
-        float2 T[N2 / 2];
-        static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = B[N2/2+j] (j < N2/2); stash B's lower half
-          constexpr int j = decltype(I_)::value;
-          T[j] = B[j];
-          B[j] = B[N2 / 2 + j];
-        });
-        static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = A[j] (j >= N2/2)
-          constexpr int j = decltype(I_)::value;
-          B[N2 / 2 + j] = A[N2 / 2 + j];
-        });
-        static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = A[s+1] (s < N2/2); A[N2/2] is still intact in newB
-          constexpr int s = decltype(I_)::value;
-          A[s] = (s + 1 < N2 / 2) ? A[s + 1] : B[N2 / 2];
-        });
-        static_for<0, N2 / 2>([&](auto I_) {  // newA[s] = old B[s-N2/2] (s >= N2/2)
-          constexpr int j = decltype(I_)::value;
-          A[N2 / 2 + j] = T[j];
-        });
-      }
-      const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
-      // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
-      float* const plo = SPEC ? pr + 2 * (u * N2) : pr + kb_lo;
-      float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * N2) : pr + (NC - kb_lo);
-      float* const phi = SPEC ? plo : pr + kb_hi;
-      float* const mhi = SPEC ? mlo : pr + (NC - kb_hi);
-      constexpr int SK = SPEC ? 2 : N1, SM = SPEC ? 2 : -N1;
-      static_for<0, N2 / 2>([&](auto I_) {
-        constexpr int k2 = 2 * decltype(I_)::value;
-        const float4 t = tw4[k2 / 2];
-        float pk, pm;
-        post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
-        emit((k2 < N2 / 2 ? plo : phi) + SK * k2, pk);
-        emit((k2 < N2 / 2 ? mlo : mhi) + SM * k2, pm);
-        post_pair(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), pk, pm);
-        emit((k2 + 1 < N2 / 2 ? plo : phi) + SK * (k2 + 1), pk);
-        emit((k2 + 1 < N2 / 2 ? mlo : mhi) + SM * (k2 + 1), pm);
-      });
-      if (u == 0) {  // after the loop: in the in-place layout DC reuses the duplicate slot of the self-paired bin Nc/2
-        emit(pr + (SPEC ? 2 * C::sig(0) : 0), dc_k);
-        emit(pr + (SPEC ? 2 * C::sig(NC) : NC), dc_m);
-      }
-    }
+    stage2_tile<C, SPEC>(E, Pw, s_twp, warp, lane, pw_only, spec_eps);
     __syncthreads();  // Pw complete, E free (Y aliases E)
     tick(2);
 
