@@ -97,6 +97,21 @@ def main():
             "dram_bytes_per_clip": dram / a.clips, "captured_clips": a.clips, "dram_bytes_per_launch_captured": dram,
             "algorithmic_bytes_per_clip": 3456000, "source": f"profiles/{r}_fast_logmel_400x160_ncu_full.json"}},
             open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    # the other kernels of the path: same summary per capture
+    for tag, what in (("fast_logmel_512", "C3 Parakeet 16 x 1 h (benchmarks/bench_configs.py --only C3)"),
+                      ("fast_logmel_1024", "C5 Vocos mel forward B=8192 (benchmarks/bench_configs.py --only C5)"),
+                      ("fast_istft_1024", "C5 Vocos iSTFT head B=1024 (benchmarks/bench_configs.py --only C5)"),
+                      ("istft_small", "C4 Kokoro iSTFT B=1024 (benchmarks/bench_configs.py --only C4)")):
+        rep = os.path.join(G, f"prof_{r}_{tag}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        raw = ncu_raw(rep)
+        out = {k: {"value": v, "unit": u} for k, (v, u) in raw.items()
+               if k in KEEP or ("issue_stalled" in k and k.endswith("per_issue_active.ratio"))}
+        out["_kernel"] = raw.get("Kernel Name", ("", ""))[0]
+        out["_workload"] = what
+        out["_command"] = "ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 (scratch/final_run.sh)"
+        json.dump(out, open(os.path.join(P, f"{r}_{tag}_ncu_full.json"), "w"), indent=1)
     print("profiles/ updated:", sorted(os.listdir(P)))
 
 

@@ -110,7 +110,8 @@ struct Cfg {
   static constexpr int P = HOP + (((HOP / 2) % 2 == 0) ? 2 : 0);  // row pitch (floats); P/2 odd
   static constexpr int ROWS = FT - 1 + (N + HOP - 1) / HOP;
   static constexpr int SPAN = (FT - 1) * HOP + N;
-  static constexpr int XS_FLOATS = ROWS * P;
+  static constexpr int XS_HEAD = 4;  // floats in front of the sample tile: [-4] raw-samples flag, [-3] sample before the span
+  static constexpr int XS_FLOATS = ROWS * P + XS_HEAD;
   static constexpr int EP = NC + 1;          // exchange pitch per frame (float2), odd
   // power pitch per frame (floats): odd (stage-2 lane==frame stores are conflict free) and == 9 (mod 32) so that
   // the mel phase's (4 frames x 8 mel rows) gathers land in distinct banks
@@ -138,6 +139,9 @@ struct Cfg {
 
 __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gmem));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100+)
   float r;
@@ -205,14 +209,19 @@ struct FillCtx {
 };
 
 // Copies the tile's sample span into shared memory (rows of HOP samples at pitch P).
-template <class C>
+template <class C, int PREK>
 __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const FillCtx<C>& fc, int clip_i, int tile_i) {
   const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
   const int64_t lt0 = (int64_t)tile_i * C::FT;
   const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
   const int64_t s0 = q0 - p.geo.pad_left;             // source coordinate
   const bool interior = p.fast_fill_ok && s0 >= 0 && (s0 + C::SPAN) <= p.valid_length && s0 >= p.sample_offset;
-  if (interior && p.preemph == 0.0f) {
+  // Interior tiles are copied RAW with cp.async (asynchronous: the copy of the next tile overlaps stage 2 / mel).  With
+  // pre-emphasis the filter y[n] = x[n] - a*x[n-1] is then applied by stage 1 as it reads (separately rounded multiply
+  // and subtract, bit-exact vs the reference's `x[1:] - a*x[:-1]`); the one sample in front of the span goes to
+  // xs[-3] — where "the last sample of the previous row" lives for every other row start (pitch = HOP + 2).
+  const bool raw_pre = PREK != 0 && p.preemph != 0.0f && s0 > p.sample_offset && C::P == C::HOP + 2;
+  if (interior && (p.preemph == 0.0f || raw_pre)) {
     const float* src = clip + (s0 - p.sample_offset) + fc.src_off;
     if (fc.active) {
 #pragma unroll
@@ -223,23 +232,15 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const 
       constexpr int i = FillCtx<C>::ITERS - 1;
       cp_async8(fc.dst + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
     }
-  } else if (interior && s0 > p.sample_offset) {
-    // pre-emphasis on the way in: y[n] = x[n] - a*x[n-1] with separately rounded multiply and subtract
-    // (bit-exact vs the reference's `x[1:] - a*x[:-1]`); vectorised, coalesced direct loads
-    const float* src = clip + (s0 - p.sample_offset);
-    const float a = p.preemph;
-    for (int j = threadIdx.x; j < C::SPAN / 2; j += C::THREADS) {
-      const int s = 2 * j;
-      const float2 x = __ldg(reinterpret_cast<const float2*>(src + s));
-      const float xm = __ldg(src + s - 1);
-      const int row = s / C::HOP, col = s - row * C::HOP;
-      *reinterpret_cast<float2*>(xs + row * C::P + col) =
-          make_float2(__fsub_rn(x.x, __fmul_rn(a, xm)), __fsub_rn(x.y, __fmul_rn(a, x.x)));
+    if (threadIdx.x == 0) {
+      reinterpret_cast<int*>(xs)[-4] = raw_pre ? 1 : 0;
+      if (raw_pre) cp_async4((unsigned)__cvta_generic_to_shared(xs - 3), clip + (s0 - p.sample_offset) - 1);
     }
   } else {
     const int64_t frames_left = p.frame_count - lt0;
     const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
     const int need = (nf - 1) * C::HOP + C::N;
+    if (threadIdx.x == 0) reinterpret_cast<int*>(xs)[-4] = 0;  // this path stores finished (pre-emphasised) samples
     for (int i = threadIdx.x; i < C::SPAN; i += C::THREADS) {
       float v = 0.0f;
       if (i < need) {
@@ -251,6 +252,18 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const 
     }
   }
   cp_async_commit();
+}
+
+// Pre-emphasis tiles are filled with ordinary loads (the copy has to compute), so their HBM latency is exposed.  Pull
+// the span of the tile AFTER the next one into L2 early: one prefetch per 128-byte line.
+template <class C>
+__device__ __forceinline__ void prefetch_span_l2(const FastParams& p, int clip_i, int tile_i) {
+  if (p.preemph == 0.0f || clip_i >= p.batch) return;
+  const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
+  const int64_t s0 = (p.frame_begin + (int64_t)tile_i * C::FT) * C::HOP - p.geo.pad_left;
+  const int64_t i = s0 + 32 * (int64_t)threadIdx.x;  // 32 floats = 128 bytes
+  if (32 * (int)threadIdx.x < C::SPAN && i >= p.sample_offset && i < p.valid_length)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(clip + (i - p.sample_offset)));
 }
 
 // real-FFT post-twiddle for one bin pair (k, Nc-k); Zk = Z[k], Zm = Z[Nc-k]; w = W_N^k; all scaled by the
@@ -309,22 +322,34 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
 };
 
 // ---- stage 1 of one tile: warp = residue n2 (RPW of them per warp), lane = frame -----------------------------------
-template <class C>
+// `preemph` != 0 with a RAW sample tile (flag at xs[-4]): y[n] = x[n] - a*x[n-1] is applied here, on the way in.
+// PREK: 0 = the kernel instance never pre-emphasises (no code for it), 1 / -1 = decided at run time.
+template <class C, int PREK>
 __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const float2* s_win2, const float2* s_tw1, int warp,
-                                            int lane) {
+                                            int lane, float preemph) {
   constexpr int N1 = C::N1, N2 = C::N2;
+  const bool pre = PREK != 0 && preemph != 0.0f && reinterpret_cast<const int*>(xs)[-4] != 0;
 #pragma unroll 1
   for (int rr = 0; rr < C::RPW; ++rr) {
     const int n2 = warp * C::RPW + rr;
     const float* xb = xs + lane * C::P + 2 * n2;
     const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
     float2 v[N1];
+    // the sample in front of a pair sits one float back — or, for the first pair of a row (n2 == 0 and column 0),
+    // behind the row padding: P - HOP + 1 floats back
+    const int back0 = n2 == 0 ? C::P - C::HOP + 1 : 1;
     static_for<0, N1 / 2>([&](auto I_) {
       constexpr int n1 = 2 * decltype(I_)::value;
       constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
       constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
-      const float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
-      const float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
+      float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
+      float2 x1 = *reinterpret_cast<const float2*>(xb + off1);
+      if (PREK != 0 && pre) {
+        const float q0 = xb[off0 - ((n1 % C::K) == 0 ? back0 : 1)];
+        const float q1 = xb[off1 - (((n1 + 1) % C::K) == 0 ? back0 : 1)];
+        x0 = regs::psub(x0, regs::pmul(make_float2(q0, x0.x), make_float2(preemph, preemph)));
+        x1 = regs::psub(x1, regs::pmul(make_float2(q1, x1.x), make_float2(preemph, preemph)));
+      }
       const float4 w = wb4[n1 / 2];
       v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
       v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
@@ -523,7 +548,8 @@ __device__ __forceinline__ void mel_runtime_tables(const FastParams& p, const fl
 }
 
 // SPECK: spectrum kind fixed at compile time (B2A_SPEC_POWER / MAGNITUDE / SQRT_POWER_EPS), or -1 = run-time
-template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK>
+// PREK: pre-emphasis support compiled in (0 = no, -1 / 1 = run-time switch); the generated-mel instances fix it per spec
+template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK, int PREK>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh); requires the (T, M) layout
@@ -541,7 +567,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   float2* const s_twp = reinterpret_cast<float2*>(smem4 + S::TWP);   // [N1/2][2*N2]
   float2* const E = reinterpret_cast<float2*>(smem4 + S::EX);        // [FT][EP]
   float* const Pw = reinterpret_cast<float*>(smem4 + S::PW);         // [FT][PP]
-  float* const xs = reinterpret_cast<float*>(smem4 + S::XS);         // [ROWS][P]
+  float* const xs = reinterpret_cast<float*>(smem4 + S::XS) + C::XS_HEAD;  // [ROWS][P] (+ XS_HEAD floats in front)
   const int M = SPEC ? MS::M : p.n_mels;
   const int G = p.mel_groups;
   double* const s_sums = reinterpret_cast<double*>(smem4 + S::DYN);   // [2*G*8]
@@ -578,7 +604,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   const int tpc = p.tiles_per_clip;
   const int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
   int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
-  if (PREFETCH && clip_i < p.batch) fill_tile<C>(p, xs, fc, clip_i, tile_i);
+  if (PREFETCH && clip_i < p.batch) fill_tile<C, PREK>(p, xs, fc, clip_i, tile_i);
 
   const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
   const bool use_log = p.use_log != 0;
@@ -701,7 +727,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
 
     if (!PREFETCH) {
       __syncthreads();  // previous tile's mel phase has finished reading P (which shares xs' memory)
-      fill_tile<C>(p, xs, fc, clip_i, tile_i);
+      fill_tile<C, PREK>(p, xs, fc, clip_i, tile_i);
     }
     cp_async_wait_all();
     __syncthreads();  // xs ready; run-time-table kernels: previous tile's Y written out; generated: Y(prev) complete
@@ -721,13 +747,21 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       __syncthreads();
     }
     // ---- stage 1 ----------------------------------------------------------------------------------------
-    stage1_tile<C>(xs, E, s_win2, s_tw1, warp, lane);
+    stage1_tile<C, PREK>(xs, E, s_win2, s_tw1, warp, lane, p.preemph);
     __syncthreads();  // E complete, xs free
     tick(1);
     fold_red();  // the per-warp max / min of the rows phase B has just written
 
     // prefetch the next tile's samples while stage 2 / mel run
-    if (PREFETCH && nclip < p.batch) fill_tile<C>(p, xs, fc, nclip, ntile);
+    if (PREFETCH && nclip < p.batch) fill_tile<C, PREK>(p, xs, fc, nclip, ntile);
+    if (PREFETCH && PREK != 0) {  // pre-emphasis configs: the tile after the next one goes to L2 now
+      int c2 = nclip + step_c, t2 = ntile + step_t;
+      if (t2 >= tpc) {
+        t2 -= tpc;
+        ++c2;
+      }
+      prefetch_span_l2<C>(p, c2, t2);
+    }
 
     // ---- stage 2 ----------------------------------------------------------------------------------------
     stage2_tile<C, SPEC>(E, Pw, s_twp, warp, lane, pw_only, spec_eps);
@@ -817,7 +851,7 @@ constexpr int spec_yp() {
   return MS::M > 0 ? ((((MS::M / 4) & 1) ? MS::M : MS::M + 4)) : 0;
 }
 
-template <class C, bool TM, bool SUMS, class MS, int SPECK = -1>
+template <class C, bool TM, bool SUMS, class MS, int SPECK = -1, int PREK = -1>
 int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   size_t smem = smem_bytes<C, spec_yp<MS>()>(p.mel_groups, p.mel_wg_count);
   if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
@@ -832,10 +866,10 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   if (grid < 1) grid = 1;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  fast_logmel_kernel<C, TM, SUMS, MS, SPECK><<<grid, C::THREADS, smem, st>>>(p);
+  fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
@@ -859,25 +893,25 @@ bool spec_matches(const b2a_plan* plan) {
 }
 
 // the specs each kernel variant is instantiated for: X(index, spec type, also with per-feature sums, spectrum kind
-// of the wrapper that uses it — any other combination takes the run-time-table kernel)
+// of the wrapper that uses it, pre-emphasis compiled in — any other combination takes the run-time-table kernel)
 #define B2A_SPECS_400(X)                                                                                    \
-  X(1, melgen::MelSpec_whisper80, false, B2A_SPEC_POWER) X(2, melgen::MelSpec_whisper128, false, B2A_SPEC_POWER) \
-  X(3, melgen::MelSpec_funasr80, false, B2A_SPEC_POWER)
+  X(1, melgen::MelSpec_whisper80, false, B2A_SPEC_POWER, 0) X(2, melgen::MelSpec_whisper128, false, B2A_SPEC_POWER, 0) \
+  X(3, melgen::MelSpec_funasr80, false, B2A_SPEC_POWER, 0)
 #define B2A_SPECS_512(X)                                                                                     \
-  X(1, melgen::MelSpec_parakeet80, true, B2A_SPEC_POWER) X(2, melgen::MelSpec_parakeet128, true, B2A_SPEC_POWER) \
-  X(3, melgen::MelSpec_nemo_slaney80, true, B2A_SPEC_POWER) X(4, melgen::MelSpec_nemo_slaney128, true, B2A_SPEC_POWER)
+  X(1, melgen::MelSpec_parakeet80, true, B2A_SPEC_POWER, 1) X(2, melgen::MelSpec_parakeet128, true, B2A_SPEC_POWER, 1) \
+  X(3, melgen::MelSpec_nemo_slaney80, true, B2A_SPEC_POWER, 1) X(4, melgen::MelSpec_nemo_slaney128, true, B2A_SPEC_POWER, 1)
 #define B2A_SPECS_1024(X) \
-  X(1, melgen::MelSpec_vocos100, false, B2A_SPEC_MAGNITUDE) X(2, melgen::MelSpec_qwen3tts128, false, B2A_SPEC_SQRT_POWER_EPS)
+  X(1, melgen::MelSpec_vocos100, false, B2A_SPEC_MAGNITUDE, 0) X(2, melgen::MelSpec_qwen3tts128, false, B2A_SPEC_SQRT_POWER_EPS, 0)
 
 template <class C>
 struct SpecList;
 
-#define B2A_MATCH(IDX, MS, SUMS_OK, SPECK) if (spec_matches<MS>(plan)) { *name = MS::kName; return IDX; }
-#define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK)                                                              \
+#define B2A_MATCH(IDX, MS, SUMS_OK, SPECK, PREK) if (spec_matches<MS>(plan)) { *name = MS::kName; return IDX; }
+#define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK, PREK)                                                        \
   case IDX:                                                                                              \
-    if (p.spec_kind != SPECK) break;                                                                     \
-    if (!sums) return launch_variant<C, true, false, MS, SPECK>(plan, p, st);                           \
-    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK>(plan, p, st);                \
+    if (p.spec_kind != SPECK || (PREK == 0 && p.preemph != 0.0f)) break;                                 \
+    if (!sums) return launch_variant<C, true, false, MS, SPECK, PREK>(plan, p, st);                     \
+    if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK, PREK>(plan, p, st);          \
     break;
 #define B2A_SPECLIST(CFG, LIST)                                                                             \
   template <>                                                                                               \
