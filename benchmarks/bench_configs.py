@@ -125,6 +125,22 @@ def main():
             ph = torch.sin(torch.randn((B, 11, 24001), generator=g, device="cuda"))
             spec = torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)).contiguous()
             res.append(inv_case(f"C4 kokoro istft, B={B} x (11,24001)", iplan, spec, 24000, a.steps))
+    if want("S"):
+        # dsp.stft itself (complex64 (T, F) rows): bytes = samples in + 8 * T * F out.  torch.stft (cuFFT, same
+        # framing) is timed beside it for context only.
+        for nm, n_fft, hop, B, n, sr in (("400/160, 1024 x 30 s", 400, 160, 1024, 480000, 16000),
+                                         ("512/160, 4 x 1 h", 512, 160, 4, 57_600_000, 16000),
+                                         ("1024/256, 4096 x 5 s", 1024, 256, 4096, 120000, 24000)):
+            w = np.asarray(hanning(n_fft))
+            x = synth(B, n, sr, 1240)
+            plan = FrontendPlan(n_fft=n_fft, hop=hop, window=w, spec_kind=L.SPEC_COMPLEX)
+            r = fwd_case(f"S dsp.stft {nm}", plan, x, sr, a.steps)
+            tw = torch.from_numpy(w).cuda()
+            r["torch_stft_ms"] = timeit(lambda: torch.stft(x, n_fft, hop, n_fft, tw, center=True, pad_mode="reflect",
+                                                           return_complex=True), max(2, a.steps // 2))
+            res.append(r)
+            del x
+            torch.cuda.empty_cache()
     for r in res:
         print(json.dumps(r), flush=True)
     if a.out:

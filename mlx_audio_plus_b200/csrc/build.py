@@ -51,8 +51,11 @@ def build(force=False, verbose=False):
         cflags += ["-DB2A_DEV_400_ONLY"]
     if os.environ.get("B2A_PHASE_CLOCKS"):
         cflags += ["-DB2A_PHASE_CLOCKS"]
+    # development: A/B builds — extra -D flags and a separate output library (selected at run time with B2A_LIB=path)
+    cflags += os.environ.get("B2A_BUILD_DEFS", "").split()
+    out_lib = os.environ.get("B2A_BUILD_OUT", LIB)
     # one nvcc per translation unit, in parallel; then one link
-    obj_dir = os.path.join(HERE, "_obj")
+    obj_dir = os.path.join(HERE, "_obj") if out_lib == LIB else os.path.join(HERE, "_obj", os.path.basename(out_lib))
     os.makedirs(obj_dir, exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
 
@@ -68,7 +71,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed building libb200audio.so")
-    r = subprocess.run([nvcc(), "-shared", "-cudart", "static", "-o", LIB] + [o for o, _ in results],
+    r = subprocess.run([nvcc(), "-shared", "-cudart", "static", "-o", out_lib] + [o for o, _ in results],
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -76,7 +79,7 @@ def build(force=False, verbose=False):
     r.stderr = log + r.stderr
     if verbose:
         print(r.stderr)
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":

@@ -9,7 +9,10 @@ namespace b2a {
 bool fast_frontend_supported(const b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
   if (getenv("B2A_FORCE_GENERIC")) return false;
-  if (d.n_mels <= 0 || d.spec_kind == B2A_SPEC_COMPLEX) return false;
+  // the spectrum itself (dsp.stft): complex64 (T, F) rows through fast_stft_kernel
+  const bool cplx = d.n_mels == 0 && d.spec_kind == B2A_SPEC_COMPLEX && d.out_layout == B2A_LAYOUT_TM &&
+                    d.clamp_kind == B2A_CLAMP_NONE && d.norm_kind == B2A_NORM_NONE && !getenv("B2A_NO_FAST_STFT");
+  if (!cplx && (d.n_mels <= 0 || d.spec_kind == B2A_SPEC_COMPLEX)) return false;
   if (d.affine_div < 0.0f) return false;
   if (d.frame_dc || d.frame_preemph != 0.0f || d.dither != 0.0f || d.frame_len != 0) return false;  // Kaldi per-frame steps
   const bool v400 = d.n_fft == 400 && d.hop == 160;
@@ -96,6 +99,8 @@ int fast_frontend_init(b2a_plan* plan) {
   B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
   plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : (fs->variant == 2 ? "fast_logmel_512x160" : "fast_logmel_1024x256");
+  if (d.spec_kind == B2A_SPEC_COMPLEX)
+    plan->kernel_name = fs->variant == 1 ? "fast_stft_400x160" : (fs->variant == 2 ? "fast_stft_512x160" : "fast_stft_1024x256");
   fs->spec = fs->variant == 1 ? fast_match_400(plan, &fs->spec_name)
                               : (fs->variant == 2 ? fast_match_512(plan, &fs->spec_name) : fast_match_1024(plan, &fs->spec_name));
   return B2A_OK;
@@ -149,7 +154,7 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   }
   p.out_layout = d.out_layout;
   p.out = reinterpret_cast<float*>(a->out);
-  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * d.n_mels;
+  p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * (d.n_mels > 0 ? d.n_mels : plan->n_freqs);
   p.clip_max = clip_max;
   p.tile_min = tile_min;
   p.feat_sums = feat_sums;

@@ -164,8 +164,29 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+template <int BYTE_OFF>
+__device__ __forceinline__ float4 lds128_at(unsigned base) {  // pinned (volatile) broadcast load: keeps its place in program order
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base), "n"(BYTE_OFF));
+  return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- mbarrier (split arrive / wait): lets a warp do independent work between reaching a sync point and needing it ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+          (unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 // Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
 // non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
@@ -278,6 +299,16 @@ __device__ __forceinline__ void post_pair(float2 zk, float2 zm, float2 w, float&
   pm = fmaf(b.y, b.y, b.x * b.x);
 }
 
+// same, returning the spectrum itself: X[k] and X[Nc-k] = conj(E - W O)
+__device__ __forceinline__ void post_pair_c(float2 zk, float2 zm, float2 w, float2& xk, float2& xm) {
+  using namespace regs;
+  const float2 e = pfma(zm, make_float2(1.0f, -1.0f), zk);
+  const float2 o = pfma(pswap(zk), make_float2(1.0f, -1.0f), pswap(zm));
+  const float2 t = cmul(o, w);
+  xk = padd(e, t);
+  xm = pmul(psub(e, t), make_float2(1.0f, -1.0f));
+}
+
 // L taps of one mel group for NFW frames with every load issued before the first FMA (one shared-memory
 // latency per <= 8 taps instead of one per tap: the mel phase is latency-, not throughput-bound)
 template <int L, int NFW, int ROWSTEP, int WSTR>
@@ -357,11 +388,23 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
     Dft<N1>::run(v);
     const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
     float2* eb = E + lane * C::EP + n2;
+#ifdef B2A_X_TWPF
+    // inter-stage twiddles: software-pipelined broadcast loads, TWD pairs ahead of their use
+    constexpr int TWD = B2A_X_TWPF;
+    const unsigned tb_sa = (unsigned)__cvta_generic_to_shared(tb4);
+    float4 tq[N1 / 2];
+    static_for<0, (TWD < N1 / 2 ? TWD : N1 / 2)>([&](auto I_) { tq[decltype(I_)::value] = lds128_at<16 * decltype(I_)::value>(tb_sa); });
+#endif
     static_for<0, N1 / 2>([&](auto I_) {
       constexpr int k1 = 2 * decltype(I_)::value;
       constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
       constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+#ifdef B2A_X_TWPF
+      if constexpr (k1 / 2 + TWD < N1 / 2) tq[k1 / 2 + TWD] = lds128_at<16 * (k1 / 2 + TWD)>(tb_sa);
+      const float4 t = tq[k1 / 2];
+#else
       const float4 t = tb4[k1 / 2];
+#endif
       float2 y0 = v[k1];
       if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
       const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
@@ -375,12 +418,17 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
 // and N1/2, whose bins pair up WITHIN a column: it runs the same post-processing code after a register permutation and
 // only its output bins differ (slots [0, N2/2) -> N1*(s+1), slots [N2/2, N2) -> N1/2 + N1*(s - N2/2)).
 // INPLACE: the power tile overwrites this frame's exchange row (Cfg::sig); otherwise it goes to Pw in natural bin order.
-template <class C, bool INPLACE>
+// CPLX (with INPLACE): the spectrum itself, one complex value per slot (fast_stft_kernel).
+template <class C, bool INPLACE, bool CPLX = false>
 __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* s_twp, int warp, int lane, bool pw_only,
                                             float spec_eps) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = INPLACE;
+#ifdef B2A_X_UREMAP
+  const int u = (C::WARPS - 1) - warp;  // unit 0 (the longest: DC / Nyquist + register permutation) on the highest warp id
+#else
   const int u = warp;
+#endif
   const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
   const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
   float2 A[N2], B[N2];
@@ -399,12 +447,14 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   float* pr = SPEC ? reinterpret_cast<float*>(E + lane * C::EP) + (lane >> 4) : Pw + lane * C::PP;
   auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
   float dc_k = 0.0f, dc_m = 0.0f;
+  float2 dc_kc = make_float2(0.f, 0.f), dc_mc = make_float2(0.f, 0.f);
+  if (CPLX && u == 0) post_pair_c(A[0], A[0], make_float2(1.0f, 0.0f), dc_kc, dc_mc);
   if (u == 0) {
     // unit 0: the DC / Nyquist pair comes from A[0] alone; then permute so that the shared post-processing
     // below pairs column 0 with itself (slots 0..N2/2-1: A[s+1] with A[N2-1-s]) and column N1/2 with itself
     // (slots N2/2..N2-1: B[s-N2/2] with B[3N2/2-1-s]).  One code path for every warp keeps the loop body
     // inside the 32 KB instruction cache.
-    post_pair(A[0], A[0], make_float2(1.0f, 0.0f), dc_k, dc_m);
+    if (!CPLX) post_pair(A[0], A[0], make_float2(1.0f, 0.0f), dc_k, dc_m);
     float2 T[N2 / 2];
     static_for<0, N2 / 2>([&](auto I_) {  // newB[j] = B[N2/2+j] (j < N2/2); stash B's lower half
       constexpr int j = decltype(I_)::value;
@@ -431,6 +481,26 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   float* const phi = SPEC ? plo : pr + kb_hi;
   float* const mhi = SPEC ? mlo : pr + (NC - kb_hi);
   constexpr int SK = SPEC ? 2 : N1, SM = SPEC ? 2 : -N1;
+  if constexpr (CPLX) {
+    float2* const ck = E + lane * C::EP + u * N2;             // slot of bin pair s: (u*N2 + s, (N1/2 + u)*N2 + s)
+    float2* const cm = E + lane * C::EP + (N1 / 2 + u) * N2;
+    static_for<0, N2 / 2>([&](auto I_) {
+      constexpr int k2 = 2 * decltype(I_)::value;
+      const float4 t = tw4[k2 / 2];
+      float2 xk, xm;
+      post_pair_c(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), xk, xm);
+      ck[k2] = xk;
+      cm[k2] = xm;
+      post_pair_c(A[k2 + 1], B[N2 - 2 - k2], make_float2(t.z, t.w), xk, xm);
+      ck[k2 + 1] = xk;
+      cm[k2 + 1] = xm;
+    });
+    if (u == 0) {
+      E[lane * C::EP + C::sig(0)] = dc_kc;
+      E[lane * C::EP + C::sig(NC)] = dc_mc;
+    }
+    return;
+  }
   static_for<0, N2 / 2>([&](auto I_) {
     constexpr int k2 = 2 * decltype(I_)::value;
     const float4 t = tw4[k2 / 2];
@@ -576,6 +646,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   int* const s_ginfo = s_start + G * 8 + ((G * 8) & 1);               // [2*G], 8-byte aligned
   __shared__ float red_max[C::WARPS], red_min[C::WARPS];
   __shared__ int s_cur_clip;
+#ifdef B2A_X_DYNB
+  constexpr bool DYNB = SPEC;  // phase B runs between "E complete" arrive and wait, frames handed out by ticket
+#else
+  constexpr bool DYNB = false;
+#endif
+  __shared__ unsigned long long s_bar1;
+  __shared__ int s_ticket;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // staging tile: own space in the generated-mel kernels (the exchange buffer then holds the power tile), else it
@@ -598,7 +675,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   const bool want_max = p.clip_max != nullptr;
   if (want_sums)
     for (int i = threadIdx.x; i < 2 * G * 8; i += C::THREADS) s_sums[i] = 0.0;
-  if (threadIdx.x == 0) s_cur_clip = -1;
+  if (threadIdx.x == 0) {
+    s_cur_clip = -1;
+    s_ticket = 0;
+    mbar_init(&s_bar1, C::WARPS);
+  }
+  unsigned bar1_parity = 0;
 
   // tile walk: tile = clip_i * tiles_per_clip + tile_i advances by gridDim.x without a division per tile
   const int tpc = p.tiles_per_clip;
@@ -664,9 +746,18 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     float* const o = p.out + (int64_t)pclip * p.out_clip_stride;
     float4* const orow = reinterpret_cast<float4*>(o + (int64_t)ptile * C::FT * MS::M) + lane;
     const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
-    if (lane < QL) {
+    auto take = [&]() {  // next unclaimed frame of the staged tile (warp-uniform)
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&s_ticket, 1);
+      return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int nxt = DYNB ? take() : warp;
 #pragma unroll 1
-      for (int f = warp; f < pnf; f += C::WARPS) {
+    for (;;) {
+      const int f = nxt;
+      if (f >= pnf) break;
+      nxt = DYNB ? take() : f + C::WARPS;
+      if (lane < QL) {
         float4 v = yb[f * (YP / 4)];
         float* e = reinterpret_cast<float*>(&v);
 #pragma unroll
@@ -732,7 +823,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     cp_async_wait_all();
     __syncthreads();  // xs ready; run-time-table kernels: previous tile's Y written out; generated: Y(prev) complete
     tick(0);
-    if (SPEC && prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
+    if (SPEC && !DYNB && prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
 
     // per-CTA running per-mel sums: flush when the clip changes
     if (!SPEC && want_sums && s_cur_clip != clip_i) {
@@ -748,9 +839,19 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
     // ---- stage 1 ----------------------------------------------------------------------------------------
     stage1_tile<C, PREK>(xs, E, s_win2, s_tw1, warp, lane, p.preemph);
-    __syncthreads();  // E complete, xs free
-    tick(1);
-    fold_red();  // the per-warp max / min of the rows phase B has just written
+    if constexpr (DYNB) {
+      // "my part of E is complete" — then the write-out of the previous tile fills the time until every warp is there:
+      // warps that finish stage 1 early claim more of its frames
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_bar1);
+      if (prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
+      mbar_wait(&s_bar1, bar1_parity);  // E complete, xs free
+      bar1_parity ^= 1u;
+    } else {
+      __syncthreads();  // E complete, xs free
+      tick(1);
+      fold_red();  // the per-warp max / min of the rows phase B has just written
+    }
 
     // prefetch the next tile's samples while stage 2 / mel run
     if (PREFETCH && nclip < p.batch) fill_tile<C, PREK>(p, xs, fc, nclip, ntile);
@@ -767,6 +868,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     stage2_tile<C, SPEC>(E, Pw, s_twp, warp, lane, pw_only, spec_eps);
     __syncthreads();  // Pw complete, E free (Y aliases E)
     tick(2);
+    if constexpr (DYNB) {
+      fold_red();  // every warp has finished phase B of the previous tile
+      if (threadIdx.x == 0) s_ticket = 0;
+    }
 
     float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
     if constexpr (SPEC) {
@@ -837,6 +942,117 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     if (prev >= 0)
       for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) atomicAdd(p.feat_sums + (int64_t)prev * 2 * M + i, s_sums[i]);
   }
+}
+
+// ---- fast_stft_kernel: the complex spectrum itself (dsp.stft, dsp.py:92-141) through the same fill / stage 1 / stage 2.
+// Stage 2 leaves X[frame][sig(k)] in place in the exchange buffer; the copy-out makes every row of the (T, F) complex64
+// output one contiguous run: warp = frame, lanes sweep the bins (coalesced 256-byte stores).
+template <class C>
+struct SmemStft {
+  static constexpr int cdiv4(int bytes) { return (bytes + 15) / 16; }
+  static constexpr int WIN = 0;
+  static constexpr int TW1 = WIN + cdiv4(8 * C::NC);
+  static constexpr int TWP = TW1 + cdiv4(8 * C::NC);
+  static constexpr int EX = TWP + cdiv4(8 * C::NC);
+  static constexpr int XS = EX + cdiv4(8 * C::FT * C::EP);
+  static constexpr int SIG = XS + cdiv4(4 * C::XS_FLOATS);
+  static constexpr int END = SIG + cdiv4(4 * C::F);
+};
+
+template <class C, int PREK>
+__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_stft_kernel(const FastParams p) {
+  constexpr int NC = C::NC, F = C::F;
+  using S = SmemStft<C>;
+  extern __shared__ float4 smem4[];
+  float2* const s_win2 = reinterpret_cast<float2*>(smem4 + S::WIN);
+  float2* const s_tw1 = reinterpret_cast<float2*>(smem4 + S::TW1);
+  float2* const s_twp = reinterpret_cast<float2*>(smem4 + S::TWP);
+  float2* const E = reinterpret_cast<float2*>(smem4 + S::EX);
+  float* const xs = reinterpret_cast<float*>(smem4 + S::XS) + C::XS_HEAD;
+  int* const s_sig = reinterpret_cast<int*>(smem4 + S::SIG);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FillCtx<C> fc;
+  fc.init((unsigned)__cvta_generic_to_shared(xs));
+  for (int i = threadIdx.x; i < NC; i += C::THREADS) {
+    s_win2[i] = p.win2[i];
+    s_tw1[i] = p.tw1[i];
+    s_twp[i] = p.twp[i];
+  }
+  for (int k = threadIdx.x; k < F; k += C::THREADS) s_sig[k] = C::sig(k);
+
+  const int tpc = p.tiles_per_clip;
+  const int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
+  int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
+  if (clip_i < p.batch) fill_tile<C, PREK>(p, xs, fc, clip_i, tile_i);
+  constexpr int J = (F + 31) / 32;  // bins per lane
+#pragma unroll 1
+  while (clip_i < p.batch) {
+    const int64_t lt0 = (int64_t)tile_i * C::FT;
+    const int64_t frames_left = p.frame_count - lt0;
+    const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
+    int nclip = clip_i + step_c, ntile = tile_i + step_t;
+    if (ntile >= tpc) {
+      ntile -= tpc;
+      ++nclip;
+    }
+    cp_async_wait_all();
+    __syncthreads();  // xs ready, E free (the previous tile's rows are on their way out)
+    stage1_tile<C, PREK>(xs, E, s_win2, s_tw1, warp, lane, p.preemph);
+    __syncthreads();  // E complete, xs free
+    if (nclip < p.batch) fill_tile<C, PREK>(p, xs, fc, nclip, ntile);
+    if (PREK != 0) {
+      int c2 = nclip + step_c, t2 = ntile + step_t;
+      if (t2 >= tpc) {
+        t2 -= tpc;
+        ++c2;
+      }
+      prefetch_span_l2<C>(p, c2, t2);
+    }
+    stage2_tile<C, true, true>(E, nullptr, s_twp, warp, lane, true, 0.0f);
+    __syncthreads();  // X complete (in place)
+    {
+      int sl[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) sl[j] = s_sig[min(lane + 32 * j, F - 1)];
+      float2* const o = reinterpret_cast<float2*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * F + lane;
+#pragma unroll 1
+      for (int f = warp; f < nf; f += C::WARPS) {
+        const float2* er = E + f * C::EP;
+        float2* orow = o + f * F;
+        float2 v[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] = er[sl[j]];
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (j < J - 1 || lane + 32 * j < F) orow[32 * j] = v[j];
+      }
+    }
+    clip_i = nclip;
+    tile_i = ntile;
+  }
+  cp_async_wait_all();
+}
+
+template <class C, int PREK>
+int launch_stft_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)16 * SmemStft<C>::END + 16;
+  if (smem > 226 * 1024) {
+    set_error("fast stft kernel: %zu bytes of shared memory needed", smem);
+    return B2A_ERR_UNSUPPORTED;
+  }
+  const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
+  if (grid < 1) grid = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2A_CUDA(cudaFuncSetAttribute(fast_stft_kernel<C, PREK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  fast_stft_kernel<C, PREK><<<grid, C::THREADS, smem, st>>>(p);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
 }
 
 template <class C, int YP>
@@ -932,6 +1148,8 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     set_error("fast kernel: %lld tiles in one launch (split the batch)", (long long)tiles);
     return B2A_ERR_UNSUPPORTED;
   }
+  if (p.spec_kind == B2A_SPEC_COMPLEX)
+    return p.preemph != 0.0f ? launch_stft_variant<C, 1>(plan, p, st) : launch_stft_variant<C, 0>(plan, p, st);
   const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
   const bool vec_ok = reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0;  // STG.128 rows
   if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel

@@ -126,6 +126,27 @@ def test_stft_edge_lengths_and_sizes(n_fft, hop, L):
     assert_stft_close(stft(dev(x), n_fft, hop), O.stft(x, n_fft, hop))
 
 
+@pytest.mark.parametrize("n_fft,hop,win,pre", [(400, 160, 400, 0.0), (512, 160, 400, 0.0), (1024, 256, 1024, 0.0),
+                                               (512, 160, 512, 0.97), (400, 160, 400, 0.97)])
+def test_fast_stft_kernel_parity(n_fft, hop, win, pre):
+    """dsp.stft for the common sizes runs on fast_stft_* (register FFT, in-place spectrum tile, coalesced complex rows):
+    same tolerance as the generic kernel, several clips, ragged last tile, reflect edges, optional pre-emphasis."""
+    from mlx_audio_plus_b200._arrays import Ingested
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+
+    w = np.asarray(O.hanning(win))
+    plan = FrontendPlan(n_fft=n_fft, hop=hop, window=w, preemph=pre)
+    assert plan.kernel_name == f"fast_stft_{n_fft}x{hop}"
+    xb = np.stack([synth(50 + i, 40017) * (0.5 + i / 5) for i in range(3)])
+    xd = dev(xb)
+    y = host(plan.run(Ingested("torch", True, xd, None, xd.device)))
+    for i in range(3):
+        xi = xb[i]
+        if pre:
+            xi = np.concatenate([xi[:1], xi[1:] - np.float32(pre) * xi[:-1]]).astype(np.float32)
+        assert_stft_close(y[i], O.stft(xi, n_fft, hop, win, w))
+
+
 # ---- istft --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", sorted(ISTFT_CASES))
 @pytest.mark.parametrize("where", ["cuda", "numpy"])
