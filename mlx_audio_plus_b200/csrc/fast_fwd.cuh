@@ -29,6 +29,10 @@
 #include "fft_regs.cuh"
 #include "mel_gen.cuh"
 
+#ifndef B2A_X_TWPF
+#define B2A_X_TWPF 3  // stage 1: inter-stage twiddle loads issued this many pairs ahead of their use (0 = compiler's order)
+#endif
+
 namespace b2a {
 
 struct FastParams {
@@ -172,21 +176,6 @@ __device__ __forceinline__ float4 lds128_at(unsigned base) {  // pinned (volatil
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-// ---- mbarrier (split arrive / wait): lets a warp do independent work between reaching a sync point and needing it ----
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
-          (unsigned)__cvta_generic_to_shared(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
 // non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
@@ -388,8 +377,10 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
     Dft<N1>::run(v);
     const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
     float2* eb = E + lane * C::EP + n2;
-#ifdef B2A_X_TWPF
-    // inter-stage twiddles: software-pipelined broadcast loads, TWD pairs ahead of their use
+#if B2A_X_TWPF > 0
+    // inter-stage twiddles: software-pipelined broadcast loads, TWD pairs ahead of their use (pinned with volatile asm:
+    // left alone, ptxas issues each LDS.128 right in front of its FMUL2 and every pair waits out a shared-memory latency;
+    // measured -1 %)
     constexpr int TWD = B2A_X_TWPF;
     const unsigned tb_sa = (unsigned)__cvta_generic_to_shared(tb4);
     float4 tq[N1 / 2];
@@ -399,7 +390,7 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
       constexpr int k1 = 2 * decltype(I_)::value;
       constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
       constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
-#ifdef B2A_X_TWPF
+#if B2A_X_TWPF > 0
       if constexpr (k1 / 2 + TWD < N1 / 2) tq[k1 / 2 + TWD] = lds128_at<16 * (k1 / 2 + TWD)>(tb_sa);
       const float4 t = tq[k1 / 2];
 #else
@@ -424,8 +415,10 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
                                             float spec_eps) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = INPLACE;
-#ifdef B2A_X_UREMAP
-  const int u = (C::WARPS - 1) - warp;  // unit 0 (the longest: DC / Nyquist + register permutation) on the highest warp id
+#ifndef B2A_NO_UREMAP
+  // unit 0 (the longest: DC / Nyquist + register permutation) goes to the highest warp id — the scheduler favours
+  // high warp ids, so the longest unit is not also the last one served (measured: -0.3 %)
+  const int u = (C::WARPS - 1) - warp;
 #else
   const int u = warp;
 #endif
@@ -646,13 +639,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   int* const s_ginfo = s_start + G * 8 + ((G * 8) & 1);               // [2*G], 8-byte aligned
   __shared__ float red_max[C::WARPS], red_min[C::WARPS];
   __shared__ int s_cur_clip;
-#ifdef B2A_X_DYNB
-  constexpr bool DYNB = SPEC;  // phase B runs between "E complete" arrive and wait, frames handed out by ticket
-#else
-  constexpr bool DYNB = false;
-#endif
-  __shared__ unsigned long long s_bar1;
-  __shared__ int s_ticket;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // staging tile: own space in the generated-mel kernels (the exchange buffer then holds the power tile), else it
@@ -675,12 +661,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   const bool want_max = p.clip_max != nullptr;
   if (want_sums)
     for (int i = threadIdx.x; i < 2 * G * 8; i += C::THREADS) s_sums[i] = 0.0;
-  if (threadIdx.x == 0) {
-    s_cur_clip = -1;
-    s_ticket = 0;
-    mbar_init(&s_bar1, C::WARPS);
-  }
-  unsigned bar1_parity = 0;
+  if (threadIdx.x == 0) s_cur_clip = -1;
 
   // tile walk: tile = clip_i * tiles_per_clip + tile_i advances by gridDim.x without a division per tile
   const int tpc = p.tiles_per_clip;
@@ -746,18 +727,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     float* const o = p.out + (int64_t)pclip * p.out_clip_stride;
     float4* const orow = reinterpret_cast<float4*>(o + (int64_t)ptile * C::FT * MS::M) + lane;
     const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
-    auto take = [&]() {  // next unclaimed frame of the staged tile (warp-uniform)
-      int t = 0;
-      if (lane == 0) t = atomicAdd(&s_ticket, 1);
-      return __shfl_sync(0xffffffffu, t, 0);
-    };
-    int nxt = DYNB ? take() : warp;
+    if (lane < QL) {
 #pragma unroll 1
-    for (;;) {
-      const int f = nxt;
-      if (f >= pnf) break;
-      nxt = DYNB ? take() : f + C::WARPS;
-      if (lane < QL) {
+      for (int f = warp; f < pnf; f += C::WARPS) {
         float4 v = yb[f * (YP / 4)];
         float* e = reinterpret_cast<float*>(&v);
 #pragma unroll
@@ -823,7 +795,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     cp_async_wait_all();
     __syncthreads();  // xs ready; run-time-table kernels: previous tile's Y written out; generated: Y(prev) complete
     tick(0);
-    if (SPEC && !DYNB && prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
+    if (SPEC && prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
 
     // per-CTA running per-mel sums: flush when the clip changes
     if (!SPEC && want_sums && s_cur_clip != clip_i) {
@@ -839,19 +811,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     }
     // ---- stage 1 ----------------------------------------------------------------------------------------
     stage1_tile<C, PREK>(xs, E, s_win2, s_tw1, warp, lane, p.preemph);
-    if constexpr (DYNB) {
-      // "my part of E is complete" — then the write-out of the previous tile fills the time until every warp is there:
-      // warps that finish stage 1 early claim more of its frames
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_bar1);
-      if (prev_clip >= 0) phase_b(prev_clip, prev_tile, prev_nf);
-      mbar_wait(&s_bar1, bar1_parity);  // E complete, xs free
-      bar1_parity ^= 1u;
-    } else {
-      __syncthreads();  // E complete, xs free
-      tick(1);
-      fold_red();  // the per-warp max / min of the rows phase B has just written
-    }
+    __syncthreads();  // E complete, xs free
+    tick(1);
+    fold_red();  // the per-warp max / min of the rows phase B has just written
 
     // prefetch the next tile's samples while stage 2 / mel run
     if (PREFETCH && nclip < p.batch) fill_tile<C, PREK>(p, xs, fc, nclip, ntile);
@@ -868,10 +830,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     stage2_tile<C, SPEC>(E, Pw, s_twp, warp, lane, pw_only, spec_eps);
     __syncthreads();  // Pw complete, E free (Y aliases E)
     tick(2);
-    if constexpr (DYNB) {
-      fold_red();  // every warp has finished phase B of the previous tile
-      if (threadIdx.x == 0) s_ticket = 0;
-    }
 
     float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
     if constexpr (SPEC) {
