@@ -205,34 +205,52 @@ struct FillCtx {
   static constexpr int TAIL = C::SPAN - (TOTAL_ROWS - 1) * C::HOP;  // samples in the last (partial) row
   static constexpr int ITERS = (TOTAL_ROWS + RPI - 1) / RPI;
   static_assert((TOTAL_ROWS - 1) / RPI == ITERS - 1, "exactly the last iteration is partial");
-  int src_off;     // floats from the tile's first sample
-  unsigned dst;    // shared-window byte address
-  bool active, last_ok;
-  __device__ __forceinline__ void init(unsigned xs_sa) {
+  const float* src0;  // this thread's first source pair of tile 0 of clip 0 (valid for interior tiles only)
+  unsigned dst;       // shared-window byte address
+  int lo, hi;         // tile indices [lo, hi] whose whole span is interior AND copyable raw (same for every clip)
+  bool active, last_ok, raw_pre;
+  static __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {  // b > 0
+    const int64_t q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+  }
+  template <int PREK>
+  __device__ __forceinline__ void init(const FastParams& p, unsigned xs_sa) {
     const int r0 = threadIdx.x / PPR, c = threadIdx.x - r0 * PPR;
-    src_off = r0 * C::HOP + 2 * c;
     dst = xs_sa + 4u * (unsigned)(r0 * C::P + 2 * c);
     active = r0 < RPI;
     const int row = r0 + RPI * (ITERS - 1);
     last_ok = active && (row < TOTAL_ROWS - 1 || (row == TOTAL_ROWS - 1 && 2 * c < TAIL));
+    // source coordinate of tile t's first sample: s0(t) = base + t * FT * HOP.  Interior: s0 >= max(0, sample_offset)
+    // and s0 + SPAN <= valid_length; with pre-emphasis the raw copy also needs the sample in front of the span
+    // (s0 > sample_offset) and the pitch HOP + 2 (see fill_tile).
+    const bool pre = p.preemph != 0.0f;
+    raw_pre = PREK != 0 && pre && C::P == C::HOP + 2;
+    const int64_t base = p.frame_begin * C::HOP - p.geo.pad_left, T = (int64_t)C::FT * C::HOP;
+    int64_t smin = p.sample_offset + (pre ? 1 : 0);
+    if (smin < 0) smin = 0;
+    int64_t l = -floor_div(-(smin - base), T);                    // ceil((smin - base) / T)
+    int64_t h = floor_div(p.valid_length - C::SPAN - base, T);
+    if (l < 0) l = 0;
+    if (h > 0x3fffffff) h = 0x3fffffff;
+    if (!p.fast_fill_ok || (pre && !raw_pre)) h = l - 1;
+    if (h < l) { l = 1; h = 0; }
+    lo = (int)l;
+    hi = (int)h;
+    src0 = p.audio + (base - p.sample_offset) + (r0 * C::HOP + 2 * c);
   }
 };
 
 // Copies the tile's sample span into shared memory (rows of HOP samples at pitch P).
 template <class C, int PREK>
 __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const FillCtx<C>& fc, int clip_i, int tile_i) {
-  const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
-  const int64_t lt0 = (int64_t)tile_i * C::FT;
-  const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
-  const int64_t s0 = q0 - p.geo.pad_left;             // source coordinate
-  const bool interior = p.fast_fill_ok && s0 >= 0 && (s0 + C::SPAN) <= p.valid_length && s0 >= p.sample_offset;
   // Interior tiles are copied RAW with cp.async (asynchronous: the copy of the next tile overlaps stage 2 / mel).  With
   // pre-emphasis the filter y[n] = x[n] - a*x[n-1] is then applied by stage 1 as it reads (separately rounded multiply
   // and subtract, bit-exact vs the reference's `x[1:] - a*x[:-1]`); the one sample in front of the span goes to
   // xs[-3] — where "the last sample of the previous row" lives for every other row start (pitch = HOP + 2).
-  const bool raw_pre = PREK != 0 && p.preemph != 0.0f && s0 > p.sample_offset && C::P == C::HOP + 2;
-  if (interior && (p.preemph == 0.0f || raw_pre)) {
-    const float* src = clip + (s0 - p.sample_offset) + fc.src_off;
+  // Whether a tile is interior depends on its index only (every clip has the same geometry): FillCtx::lo / hi.
+  if (tile_i >= fc.lo && tile_i <= fc.hi) {
+    const bool raw_pre = PREK != 0 && fc.raw_pre;
+    const float* src = fc.src0 + ((int64_t)clip_i * p.clip_stride + (int64_t)tile_i * (C::FT * C::HOP));
     if (fc.active) {
 #pragma unroll
       for (int i = 0; i < FillCtx<C>::ITERS - 1; ++i)
@@ -244,9 +262,13 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const 
     }
     if (threadIdx.x == 0) {
       reinterpret_cast<int*>(xs)[-4] = raw_pre ? 1 : 0;
-      if (raw_pre) cp_async4((unsigned)__cvta_generic_to_shared(xs - 3), clip + (s0 - p.sample_offset) - 1);
+      // thread 0's first pair is the span's first sample: the one in front of it is src[-1]
+      if (raw_pre) cp_async4((unsigned)__cvta_generic_to_shared(xs - 3), src - 1);
     }
   } else {
+    const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
+    const int64_t lt0 = (int64_t)tile_i * C::FT;
+    const int64_t q0 = (p.frame_begin + lt0) * C::HOP;  // padded coordinate of the tile's first sample
     const int64_t frames_left = p.frame_count - lt0;
     const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
     const int need = (nf - 1) * C::HOP + C::N;
@@ -645,7 +667,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   // aliases the exchange buffer
   float* const Y = SPEC ? Pw : reinterpret_cast<float*>(E);
   FillCtx<C> fc;
-  fc.init((unsigned)__cvta_generic_to_shared(xs));
+  fc.template init<PREK>(p, (unsigned)__cvta_generic_to_shared(xs));
 
   for (int i = threadIdx.x; i < NC; i += C::THREADS) {
     s_win2[i] = p.win2[i];
@@ -930,7 +952,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_stft_kernel(co
   int* const s_sig = reinterpret_cast<int*>(smem4 + S::SIG);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FillCtx<C> fc;
-  fc.init((unsigned)__cvta_generic_to_shared(xs));
+  fc.template init<PREK>(p, (unsigned)__cvta_generic_to_shared(xs));
   for (int i = threadIdx.x; i < NC; i += C::THREADS) {
     s_win2[i] = p.win2[i];
     s_tw1[i] = p.tw1[i];
