@@ -860,10 +860,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       // as an immediate; four finished rows are parked in Y[frame][m..m+3] with one STS.128.
       {
         const float* pr = reinterpret_cast<const float*>(E + lane * C::EP) + (lane >> 4);  // in-place power tile
-        float4* const yl = reinterpret_cast<float4*>(Y + lane * YP);
+        // one STS.128 per finished row quad, as inline PTX with the row offset as an immediate: written as a C++ store,
+        // the last quad of every warp's branch is tail-merged into a register-addressed store of unknown alignment and
+        // split into four conflicting scalar STS (+120 shared-memory wavefronts per tile)
+        const unsigned yl_sa = (unsigned)__cvta_generic_to_shared(Y + lane * YP);
         MS::template run<C>(warp, pr, [&](auto M_, float a0, float a1, float a2, float a3) {
           constexpr int m = decltype(M_)::value;
-          yl[m / 4] = make_float4(a0, a1, a2, a3);
+          asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(yl_sa), "n"(4 * (m / 4) * 4), "f"(a0), "f"(a1), "f"(a2),
+                       "f"(a3));
         });
       }
       prev_clip = clip_i;  // phase B of this tile runs after the next barrier, next to stage 1 of the next tile
