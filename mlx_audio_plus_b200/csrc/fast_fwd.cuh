@@ -29,6 +29,9 @@
 #include "fft_regs.cuh"
 #include "mel_gen.cuh"
 
+#ifndef B2A_X_TWPF2
+#define B2A_X_TWPF2 2  // stage 2: post-twiddle loads, same idea
+#endif
 #ifndef B2A_X_TWPF
 #define B2A_X_TWPF 3  // stage 1: inter-stage twiddle loads issued this many pairs ahead of their use (0 = compiler's order)
 #endif
@@ -273,14 +276,31 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const 
     const int nf = (int)(frames_left < C::FT ? frames_left : C::FT);
     const int need = (nf - 1) * C::HOP + C::N;
     if (threadIdx.x == 0) reinterpret_cast<int*>(xs)[-4] = 0;  // this path stores finished (pre-emphasised) samples
-    for (int i = threadIdx.x; i < C::SPAN; i += C::THREADS) {
+    // Edge tiles (clip start / end: 2 per clip): sample PAIRS that lie inside the signal still go through cp.async —
+    // asynchronous like an interior tile — and only the padded / reflected / virtual part (a few hundred samples) is
+    // computed with ordinary loads.  With pre-emphasis every sample has to be computed (the padding reflects the
+    // FILTERED signal), so the whole tile takes the scalar path.
+    const bool pairs_ok = p.fast_fill_ok && p.preemph == 0.0f;
+    const int64_t s0 = q0 - p.geo.pad_left;
+    const int64_t smin = p.sample_offset > 0 ? p.sample_offset : 0;
+    const unsigned xs_sa = (unsigned)__cvta_generic_to_shared(xs);
+    auto sample = [&](int j) {
       float v = 0.0f;
-      if (i < need) {
-        const int64_t s = source_index(p.geo, p.pad_mode, q0 + i);
+      if (j < need) {
+        const int64_t s = source_index(p.geo, p.pad_mode, q0 + j);
         if (s >= 0) v = fetch_sample_f(p, clip, s);
       }
-      const int row = i / C::HOP, col = i - row * C::HOP;
-      xs[row * C::P + col] = v;
+      return v;
+    };
+    static_assert(C::SPAN % 2 == 0 && C::HOP % 2 == 0 && C::P % 2 == 0, "pairs stay inside a row");
+    for (int i = threadIdx.x; i < C::SPAN / 2; i += C::THREADS) {
+      const int e = 2 * i, row = e / C::HOP, col = e - row * C::HOP;
+      const int64_t s = s0 + e;
+      if (pairs_ok && e + 1 < need && s >= smin && s + 1 < p.valid_length) {
+        cp_async8(xs_sa + 4u * (unsigned)(row * C::P + col), clip + (s - p.sample_offset));
+      } else {
+        *reinterpret_cast<float2*>(xs + row * C::P + col) = make_float2(sample(e), sample(e + 1));
+      }
     }
   }
   cp_async_commit();
@@ -489,7 +509,11 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
       A[N2 / 2 + j] = T[j];
     });
   }
-  const float4* tw4 = reinterpret_cast<const float4*>(s_twp + u * 2 * N2);
+  // post-twiddles: broadcast loads issued TWD2 pairs ahead of their use (pinned), like the inter-stage twiddles of stage 1
+  constexpr int TWD2 = B2A_X_TWPF2 < N2 / 2 ? B2A_X_TWPF2 : N2 / 2;
+  const unsigned tw_sa = (unsigned)__cvta_generic_to_shared(s_twp + u * 2 * N2);
+  float4 tw4[N2 / 2];
+  static_for<0, TWD2>([&](auto I_) { tw4[decltype(I_)::value] = lds128_at<16 * decltype(I_)::value>(tw_sa); });
   // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
   float* const plo = SPEC ? pr + 2 * (u * N2) : pr + kb_lo;
   float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * N2) : pr + (NC - kb_lo);
@@ -501,6 +525,7 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
     float2* const cm = E + lane * C::EP + (N1 / 2 + u) * N2;
     static_for<0, N2 / 2>([&](auto I_) {
       constexpr int k2 = 2 * decltype(I_)::value;
+      if constexpr (k2 / 2 + TWD2 < N2 / 2) tw4[k2 / 2 + TWD2] = lds128_at<16 * (k2 / 2 + TWD2)>(tw_sa);
       const float4 t = tw4[k2 / 2];
       float2 xk, xm;
       post_pair_c(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), xk, xm);
@@ -518,6 +543,7 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   }
   static_for<0, N2 / 2>([&](auto I_) {
     constexpr int k2 = 2 * decltype(I_)::value;
+    if constexpr (k2 / 2 + TWD2 < N2 / 2) tw4[k2 / 2 + TWD2] = lds128_at<16 * (k2 / 2 + TWD2)>(tw_sa);
     const float4 t = tw4[k2 / 2];
     float pk, pm;
     post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
