@@ -141,6 +141,34 @@ def main():
             res.append(r)
             del x
             torch.cuda.empty_cache()
+    if want("R"):
+        # the step in front of the path: decoded PCM -> resample -> mono float32, one kernel.
+        # bytes = interleaved PCM in + float32 mono out; scipy (the reference's own call) timed on one host core beside it.
+        from mlx_audio_plus_b200.stt.utils import load_audio
+        for nm, orig, ch, secs in (("44.1 kHz stereo int16 -> 16 kHz mono, 1 h", 44100, 2, 3600),
+                                   ("48 kHz mono int16 -> 16 kHz, 1 h", 48000, 1, 3600)):
+            n = orig * secs
+            g = torch.Generator(device="cuda")
+            g.manual_seed(11)
+            pcm = (torch.randn((n, ch), generator=g, device="cuda") * 3000).to(torch.int16)
+            out = load_audio(pcm=pcm, sample_rate=orig, sr=16000)
+            ms = timeit(lambda: load_audio(pcm=pcm, sample_rate=orig, sr=16000), a.steps)
+            by = pcm.numel() * 2 + out.numel() * 4
+            r = {"config": f"R load_audio {nm}", "kernel": "resample_kernel", "batch": 1, "samples": n, "ms": ms,
+                 "audio_hours_per_s": secs / 3600.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)}
+            try:
+                import time
+                from oracle import pre_oracle as P
+                sub = pcm[: orig * 60].cpu().numpy()
+                t0 = time.perf_counter()
+                P.load_audio_from_pcm(sub, orig, 16000)
+                r["scipy_cpu_1core_audio_hours_per_s"] = (60 / 3600.0) / (time.perf_counter() - t0)
+            except Exception as e:  # noqa: BLE001
+                r["scipy_cpu_1core_audio_hours_per_s"] = str(e)
+            res.append(r)
+            del pcm
+            torch.cuda.empty_cache()
     for r in res:
         print(json.dumps(r), flush=True)
     if a.out:

@@ -190,6 +190,31 @@ int b2a_frontend_dump_frames(b2a_plan* plan, const b2a_forward_args* args, int a
 /* which kernel family a plan dispatches to: "fast400", "fast512", "generic", "small", ... */
 const char* b2a_plan_kernel_name(const b2a_plan* plan);
 
+/* ---- the step in front of the path: PCM -> resampled float32 (mono) ----------------------------------
+ * What load_audio does after the decoder (stt/utils.py:21-57: resample_audio = scipy.signal.resample_poly(audio, up, down,
+ * padtype="edge") per channel, then mx.array(audio, float32).mean(axis=1); audio_io.py:258-262: int16 / 32768.0).
+ * The polyphase filter is designed on the host (scipy's Kaiser(5.0) windowed sinc, zero-padded as resample_poly does) and
+ * handed over as h_taps[j][phase] = h_padded[phase + j * up], taps_per_phase = ceil(len(h_padded) / up);
+ * pre_remove = resample_poly's n_pre_remove.  Output sample n = sum_j taps[j][t % up] * x_edge[t / up - j], t = (n + pre_remove) * down. */
+typedef struct b2a_resampler b2a_resampler;
+enum { B2A_PCM_F32 = 0, B2A_PCM_I16 = 1 };
+typedef struct b2a_resample_args {
+  const void* in;          /* device: (batch, n_in, channels) interleaved float32 or int16 */
+  float* out;              /* device: (batch, n_out) when mono, else (batch, n_out, channels) */
+  int64_t n_in;            /* frames per clip */
+  int64_t in_clip_stride;  /* elements between clips (0 = n_in * channels) */
+  int64_t out_clip_stride; /* elements between clips (0 = dense) */
+  int32_t batch;
+  int32_t channels;
+  int32_t in_kind;         /* B2A_PCM_* */
+  int32_t mono;            /* 1: mean over channels (float32) */
+} b2a_resample_args;
+int b2a_resampler_create(int32_t up, int32_t down, int32_t taps_per_phase, int64_t pre_remove, const float* h_taps,
+                         b2a_resampler** out);
+int b2a_resampler_destroy(b2a_resampler* r);
+int b2a_resampler_out_len(const b2a_resampler* r, int64_t n_in, int64_t* n_out); /* ceil(n_in * up / down) */
+int b2a_resample(b2a_resampler* r, const b2a_resample_args* args, void* stream);
+
 /* ---- inverse: iSTFT with windowed overlap-add -----------------------------------------------------
  * dsp.istft (dsp.py:144-217) and ISTFTCache.istft (dsp.py:350-417). */
 typedef struct b2a_istft_desc {

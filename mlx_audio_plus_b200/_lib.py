@@ -68,6 +68,16 @@ class InverseArgs(C.Structure):
     ]
 
 
+class ResampleArgs(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p), ("out", C.c_void_p), ("n_in", C.c_int64), ("in_clip_stride", C.c_int64),
+        ("out_clip_stride", C.c_int64), ("batch", C.c_int32), ("channels", C.c_int32), ("in_kind", C.c_int32),
+        ("mono", C.c_int32),
+    ]
+
+
+PCM_F32, PCM_I16 = 0, 1
+
 # every symbol include/b200audio.h declares; tests/test_abi.py checks the library exports them all
 SYMBOLS = {
     "b2a_version": (C.c_int, []),
@@ -93,6 +103,10 @@ SYMBOLS = {
     "b2a_istft_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "b2a_istft_inverse": (C.c_int, [C.c_void_p, C.POINTER(InverseArgs), C.c_void_p]),
     "b2a_istft_inverse_host": (C.c_int, [C.c_void_p, C.POINTER(InverseArgs)]),
+    "b2a_resampler_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2a_resampler_destroy": (C.c_int, [C.c_void_p]),
+    "b2a_resampler_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "b2a_resample": (C.c_int, [C.c_void_p, C.POINTER(ResampleArgs), C.c_void_p]),
     "b2a_measure_fp32_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
     "b2a_measure_copy_gbs": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -40,15 +40,17 @@ def test_struct_sizes_match_header():
     """ctypes mirrors of the C structs: compile a tiny C program printing sizeof and compare."""
     from mlx_audio_plus_b200 import _lib
 
-    src = ('#include <stdio.h>\n#include "b200audio.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
-           "sizeof(b2a_frontend_desc),sizeof(b2a_forward_args),sizeof(b2a_istft_desc),sizeof(b2a_inverse_args));return 0;}")
+    src = ('#include <stdio.h>\n#include "b200audio.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+           "sizeof(b2a_frontend_desc),sizeof(b2a_forward_args),sizeof(b2a_istft_desc),sizeof(b2a_inverse_args),"
+           "sizeof(b2a_resample_args));return 0;}")
     import tempfile
 
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "s.c"), "-o", os.path.join(td, "s")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(td, "s")]).split()]
-    assert sizes == [C.sizeof(_lib.FrontendDesc), C.sizeof(_lib.ForwardArgs), C.sizeof(_lib.IstftDesc), C.sizeof(_lib.InverseArgs)]
+    assert sizes == [C.sizeof(_lib.FrontendDesc), C.sizeof(_lib.ForwardArgs), C.sizeof(_lib.IstftDesc), C.sizeof(_lib.InverseArgs),
+                     C.sizeof(_lib.ResampleArgs)]
 
 
 def test_windows_bit_exact_vs_oracle_and_fixture(golden):

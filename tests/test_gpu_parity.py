@@ -461,3 +461,42 @@ def test_c3_one_hour_file_full_size_vs_oracle():
         "sample_rate", "normalize", "window_size", "window_stride", "window", "features", "n_fft", "dither")}))
     assert ref.shape == (1, 360001, 80)
     assert np.abs(y.cpu().numpy() - ref).max() <= 5e-4
+
+
+# ---- the step in front of the path: PCM -> resample -> mono (stt/utils.py:21-57) -------------------------------
+@pytest.mark.parametrize("orig,target,ch,kind", [(44100, 16000, 2, "i16"), (48000, 16000, 1, "i16"), (8000, 16000, 1, "f32"),
+                                                 (22050, 16000, 2, "f32"), (24000, 16000, 3, "i16"), (16000, 16000, 2, "i16"),
+                                                 (16000, 24000, 1, "f32"), (44100, 48000, 2, "i16")])
+@pytest.mark.parametrize("n", [9, 30011])
+def test_load_audio_resample_parity(orig, target, ch, kind, n):
+    """one kernel: int16 / 32768 -> resample_poly(padtype="edge") per channel -> float32 mean over channels, against
+    scipy in float64 (the reference's own arithmetic); tolerance 1e-5 of the peak (fp32 FIR of <= 61 taps)."""
+    from mlx_audio_plus_b200.stt.utils import load_audio, resample_audio
+    from oracle import pre_oracle as P
+
+    rng = np.random.default_rng(n + ch)
+    t = np.arange(n) / orig
+    wave = 0.4 * np.sin(2 * np.pi * 440 * t)[:, None] + 0.1 * rng.standard_normal((n, ch))
+    pcm = np.clip(np.round(wave * 32768), -32768, 32767).astype(np.int16)
+    src = pcm if kind == "i16" else (pcm.astype(np.float64) / 32768.0).astype(np.float32)
+    ref = P.load_audio_from_pcm(src if kind == "i16" else src.astype(np.float64), orig, target)
+    for put in (lambda a: a, dev):
+        y = host(load_audio(pcm=put(src), sample_rate=orig, sr=target))
+        assert y.shape == ref.shape and y.dtype == np.float32
+        tol = 0.0 if orig == target else 1e-5 * max(np.abs(ref).max(), 1e-3)
+        assert np.abs(y - ref).max() <= tol, np.abs(y - ref).max()
+    if orig != target:  # per-channel resampling (stt/utils.py:21-29)
+        r2 = P.resample_audio(P.pcm_to_float(src if kind == "i16" else src.astype(np.float64)), orig, target)
+        y2 = host(resample_audio(dev(src), orig, target))
+        assert y2.shape == r2.shape
+        assert np.abs(y2 - r2).max() <= 1e-5 * max(np.abs(r2).max(), 1e-3)
+
+
+def test_resample_batch_matches_loop():
+    from mlx_audio_plus_b200.stt.utils import _run
+
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-20000, 20000, size=(3, 5000, 2), dtype=np.int16)
+    yb = host(_run(dev(pcm), 160, 441, True))
+    for i in range(3):
+        np.testing.assert_array_equal(yb[i], host(_run(dev(pcm[i]), 160, 441, True)))
