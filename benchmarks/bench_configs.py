@@ -169,6 +169,26 @@ def main():
             res.append(r)
             del pcm
             torch.cuda.empty_cache()
+    if want("P"):
+        # the steps right after the path: Whisper (B, 3000, 128) float32 -> float16 segments; FunASR LFR + CMVN
+        from mlx_audio_plus_b200._post import lfr, rows_pad_cast
+        mel = torch.randn((1024, 3000, 128), device="cuda")
+        out = rows_pad_cast(mel, 0, 3000, 3000, "float16")
+        ms = timeit(lambda: rows_pad_cast(mel, 0, 3000, 3000, "float16"), a.steps)
+        by = mel.numel() * 4 + out.numel() * 2
+        res.append({"config": "P whisper segments 1024 x (3000,128) f32 -> f16", "kernel": "rows_pad_cast_kernel", "batch": 1024, "ms": ms,
+                    "audio_hours_per_s": 1024 * 30 / 3600.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+        feats = torch.randn((64, 360000, 80), device="cuda")
+        sh, sc = torch.randn(560, device="cuda"), torch.rand(560, device="cuda") + 0.5
+        out = lfr(feats, 7, 6, sh, sc)
+        ms = timeit(lambda: lfr(feats, 7, 6, sh, sc), a.steps)
+        by = feats.numel() * 4 + out.numel() * 4
+        res.append({"config": "P funasr LFR 7/6 + CMVN, 64 x 1 h of (T,80)", "kernel": "lfr_kernel", "batch": 64, "ms": ms,
+                    "audio_hours_per_s": 64.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+        del mel, feats
+        torch.cuda.empty_cache()
     for r in res:
         print(json.dumps(r), flush=True)
     if a.out:

@@ -215,6 +215,18 @@ int b2a_resampler_destroy(b2a_resampler* r);
 int b2a_resampler_out_len(const b2a_resampler* r, int64_t n_in, int64_t* n_out); /* ceil(n_in * up / down) */
 int b2a_resample(b2a_resampler* r, const b2a_resample_args* args, void* stream);
 
+/* ---- the steps right after the path: the layouts the encoders read -------------------------------------
+ * b2a_rows_pad_cast: whisper/whisper.py:990-996  pad_or_trim(mel[seek : seek + segment_size], N_FRAMES, axis=-2).astype(dtype)
+ *   in (batch, *, cols) float32 with in_clip_stride elements between clips; rows [row_begin, row_begin + rows_valid) are
+ *   copied, rows up to rows_out are zero; out (batch, rows_out, cols) dense in out_dtype.
+ * b2a_lfr: funasr/audio.py:84-139 apply_lfr (+ the precomputed CMVN of apply_cmvn, funasr/audio.py:166-169, when
+ *   cmvn_shift / cmvn_scale [lfr_m * n_mels] are given): out (batch, ceil(frames / lfr_n), lfr_m * n_mels). */
+enum { B2A_DTYPE_F32 = 0, B2A_DTYPE_F16 = 1, B2A_DTYPE_BF16 = 2 };
+int b2a_rows_pad_cast(const float* in, int64_t in_clip_stride, int64_t row_begin, int64_t rows_valid, int32_t cols, void* out,
+                      int64_t rows_out, int32_t out_dtype, int32_t batch, void* stream);
+int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_mels, int32_t lfr_m, int32_t lfr_n,
+            const float* cmvn_shift, const float* cmvn_scale, float* out, int64_t out_clip_stride, int32_t batch, void* stream);
+
 /* ---- inverse: iSTFT with windowed overlap-add -----------------------------------------------------
  * dsp.istft (dsp.py:144-217) and ISTFTCache.istft (dsp.py:350-417). */
 typedef struct b2a_istft_desc {

@@ -77,6 +77,7 @@ class ResampleArgs(C.Structure):
 
 
 PCM_F32, PCM_I16 = 0, 1
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 
 # every symbol include/b200audio.h declares; tests/test_abi.py checks the library exports them all
 SYMBOLS = {
@@ -107,6 +108,10 @@ SYMBOLS = {
     "b2a_resampler_destroy": (C.c_int, [C.c_void_p]),
     "b2a_resampler_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "b2a_resample": (C.c_int, [C.c_void_p, C.POINTER(ResampleArgs), C.c_void_p]),
+    "b2a_rows_pad_cast": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
+    "b2a_lfr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                          C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "b2a_measure_fp32_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
     "b2a_measure_copy_gbs": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -1,0 +1,148 @@
+// b200audio — the steps right after the path: the layouts the encoders read.
+//   b2a_rows_pad_cast  Whisper's segment builder, whisper/whisper.py:990-996:
+//                      pad_or_trim(mel[seek : seek + segment_size], N_FRAMES, axis=-2).astype(dtype)
+//                      -> (batch, rows_out, cols) float32 / float16 / bfloat16, zero rows after the valid ones.
+//   b2a_lfr            FunASR low-frame-rate stacking, funasr/audio.py:84-139 (first / last frame replicated at the
+//                      ends, lfr_m frames stacked every lfr_n), with the precomputed CMVN of apply_cmvn
+//                      ((x + shift) * scale, funasr/audio.py:166-169) applied on the way out when given.
+// Both are single-pass, HBM-bound copies: every input row is read once (LFR: lfr_m / lfr_n times, from L2), every
+// output element written once.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b2a {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T cast_out(float v);
+template <>
+__device__ __forceinline__ float cast_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half cast_out<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) rows_pad_cast_kernel(const float* __restrict__ in, int64_t in_clip_stride, int64_t row_begin,
+                                                             int64_t rows_valid, int cols, T* __restrict__ out, int64_t rows_out) {
+  const int64_t per_clip = rows_out * cols, valid = rows_valid * cols;
+  const float* src = in + (int64_t)blockIdx.y * in_clip_stride + row_begin * cols;
+  T* dst = out + (int64_t)blockIdx.y * per_clip;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < per_clip; i += (int64_t)gridDim.x * blockDim.x * VEC) {
+    float v[VEC];
+    if (VEC == 4 && i + 3 < valid) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src + i));
+      v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = (i + k < valid) ? __ldg(src + i + k) : 0.0f;
+    }
+    T o[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o[k] = cast_out<T>(v[k]);
+    if (VEC == 4) {
+      if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<float4*>(o);
+      else *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<float2*>(o);
+    } else {
+      dst[i] = o[0];
+    }
+  }
+}
+
+template <typename T>
+int launch_rows(const float* in, int64_t in_clip_stride, int64_t row_begin, int64_t rows_valid, int cols, void* out,
+                int64_t rows_out, int batch, cudaStream_t st) {
+  const int64_t per_clip = rows_out * cols;
+  const bool vec = per_clip % 4 == 0 && (row_begin * cols) % 4 == 0 && in_clip_stride % 4 == 0 &&
+                   reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  const int64_t work = vec ? per_clip / 4 : per_clip;
+  int64_t gx = (work + 255) / 256;
+  if (gx > 148 * 16) gx = 148 * 16;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)batch);
+  if (vec) rows_pad_cast_kernel<T, 4><<<grid, 256, 0, st>>>(in, in_clip_stride, row_begin, rows_valid, cols, (T*)out, rows_out);
+  else rows_pad_cast_kernel<T, 1><<<grid, 256, 0, st>>>(in, in_clip_stride, row_begin, rows_valid, cols, (T*)out, rows_out);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+// VEC = 4: four consecutive mel bins of one stacked frame per thread (n_mels % 4 == 0: they never straddle a frame)
+template <int VEC>
+__global__ void __launch_bounds__(256) lfr_kernel(const float* __restrict__ in, int64_t in_clip_stride, int64_t frames, int n_mels, int lfr_m,
+                                                   int lfr_n, const float* __restrict__ shift, const float* __restrict__ scale,
+                                                   float* __restrict__ out, int64_t out_clip_stride, int64_t t_lfr) {
+  const int width = lfr_m * n_mels, left = (lfr_m - 1) / 2;
+  const float* src = in + (int64_t)blockIdx.y * in_clip_stride;
+  float* dst = out + (int64_t)blockIdx.y * out_clip_stride;
+  const int64_t total = t_lfr * width;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total; i += (int64_t)gridDim.x * blockDim.x * VEC) {
+    const int64_t t = i / width;
+    const int c = (int)(i - t * width);
+    const int k = c / n_mels, m = c - k * n_mels;
+    int64_t f = t * lfr_n + k - left;  // index into the unpadded features; the pads replicate frame 0 / frame T-1
+    f = f < 0 ? 0 : (f > frames - 1 ? frames - 1 : f);
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src + f * n_mels + m));
+      if (shift) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(shift + c)), b = __ldg(reinterpret_cast<const float4*>(scale + c));
+        v.x = (v.x + a.x) * b.x; v.y = (v.y + a.y) * b.y; v.z = (v.z + a.z) * b.z; v.w = (v.w + a.w) * b.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = v;
+    } else {
+      float v = __ldg(src + f * n_mels + m);
+      if (shift) v = (v + __ldg(shift + c)) * __ldg(scale + c);
+      dst[i] = v;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace b2a
+
+using namespace b2a;
+
+extern "C" {
+
+int b2a_rows_pad_cast(const float* in, int64_t in_clip_stride, int64_t row_begin, int64_t rows_valid, int32_t cols, void* out,
+                      int64_t rows_out, int32_t out_dtype, int32_t batch, void* stream) {
+  if (!in || !out || cols <= 0 || rows_out <= 0 || batch <= 0 || batch > 65535 || row_begin < 0 || rows_valid < 0) {
+    set_error("rows_pad_cast: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  if (rows_valid > rows_out) rows_valid = rows_out;  // trim
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (out_dtype) {
+    case B2A_DTYPE_F32: return launch_rows<float>(in, in_clip_stride, row_begin, rows_valid, cols, out, rows_out, batch, st);
+    case B2A_DTYPE_F16: return launch_rows<__half>(in, in_clip_stride, row_begin, rows_valid, cols, out, rows_out, batch, st);
+    case B2A_DTYPE_BF16: return launch_rows<__nv_bfloat16>(in, in_clip_stride, row_begin, rows_valid, cols, out, rows_out, batch, st);
+    default: set_error("rows_pad_cast: out_dtype %d", out_dtype); return B2A_ERR_INVALID_ARG;
+  }
+}
+
+int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_mels, int32_t lfr_m, int32_t lfr_n,
+            const float* cmvn_shift, const float* cmvn_scale, float* out, int64_t out_clip_stride, int32_t batch, void* stream) {
+  if (!in || !out || frames <= 0 || n_mels <= 0 || lfr_m <= 0 || lfr_n <= 0 || batch <= 0 || batch > 65535 ||
+      ((cmvn_shift == nullptr) != (cmvn_scale == nullptr))) {
+    set_error("lfr: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  const int64_t t_lfr = (frames + lfr_n - 1) / lfr_n;  // ceil(T / lfr_n), funasr/audio.py:114
+  const int64_t total = t_lfr * lfr_m * n_mels;
+  const int64_t ics = in_clip_stride ? in_clip_stride : frames * n_mels, ocs = out_clip_stride ? out_clip_stride : total;
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool vec = n_mels % 4 == 0 && ics % 4 == 0 && ocs % 4 == 0 && al16(in) && al16(out) && al16(cmvn_shift) && al16(cmvn_scale);
+  int64_t gx = ((vec ? total / 4 : total) + 255) / 256;
+  if (gx > 148 * 32) gx = 148 * 32;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)batch);
+  if (vec) lfr_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(in, ics, frames, n_mels, lfr_m, lfr_n, cmvn_shift, cmvn_scale, out, ocs, t_lfr);
+  else lfr_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(in, ics, frames, n_mels, lfr_m, lfr_n, cmvn_shift, cmvn_scale, out, ocs, t_lfr);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+}  // extern "C"

@@ -59,3 +59,12 @@ def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0):
         spec_kind=L.SPEC_POWER, log_kind=L.LOG_LOG10, guard_kind=L.GUARD_MAX, guard_eps=1e-10,
         clamp_kind=L.CLAMP_CLIP_MAX, clamp_value=8.0, affine_add=4.0, affine_div=4.0)
     return emit(ing, out[0] if was_1d else out)
+
+
+def mel_segment(mel, seek: int, segment_size: int, n_frames: int = N_FRAMES, dtype="float16"):
+    """The decoder loop's segment builder (reference whisper/whisper.py:990-996),
+    ``pad_or_trim(mel[seek : seek + segment_size], N_FRAMES, axis=-2).astype(dtype)``, as one kernel: slice, zero rows up to
+    `n_frames`, cast to the encoder dtype ("float16" / "bfloat16" / "float32").  mel: (T, n_mels) or (B, T, n_mels)."""
+    from ...._post import rows_pad_cast
+
+    return rows_pad_cast(mel, seek, segment_size, n_frames, dtype)

@@ -77,6 +77,7 @@ def _load_reference():
         "voxtral": load("mlx_audio.stt.models.voxtral_rt_audio", "mlx_audio/stt/models/voxtral_realtime/audio.py"),
         "vocos_mel": load("mlx_audio.codec.models.vocos_mel", "mlx_audio/codec/models/vocos/mel.py"),
         "s3tok": load("mlx_audio.codec.models.s3tok_utils", "mlx_audio/codec/models/s3tokenizer/utils.py"),
+        "funasr": load("mlx_audio.stt.models.funasr_audio", "mlx_audio/stt/models/funasr/audio.py"),
     }
 
     def extract(rel, names, extra=None):
@@ -127,6 +128,34 @@ def hift_goldens(mx, R):
             g[f"n{n_fft}|{name}|re"], g[f"n{n_fft}|{name}|im"] = A(re), A(im)
             g[f"n{n_fft}|{name}|y"] = A(R[name].istft(mx.array(mag), mx.array(ph), n_fft, hop, mx.array(w)))
     np.savez_compressed(os.path.join(OUT, "refshim_hift.npz"), **g)
+
+
+def post_goldens(mx, R):
+    """tests/golden/refshim_post.npz: the steps AFTER the path — FunASR log-mel + apply_lfr +
+    apply_cmvn (funasr/audio.py:32-169) and Whisper's segment builder pad_or_trim(mel[seek:seek+n], N_FRAMES,
+    axis=-2).astype(float16) (whisper/whisper.py:990-996), from the reference's own functions."""
+    F, W = R["funasr"], R["whisper"]
+    A = np.asarray
+    g = {}
+    x = synth(300, 16000 * 3 + 77)
+    g["funasr|x"] = x
+    lm = F.log_mel_spectrogram(mx.array(x))
+    g["funasr|logmel"] = A(lm)
+    g["funasr|lfr"] = A(F.apply_lfr(lm))
+    g["funasr|lfr_5_3"] = A(F.apply_lfr(lm, 5, 3))
+    short = lm[:4]
+    g["funasr|lfr_short"] = A(F.apply_lfr(short))
+    rng = np.random.default_rng(12)
+    mean = rng.standard_normal(560).astype(np.float32)
+    istd = (0.5 + rng.random(560)).astype(np.float32)
+    g["funasr|cmvn_mean"], g["funasr|cmvn_istd"] = mean, istd
+    g["funasr|lfr_cmvn"] = A(F.apply_cmvn(F.apply_lfr(lm), mx.array(mean), mx.array(istd)))
+    mel = W.log_mel_spectrogram(synth(301, 16000 * 4), n_mels=80)
+    g["whisper|mel"] = A(mel)
+    for seek, size in ((0, 400), (100, 300), (250, 150)):
+        seg = W.pad_or_trim(mel[seek: seek + size], 500, axis=-2).astype(mx.float16)
+        g[f"whisper|seg|{seek}|{size}"] = A(seg)
+    np.savez_compressed(os.path.join(OUT, "refshim_post.npz"), **g)
 
 
 def kaldi_goldens(mx, R):
@@ -349,6 +378,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "refshim_models.npz"), **g)
     hift_goldens(mx, R)
     kaldi_goldens(mx, R)
+    post_goldens(mx, R)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -179,6 +179,7 @@ tile = _unary(_np.tile)
 expand_dims = _unary(_np.expand_dims)
 squeeze = _unary(_np.squeeze)
 swapaxes = _unary(_np.swapaxes)
+broadcast_to = _unary(_np.broadcast_to)
 
 
 def take(x, indices, axis=None):

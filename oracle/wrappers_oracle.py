@@ -370,3 +370,34 @@ def kaldi_fbank(waveform, sample_rate=48000, win_len=1920, win_inc=384, num_mels
     bins, _ = kaldi_mel_banks(num_mels, n_fft, float(sample_rate), low_freq, high_freq)
     fb = np.pad(bins, [(0, 0), (0, 1)])
     return np.log(np.maximum(spec.astype(F32) @ fb.T, F32(1e-8))).astype(F32)
+
+
+# ---- the steps right after the path -----------------------------------------------------------
+def funasr_log_mel(audio, n_mels=80, n_fft=400, hop_length=160, sample_rate=16000):  # funasr/audio.py:32-81
+    freqs = D.stft(np.asarray(audio, np.float32), n_fft, hop_length, window=D.hamming(n_fft))
+    mags = np.square(np.abs(freqs[:-1, :])).astype(np.float32)
+    fb = D.mel_filters(sample_rate, n_fft, n_mels, norm="slaney", mel_scale="htk")
+    return np.log(np.maximum((mags @ fb.T).astype(np.float32), np.float32(1e-10))).astype(np.float32)
+
+
+def funasr_apply_lfr(features, lfr_m=7, lfr_n=6):  # funasr/audio.py:84-139
+    f = np.asarray(features, np.float32)
+    T, n_mels = f.shape
+    t_lfr = int(math.ceil(T / lfr_n))
+    left = (lfr_m - 1) // 2
+    if left > 0:
+        f = np.concatenate([np.broadcast_to(f[0:1], (left, n_mels)), f], axis=0)
+    need = (t_lfr - 1) * lfr_n + lfr_m
+    if need > f.shape[0]:
+        f = np.concatenate([f, np.broadcast_to(f[-1:], (need - f.shape[0], n_mels))], axis=0)
+    idx = (np.arange(t_lfr) * lfr_n)[:, None] + np.arange(lfr_m)[None, :]
+    return f[idx].reshape(t_lfr, -1)
+
+
+def funasr_apply_cmvn(features, cmvn_mean, cmvn_istd):  # funasr/audio.py:166-169 (precomputed statistics)
+    return ((np.asarray(features, np.float32) + np.asarray(cmvn_mean, np.float32)) * np.asarray(cmvn_istd, np.float32)).astype(np.float32)
+
+
+def whisper_mel_segment(mel, seek, segment_size, n_frames=3000, dtype=np.float16):  # whisper/whisper.py:990-996
+    seg = np.asarray(mel)[seek: seek + segment_size]
+    return whisper_pad_or_trim(seg, n_frames, axis=-2).astype(dtype)

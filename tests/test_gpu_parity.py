@@ -500,3 +500,45 @@ def test_resample_batch_matches_loop():
     yb = host(_run(dev(pcm), 160, 441, True))
     for i in range(3):
         np.testing.assert_array_equal(yb[i], host(_run(dev(pcm[i]), 160, 441, True)))
+
+
+# ---- the steps right after the path ----------------------------------------------------------
+def test_funasr_frontend_lfr_cmvn_parity(golden):
+    from mlx_audio_plus_b200.stt.models.funasr import audio as FA
+
+    g = golden("post")
+    for put in (lambda a: a, dev):
+        lm = FA.log_mel_spectrogram(put(g["funasr|x"]))
+        assert np.abs(host(lm) - g["funasr|logmel"]).max() <= 1e-4 * np.log(10) * 4  # the Whisper bound in ln units
+        np.testing.assert_array_equal(host(FA.apply_lfr(put(g["funasr|logmel"]))), g["funasr|lfr"])  # a gather: bit-exact
+        np.testing.assert_array_equal(host(FA.apply_lfr(put(g["funasr|logmel"]), 5, 3)), g["funasr|lfr_5_3"])
+        np.testing.assert_array_equal(host(FA.apply_lfr(put(g["funasr|logmel"][:4]))), g["funasr|lfr_short"])
+        np.testing.assert_array_equal(host(FA.apply_cmvn(put(g["funasr|lfr"]), g["funasr|cmvn_mean"], g["funasr|cmvn_istd"])),
+                                      g["funasr|lfr_cmvn"])
+    fused = host(FA.preprocess_audio(dev(g["funasr|x"]), cmvn_mean=g["funasr|cmvn_mean"], cmvn_istd=g["funasr|cmvn_istd"]))
+    assert fused.shape == g["funasr|lfr_cmvn"].shape
+    assert np.abs(fused - g["funasr|lfr_cmvn"]).max() <= 1e-3 * 1.5  # log-mel tolerance times the largest istd (1.5)
+    xb = np.stack([g["funasr|logmel"][:100], g["funasr|logmel"][50:150]])
+    yb = host(FA.apply_lfr(dev(xb)))
+    for i in range(2):
+        np.testing.assert_array_equal(yb[i], W.funasr_apply_lfr(xb[i]))
+
+
+def test_whisper_mel_segment_parity(golden):
+    from mlx_audio_plus_b200.stt.models.whisper.audio import mel_segment
+
+    g = golden("post")
+    mel = g["whisper|mel"]
+    for k in [k for k in g.files if k.startswith("whisper|seg|")]:
+        _, _, seek, size = k.split("|")
+        for put in (lambda a: a, dev):
+            y = host(mel_segment(put(mel), int(seek), int(size), 500))
+            assert y.dtype == np.float16
+            np.testing.assert_array_equal(y, g[k])  # float32 -> float16 round-to-nearest-even, zero rows: bit-exact
+    y32 = host(mel_segment(dev(mel), 10, 10_000, 3000, "float32"))  # segment longer than what is left: trimmed to T - seek
+    np.testing.assert_array_equal(y32, W.whisper_mel_segment(mel, 10, 10_000, 3000, np.float32))
+    yb = mel_segment(dev(mel), 0, 77, 96, "bfloat16")
+    ref = torch.from_numpy(W.whisper_mel_segment(mel, 0, 77, 96, np.float32)).to(torch.bfloat16)
+    assert yb.dtype == torch.bfloat16 and torch.equal(yb.cpu(), ref)
+    b = host(mel_segment(dev(np.stack([mel, 2 * mel])), 5, 50, 64))
+    np.testing.assert_array_equal(b[1], W.whisper_mel_segment(2 * mel, 5, 50, 64))
