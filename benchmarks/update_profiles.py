@@ -47,7 +47,7 @@ def main():
     r = a.round
     os.makedirs(P, exist_ok=True)
     for src, dst in ((f"bench_{r}_final.json", f"{r}_bench_n1.json"), (f"bench_{r}_reference.json", f"{r}_bench_reference_arm.json"),
-                     (f"configs_{r}.json", f"{r}_configs_c1_c3_c4_c5.json"), (f"launches_{r}.csv", f"{r}_launches_raw.csv")):
+                     (f"configs_{r}.json", f"{r}_configs_all.json"), (f"launches_{r}.csv", f"{r}_launches_raw.csv")):
         if os.path.exists(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst))
     # launch-list summary: time per kernel name and the fused kernel's share of the library's own launches
@@ -101,7 +101,9 @@ def main():
     for tag, what in (("fast_logmel_512", "C3 Parakeet 16 x 1 h (benchmarks/bench_configs.py --only C3)"),
                       ("fast_logmel_1024", "C5 Vocos mel forward B=8192 (benchmarks/bench_configs.py --only C5)"),
                       ("fast_istft_1024", "C5 Vocos iSTFT head B=1024 (benchmarks/bench_configs.py --only C5)"),
-                      ("istft_small", "C4 Kokoro iSTFT B=1024 (benchmarks/bench_configs.py --only C4)")):
+                      ("istft_small", "C4 Kokoro iSTFT B=1024 (benchmarks/bench_configs.py --only C4)"),
+                      ("fast_stft_400", "dsp.stft 400/160, 1024 x 30 s, complex64 rows (benchmarks/bench_configs.py --only S)"),
+                      ("resample", "load_audio: 1 h of 44.1 kHz stereo int16 -> 16 kHz mono (benchmarks/bench_configs.py --only R)")):
         rep = os.path.join(G, f"prof_{r}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue

@@ -16,6 +16,10 @@ $C5 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -
 ncu --set full --clock-control none --import-source on -k regex:fast_istft -s 10 -c 1 -f -o gpurun_out/prof_r01_fast_istft_1024 $C5 > gpurun_out/ncu_c5i.log 2>&1
 C4="python benchmarks/bench_configs.py --only C4 --steps 1"
 $C4 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:istft_small -s 10 -c 1 -f -o gpurun_out/prof_r01_istft_small $C4 > gpurun_out/ncu_c4.log 2>&1
+S="python benchmarks/bench_configs.py --only S --steps 1"
+$S > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:fast_stft -s 2 -c 1 -f -o gpurun_out/prof_r01_fast_stft_400 $S > gpurun_out/ncu_s.log 2>&1
+R="python benchmarks/bench_configs.py --only R --steps 1"
+$R > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:resample -s 2 -c 1 -f -o gpurun_out/prof_r01_resample $R > gpurun_out/ncu_r.log 2>&1
 ls -la gpurun_out/prof_r01_*.ncu-rep | awk '{print $5, $9}'
 cat gpurun_out/bench_r01_final.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['cpu_baseline']['value'], d['clocks'])"
 cat gpurun_out/bench_r01_reference.json | cut -c1-300
