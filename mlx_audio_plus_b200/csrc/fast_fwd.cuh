@@ -102,9 +102,13 @@ struct NoSpec {  // run-time mel tables (any filterbank); melgen::MelSpec_* bake
   static __device__ __forceinline__ void run(int, const float*, Emit&&) {}
 };
 
-template <int N1_, int N2_, int HOP_, bool ALIAS_, int MIN_BLOCKS_>
+// CP_: pitch (float2 slots) of one column of the exchange buffer.  N2 for the log-mel kernels; N2 + 1 (odd) for the
+// complex-spectrum kernel, whose copy-out reads consecutive BINS = consecutive columns: an odd pitch keeps those LDS.64
+// bank-conflict free (with pitch N2 = 10 or 16 they were 2-way / 8-way conflicts).
+template <int N1_, int N2_, int HOP_, bool ALIAS_, int MIN_BLOCKS_, int CP_ = N2_>
 struct Cfg {
-  static constexpr int N1 = N1_, N2 = N2_, HOP = HOP_;
+  using Padded = Cfg<N1_, N2_, HOP_, ALIAS_, MIN_BLOCKS_, N2_ + 1>;
+  static constexpr int N1 = N1_, N2 = N2_, HOP = HOP_, CP = CP_;
   // ALIAS: the power tile P reuses the sample tile's shared memory (no prefetch of the next tile) so that the
   // CTA fits the occupancy target; otherwise the next tile's samples are prefetched during stage 2 / mel.
   static constexpr bool ALIAS = ALIAS_;
@@ -119,7 +123,7 @@ struct Cfg {
   static constexpr int SPAN = (FT - 1) * HOP + N;
   static constexpr int XS_HEAD = 4;  // floats in front of the sample tile: [-4] raw-samples flag, [-3] sample before the span
   static constexpr int XS_FLOATS = ROWS * P + XS_HEAD;
-  static constexpr int EP = NC + 1;          // exchange pitch per frame (float2), odd
+  static constexpr int EP = N1 * CP + 1;     // exchange pitch per frame (float2), odd
   // power pitch per frame (floats): odd (stage-2 lane==frame stores are conflict free) and == 9 (mod 32) so that
   // the mel phase's (4 frames x 8 mel rows) gathers land in distinct banks
   static constexpr int PP = F + ((9 - F % 32 + 32) % 32);
@@ -129,16 +133,17 @@ struct Cfg {
   // consumed — unit u: bin u + N1*s -> slot u*N2 + s, its mirror Nc - k -> slot (N1/2 + u)*N2 + s; unit 0 keeps its
   // slot order (see stage 2), parks DC in the duplicate slot of its self-paired bin Nc/2 and Nyquist in the pad slot.
   __host__ __device__ static constexpr int sig(int k) {
-    if (k == 0) return (N1 / 2) * N2 + N2 / 2 - 1;
-    if (k == NC) return NC;
+    if (k == 0) return (N1 / 2) * CP + N2 / 2 - 1;
+    if (k == NC) return N1 * CP;
     const int r = k % N1, q = k / N1;
-    if (r == 0) return q <= N2 / 2 ? (q - 1) : (N1 / 2) * N2 + (N2 - 1 - q);
-    if (r == N1 / 2) return q < N2 / 2 ? (N2 / 2 + q) : (N1 / 2) * N2 + (N2 / 2 + (N2 - 1 - q));
-    if (r < N1 / 2) return r * N2 + q;
+    if (r == 0) return q <= N2 / 2 ? (q - 1) : (N1 / 2) * CP + (N2 - 1 - q);
+    if (r == N1 / 2) return q < N2 / 2 ? (N2 / 2 + q) : (N1 / 2) * CP + (N2 / 2 + (N2 - 1 - q));
+    if (r < N1 / 2) return r * CP + q;
     const int u = N1 - r;
-    return (N1 / 2 + u) * N2 + (NC - k - u) / N1;
+    return (N1 / 2 + u) * CP + (NC - k - u) / N1;
   }
   static_assert(N1 % 2 == 0 && N2 % WARPS == 0, "role split");
+  static_assert(EP % 2 == 1 && CP >= N2, "odd frame pitch; columns do not overlap");
   static_assert(HOP % (2 * N2) == 0, "hop must be a multiple of 2*N2");
   static_assert(NC % 2 == 0, "Nc even");
 };
@@ -441,8 +446,8 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
       float2 y0 = v[k1];
       if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t.x, t.y));
       const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t.z, t.w));
-      eb[slot0 * N2] = y0;
-      eb[slot1 * N2] = y1;
+      eb[slot0 * C::CP] = y0;
+      eb[slot1 * C::CP] = y1;
     });
   }
 }
@@ -467,8 +472,8 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
   const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
   float2 A[N2], B[N2];
-  const float2* ea = E + lane * C::EP + u * N2;
-  const float2* eb = E + lane * C::EP + (N1 / 2 + u) * N2;
+  const float2* ea = E + lane * C::EP + u * C::CP;
+  const float2* eb = E + lane * C::EP + (N1 / 2 + u) * C::CP;
   static_for<0, N2>([&](auto I_) {
     constexpr int j = decltype(I_)::value;
     A[j] = ea[j];
@@ -515,14 +520,14 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   float4 tw4[N2 / 2];
   static_for<0, TWD2>([&](auto I_) { tw4[decltype(I_)::value] = lds128_at<16 * decltype(I_)::value>(tw_sa); });
   // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
-  float* const plo = SPEC ? pr + 2 * (u * N2) : pr + kb_lo;
-  float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * N2) : pr + (NC - kb_lo);
+  float* const plo = SPEC ? pr + 2 * (u * C::CP) : pr + kb_lo;
+  float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * C::CP) : pr + (NC - kb_lo);
   float* const phi = SPEC ? plo : pr + kb_hi;
   float* const mhi = SPEC ? mlo : pr + (NC - kb_hi);
   constexpr int SK = SPEC ? 2 : N1, SM = SPEC ? 2 : -N1;
   if constexpr (CPLX) {
-    float2* const ck = E + lane * C::EP + u * N2;             // slot of bin pair s: (u*N2 + s, (N1/2 + u)*N2 + s)
-    float2* const cm = E + lane * C::EP + (N1 / 2 + u) * N2;
+    float2* const ck = E + lane * C::EP + u * C::CP;             // slot of bin pair s: (u*CP + s, (N1/2 + u)*CP + s)
+    float2* const cm = E + lane * C::EP + (N1 / 2 + u) * C::CP;
     static_for<0, N2 / 2>([&](auto I_) {
       constexpr int k2 = 2 * decltype(I_)::value;
       if constexpr (k2 / 2 + TWD2 < N2 / 2) tw4[k2 / 2 + TWD2] = lds128_at<16 * (k2 / 2 + TWD2)>(tw_sa);
@@ -1158,8 +1163,10 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     set_error("fast kernel: %lld tiles in one launch (split the batch)", (long long)tiles);
     return B2A_ERR_UNSUPPORTED;
   }
-  if (p.spec_kind == B2A_SPEC_COMPLEX)
-    return p.preemph != 0.0f ? launch_stft_variant<C, 1>(plan, p, st) : launch_stft_variant<C, 0>(plan, p, st);
+  if (p.spec_kind == B2A_SPEC_COMPLEX) {
+    using CS = typename C::Padded;
+    return p.preemph != 0.0f ? launch_stft_variant<CS, 1>(plan, p, st) : launch_stft_variant<CS, 0>(plan, p, st);
+  }
   const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
   const bool vec_ok = reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0;  // STG.128 rows
   if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel
