@@ -52,6 +52,7 @@ enum { /* what is taken from each STFT bin */
   B2A_SPEC_SQRT_POWER_EPS = 3 /* sqrt(|X|^2 + eps)  qwen3_tts.py:85 */
 };
 enum { B2A_LOG_NONE = 0, B2A_LOG_LOG10 = 1, B2A_LOG_LN = 2 };
+enum { B2A_DTYPE_F32 = 0, B2A_DTYPE_F16 = 1, B2A_DTYPE_BF16 = 2 }; /* output element types */
 enum { B2A_GUARD_NONE = 0, B2A_GUARD_MAX = 1 /* max(x,eps) */, B2A_GUARD_ADD = 2 /* x+eps */ };
 enum {
   B2A_CLAMP_NONE = 0,
@@ -113,6 +114,12 @@ typedef struct b2a_frontend_desc {
   float frame_preemph;  /* y[0]=x[0], y[k]=x[k]-a*x[k-1] WITHIN the frame, after DC removal (dsp.py:628-632) */
   float dither;         /* add dither * N(0,1), drawn independently per frame element (dsp.py:619-622); the stream
                            is Philox keyed by b2a_forward_args.seed — reproducible, not MLX's generator */
+  /* B2A_DTYPE_*: element type of the FEATURES.  F16 / BF16 write the encoder's input dtype straight from the fused
+   * kernel's epilogue (the `.astype(self.dtype)` of whisper/whisper.py:994-996 without a second pass; bit-identical to
+   * casting the float32 result: the clamp commutes with the monotone cast).  Supported by the 400/160 generated-mel
+   * kernels (Whisper, FunASR, Voxtral-RT, S3Tokenizer front-ends) without cross-frame normalisation; anything else
+   * returns B2A_ERR_UNSUPPORTED at create time. */
+  int32_t out_dtype;
 } b2a_frontend_desc;
 
 /* Arguments of one forward launch over `batch` equal-length clips.
@@ -221,7 +228,6 @@ int b2a_resample(b2a_resampler* r, const b2a_resample_args* args, void* stream);
  *   copied, rows up to rows_out are zero; out (batch, rows_out, cols) dense in out_dtype.
  * b2a_lfr: funasr/audio.py:84-139 apply_lfr (+ the precomputed CMVN of apply_cmvn, funasr/audio.py:166-169, when
  *   cmvn_shift / cmvn_scale [lfr_m * n_mels] are given): out (batch, ceil(frames / lfr_n), lfr_m * n_mels). */
-enum { B2A_DTYPE_F32 = 0, B2A_DTYPE_F16 = 1, B2A_DTYPE_BF16 = 2 };
 int b2a_rows_pad_cast(const float* in, int64_t in_clip_stride, int64_t row_begin, int64_t rows_valid, int32_t cols, void* out,
                       int64_t rows_out, int32_t out_dtype, int32_t batch, void* stream);
 int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_mels, int32_t lfr_m, int32_t lfr_n,

@@ -39,6 +39,7 @@ class FrontendDesc(C.Structure):
         ("affine_div", C.c_float), ("norm_kind", C.c_int32), ("norm_ddof", C.c_int32),
         ("norm_eps", C.c_float), ("out_layout", C.c_int32),
         ("frame_len", C.c_int32), ("frame_dc", C.c_int32), ("frame_preemph", C.c_float), ("dither", C.c_float),
+        ("out_dtype", C.c_int32),
     ]
 
 

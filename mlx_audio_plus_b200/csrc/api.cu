@@ -252,6 +252,12 @@ int b2a_frontend_create(const b2a_frontend_desc* d, const float* h_window, const
     p->family = KF_SMALL;
     p->kernel_name = "stft_small";
   }
+  if (rc == B2A_OK && d->out_dtype != B2A_DTYPE_F32 &&
+      !((d->out_dtype == B2A_DTYPE_F16 || d->out_dtype == B2A_DTYPE_BF16) && p->family == KF_FAST && fast_frontend_out16_ok(p))) {
+    set_error("out_dtype %d: 16-bit features are written by the 400/160 generated-mel kernels only ((T, M) layout, named "
+              "filterbank, no cross-frame normalisation)", d->out_dtype);
+    rc = B2A_ERR_UNSUPPORTED;
+  }
   if (rc != B2A_OK) {
     b2a_plan_destroy(p);
     return rc;
@@ -415,7 +421,7 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
   if (rc) return rc;
   const b2a_frontend_desc& d = p->fd;
   const int M = d.n_mels > 0 ? d.n_mels : p->n_freqs;
-  const size_t out_elem = (d.n_mels == 0 && d.spec_kind == B2A_SPEC_COMPLEX) ? 8 : 4;
+  const size_t out_elem = (d.n_mels == 0 && d.spec_kind == B2A_SPEC_COMPLEX) ? 8 : (d.out_dtype != B2A_DTYPE_F32 ? 2 : 4);
   const int64_t in_per_clip = a.valid_length - a.sample_offset;  // samples physically present per clip
   const int64_t out_per_clip = a.frame_count * M;
   const int64_t out_stride = a.out_clip_stride ? a.out_clip_stride : out_per_clip;

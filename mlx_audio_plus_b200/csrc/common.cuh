@@ -146,6 +146,7 @@ size_t generic_smem_limit(const b2a_plan* plan);
 bool fast_frontend_supported(const b2a_plan* plan);
 int fast_frontend_init(b2a_plan* plan);
 void fast_frontend_destroy(b2a_plan* plan);
+bool fast_frontend_out16_ok(const b2a_plan* plan);
 int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);
 // fused iSTFT for n_fft = 4*hop vocoder heads (1024/256) — fast_inv.cu

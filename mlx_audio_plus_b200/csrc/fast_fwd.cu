@@ -23,6 +23,12 @@ bool fast_frontend_supported(const b2a_plan* plan) {
   return true;
 }
 
+bool fast_frontend_out16_ok(const b2a_plan* plan) {
+  const FastState* fs = reinterpret_cast<const FastState*>(plan->fast);
+  const b2a_frontend_desc& d = plan->fd;
+  return fs && fs->variant == 1 && fs->spec > 0 && d.n_mels > 0 && d.out_layout == B2A_LAYOUT_TM && d.norm_kind == B2A_NORM_NONE;
+}
+
 int fast_frontend_init(b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
   FastState* fs = new FastState();
@@ -153,6 +159,7 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
     p.y_add = 0.0f;
   }
   p.out_layout = d.out_layout;
+  p.out_dtype = d.out_dtype;
   p.out = reinterpret_cast<float*>(a->out);
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * (d.n_mels > 0 ? d.n_mels : plan->n_freqs);
   p.clip_max = clip_max;

@@ -25,6 +25,9 @@
 #include <algorithm>
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "fft_regs.cuh"
 #include "mel_gen.cuh"
@@ -54,6 +57,7 @@ struct FastParams {
   int use_log;                   // y = log2(a) if use_log else a
   float y_mul, y_add;            // y' = y * y_mul + y_add   (log base change and the affine map folded together)
   int out_layout;
+  int out_dtype;  // B2A_DTYPE_*: float16 / bfloat16 features straight from phase B (generated-mel 400/160 kernels)
   float* out;
   int64_t out_clip_stride;
   float *clip_max, *tile_min;  // affine-domain statistics (per clip max, per tile min)
@@ -665,7 +669,27 @@ __device__ __forceinline__ void mel_runtime_tables(const FastParams& p, const fl
 
 // SPECK: spectrum kind fixed at compile time (B2A_SPEC_POWER / MAGNITUDE / SQRT_POWER_EPS), or -1 = run-time
 // PREK: pre-emphasis support compiled in (0 = no, -1 / 1 = run-time switch); the generated-mel instances fix it per spec
-template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK, int PREK>
+// four finished values -> one store in the output element type (ODT: B2A_DTYPE_*); round-to-nearest-even like astype()
+template <int ODT>
+__device__ __forceinline__ void store_quad(void* base, int64_t quad_index, const float4& v) {
+  if constexpr (ODT == B2A_DTYPE_F32) {
+    reinterpret_cast<float4*>(base)[quad_index] = v;
+  } else if constexpr (ODT == B2A_DTYPE_F16) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a);
+    u.y = *reinterpret_cast<const unsigned*>(&b);
+    reinterpret_cast<uint2*>(base)[quad_index] = u;
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a);
+    u.y = *reinterpret_cast<const unsigned*>(&b);
+    reinterpret_cast<uint2*>(base)[quad_index] = u;
+  }
+}
+
+template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK, int PREK, int ODT = B2A_DTYPE_F32>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh); requires the (T, M) layout
@@ -777,8 +801,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       sum_clip = pclip;
     }
     float lmax = -INFINITY, lmin = INFINITY;
-    float* const o = p.out + (int64_t)pclip * p.out_clip_stride;
-    float4* const orow = reinterpret_cast<float4*>(o + (int64_t)ptile * C::FT * MS::M) + lane;
+    // element offset of the tile's first row; quads are indexed from there (the element size is ODT's)
+    const int64_t obase = (int64_t)pclip * p.out_clip_stride + (int64_t)ptile * C::FT * MS::M;
+    char* const orow = reinterpret_cast<char*>(p.out) + obase * (ODT == B2A_DTYPE_F32 ? 4 : 2);
     const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
     if (lane < QL) {
 #pragma unroll 1
@@ -795,7 +820,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
             d2[c % NS] += (double)e[c] * (double)e[c];
           }
         }
-        orow[f * (MS::M / 4)] = v;
+        store_quad<ODT>(orow, f * (MS::M / 4) + lane, v);
         lmax = fmax3(lmax, v.x, v.y);
         lmin = fmin3(lmin, v.x, v.y);
         lmax = fmax3(lmax, v.z, v.w);
@@ -1082,7 +1107,7 @@ constexpr int spec_yp() {
   return MS::M > 0 ? ((((MS::M / 4) & 1) ? MS::M : MS::M + 4)) : 0;
 }
 
-template <class C, bool TM, bool SUMS, class MS, int SPECK = -1, int PREK = -1>
+template <class C, bool TM, bool SUMS, class MS, int SPECK = -1, int PREK = -1, int ODT = B2A_DTYPE_F32>
 int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   size_t smem = smem_bytes<C, spec_yp<MS>()>(p.mel_groups, p.mel_wg_count);
   if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
@@ -1097,10 +1122,10 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   if (grid < 1) grid = 1;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK><<<grid, C::THREADS, smem, st>>>(p);
+  fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }
@@ -1141,6 +1166,13 @@ struct SpecList;
 #define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK, PREK)                                                        \
   case IDX:                                                                                              \
     if (p.spec_kind != SPECK || (PREK == 0 && p.preemph != 0.0f)) break;                                 \
+    if constexpr (C::N == 400) { /* 16-bit feature output: the encoder-facing 400/160 family */          \
+      if (!sums && p.out_dtype == B2A_DTYPE_F16)                                                         \
+        return launch_variant<C, true, false, MS, SPECK, PREK, B2A_DTYPE_F16>(plan, p, st);             \
+      if (!sums && p.out_dtype == B2A_DTYPE_BF16)                                                        \
+        return launch_variant<C, true, false, MS, SPECK, PREK, B2A_DTYPE_BF16>(plan, p, st);            \
+    }                                                                                                    \
+    if (p.out_dtype != B2A_DTYPE_F32) return B2A_ERR_UNSUPPORTED;                                        \
     if (!sums) return launch_variant<C, true, false, MS, SPECK, PREK>(plan, p, st);                     \
     if constexpr (SUMS_OK) return launch_variant<C, true, true, MS, SPECK, PREK>(plan, p, st);          \
     break;
@@ -1169,6 +1201,10 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
   }
   const bool tm = p.out_layout == B2A_LAYOUT_TM, sums = p.feat_sums != nullptr;
   const bool vec_ok = reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0;  // STG.128 rows
+  if (p.out_dtype != B2A_DTYPE_F32 && !(tm && vec_ok && fs->spec > 0 && !sums && C::N == 400)) {
+    set_error("16-bit feature output needs a 400/160 generated-mel kernel, (T, M) layout, 16-byte aligned rows, no normalisation");
+    return B2A_ERR_UNSUPPORTED;
+  }
   if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel
     const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, st);
     if (rc != 1) return rc;

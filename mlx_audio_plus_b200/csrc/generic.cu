@@ -15,6 +15,8 @@
 // the same way, and is written once.  No atomics, no materialised index arrays.
 #include <algorithm>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <curand_kernel.h>
 
 #include "common.cuh"
@@ -443,6 +445,7 @@ struct FinParams {
   int tile_frames, tiles_per_clip;
   const double* feat_sums;
   int stats_affine;  // 1: clip_max / tile_min were recorded AFTER the affine map (fast kernels)
+  int out_dtype;     // B2A_DTYPE_*: 16-bit features (fast 400/160 kernels, (T, M) layout): the floor is cast the same way
 };
 
 // B2A_CLAMP_BATCH_MAX: one max over the whole batch (s3tokenizer/utils.py:131) -> broadcast into clip_max
@@ -488,7 +491,17 @@ __global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
   const int M = p.n_mels;
   const int64_t f0 = (int64_t)tile * p.tile_frames;
   const int nf = (int)min((int64_t)p.tile_frames, p.frames - f0);
-  if (p.out_layout == B2A_LAYOUT_TM) {
+  if (p.out_dtype == B2A_DTYPE_F16) {  // cast(max(y, floor)) == max(cast(y), cast(floor)): the cast is monotone
+    __half* t = reinterpret_cast<__half*>(p.out) + (int64_t)clip_i * p.out_clip_stride + f0 * M;
+    const __half fl = __float2half_rn(floor_out);
+    for (int i = lane; i < nf * M; i += 32)
+      if (__hlt(t[i], fl)) t[i] = fl;
+  } else if (p.out_dtype == B2A_DTYPE_BF16) {
+    __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)clip_i * p.out_clip_stride + f0 * M;
+    const __nv_bfloat16 fl = __float2bfloat16_rn(floor_out);
+    for (int i = lane; i < nf * M; i += 32)
+      if (__hlt(t[i], fl)) t[i] = fl;
+  } else if (p.out_layout == B2A_LAYOUT_TM) {
     float* t = o + f0 * M;
     for (int i = lane; i < nf * M; i += 32) {
       const float v = t[i];
@@ -887,6 +900,7 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   p.tiles_per_clip = (int)((a->frame_count + tile_frames - 1) / tile_frames);
   p.feat_sums = feat_sums;
   p.stats_affine = plan->family == KF_FAST ? 1 : 0;
+  p.out_dtype = d.out_dtype;
   if (d.clamp_kind != B2A_CLAMP_NONE) {
     if (d.clamp_kind == B2A_CLAMP_BATCH_MAX) {
       batch_max_kernel<<<1, 256, 0, st>>>(clip_max, a->batch);

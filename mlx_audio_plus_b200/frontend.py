@@ -49,7 +49,7 @@ class FrontendPlan(_PlanBase):
                  spec_kind=L.SPEC_COMPLEX, spec_eps=0.0, filterbank=None, log_kind=L.LOG_NONE,
                  guard_kind=L.GUARD_NONE, guard_eps=0.0, clamp_kind=L.CLAMP_NONE, clamp_value=0.0,
                  affine_add=0.0, affine_div=0.0, norm_kind=L.NORM_NONE, norm_ddof=0, norm_eps=0.0,
-                 out_layout=L.LAYOUT_TM, frame_len=0, frame_dc=False, frame_preemph=0.0, dither=0.0):
+                 out_layout=L.LAYOUT_TM, frame_len=0, frame_dc=False, frame_preemph=0.0, dither=0.0, out_dtype="float32"):
         super().__init__()
         window = np.ascontiguousarray(window, dtype=np.float32)
         if center and pad_mode not in ("reflect", "constant"):
@@ -72,6 +72,10 @@ class FrontendPlan(_PlanBase):
         d.out_layout = int(out_layout)
         d.frame_len, d.frame_dc = int(frame_len), int(bool(frame_dc))
         d.frame_preemph, d.dither = float(frame_preemph), float(dither)
+        self.out_dtype = str(out_dtype).split(".")[-1]
+        if self.out_dtype not in ("float32", "float16", "bfloat16"):
+            raise ValueError(f"unsupported out_dtype {out_dtype}")
+        d.out_dtype = {"float32": L.DTYPE_F32, "float16": L.DTYPE_F16, "bfloat16": L.DTYPE_BF16}[self.out_dtype]
         self.desc = d
         self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
         self.n_out = d.n_mels if d.n_mels > 0 else self.n_freqs
@@ -116,7 +120,8 @@ class FrontendPlan(_PlanBase):
             import torch
 
             with torch.cuda.device(ing.device):
-                out = torch.empty(shape, dtype=torch.complex64 if self.complex_out else torch.float32, device=ing.device)
+                out = torch.empty(shape, dtype=torch.complex64 if self.complex_out else getattr(torch, self.out_dtype),
+                                  device=ing.device)
                 st = torch.cuda.current_stream(ing.device).cuda_stream
                 a = self._args(x.data_ptr(), Lx, length, Lx, B, out.data_ptr(), pad_value=pad_value, frame_count=T)
                 a.seed = int(seed)
@@ -124,7 +129,9 @@ class FrontendPlan(_PlanBase):
                     L.check(L.lib.b2a_frontend_forward(self._h, C.byref(a), C.c_void_p(st)))
             return out
         _current_device_and_stream()  # fail loudly without a GPU
-        out = np.empty(shape, dtype=np.complex64 if self.complex_out else np.float32)
+        if self.out_dtype == "bfloat16":
+            raise TypeError("bfloat16 features need a torch CUDA input (NumPy has no bfloat16)")
+        out = np.empty(shape, dtype=np.complex64 if self.complex_out else np.dtype(self.out_dtype))
         a = self._args(x.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value, frame_count=T)
         a.seed = int(seed)
         if T > 0:

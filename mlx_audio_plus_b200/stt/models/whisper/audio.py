@@ -47,8 +47,10 @@ def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
     return array
 
 
-def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0):
-    """Whisper log-mel features, shape (T, n_mels) float32 (reference audio.py:44-85)."""
+def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0, *, dtype="float32"):
+    """Whisper log-mel features, shape (T, n_mels) float32 (reference audio.py:44-85).
+    Extension: dtype="float16" / "bfloat16" writes the encoder's input dtype straight from the fused kernel — the
+    `.astype(self.dtype)` of whisper/whisper.py:994-996 without a second pass, bit-identical to casting the float32 result."""
     if isinstance(audio, str):
         raise NotImplementedError("file decoding (load_audio) is outside the DSP hot path; pass a waveform array")
     ing, was_1d = as_batch(audio)
@@ -57,7 +59,7 @@ def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0):
         ing, hanning(N_FFT), fb, length=ing.data.shape[1] + max(int(padding), 0),
         n_fft=N_FFT, hop=HOP_LENGTH, center=True, pad_mode="reflect", drop_last=True,
         spec_kind=L.SPEC_POWER, log_kind=L.LOG_LOG10, guard_kind=L.GUARD_MAX, guard_eps=1e-10,
-        clamp_kind=L.CLAMP_CLIP_MAX, clamp_value=8.0, affine_add=4.0, affine_div=4.0)
+        clamp_kind=L.CLAMP_CLIP_MAX, clamp_value=8.0, affine_add=4.0, affine_div=4.0, out_dtype=str(dtype).split(".")[-1])
     return emit(ing, out[0] if was_1d else out)
 
 

@@ -1,0 +1,14 @@
+python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+python - <<'P'
+import torch, numpy as np, sys
+sys.path.insert(0, '.')
+from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+x = torch.randn(1024, 480000, device='cuda') * 0.1
+def t(fn, n=5):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True); a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/n
+print('f32', t(lambda: log_mel_spectrogram(x, n_mels=128)), 'f16 fused', t(lambda: log_mel_spectrogram(x, n_mels=128, dtype='float16')), 'f32 + torch cast', t(lambda: log_mel_spectrogram(x, n_mels=128).to(torch.float16)))
+P
+python bench.py --clips 4096 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('C2', d['ms_per_step'], d['roofline']['kernel_ms'])"

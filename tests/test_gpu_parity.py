@@ -542,3 +542,34 @@ def test_whisper_mel_segment_parity(golden):
     assert yb.dtype == torch.bfloat16 and torch.equal(yb.cpu(), ref)
     b = host(mel_segment(dev(np.stack([mel, 2 * mel])), 5, 50, 64))
     np.testing.assert_array_equal(b[1], W.whisper_mel_segment(2 * mel, 5, 50, 64))
+
+
+def test_whisper_16bit_epilogue_is_the_cast_of_the_float32_result(golden):
+    """out_dtype float16 / bfloat16: phase B stores the encoder's dtype directly; the clamp fix-up works on the 16-bit rows.
+    cast(max(y, floor)) == max(cast(y), cast(floor)), so the result is BIT-identical to casting the float32 features
+    (whisper/whisper.py:994-996 `.astype(self.dtype)`), also where the max-8 clamp is active."""
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    g = golden("models")
+    for key in ("whisper|x", "whisper|sil|x"):
+        x = g[key]
+        for n_mels in (80, 128):
+            y32 = log_mel_spectrogram(dev(x), n_mels=n_mels)
+            y16 = log_mel_spectrogram(dev(x), n_mels=n_mels, dtype="float16")
+            yb = log_mel_spectrogram(dev(x), n_mels=n_mels, dtype=torch.bfloat16)
+            assert y16.dtype == torch.float16 and yb.dtype == torch.bfloat16 and y16.shape == y32.shape
+            assert torch.equal(y16, y32.to(torch.float16))
+            assert torch.equal(yb, y32.to(torch.bfloat16))
+    xb = np.stack([g["whisper|x"], g["whisper|sil|x"]])
+    y = log_mel_spectrogram(dev(xb), n_mels=128, padding=4000, dtype="float16")
+    assert torch.equal(y, log_mel_spectrogram(dev(xb), n_mels=128, padding=4000).to(torch.float16))
+    yh = log_mel_spectrogram(g["whisper|sil|x"], n_mels=80, dtype="float16")  # host path: half the D2H bytes
+    assert yh.dtype == np.float16
+    np.testing.assert_array_equal(np.asarray(yh), host(log_mel_spectrogram(dev(g["whisper|sil|x"]), n_mels=80)).astype(np.float16))
+    with pytest.raises(NotImplementedError):  # Parakeet: cross-frame normalisation needs the float32 second sweep
+        FrontendPlan(n_fft=512, hop=160, window=np.asarray(O.hanning(400)), spec_kind=1, log_kind=2, guard_kind=2,
+                     guard_eps=1e-5, filterbank=np.asarray(O.mel_filters(16000, 512, 80, norm=None, mel_scale=None)),
+                     norm_kind=1, norm_eps=1e-5, out_dtype="float16")
+    with pytest.raises(NotImplementedError):  # complex spectrum
+        FrontendPlan(n_fft=400, hop=160, window=np.asarray(O.hanning(400)), out_dtype="bfloat16")
