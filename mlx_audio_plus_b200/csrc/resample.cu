@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,6 +24,8 @@ struct Resampler {
   int64_t pre_remove = 0;
   float* d_taps = nullptr;  // [J][up]
   size_t taps_bytes = 0;
+  float* d_taps_pm = nullptr;  // [up][4 * J4]: phase-major, tap count padded to a multiple of 4 with zeros
+  int J4 = 1;
 };
 
 namespace {
@@ -111,47 +114,109 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleParams p) {
   }
 }
 
-// Single-channel path (load_audio of mono files): the tile's input span is converted to float32 ONCE into shared memory; a block then produces TILE consecutive output samples from it.  Per tap: one
-// conflict-free tap read, one input read, one FMA — no global loads, no conversions, no per-channel work in the inner loop.
-constexpr int kTile = 2048;  // outputs per block iteration
-template <typename T>
-__global__ void __launch_bounds__(256) resample_mono_tiled_kernel(const ResampleParams p, int span_max) {
-  extern __shared__ float s_mem[];
-  float* const s_taps = s_mem;                 // [J][up]
-  float* const xs = s_mem + p.J * p.up;        // [span_max]
-  for (int i = threadIdx.x; i < p.J * p.up; i += blockDim.x) s_taps[i] = p.taps[i];
+// Mono output (load_audio): SAME-PHASE lane mapping.  A tile is 32 * up * R consecutive output samples; a warp takes one
+// (q, r) item at a time and its lanes compute outputs n = N0 + q + up * (lane + 32 r).  All 32 share the filter phase
+// ((n + pre) * down mod up does not depend on the lane), so the taps are warp-uniform LDS.128 broadcasts of 4 taps each from
+// a [phase][tap] table, and the lanes' input windows start `down` samples apart — an odd stride for every common rate pair,
+// i.e. bank-conflict free.  Per tap: one input LDS + one FMA + a quarter of a tap load (the direct kernel spends ~6
+// instructions and ~4 shared-memory wavefronts per tap).  The tile's input span is converted to float32 and mixed to mono
+// ONCE into shared memory (the filter is linear: mean first, then filter); results are staged at an odd pitch and written
+// out as contiguous rows.
+struct PhaseParams {
+  const void* in;
+  float* out;
+  int64_t n_in, n_out, in_clip_stride, out_clip_stride, pre_remove;
+  int channels, up, down, J4, R, tile, ypitch, span_max;
+  const float* taps_pm;  // [up][4 * J4], zero padded
+};
+
+template <typename T, int CH>  // CH: 1, 2 or 0 (any channel count)
+__global__ void __launch_bounds__(512) resample_phase_kernel(const PhaseParams p) {
+  extern __shared__ float4 s_mem4[];
+  float* const s_taps = reinterpret_cast<float*>(s_mem4);            // [up][4 * J4]
+  float* const xs = s_taps + p.up * 4 * p.J4;                         // [span_max]
+  float* const ys = xs + ((p.span_max + 3) & ~3);                     // [32 * R * ypitch]
+  const int JP = 4 * p.J4;
+  for (int i = threadIdx.x; i < p.up * JP; i += blockDim.x) s_taps[i] = p.taps_pm[i];
   const int ch = p.channels;
   const T* x = reinterpret_cast<const T*>(p.in) + (int64_t)blockIdx.y * p.in_clip_stride;
   float* y = p.out + (int64_t)blockIdx.y * p.out_clip_stride;
   const int64_t last = p.n_in - 1;
-  const int64_t tiles = (p.n_out + kTile - 1) / kTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t tiles = (p.n_out + p.tile - 1) / p.tile;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t n0 = tile * kTile;
-    const int64_t n1 = (n0 + kTile < p.n_out ? n0 + kTile : p.n_out) - 1;   // last output of the tile
-    const int64_t base = ((n0 + p.pre_remove) * p.down) / p.up - (p.J - 1);  // lowest input index any output reads
-    const int span = (int)(((n1 + p.pre_remove) * p.down) / p.up - base + 1);
-    __syncthreads();  // the previous tile's reads of xs are done (and s_taps is loaded)
-    for (int s = threadIdx.x; s < span; s += blockDim.x) {
-      int64_t i = base + s;
-      i = i < 0 ? 0 : (i > last ? last : i);  // upfirdn mode "edge"
-      float v = load_sample<T>(x, i * ch);
-      for (int c = 1; c < ch; ++c) v += load_sample<T>(x, i * ch + c);
-      xs[s] = ch > 1 ? v / (float)ch : v;
+    const int64_t n0 = tile * p.tile;
+    const int cnt = (int)(p.n_out - n0 < p.tile ? p.n_out - n0 : p.tile);  // outputs in this tile
+    const int64_t t0 = (n0 + p.pre_remove) * p.down;
+    const int64_t b0 = t0 / p.up;
+    const int m0 = (int)(t0 - b0 * p.up);
+    const int64_t base = b0 - (JP - 1);                                    // input index of xs[0]
+    const int span = (int)(((n0 + cnt - 1 + p.pre_remove) * p.down) / p.up - base + 1);
+    __syncthreads();  // previous tile: xs / ys free (and s_taps loaded)
+    // fill: 8 frames per thread per round with every global load issued before the first use (one load in flight per
+    // thread made this phase latency bound: 1.3 ms -> see DESIGN.md K5)
+    for (int s0 = threadIdx.x; s0 < span; s0 += 8 * blockDim.x) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int64_t i = base + s0 + k * (int)blockDim.x;
+        i = i < 0 ? 0 : (i > last ? last : i);  // upfirdn mode "edge" (indices past the span are clamped too: harmless)
+        if (CH == 1) {
+          v[k] = load_sample<T>(x, i);
+        } else if (CH == 2) {
+          v[k] = (load_sample<T>(x, 2 * i) + load_sample<T>(x, 2 * i + 1)) / 2.0f;
+        } else {
+          float a = load_sample<T>(x, i * ch);
+          for (int c = 1; c < ch; ++c) a += load_sample<T>(x, i * ch + c);
+          v[k] = a / (float)ch;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (s0 + k * (int)blockDim.x < span) xs[s0 + k * (int)blockDim.x] = v[k];
     }
     __syncthreads();
-    for (int64_t n = n0 + threadIdx.x; n <= n1; n += blockDim.x) {
-      const int64_t t = (n + p.pre_remove) * p.down;
-      const int64_t i0 = t / p.up;
-      const float* w = s_taps + (int)(t - i0 * p.up);
-      const float* xp = xs + (int)(i0 - base);
-      float a0 = 0.0f, a1 = 0.0f;  // two chains: the FMA latency is not the loop's critical path
-      int j = 0;
-      for (; j + 1 < p.J; j += 2) {
-        a0 = fmaf(w[j * p.up], xp[-j], a0);
-        a1 = fmaf(w[(j + 1) * p.up], xp[-j - 1], a1);
+    const int items = p.up * p.R;
+    // two items per round, four accumulator chains each: 16 independent input loads per tap quad pair are in flight (with
+    // one item and two chains the loop waited out a shared-memory latency per FMA: short_scoreboard 2.3 per issue)
+    for (int item = 2 * warp; item < items; item += 2 * nwarps) {
+      const float4* w4[2];
+      const float* xp[2];
+      int dst[2];
+      bool ok[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int it = item + e < items ? item + e : item;
+        const int r = it / p.up, q = it - r * p.up;
+        const int l = lane + 32 * r;                  // "row" of this lane's output inside the tile
+        const unsigned t = (unsigned)m0 + (unsigned)q * (unsigned)p.down;   // < up + up * down: fits 32 bits
+        const unsigned bq = t / (unsigned)p.up;
+        const int ph = (int)(t - bq * (unsigned)p.up);
+        ok[e] = item + e < items && q + p.up * l < cnt;
+        w4[e] = reinterpret_cast<const float4*>(s_taps + ph * JP);
+        xp[e] = xs + (ok[e] ? (int)bq + p.down * l : 0) + (JP - 1);  // tap j reads xp[-j]
+        dst[e] = q + p.ypitch * l;
       }
-      if (j < p.J) a0 = fmaf(w[j * p.up], xp[-j], a0);
-      y[n] = a0 + a1;
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
+      for (int j4 = 0; j4 < p.J4; ++j4) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float4 w = w4[e][j4];
+          acc[e][0] = fmaf(w.x, xp[e][-4 * j4], acc[e][0]);
+          acc[e][1] = fmaf(w.y, xp[e][-4 * j4 - 1], acc[e][1]);
+          acc[e][2] = fmaf(w.z, xp[e][-4 * j4 - 2], acc[e][2]);
+          acc[e][3] = fmaf(w.w, xp[e][-4 * j4 - 3], acc[e][3]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (ok[e]) ys[dst[e]] = (acc[e][0] + acc[e][1]) + (acc[e][2] + acc[e][3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int l = i / p.up, q = i - l * p.up;
+      y[n0 + i] = ys[q + p.ypitch * l];
     }
   }
 }
@@ -163,25 +228,6 @@ int launch_resample(const ResampleParams& p, int sm_count, int64_t batch, cudaSt
   const int64_t cap = (int64_t)sm_count * 16;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  // tiled path for single-channel input when the taps + one tile's input span fit in shared memory (measured on 1 h of
-  // audio: 48 kHz mono 1.53 -> 1.32 ms; 44.1 kHz stereo is faster on the direct kernel, 2.21 vs 2.44 ms)
-  if (p.mono && p.channels == 1) {
-    const int span_max = (int)(((int64_t)kTile * p.down) / p.up + p.J + 2);
-    const size_t need = sizeof(float) * ((size_t)p.J * p.up + span_max);
-    if (need <= 200 * 1024) {
-      int64_t tiles = (p.n_out + kTile - 1) / kTile;
-      int64_t g = tiles < (int64_t)sm_count * 4 ? tiles : (int64_t)sm_count * 4;
-      if (g < 1) g = 1;
-      static size_t attr = 0;  // per element type (template instance)
-      if (need > attr) {
-        B2A_CUDA(cudaFuncSetAttribute(resample_mono_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        attr = need;
-      }
-      resample_mono_tiled_kernel<T><<<dim3((unsigned)g, (unsigned)batch), 256, need, st>>>(p, span_max);
-      B2A_CUDA(cudaGetLastError());
-      return B2A_OK;
-    }
-  }
   dim3 grid((unsigned)gx, (unsigned)batch);
   auto go = [&](auto kernel) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -214,11 +260,18 @@ int b2a_resampler_create(int32_t up, int32_t down, int32_t taps_per_phase, int64
   r->J = taps_per_phase;
   r->pre_remove = pre_remove;
   r->taps_bytes = sizeof(float) * (size_t)up * taps_per_phase;
+  r->J4 = (taps_per_phase + 3) / 4;
+  std::vector<float> pm((size_t)up * 4 * r->J4, 0.0f);
+  for (int j = 0; j < taps_per_phase; ++j)
+    for (int ph = 0; ph < up; ++ph) pm[(size_t)ph * 4 * r->J4 + j] = h_taps[(size_t)j * up + ph];
   cudaError_t e = cudaMalloc(&r->d_taps, r->taps_bytes);
   if (e == cudaSuccess) e = cudaMemcpy(r->d_taps, h_taps, r->taps_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&r->d_taps_pm, sizeof(float) * pm.size());
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_taps_pm, pm.data(), sizeof(float) * pm.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     set_error("resampler_create: %s (no CUDA device? there is no CPU fallback)", cudaGetErrorString(e));
     cudaFree(r->d_taps);
+    cudaFree(r->d_taps_pm);
     delete r;
     return B2A_ERR_CUDA;
   }
@@ -230,6 +283,7 @@ int b2a_resampler_destroy(b2a_resampler* h) {
   Resampler* r = reinterpret_cast<Resampler*>(h);
   if (!r) return B2A_OK;
   cudaFree(r->d_taps);
+  cudaFree(r->d_taps_pm);
   delete r;
   return B2A_OK;
 }
@@ -273,6 +327,35 @@ int b2a_resample(b2a_resampler* h, const b2a_resample_args* a, void* stream) {
     return B2A_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->mono && (int64_t)r->up * r->down < ((int64_t)1 << 30)) {  // same-phase kernel (32-bit phase arithmetic inside a tile)
+    PhaseParams q;
+    q.in = a->in; q.out = a->out; q.n_in = p.n_in; q.n_out = p.n_out;
+    q.in_clip_stride = p.in_clip_stride; q.out_clip_stride = p.out_clip_stride; q.pre_remove = r->pre_remove;
+    q.channels = a->channels; q.up = r->up; q.down = r->down; q.J4 = r->J4;
+    q.R = (4096 + 32 * r->up - 1) / (32 * r->up);
+    if (q.R < 1) q.R = 1;
+    q.tile = 32 * r->up * q.R;
+    q.ypitch = r->up | 1;
+    q.span_max = (int)(((int64_t)q.tile * r->down) / r->up + 4 * r->J4 + 2);
+    q.taps_pm = r->d_taps_pm;
+    const size_t need = sizeof(float) * ((size_t)r->up * 4 * r->J4 + ((q.span_max + 3) & ~3) + (size_t)32 * q.R * q.ypitch) + 16;
+    if (need <= 200 * 1024) {
+      const int64_t tiles = (p.n_out + q.tile - 1) / q.tile;
+      int64_t g = tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2;
+      if (g < 1) g = 1;
+      dim3 grid((unsigned)g, (unsigned)a->batch);
+      auto go = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        kernel<<<grid, 512, need, st>>>(q);
+      };
+      const bool i16 = a->in_kind == B2A_PCM_I16;
+      if (a->channels == 1) i16 ? go(resample_phase_kernel<int16_t, 1>) : go(resample_phase_kernel<float, 1>);
+      else if (a->channels == 2) i16 ? go(resample_phase_kernel<int16_t, 2>) : go(resample_phase_kernel<float, 2>);
+      else i16 ? go(resample_phase_kernel<int16_t, 0>) : go(resample_phase_kernel<float, 0>);
+      B2A_CUDA(cudaGetLastError());
+      return B2A_OK;
+    }
+  }
   return a->in_kind == B2A_PCM_I16 ? launch_resample<int16_t>(p, sms, a->batch, st) : launch_resample<float>(p, sms, a->batch, st);
 }
 
