@@ -573,3 +573,92 @@ def test_whisper_16bit_epilogue_is_the_cast_of_the_float32_result(golden):
                      norm_kind=1, norm_eps=1e-5, out_dtype="float16")
     with pytest.raises(NotImplementedError):  # complex spectrum
         FrontendPlan(n_fft=400, hop=160, window=np.asarray(O.hanning(400)), out_dtype="bfloat16")
+
+
+# ---- seeded random sweeps (property-style coverage of the parameter space against the oracle) -------------
+def _sweep_cases(seed, n):
+    rng = np.random.default_rng(seed)
+    sizes = [(400, 160), (512, 160), (1024, 256), (800, 200), (20, 5), (16, 4), (64, 16), (360, 90), (1920, 480), (48, 12)]
+    out = []
+    for i in range(n):
+        n_fft, hop = sizes[int(rng.integers(len(sizes)))]
+        if rng.random() < 0.25:
+            hop = int(rng.integers(1, n_fft // 2 + 1))
+        win = n_fft if rng.random() < 0.6 else int(rng.integers(max(2, n_fft // 3), n_fft + 1))
+        center = bool(rng.random() < 0.75)
+        mode = "reflect" if rng.random() < 0.7 else "constant"
+        wname = ["hann", "hamming", "blackman", "bartlett"][int(rng.integers(4))]
+        p = n_fft // 2
+        edge = [p + 1, p + 2, n_fft, n_fft + 1, 3 * hop + n_fft - 1, 10 * hop, 10 * hop + 1, 11 * hop - 1]
+        L = int(edge[int(rng.integers(len(edge)))]) if rng.random() < 0.5 else int(rng.integers(n_fft, 6 * n_fft + 40 * hop))
+        if not center:
+            L = max(L, n_fft)
+        out.append((n_fft, hop, win, wname, center, mode, L, int(rng.integers(1, 4))))
+    return out
+
+
+@pytest.mark.parametrize("case", _sweep_cases(2024, 48), ids=lambda c: "-".join(map(str, c)))
+def test_stft_random_sweep(case):
+    from mlx_audio_plus_b200.dsp import stft
+
+    n_fft, hop, win, wname, center, mode, L, B = case
+    xb = np.stack([synth(1000 + i + L, L) * (0.3 + 0.4 * i) for i in range(B)])
+    y = host(stft(dev(xb if B > 1 else xb[0]), n_fft, hop, win, wname, center, mode))
+    y = y if B > 1 else y[None]
+    for i in range(B):
+        assert_stft_close(y[i], O.stft(xb[i], n_fft, hop, win, wname, center, mode))
+
+
+@pytest.mark.parametrize("case", _sweep_cases(77, 32), ids=lambda c: "-".join(map(str, c)))
+def test_istft_random_sweep(case):
+    from mlx_audio_plus_b200.dsp import istft
+
+    n_fft, hop, _, wname, center, _, L, B = case
+    if n_fft % 2 or hop > n_fft:
+        pytest.skip("istft needs an even n_fft and hop <= n_fft")
+    rng = np.random.default_rng(L + n_fft)
+    T = max(2, L // hop % 97 + 2)
+    F = n_fft // 2 + 1
+    spec = (rng.standard_normal((B, F, T)) + 1j * rng.standard_normal((B, F, T))).astype(np.complex64)
+    normalized = bool(rng.random() < 0.5)
+    length = None if rng.random() < 0.6 else int(rng.integers(1, (T - 1) * hop + n_fft))
+    y = host(istft(dev(spec if B > 1 else spec[0]), hop, n_fft, wname, center, length, normalized))
+    y = y if B > 1 else y[None]
+    for i in range(B):
+        assert_wave_close(y[i], O.istft(spec[i], hop, n_fft, wname, center, length, normalized))
+
+
+@pytest.mark.parametrize("L,padding,n_mels,B", [(201, 0, 80, 1), (400, 0, 128, 1), (5279, 0, 80, 2), (5280, 160, 128, 1), (16001, 0, 128, 3),
+                                                (31999, 4000, 80, 2), (48000, 48000, 128, 1), (160 * 37 + 1, 7, 80, 1)])
+def test_whisper_length_sweep(L, padding, n_mels, B):
+    """edge tiles of the fused kernel (clip start / end inside one tile, ragged last tile, virtual right padding, odd lengths)
+    against the oracle; batch == per-clip calls"""
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    xb = np.stack([synth(500 + i + L, L) * (0.2 + 0.5 * i) for i in range(B)])
+    y = host(log_mel_spectrogram(dev(xb if B > 1 else xb[0]), n_mels=n_mels, padding=padding))
+    y = y if B > 1 else y[None]
+    for i in range(B):
+        ref = W.whisper_log_mel(xb[i], n_mels, padding)
+        assert y[i].shape == ref.shape
+        assert np.abs(y[i] - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("L", [400, 4001, 16000, 160 * 64 + 3])
+def test_parakeet_and_vocos_length_sweep(L):
+    from mlx_audio_plus_b200.codec.models.vocos.mel import log_mel_spectrogram as vocos_mel
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram as pk_mel
+
+    x = synth(900 + L, L)
+    pa = PreprocessArgs(sample_rate=16000, normalize="per_feature", window_size=0.025, window_stride=0.01, window="hann",
+                        features=80, n_fft=512, dither=0.0)
+    opa = W.PreprocessArgs(sample_rate=16000, normalize="per_feature", window_size=0.025, window_stride=0.01, window="hann",
+                           features=80, n_fft=512, dither=0.0)
+    y = host(pk_mel(dev(x), pa))
+    ref = W.parakeet_log_mel(x, opa)
+    assert y.shape == ref.shape and np.abs(y - ref).max() <= 5e-4 * max(1.0, np.abs(ref).max() / 5)
+    if L >= 1024:
+        x24 = synth(901 + L, L, sr=24000)
+        yv = host(vocos_mel(dev(x24)))
+        rv = W.vocos_log_mel(x24)
+        assert yv.shape == rv.shape and np.abs(yv - rv).max() <= 1e-4 * np.log(10) * 4
