@@ -180,6 +180,11 @@ def main():
         a.warmup = 3  # timing rule: W >= 3
     if a.impl == "reference":
         return reference_arm(a)
+    # stdout carries exactly ONE JSON line: anything a library prints there on the way (NCCL's "NCCL version ..." banner
+    # when NCCL_DEBUG is set in the environment) is sent to stderr; the real stdout comes back for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -323,7 +328,10 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes},
             "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": 3 * a.steps, "clocks": clocks,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
