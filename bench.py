@@ -163,6 +163,37 @@ def reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(torch, dev_index):
+    """Host memory of the end-to-end path (pinned input / output) should live on the NUMA node the GPU hangs off.  Prefers
+    that node for this process's allocations (set_mempolicy, MPOL_PREFERRED) and, when the cgroup allows, runs on its cores.
+    Best effort: returns the node or None.  (This pool's boxes are VMs with ONE NUMA node and no GPU affinity — it is a
+    no-op there; multi-GPU e2e on them is bound by the host side, 218 / 323 / 260-354 / 335 audio-hours/s at 1 / 2 / 4 / 8
+    GPUs, while the device-resident value scales 1.00 / 2.00 / 3.99 / 7.98.)"""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        try:
+            libc = C.CDLL(None, use_errno=True)
+            mask = (C.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            libc.syscall(C.c_long(238), C.c_int(1), mask, C.c_ulong(16 * 64))  # SYS_set_mempolicy, MPOL_PREFERRED (x86-64)
+        except Exception:
+            pass
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,6 +241,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     devt = torch.device("cuda", local_rank)
+    numa_node = bind_near_gpu(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=devt)
 
@@ -299,7 +331,8 @@ def main():
         e2e = {"value": world * Be * CLIP_S / 3600.0 / float(dt.item()), "unit": "audio-hours/s",
                "h2d_bytes_per_step": int(Be * CLIP_LEN * 4), "d2h_bytes_per_step": int(Be * T * n_mels * 4),
                "ms_per_step": float(dt.item()) * 1e3, "steps": a.e2e_steps,
-               "api": "b2a_frontend_forward_host (pinned host in/out, chunked H2D/compute/D2H on 2 streams)"}
+               "api": "b2a_frontend_forward_host (pinned host in/out, chunked H2D/compute/D2H on 2 streams)",
+               "host_numa_node": numa_node}
         chk = float((hy[:4] - out[:4].cpu()).abs().max())
         assert chk == 0.0, f"host path and device path disagree: {chk}"
 
