@@ -6,6 +6,36 @@
 
 namespace b2a {
 
+namespace {
+
+// Rows of all-padding frames (Whisper is always called with `padding = N_SAMPLES` zero samples behind the clip,
+// whisper/whisper.py: a 30 s clip yields 6000 frames of which the last ~3000 see nothing but zeros): every mel value of such
+// a frame is the same constant c = affine(log(guard(0))).  They are not transformed: this kernel writes c (computed on the
+// device exactly as the fused kernel's phase B does), records it as those tiles' minimum and folds it into the clip max, so
+// that the clamp fix-up treats the rows like any others.
+template <typename T>
+__global__ void __launch_bounds__(256) const_rows_kernel(T* out, int64_t out_clip_stride, int64_t row0, int64_t rows, int M, float guard_add,
+                                                          float guard_floor, int use_log, float y_mul, float y_add, float* clip_max,
+                                                          float* tile_min, int tile_min_pitch, int tile0) {
+  const float a = fmaxf(0.0f + guard_add, guard_floor);
+  const float c = fmaf(use_log ? lg2_approx(a) : a, y_mul, y_add);
+  const int clip = blockIdx.y;
+  T* o = out + (int64_t)clip * out_clip_stride + row0 * M;
+  const int64_t total = rows * M;
+  T cv;
+  if constexpr (sizeof(T) == 4) cv = c;
+  else if constexpr (std::is_same<T, __half>::value) cv = __float2half_rn(c);
+  else cv = __float2bfloat16_rn(c);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) o[i] = cv;
+  if (clip_max && blockIdx.x == 0) {
+    const int tiles = (int)((rows + 31) / 32);
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) tile_min[(int64_t)clip * tile_min_pitch + tile0 + t] = c;
+    if (threadIdx.x == 0) atomic_max_f(clip_max + clip, c);
+  }
+}
+
+}  // namespace
+
 bool fast_frontend_supported(const b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
   if (getenv("B2A_FORCE_GENERIC")) return false;
@@ -174,6 +204,26 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.mel_groups = fs->groups;
   p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
+  p.tile_min_pitch = p.tiles_per_clip;
+  // Trailing frames that see only virtual zero padding are constant rows: transform the frames that touch the signal
+  // (rounded up to a tile) and fill the rest.  Conditions: zero pad value, no pre-emphasis, power / magnitude spectrum,
+  // (T, M) layout, no per-feature sums, unsharded call, and the reflected tail must not reach back into the signal.
+  int64_t const_row0 = -1;
+  {
+    const int64_t pc = d.center ? d.n_fft / 2 : 0;
+    const bool tail_ok = !d.center || d.pad_mode == B2A_PAD_CONSTANT || a->length - pc - 1 >= a->valid_length;
+    if (a->pad_value == 0.0f && d.preemph == 0.0f && d.n_mels > 0 && feat_sums == nullptr && tail_ok &&
+        (d.spec_kind == B2A_SPEC_POWER || d.spec_kind == B2A_SPEC_MAGNITUDE) && d.out_layout == B2A_LAYOUT_TM &&
+        a->frame_begin == 0 && a->sample_offset == 0 && a->valid_length < a->length && !getenv("B2A_NO_PAD_SKIP")) {
+      const int64_t first_pad = (a->valid_length + pc + d.hop - 1) / d.hop;  // first frame t with t*hop - pc >= valid_length
+      const int64_t r0 = (first_pad + 31) / 32 * 32;
+      if (r0 + 32 <= a->frame_count) {
+        const_row0 = r0;
+        p.frame_count = r0;
+        p.tiles_per_clip = (int)(r0 / 32);
+      }
+    }
+  }
 #ifdef B2A_PHASE_CLOCKS
   const char* clk_path = getenv("B2A_CLOCKS");
 #else
@@ -188,6 +238,22 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   if (fs->variant == 1) rc = fast_launch_400(plan, fs, p, st);
   else if (fs->variant == 2) rc = fast_launch_512(plan, fs, p, st);
   else rc = fast_launch_1024(plan, fs, p, st);
+  if (rc == B2A_OK && const_row0 >= 0) {
+    const int64_t rows = a->frame_count - const_row0;
+    int64_t gx = (rows * d.n_mels + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid((unsigned)gx, (unsigned)a->batch);
+    const int tile0 = (int)(const_row0 / 32);
+#define B2A_CONST_ROWS(TT)                                                                                              \
+    const_rows_kernel<TT><<<grid, 256, 0, st>>>(reinterpret_cast<TT*>(a->out), p.out_clip_stride, const_row0, rows, d.n_mels, \
+                                                p.guard_add, p.guard_floor, p.use_log, p.y_mul, p.y_add, clip_max, tile_min, \
+                                                p.tile_min_pitch, tile0)
+    if (d.out_dtype == B2A_DTYPE_F16) B2A_CONST_ROWS(__half);
+    else if (d.out_dtype == B2A_DTYPE_BF16) B2A_CONST_ROWS(__nv_bfloat16);
+    else B2A_CONST_ROWS(float);
+#undef B2A_CONST_ROWS
+    B2A_CUDA(cudaGetLastError());
+  }
   if (clk_path && rc == B2A_OK) {  // debugging only: synchronises the stream
     const int maxg = plan->sm_count * 4;
     std::vector<long long> h(8 * (size_t)maxg);

@@ -71,6 +71,7 @@ struct FastParams {
   const float* mel_wg;    // [sum_g glen[g]*32]  W[g][j][lane], zero padded
   int mel_groups, mel_wg_count;
   int tiles_per_clip;
+  int tile_min_pitch;  // tiles per clip in the tile_min table (>= tiles_per_clip when trailing all-padding tiles are skipped)
   long long* dbg_clk;  // profiling aid (B2A_CLOCKS=file): per CTA, cycles accumulated per phase [8] (thread 0's view)
 };
 
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         b = fminf(b, red_min[w]);
       }
       atomic_max_f(p.clip_max + red_clip, a);
-      p.tile_min[(int64_t)red_clip * tpc + red_tile] = b;
+      p.tile_min[(int64_t)red_clip * p.tile_min_pitch + red_tile] = b;
     }
   };
   auto flush_sums = [&]() {  // SPEC path; called by every thread of the CTA (the clip change is CTA-uniform)
@@ -953,7 +954,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
           b = fminf(b, red_min[w]);
         }
         atomic_max_f(p.clip_max + clip_i, a);
-        p.tile_min[(int64_t)clip_i * tpc + tile_i] = b;
+        p.tile_min[(int64_t)clip_i * p.tile_min_pitch + tile_i] = b;
       }
       if (!LAYOUT_TM && lane < nf)
         for (int m = warp; m < M; m += C::WARPS) o[(int64_t)m * p.frame_count + lt0 + lane] = Y[m * 33 + lane];

@@ -662,3 +662,25 @@ def test_parakeet_and_vocos_length_sweep(L):
         yv = host(vocos_mel(dev(x24)))
         rv = W.vocos_log_mel(x24)
         assert yv.shape == rv.shape and np.abs(yv - rv).max() <= 1e-4 * np.log(10) * 4
+
+
+def test_whisper_padding_rows_are_filled_not_transformed():
+    """log_mel_spectrogram(audio, padding=N_SAMPLES) (how whisper.py always calls it): frames that see only the virtual zero
+    padding are written as constant rows; the result is bit-identical to transforming them, also in float16, and the
+    max-8 clamp still applies to them."""
+    import os
+
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    for L, padding, scale in ((16000 * 3, 480000, 1.0), (16000 * 2 + 123, 16000 * 4, 1e-4), (5000, 12000, 1.0)):
+        xb = np.stack([synth(700 + L, L) * scale, synth(701 + L, L) * scale * 0.1])
+        for dt in ("float32", "float16"):
+            y = log_mel_spectrogram(dev(xb), n_mels=128, padding=padding, dtype=dt)
+            os.environ["B2A_NO_PAD_SKIP"] = "1"
+            try:
+                y_full = log_mel_spectrogram(dev(xb), n_mels=128, padding=padding, dtype=dt)
+            finally:
+                del os.environ["B2A_NO_PAD_SKIP"]
+            assert torch.equal(y, y_full)
+        ref = W.whisper_log_mel(xb[0], 128, padding)
+        assert np.abs(host(log_mel_spectrogram(dev(xb[0]), n_mels=128, padding=padding)) - ref).max() <= 1e-4
