@@ -169,6 +169,21 @@ def main():
             res.append(r)
             del pcm
             torch.cuda.empty_cache()
+    if want("W"):
+        # Whisper as the reference's transcription loop calls it: padding = N_SAMPLES zero samples behind every clip
+        # (all-padding frames are filled, not transformed) and the encoder's float16 straight from the epilogue
+        from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram as wmel
+        x = synth(1024, 480000, 16000, 1242)
+        for nm, kw in (("padding=0, float32", dict(padding=0)), ("padding=N_SAMPLES, float32", dict(padding=480000)),
+                       ("padding=N_SAMPLES, float16 epilogue", dict(padding=480000, dtype="float16"))):
+            out = wmel(x, n_mels=128, **kw)
+            ms = timeit(lambda: wmel(x, n_mels=128, **kw), a.steps)
+            by = x.numel() * 4 + out.numel() * out.element_size()
+            res.append({"config": f"W whisper-128 1024 x 30 s, {nm}", "kernel": "fast_logmel_400x160 (+ const_rows)", "batch": 1024,
+                        "ms": ms, "audio_hours_per_s": 1024 * 30 / 3600.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+        del x
+        torch.cuda.empty_cache()
     if want("P"):
         # the steps right after the path: Whisper (B, 3000, 128) float32 -> float16 segments; FunASR LFR + CMVN
         from mlx_audio_plus_b200._post import lfr, rows_pad_cast

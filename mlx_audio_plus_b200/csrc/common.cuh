@@ -13,6 +13,18 @@
 namespace b2a {
 
 void set_error(const char* fmt, ...);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: one process driving several GPUs (plans are per device)
+// must set it on each of them.  One instance per kernel instantiation (function-local static).
+struct SmemAttrOnce {
+  size_t set[64] = {};
+  bool need(int device, size_t smem) {
+    size_t& s = set[device & 63];
+    if (smem <= s) return false;
+    s = smem;
+    return true;
+  }
+};
 int cuda_fail(cudaError_t e, const char* what);
 
 #define B2A_CUDA(call)                                        \
@@ -147,6 +159,8 @@ bool fast_frontend_supported(const b2a_plan* plan);
 int fast_frontend_init(b2a_plan* plan);
 void fast_frontend_destroy(b2a_plan* plan);
 bool fast_frontend_out16_ok(const b2a_plan* plan);
+int64_t fast_const_row0(const b2a_plan* plan, const b2a_forward_args* a);
+int fast_const_rows_finalize(const b2a_plan* plan, const b2a_forward_args* a, int64_t row0, float* clip_max, cudaStream_t st);
 int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);
 // fused iSTFT for n_fft = 4*hop vocoder heads (1024/256) — fast_inv.cu

@@ -10,31 +10,121 @@ namespace {
 
 // Rows of all-padding frames (Whisper is always called with `padding = N_SAMPLES` zero samples behind the clip,
 // whisper/whisper.py: a 30 s clip yields 6000 frames of which the last ~3000 see nothing but zeros): every mel value of such
-// a frame is the same constant c = affine(log(guard(0))).  They are not transformed: this kernel writes c (computed on the
-// device exactly as the fused kernel's phase B does), records it as those tiles' minimum and folds it into the clip max, so
-// that the clamp fix-up treats the rows like any others.
+// a frame is the same constant c = affine(log(guard(0))).  They are not transformed.  c is computed on the device exactly as
+// the fused kernel's phase B does.  Without a clamp the rows are written right away; with one, c is only folded into the
+// clip max by the partial step, and the finalize step writes max(c, floor) ONCE (no read-modify-write by the fix-up).
+struct ConstRows {
+  float guard_add, guard_floor, y_mul, y_add;
+  int use_log;
+  int floor_mode;      // 0: none, 1: clip_max[clip] - delta, 2: fixed
+  float floor_delta, floor_fixed;
+  __device__ __forceinline__ float value() const {
+    const float a = fmaxf(0.0f + guard_add, guard_floor);
+    return fmaf(use_log ? lg2_approx(a) : a, y_mul, y_add);
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) const_rows_kernel(T* out, int64_t out_clip_stride, int64_t row0, int64_t rows, int M, float guard_add,
-                                                          float guard_floor, int use_log, float y_mul, float y_add, float* clip_max,
-                                                          float* tile_min, int tile_min_pitch, int tile0) {
-  const float a = fmaxf(0.0f + guard_add, guard_floor);
-  const float c = fmaf(use_log ? lg2_approx(a) : a, y_mul, y_add);
+__global__ void __launch_bounds__(256) const_rows_kernel(T* out, int64_t out_clip_stride, int64_t row0, int64_t rows, int M, ConstRows cr,
+                                                          float* clip_max) {
+  float c = cr.value();
   const int clip = blockIdx.y;
+  if (cr.floor_mode == 1) c = fmaxf(c, clip_max[clip] - cr.floor_delta);
+  else if (cr.floor_mode == 2) c = fmaxf(c, cr.floor_fixed);
+  else if (clip_max && blockIdx.x == 0 && threadIdx.x == 0) atomic_max_f(clip_max + clip, c);  // caller-visible statistic
   T* o = out + (int64_t)clip * out_clip_stride + row0 * M;
   const int64_t total = rows * M;
   T cv;
   if constexpr (sizeof(T) == 4) cv = c;
   else if constexpr (std::is_same<T, __half>::value) cv = __float2half_rn(c);
   else cv = __float2bfloat16_rn(c);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) o[i] = cv;
-  if (clip_max && blockIdx.x == 0) {
-    const int tiles = (int)((rows + 31) / 32);
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) tile_min[(int64_t)clip * tile_min_pitch + tile0 + t] = c;
-    if (threadIdx.x == 0) atomic_max_f(clip_max + clip, c);
+  constexpr int PER = 16 / (int)sizeof(T);  // elements per 16-byte store
+  if (reinterpret_cast<uintptr_t>(o) % 16 == 0 && total % PER == 0) {
+    union { uint4 v; T e[PER]; } u;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) u.e[k] = cv;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / PER; i += (int64_t)gridDim.x * blockDim.x) o4[i] = u.v;
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) o[i] = cv;
   }
 }
 
+__global__ void const_fold_max_kernel(float* clip_max, int batch, ConstRows cr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) atomic_max_f(clip_max + b, cr.value());
+}
+
+ConstRows make_const_rows(const b2a_frontend_desc& d) {
+  ConstRows cr;
+  cr.guard_add = d.guard_kind == B2A_GUARD_ADD ? d.guard_eps : 0.0f;
+  cr.guard_floor = d.guard_kind == B2A_GUARD_MAX ? d.guard_eps : -INFINITY;
+  cr.use_log = d.log_kind != B2A_LOG_NONE;
+  const double lscale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521 : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942 : 1.0);
+  if (d.affine_div != 0.0f) {
+    cr.y_mul = (float)(lscale / (double)d.affine_div);
+    cr.y_add = (float)((double)d.affine_add / (double)d.affine_div);
+  } else {
+    cr.y_mul = (float)lscale;
+    cr.y_add = 0.0f;
+  }
+  cr.floor_mode = 0;
+  cr.floor_delta = cr.floor_fixed = 0.0f;
+  return cr;
+}
+
+int launch_const_rows(const b2a_plan* plan, const b2a_forward_args* a, int64_t row0, const ConstRows& cr, float* clip_max, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  const int64_t rows = a->frame_count - row0;
+  const int64_t stride = a->out_clip_stride ? a->out_clip_stride : a->frame_count * d.n_mels;
+  int64_t gx = (rows * d.n_mels / 4 + 255) / 256;
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)a->batch);
+  if (d.out_dtype == B2A_DTYPE_F16)
+    const_rows_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<__half*>(a->out), stride, row0, rows, d.n_mels, cr, clip_max);
+  else if (d.out_dtype == B2A_DTYPE_BF16)
+    const_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(a->out), stride, row0, rows, d.n_mels, cr, clip_max);
+  else
+    const_rows_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(a->out), stride, row0, rows, d.n_mels, cr, clip_max);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
 }  // namespace
+
+// First row of the trailing block of all-padding frames that is filled instead of transformed (a multiple of the 32-frame
+// tile), or -1.  A pure function of the plan and the call's arguments: the partial and the finalize step both derive it.
+// Conditions: zero pad value, no pre-emphasis, power / magnitude spectrum, (T, M) layout, no per-feature sums, unsharded
+// call, and the reflected tail must not reach back into the signal.
+int64_t fast_const_row0(const b2a_plan* plan, const b2a_forward_args* a) {
+  const b2a_frontend_desc& d = plan->fd;
+  if (plan->family != KF_FAST || getenv("B2A_NO_PAD_SKIP")) return -1;
+  const int64_t pc = d.center ? d.n_fft / 2 : 0;
+  const bool tail_ok = !d.center || d.pad_mode == B2A_PAD_CONSTANT || a->length - pc - 1 >= a->valid_length;
+  if (!(a->pad_value == 0.0f && d.preemph == 0.0f && d.n_mels > 0 && d.norm_kind == B2A_NORM_NONE && a->feat_sums == nullptr && tail_ok &&
+        (d.spec_kind == B2A_SPEC_POWER || d.spec_kind == B2A_SPEC_MAGNITUDE) && d.out_layout == B2A_LAYOUT_TM &&
+        a->frame_begin == 0 && a->sample_offset == 0 && a->valid_length < a->length))
+    return -1;
+  const int64_t first_pad = (a->valid_length + pc + d.hop - 1) / d.hop;  // first frame t with t*hop - pc >= valid_length
+  const int64_t r0 = (first_pad + 31) / 32 * 32;
+  return r0 + 32 <= a->frame_count ? r0 : -1;
+}
+
+// finalize side (clamp configured): the constant rows get max(c, floor) in one write pass
+int fast_const_rows_finalize(const b2a_plan* plan, const b2a_forward_args* a, int64_t row0, float* clip_max, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  ConstRows cr = make_const_rows(d);
+  const bool affine = d.affine_div != 0.0f;
+  if (d.clamp_kind == B2A_CLAMP_FIXED) {
+    cr.floor_mode = 2;
+    cr.floor_fixed = affine ? (d.clamp_value + d.affine_add) / d.affine_div : d.clamp_value;
+  } else {
+    cr.floor_mode = 1;
+    cr.floor_delta = affine ? d.clamp_value / d.affine_div : d.clamp_value;  // clamp_fixup_kernel: mx - clamp_value / affine_div
+  }
+  return launch_const_rows(plan, a, row0, cr, clip_max, st);
+}
 
 bool fast_frontend_supported(const b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
@@ -205,24 +295,12 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
   p.tile_min_pitch = p.tiles_per_clip;
-  // Trailing frames that see only virtual zero padding are constant rows: transform the frames that touch the signal
-  // (rounded up to a tile) and fill the rest.  Conditions: zero pad value, no pre-emphasis, power / magnitude spectrum,
-  // (T, M) layout, no per-feature sums, unsharded call, and the reflected tail must not reach back into the signal.
-  int64_t const_row0 = -1;
-  {
-    const int64_t pc = d.center ? d.n_fft / 2 : 0;
-    const bool tail_ok = !d.center || d.pad_mode == B2A_PAD_CONSTANT || a->length - pc - 1 >= a->valid_length;
-    if (a->pad_value == 0.0f && d.preemph == 0.0f && d.n_mels > 0 && feat_sums == nullptr && tail_ok &&
-        (d.spec_kind == B2A_SPEC_POWER || d.spec_kind == B2A_SPEC_MAGNITUDE) && d.out_layout == B2A_LAYOUT_TM &&
-        a->frame_begin == 0 && a->sample_offset == 0 && a->valid_length < a->length && !getenv("B2A_NO_PAD_SKIP")) {
-      const int64_t first_pad = (a->valid_length + pc + d.hop - 1) / d.hop;  // first frame t with t*hop - pc >= valid_length
-      const int64_t r0 = (first_pad + 31) / 32 * 32;
-      if (r0 + 32 <= a->frame_count) {
-        const_row0 = r0;
-        p.frame_count = r0;
-        p.tiles_per_clip = (int)(r0 / 32);
-      }
-    }
+  // Trailing frames that see only virtual zero padding are constant rows (fast_const_row0): transform the frames that
+  // touch the signal, rounded up to a tile, and fill the rest — here when there is no clamp, in the finalize step otherwise.
+  const int64_t const_row0 = fast_const_row0(plan, a);
+  if (const_row0 >= 0) {
+    p.frame_count = const_row0;
+    p.tiles_per_clip = (int)(const_row0 / 32);
   }
 #ifdef B2A_PHASE_CLOCKS
   const char* clk_path = getenv("B2A_CLOCKS");
@@ -239,20 +317,13 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   else if (fs->variant == 2) rc = fast_launch_512(plan, fs, p, st);
   else rc = fast_launch_1024(plan, fs, p, st);
   if (rc == B2A_OK && const_row0 >= 0) {
-    const int64_t rows = a->frame_count - const_row0;
-    int64_t gx = (rows * d.n_mels + 255) / 256;
-    if (gx > 64) gx = 64;
-    dim3 grid((unsigned)gx, (unsigned)a->batch);
-    const int tile0 = (int)(const_row0 / 32);
-#define B2A_CONST_ROWS(TT)                                                                                              \
-    const_rows_kernel<TT><<<grid, 256, 0, st>>>(reinterpret_cast<TT*>(a->out), p.out_clip_stride, const_row0, rows, d.n_mels, \
-                                                p.guard_add, p.guard_floor, p.use_log, p.y_mul, p.y_add, clip_max, tile_min, \
-                                                p.tile_min_pitch, tile0)
-    if (d.out_dtype == B2A_DTYPE_F16) B2A_CONST_ROWS(__half);
-    else if (d.out_dtype == B2A_DTYPE_BF16) B2A_CONST_ROWS(__nv_bfloat16);
-    else B2A_CONST_ROWS(float);
-#undef B2A_CONST_ROWS
-    B2A_CUDA(cudaGetLastError());
+    const ConstRows cr = make_const_rows(d);
+    if (d.clamp_kind == B2A_CLAMP_NONE) {
+      rc = launch_const_rows(plan, a, const_row0, cr, clip_max, st);
+    } else {  // the rows are written by the finalize step (max(c, floor), one pass); their value counts for the clip max
+      const_fold_max_kernel<<<(a->batch + 255) / 256, 256, 0, st>>>(clip_max, a->batch, cr);
+      B2A_CUDA(cudaGetLastError());
+    }
   }
   if (clk_path && rc == B2A_OK) {  // debugging only: synchronises the stream
     const int maxg = plan->sm_count * 4;

@@ -1086,11 +1086,9 @@ int launch_stft_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemAttrOnce attr;
+  if (attr.need(plan->device, smem))
     B2A_CUDA(cudaFuncSetAttribute(fast_stft_kernel<C, PREK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   fast_stft_kernel<C, PREK><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
@@ -1121,11 +1119,9 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static SmemAttrOnce attr;
+  if (attr.need(plan->device, smem))
     B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
   fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;

@@ -284,11 +284,9 @@ size_t inv_smem_bytes() {
 template <class C, bool POLAR>
 int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
   const size_t smem = inv_smem_bytes<C>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SmemAttrOnce attr;
+  if (attr.need(plan->device, smem))
     B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C, POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, plan->sm_count));
   fast_istft_kernel<C, POLAR><<<grid, C::THREADS, smem, st>>>(p);

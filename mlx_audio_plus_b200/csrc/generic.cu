@@ -445,6 +445,7 @@ struct FinParams {
   int tile_frames, tiles_per_clip;
   const double* feat_sums;
   int stats_affine;  // 1: clip_max / tile_min were recorded AFTER the affine map (fast kernels)
+  int tile_min_pitch;  // tiles per clip in the tile_min table (tiles_per_clip may be cut short: constant padding rows)
   int out_dtype;     // B2A_DTYPE_*: 16-bit features (fast 400/160 kernels, (T, M) layout): the floor is cast the same way
 };
 
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
       floor_out = p.apply_affine ? (floor_cmp + p.affine_add) / p.affine_div : floor_cmp;
     }
   }
-  if (!(p.tile_min[(int64_t)clip_i * p.tiles_per_clip + tile] < floor_cmp)) return;
+  if (!(p.tile_min[(int64_t)clip_i * p.tile_min_pitch + tile] < floor_cmp)) return;
   float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
   const int M = p.n_mels;
   const int64_t f0 = (int64_t)tile * p.tile_frames;
@@ -898,6 +899,10 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   p.tile_min = tile_min;
   p.tile_frames = tile_frames;
   p.tiles_per_clip = (int)((a->frame_count + tile_frames - 1) / tile_frames);
+  p.tile_min_pitch = p.tiles_per_clip;
+  // trailing all-padding frames (fast family): constant rows, written below with the clamp applied — not fixed up
+  const int64_t const_row0 = fast_const_row0(plan, a);
+  if (const_row0 >= 0) p.tiles_per_clip = (int)(const_row0 / tile_frames);
   p.feat_sums = feat_sums;
   p.stats_affine = plan->family == KF_FAST ? 1 : 0;
   p.out_dtype = d.out_dtype;
@@ -909,6 +914,7 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
     dim3 grid((p.tiles_per_clip + 7) / 8, a->batch);
     clamp_fixup_kernel<<<grid, 256, 0, st>>>(p);
     B2A_CUDA(cudaGetLastError());
+    if (const_row0 >= 0) return fast_const_rows_finalize(plan, a, const_row0, clip_max, st);
     return B2A_OK;
   }
   const int64_t total = a->frame_count * M;
