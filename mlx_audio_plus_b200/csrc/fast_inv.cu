@@ -73,6 +73,13 @@ struct InvFastState {
 
 // POLAR (magnitude / phase planes) is a compile-time variant: the accurate sincosf is ~100 instructions per call
 // site and would otherwise sit, unused, in the instruction stream of the complex-input kernel (32 KB I-cache).
+template <int BYTE_OFF>
+__device__ __forceinline__ float4 lds128_pinned(unsigned base) {  // volatile: keeps its place in program order
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base), "n"(BYTE_OFF));
+  return v;
+}
+
 template <class C, bool POLAR>
 __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, HOP = C::HOP;
@@ -204,10 +211,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
         v[k1] = er[k1 * N2];
       });
       Dft<N1>::run(v);
-      const float4* wb4 = reinterpret_cast<const float4*>(s_win2 + n2 * N1);
+      // window pairs: pinned broadcast loads issued WPD pairs ahead of their use (as the twiddles of the forward kernel)
+      constexpr int WPD = 2;
+      const unsigned wb_sa = (unsigned)__cvta_generic_to_shared(s_win2 + n2 * N1);
+      float4 wq[N1 / 2];
+      static_for<0, WPD>([&](auto I_) { wq[decltype(I_)::value] = lds128_pinned<16 * decltype(I_)::value>(wb_sa); });
       static_for<0, N1 / 2>([&](auto I_) {
         constexpr int n1 = 2 * decltype(I_)::value;
-        const float4 w = wb4[n1 / 2];
+        if constexpr (n1 / 2 + WPD < N1 / 2) wq[n1 / 2 + WPD] = lds128_pinned<16 * (n1 / 2 + WPD)>(wb_sa);
+        const float4 w = wq[n1 / 2];
         // swapped domain: v = (Im z, Re z); sample pair (x[2m], x[2m+1]) = (Re z, Im z) * (w[2m], w[2m+1]) / N
         er[n1 * N2] = regs::pmul(regs::pswap(v[n1]), make_float2(w.x, w.y));
         er[(n1 + 1) * N2] = regs::pmul(regs::pswap(v[n1 + 1]), make_float2(w.z, w.w));
