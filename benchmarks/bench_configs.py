@@ -130,7 +130,8 @@ def main():
         # framing) is timed beside it for context only.
         for nm, n_fft, hop, B, n, sr in (("400/160, 1024 x 30 s", 400, 160, 1024, 480000, 16000),
                                          ("512/160, 4 x 1 h", 512, 160, 4, 57_600_000, 16000),
-                                         ("1024/256, 4096 x 5 s", 1024, 256, 4096, 120000, 24000)):
+                                         ("1024/256, 4096 x 5 s", 1024, 256, 4096, 120000, 24000),
+                                         ("800/200 (the module defaults), 1024 x 30 s", 800, 200, 1024, 480000, 16000)):
             w = np.asarray(hanning(n_fft))
             x = synth(B, n, sr, 1240)
             plan = FrontendPlan(n_fft=n_fft, hop=hop, window=w, spec_kind=L.SPEC_COMPLEX)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libb200audio.so")
-SOURCES = ["tables.cu", "generic.cu", "fast_fwd.cu", "fast_400.cu", "fast_512.cu", "fast_1024.cu", "fast_inv.cu", "small.cu", "resample.cu", "post.cu", "api.cu"]
+SOURCES = ["tables.cu", "generic.cu", "fast_fwd.cu", "fast_400.cu", "fast_512.cu", "fast_1024.cu", "fast_800.cu", "fast_inv.cu", "small.cu", "resample.cu", "post.cu", "api.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static",

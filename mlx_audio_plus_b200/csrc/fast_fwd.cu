@@ -138,7 +138,8 @@ bool fast_frontend_supported(const b2a_plan* plan) {
   const bool v400 = d.n_fft == 400 && d.hop == 160;
   const bool v512 = d.n_fft == 512 && d.hop == 160;
   const bool v1024 = d.n_fft == 1024 && d.hop == 256;
-  if (!(v400 || v512 || v1024)) return false;
+  const bool v800 = d.n_fft == 800 && d.hop == 200, v1024h320 = d.n_fft == 1024 && d.hop == 320;
+  if (!(v400 || v512 || v1024 || v800 || v1024h320)) return false;
   if (d.n_mels > 256) return false;
   return true;
 }
@@ -156,6 +157,8 @@ int fast_frontend_init(b2a_plan* plan) {
   int N1, N2;
   if (d.n_fft == 400) { fs->variant = 1; N1 = 20; N2 = 10; }
   else if (d.n_fft == 512) { fs->variant = 2; N1 = 16; N2 = 16; }
+  else if (d.n_fft == 800) { fs->variant = 4; N1 = 20; N2 = 20; }
+  else if (d.hop == 320) { fs->variant = 5; N1 = 32; N2 = 16; }
   else { fs->variant = 3; N1 = 32; N2 = 16; }
   const int NC = N1 * N2, N = 2 * NC;
   std::vector<float2> win2(NC);
@@ -224,11 +227,18 @@ int fast_frontend_init(b2a_plan* plan) {
   B2A_CUDA(cudaMemcpy(fs->d_start, start.data(), sizeof(int) * G * 8, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_ginfo, ginfo.data(), sizeof(int) * 2 * G, cudaMemcpyHostToDevice));
   B2A_CUDA(cudaMemcpy(fs->d_wg, wg.data(), sizeof(float) * wg.size(), cudaMemcpyHostToDevice));
-  plan->kernel_name = fs->variant == 1 ? "fast_logmel_400x160" : (fs->variant == 2 ? "fast_logmel_512x160" : "fast_logmel_1024x256");
-  if (d.spec_kind == B2A_SPEC_COMPLEX)
-    plan->kernel_name = fs->variant == 1 ? "fast_stft_400x160" : (fs->variant == 2 ? "fast_stft_512x160" : "fast_stft_1024x256");
-  fs->spec = fs->variant == 1 ? fast_match_400(plan, &fs->spec_name)
-                              : (fs->variant == 2 ? fast_match_512(plan, &fs->spec_name) : fast_match_1024(plan, &fs->spec_name));
+  static const char* const kLogmel[] = {"", "fast_logmel_400x160", "fast_logmel_512x160", "fast_logmel_1024x256", "fast_logmel_800x200",
+                                        "fast_logmel_1024x320"};
+  static const char* const kStft[] = {"", "fast_stft_400x160", "fast_stft_512x160", "fast_stft_1024x256", "fast_stft_800x200",
+                                      "fast_stft_1024x320"};
+  plan->kernel_name = d.spec_kind == B2A_SPEC_COMPLEX ? kStft[fs->variant] : kLogmel[fs->variant];
+  switch (fs->variant) {
+    case 1: fs->spec = fast_match_400(plan, &fs->spec_name); break;
+    case 2: fs->spec = fast_match_512(plan, &fs->spec_name); break;
+    case 3: fs->spec = fast_match_1024(plan, &fs->spec_name); break;
+    case 4: fs->spec = fast_match_800(plan, &fs->spec_name); break;
+    default: fs->spec = fast_match_1024h320(plan, &fs->spec_name); break;
+  }
   return B2A_OK;
 }
 
@@ -315,7 +325,9 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   int rc;
   if (fs->variant == 1) rc = fast_launch_400(plan, fs, p, st);
   else if (fs->variant == 2) rc = fast_launch_512(plan, fs, p, st);
-  else rc = fast_launch_1024(plan, fs, p, st);
+  else if (fs->variant == 3) rc = fast_launch_1024(plan, fs, p, st);
+  else if (fs->variant == 4) rc = fast_launch_800(plan, fs, p, st);
+  else rc = fast_launch_1024h320(plan, fs, p, st);
   if (rc == B2A_OK && const_row0 >= 0) {
     const ConstRows cr = make_const_rows(d);
     if (d.clamp_kind == B2A_CLAMP_NONE) {

@@ -83,7 +83,7 @@ struct FastState {
   int* d_ginfo = nullptr;
   float* d_wg = nullptr;
   int groups = 0, wg_count = 0;
-  int variant = 0;  // 1: 400/160, 2: 512/160, 3: 1024/256
+  int variant = 0;  // 1: 400/160, 2: 512/160, 3: 1024/256, 4: 800/200, 5: 1024/320
   int spec = 0;     // index into the variant's generated mel specs (0: run-time tables)
   const char* spec_name = nullptr;
 };
@@ -95,6 +95,10 @@ int fast_match_1024(const b2a_plan* plan, const char** name);
 int fast_launch_400(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
 int fast_launch_512(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
 int fast_launch_1024(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
+int fast_match_800(const b2a_plan* plan, const char** name);
+int fast_launch_800(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
+int fast_match_1024h320(const b2a_plan* plan, const char** name);
+int fast_launch_1024h320(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st);
 
 namespace {
 

@@ -127,7 +127,8 @@ def test_stft_edge_lengths_and_sizes(n_fft, hop, L):
 
 
 @pytest.mark.parametrize("n_fft,hop,win,pre", [(400, 160, 400, 0.0), (512, 160, 400, 0.0), (1024, 256, 1024, 0.0),
-                                               (512, 160, 512, 0.97), (400, 160, 400, 0.97)])
+                                               (512, 160, 512, 0.97), (400, 160, 400, 0.97), (800, 200, 800, 0.0),
+                                               (800, 200, 600, 0.97), (1024, 320, 640, 0.0)])
 def test_fast_stft_kernel_parity(n_fft, hop, win, pre):
     """dsp.stft for the common sizes runs on fast_stft_* (register FFT, in-place spectrum tile, coalesced complex rows):
     same tolerance as the generic kernel, several clips, ragged last tile, reflect edges, optional pre-emphasis."""
@@ -684,3 +685,26 @@ def test_whisper_padding_rows_are_filled_not_transformed():
             assert torch.equal(y, y_full)
         ref = W.whisper_log_mel(xb[0], 128, padding)
         assert np.abs(host(log_mel_spectrogram(dev(xb[0]), n_mels=128, padding=padding)) - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("n_fft,hop,win,n_mels,sr,kind", [(800, 200, 800, 80, 16000, "power"), (1024, 320, 640, 128, 16000, "magnitude")])
+def test_fast_logmel_800_and_1024x320(n_fft, hop, win, n_mels, sr, kind):
+    """the two extra sizes of the fast family (dsp.stft's defaults 800/200; Spark's 1024/320 with a 640-tap window,
+    bicodec.py:20-49) with a run-time filterbank: log-mel against the oracle's stft + mel_filters"""
+    from mlx_audio_plus_b200 import _lib as L
+    from mlx_audio_plus_b200._arrays import Ingested
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+
+    w = np.asarray(O.hanning(win + 1)[:-1]) if win != n_fft else np.asarray(O.hanning(win))
+    fb = np.asarray(O.mel_filters(sr, n_fft, n_mels, norm="slaney", mel_scale=None))
+    plan = FrontendPlan(n_fft=n_fft, hop=hop, window=w, filterbank=fb, spec_kind=L.SPEC_POWER if kind == "power" else L.SPEC_MAGNITUDE,
+                        log_kind=L.LOG_LN, guard_kind=L.GUARD_MAX, guard_eps=1e-5)
+    assert plan.kernel_name == f"fast_logmel_{n_fft}x{hop}"
+    xb = np.stack([synth(60 + i, 30011) * (0.5 + i) for i in range(2)])
+    xd = dev(xb)
+    y = host(plan.run(Ingested("torch", True, xd, None, xd.device)))
+    for i in range(2):
+        S = np.abs(O.stft(xb[i], n_fft, hop, win, w))
+        S = np.square(S) if kind == "power" else S
+        ref = np.log(np.maximum((S.astype(np.float32) @ fb.T).astype(np.float32), np.float32(1e-5)))
+        assert y[i].shape == ref.shape and np.abs(y[i] - ref).max() <= 1e-4 * np.log(10) * 4
