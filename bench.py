@@ -223,7 +223,7 @@ def main():
     n_mels, bytes_per_clip = WORKLOADS[a.workload]
 
     cpu_base = None
-    if rank == 0 and not a.no_cpu_baseline:  # before CUDA is initialised (fork-safe)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:  # N = 1 only; before CUDA is initialised (fork-safe)
         cores = host_cores()
         sample = max(cores, min(a.cpu_sample, 32 * cores))
         cps, n, dt = cpu_clips_per_second(n_mels, sample, cores)
