@@ -348,6 +348,21 @@ def main():
                 traffic = per_clip * B if per_clip else None  # ncu --set full capture, scaled per launch
             except Exception:
                 traffic = None
+        # the FP32 side of the roofline too.  Algorithmic flops per frame: window N + real FFT 2.5 N log2 N + power
+        # 3 F + banded mel 2 nnz + ~4 M epilogue (10 749 / 10 947 for M = 80 / 128), 3001 frames per clip; the FP32 peak is
+        # measured live with the library's own FFMA microbenchmark.  binding_frac = max(t_hbm, t_fp32) / t_measured.
+        fp32 = None
+        try:
+            tf = C.c_double(0.0)
+            L.check(L.lib.b2a_measure_fp32_tflops(C.byref(tf), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            flops = {80: 10749.0, 128: 10947.0}[n_mels] * 3001 * B
+            ach = flops / (kms * 1e-3) / 1e12
+            t_hbm, t_fp = algo_bytes / (peak * 1e9), flops / (tf.value * 1e12)
+            fp32 = {"achieved_tflops": ach, "peak_tflops_measured": tf.value, "frac": ach / tf.value,
+                    "algorithmic_flops_per_launch": flops, "binding": "hbm" if t_hbm >= t_fp else "fp32",
+                    "binding_frac": max(t_hbm, t_fp) / (kms * 1e-3)}
+        except Exception as e:  # noqa: BLE001
+            fp32 = {"error": str(e)}
         line = {
             "metric": "log-mel audio-hours/sec", "value": ah_per_s, "unit": "audio-hours/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -358,7 +373,7 @@ def main():
                        "kernel": plan.kernel_name},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms,
-                         "algorithmic_bytes_per_launch": algo_bytes},
+                         "algorithmic_bytes_per_launch": algo_bytes, "fp32": fp32},
             "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": 3 * a.steps, "clocks": clocks,
         }
         sys.stdout.flush()
