@@ -60,6 +60,22 @@ def rows_pad_cast(x, row_begin: int, rows_valid: int, rows_out: int, dtype="floa
     return _back(x, out[0] if one else out)
 
 
+def cmvn_utterance(features, eps: float = 1e-6):
+    """(x - mean) / (std + eps) over the frames of every feature column (funasr/audio.py:160-164); (T, M) or (B, T, M)"""
+    import torch
+
+    t = _to_cuda_f32(features)
+    one = t.ndim == 2
+    if one:
+        t = t[None]
+    B, T, M = t.shape
+    out = torch.empty_like(t)
+    ws = torch.empty((B, M, 2), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        L.check(L.lib.b2a_cmvn_utterance(t.data_ptr(), out.data_ptr(), 0, T, M, float(eps), ws.data_ptr(), B, _stream()))
+    return _back(features, out[0] if one else out)
+
+
 def lfr(features, lfr_m: int, lfr_n: int, cmvn_shift=None, cmvn_scale=None):
     """features: (T, M) or (B, T, M) float32 -> (ceil(T / lfr_n), lfr_m * M) [batched alike] (funasr/audio.py:84-139)"""
     import torch

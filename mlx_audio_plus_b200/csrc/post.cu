@@ -100,6 +100,45 @@ __global__ void __launch_bounds__(256) lfr_kernel(const float* __restrict__ in, 
   }
 }
 
+// per-utterance CMVN (funasr/audio.py:160-164): mean / std over the frames of each feature column (mx.std: ddof 0),
+// (x - mean) / (std + eps).  Pass 1: per-column sum and sum of squares in float64 (one atomicAdd pair per block and column);
+// pass 2: apply.  stats: [batch][cols][2] doubles, zeroed by the caller side of the ABI function.
+__global__ void __launch_bounds__(256) cmvn_stats_kernel(const float* __restrict__ x, int64_t clip_stride, int64_t rows, int cols, double* stats) {
+  const float* src = x + (int64_t)blockIdx.y * clip_stride;
+  double* st = stats + (int64_t)blockIdx.y * cols * 2;
+  // a block owns a contiguous slab of rows; thread t walks columns t, t + 256, ... of that slab
+  const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const double v = (double)__ldg(src + r * cols + c);
+      s1 += v;
+      s2 += v * v;
+    }
+    if (r1 > r0) {
+      atomicAdd(st + 2 * c, s1);
+      atomicAdd(st + 2 * c + 1, s2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t clip_stride, int64_t rows, int cols,
+                                                          const double* stats, float eps) {
+  const float* src = x + (int64_t)blockIdx.y * clip_stride;
+  float* dst = out + (int64_t)blockIdx.y * clip_stride;
+  const double* st = stats + (int64_t)blockIdx.y * cols * 2;
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const double mean = st[2 * c] / (double)rows;
+    double var = st[2 * c + 1] / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean, sd = (float)sqrt(var) + eps;
+    dst[i] = (__ldg(src + i) - m) / sd;
+  }
+}
+
 }  // namespace
 }  // namespace b2a
 
@@ -121,6 +160,26 @@ int b2a_rows_pad_cast(const float* in, int64_t in_clip_stride, int64_t row_begin
     case B2A_DTYPE_BF16: return launch_rows<__nv_bfloat16>(in, in_clip_stride, row_begin, rows_valid, cols, out, rows_out, batch, st);
     default: set_error("rows_pad_cast: out_dtype %d", out_dtype); return B2A_ERR_INVALID_ARG;
   }
+}
+
+int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t rows, int32_t cols, float eps, double* stats_ws,
+                       int32_t batch, void* stream) {
+  if (!in || !out || !stats_ws || rows <= 0 || cols <= 0 || batch <= 0 || batch > 65535) {
+    set_error("cmvn_utterance: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cs = clip_stride ? clip_stride : rows * cols;
+  B2A_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)cols * batch, st));
+  int64_t gx = (rows + 63) / 64;
+  if (gx > 148 * 4) gx = 148 * 4;
+  cmvn_stats_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, st>>>(in, cs, rows, cols, stats_ws);
+  B2A_CUDA(cudaGetLastError());
+  int64_t ga = (rows * cols + 255) / 256;
+  if (ga > 148 * 16) ga = 148 * 16;
+  cmvn_apply_kernel<<<dim3((unsigned)ga, (unsigned)batch), 256, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
 }
 
 int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_mels, int32_t lfr_m, int32_t lfr_n,

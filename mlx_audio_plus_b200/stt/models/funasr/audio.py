@@ -4,7 +4,7 @@ the precomputed CMVN of apply_cmvn as one gather kernel (csrc/post.cu)."""
 from __future__ import annotations
 
 from ...._arrays import emit
-from ...._post import lfr
+from ...._post import cmvn_utterance, lfr
 from ...._wrap import as_batch, run_frontend
 from .... import _lib as L
 from ....dsp import hamming, mel_filters
@@ -35,11 +35,10 @@ def apply_lfr(features, lfr_m: int = LFR_M, lfr_n: int = LFR_N):
 
 
 def apply_cmvn(features, cmvn_mean=None, cmvn_istd=None):
-    """funasr/audio.py:142-169 with precomputed statistics: (features + mean) * istd.  (An LFR of one frame per row with
-    stride one is the identity gather, so the same kernel applies the affine map.)"""
-    if cmvn_mean is None or cmvn_istd is None:
-        raise NotImplementedError("per-utterance CMVN (funasr/audio.py:160-164) is not on the accelerated path; "
-                                  "Fun-ASR checkpoints ship precomputed statistics")
+    """funasr/audio.py:142-169.  Precomputed statistics: (features + mean) * istd (an LFR of one frame per row with stride one
+    is the identity gather, so the same kernel applies the affine map); without them: per-utterance normalisation."""
+    if cmvn_mean is None or cmvn_istd is None:  # per-utterance: mean / std (ddof 0) over the frames, eps 1e-6 (160-164)
+        return cmvn_utterance(features, 1e-6)
     return lfr(features, 1, 1, cmvn_mean, cmvn_istd)
 
 

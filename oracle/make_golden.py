@@ -150,6 +150,7 @@ def post_goldens(mx, R):
     istd = (0.5 + rng.random(560)).astype(np.float32)
     g["funasr|cmvn_mean"], g["funasr|cmvn_istd"] = mean, istd
     g["funasr|lfr_cmvn"] = A(F.apply_cmvn(F.apply_lfr(lm), mx.array(mean), mx.array(istd)))
+    g["funasr|lfr_cmvn_utt"] = A(F.apply_cmvn(F.apply_lfr(lm)))  # per-utterance mean / std (funasr/audio.py:160-164)
     mel = W.log_mel_spectrogram(synth(301, 16000 * 4), n_mels=80)
     g["whisper|mel"] = A(mel)
     for seek, size in ((0, 400), (100, 300), (250, 150)):

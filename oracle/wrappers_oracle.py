@@ -394,7 +394,12 @@ def funasr_apply_lfr(features, lfr_m=7, lfr_n=6):  # funasr/audio.py:84-139
     return f[idx].reshape(t_lfr, -1)
 
 
-def funasr_apply_cmvn(features, cmvn_mean, cmvn_istd):  # funasr/audio.py:166-169 (precomputed statistics)
+def funasr_apply_cmvn(features, cmvn_mean=None, cmvn_istd=None):  # funasr/audio.py:142-169
+    if cmvn_mean is None or cmvn_istd is None:  # per-utterance (160-164): mx.mean / mx.std (ddof 0) over axis 0, std + 1e-6
+        f = np.asarray(features, np.float32)
+        mean = f.mean(axis=0, keepdims=True, dtype=np.float32)
+        std = f.std(axis=0, keepdims=True, dtype=np.float32) + np.float32(1e-6)
+        return ((f - mean) / std).astype(np.float32)
     return ((np.asarray(features, np.float32) + np.asarray(cmvn_mean, np.float32)) * np.asarray(cmvn_istd, np.float32)).astype(np.float32)
 
 

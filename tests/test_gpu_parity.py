@@ -516,6 +516,10 @@ def test_funasr_frontend_lfr_cmvn_parity(golden):
         np.testing.assert_array_equal(host(FA.apply_lfr(put(g["funasr|logmel"][:4]))), g["funasr|lfr_short"])
         np.testing.assert_array_equal(host(FA.apply_cmvn(put(g["funasr|lfr"]), g["funasr|cmvn_mean"], g["funasr|cmvn_istd"])),
                                       g["funasr|lfr_cmvn"])
+        u = host(FA.apply_cmvn(put(g["funasr|lfr"])))  # per-utterance: float64 statistics on the device
+        assert u.shape == g["funasr|lfr_cmvn_utt"].shape and np.abs(u - g["funasr|lfr_cmvn_utt"]).max() <= 5e-5
+    ub = host(FA.apply_cmvn(dev(np.stack([g["funasr|lfr"], 2 * g["funasr|lfr"] + 1]))))
+    assert np.abs(ub[1] - ub[0]).max() <= 5e-5  # (x - mean) / std is invariant under x -> 2x + 1
     fused = host(FA.preprocess_audio(dev(g["funasr|x"]), cmvn_mean=g["funasr|cmvn_mean"], cmvn_istd=g["funasr|cmvn_istd"]))
     assert fused.shape == g["funasr|lfr_cmvn"].shape
     assert np.abs(fused - g["funasr|lfr_cmvn"]).max() <= 1e-3 * 1.5  # log-mel tolerance times the largest istd (1.5)
