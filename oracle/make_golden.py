@@ -20,6 +20,17 @@ Reference files executed (whole file or AST-extracted definitions, never copied)
   mlx_audio/tts/models/kokoro/istftnet.py            (mlx_angle, mlx_unwrap, MLXSTFT)
   mlx_audio/tts/models/qwen3_tts/qwen3_tts.py        (mel_spectrogram)
   mlx_audio/vad/models/sortformer/sortformer.py      (preemphasis_filter, extract_mel_features)
+  SURVEY §8a row a12 (refshim_variants.npz):
+  mlx_audio/codec/models/s3gen/mel.py                (_reflect_pad_2d, mel_spectrogram)
+  mlx_audio/tts/models/indextts/mel.py               (whole module)
+  mlx_audio/tts/models/spark/bicodec.py              (mel_spectrogram)
+  mlx_audio/tts/models/chatterbox/voice_encoder/melspec.py, config.py (melspectrogram, VoiceEncConfig)
+  mlx_audio/tts/models/soprano/decoder.py            (class ISTFTHead)
+  mlx_audio/stt/models/glmasr/glmasr.py              (method Model._preprocess_audio)
+  mlx_audio/vad/models/smart_turn/smart_turn.py      (methods _prepare_audio_array, prepare_input_features)
+  mlx_audio/sts/models/lfm_audio/processor.py        (class AudioPreprocessor)
+  mlx_audio/sts/models/lfm_audio/detokenizer.py      (method _istft)
+  mlx_audio/sts/models/mossformer2_se/model.py:396-428 (its two dsp calls, made with the same positional arguments)
 """
 from __future__ import annotations
 
@@ -93,6 +104,19 @@ def _load_reference():
         exec(compile(ast.Module(body=keep, type_ignores=[]), rel, "exec"), ns)
         return types.SimpleNamespace(**{n: ns[n] for n in names})
 
+    def extract_methods(rel, cls, names, extra=None):
+        """exec selected methods of a reference class (verbatim AST nodes) as free functions taking `self`."""
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        c = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls)
+        keep = [n for n in c.body if isinstance(n, ast.FunctionDef) and n.name in names]
+        for n in keep:
+            n.decorator_list = []
+        ns = {"mx": mx, "nn": nn, "np": np, "math": math, "Union": tuple, "Optional": tuple}
+        ns.update(extra or {})
+        exec(compile(ast.Module(body=keep, type_ignores=[]), rel, "exec"), ns)
+        return types.SimpleNamespace(**{n: ns[n] for n in names})
+
+    mods["extract"], mods["extract_methods"] = extract, extract_methods
     mods["vocos"] = extract("mlx_audio/codec/models/vocos/vocos.py", ["ISTFTHead"])
     mods["kokoro"] = extract("mlx_audio/tts/models/kokoro/istftnet.py", ["mlx_angle", "mlx_unwrap", "MLXSTFT"])
     mods["qwen3"] = extract("mlx_audio/tts/models/qwen3_tts/qwen3_tts.py", ["mel_spectrogram"])
@@ -189,8 +213,87 @@ def kaldi_goldens(mx, R):
     np.savez_compressed(os.path.join(OUT, "refshim_kaldi.npz"), **g)
 
 
+def variants_goldens(mx, R):
+    """tests/golden/refshim_variants.npz: the thin dsp callers of SURVEY §8a row a12, each from the reference's own code."""
+    A = np.asarray
+    dsp, extract, extract_methods = R["dsp"], R["extract"], R["extract_methods"]
+    g = {}
+    # S3Gen mel (codec/models/s3gen/mel.py:25-100)
+    s3 = extract("mlx_audio/codec/models/s3gen/mel.py", ["_reflect_pad_2d", "mel_spectrogram"])
+    x = np.stack([synth(500, 12000, 24000), 0.3 * synth(501, 12000, 24000)])
+    g["s3gen|x"], g["s3gen|y"] = x, A(s3.mel_spectrogram(mx.array(x)))
+    g["s3gen|y1d"] = A(s3.mel_spectrogram(mx.array(x[1])))
+    # IndexTTS (tts/models/indextts/mel.py)
+    spec = importlib.util.spec_from_file_location("mlx_audio.tts_indextts_mel", os.path.join(REF, "mlx_audio/tts/models/indextts/mel.py"))
+    it = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(it)
+    x = synth(502, 9000, 24000)
+    g["indextts|x"], g["indextts|y"] = x, A(it.log_mel_spectrogram(mx.array(x)))
+    g["indextts|ypad"] = A(it.log_mel_spectrogram(x, padding=500))
+    # Spark BiCodec (tts/models/spark/bicodec.py:20-49)
+    sp = extract("mlx_audio/tts/models/spark/bicodec.py", ["mel_spectrogram"], {"Optional": tuple})
+    x = synth(503, 16000)
+    g["spark|x"], g["spark|y"] = x, A(sp.mel_spectrogram(mx.array(x)))
+    # Chatterbox voice encoder (tts/models/chatterbox/voice_encoder/melspec.py:13-77)
+    cfg = extract("mlx_audio/tts/models/chatterbox/voice_encoder/config.py", ["VoiceEncConfig"],
+                  {"dataclass": __import__("dataclasses").dataclass})
+    ve = extract("mlx_audio/tts/models/chatterbox/voice_encoder/melspec.py", ["melspectrogram"], {"VoiceEncConfig": cfg.VoiceEncConfig})
+    x = np.stack([synth(504, 8000), 0.5 * synth(505, 8000)])
+    g["ve|x"] = x
+    g["ve|amp"] = A(ve.melspectrogram(mx.array(x), cfg.VoiceEncConfig()))
+    g["ve|amp1d"] = A(ve.melspectrogram(mx.array(x[0]), cfg.VoiceEncConfig()))
+    g["ve|db_norm"] = A(ve.melspectrogram(mx.array(x), cfg.VoiceEncConfig(mel_power=1.0, mel_type="db", normalized_mels=True)))
+    g["ve|db"] = A(ve.melspectrogram(mx.array(x), cfg.VoiceEncConfig(mel_type="db")))
+    # Soprano decoder head (tts/models/soprano/decoder.py:14-49), n_fft 2048 / hop 512
+    so = extract("mlx_audio/tts/models/soprano/decoder.py", ["ISTFTHead"])
+    lin = (0.5 * np.random.default_rng(15).standard_normal((1, 12, 2050))).astype(np.float32)
+    g["soprano|head_in"], g["soprano|head_out"] = lin, A(so.ISTFTHead(8, 2048, 512)(mx.array(lin)))
+    # GLM-ASR (stt/models/glmasr/glmasr.py:547-589)
+    glm = extract_methods("mlx_audio/stt/models/glmasr/glmasr.py", "Model", ["_preprocess_audio"])
+    me = types.SimpleNamespace(sample_rate=16000, config=types.SimpleNamespace(whisper_config=types.SimpleNamespace(num_mel_bins=128)))
+    x = synth(506, 16000 * 2 + 40)
+    g["glmasr|x"], g["glmasr|y"] = x, A(glm._preprocess_audio(me, x))
+    # Smart-Turn (vad/models/smart_turn/smart_turn.py:158-229)
+    st = extract_methods("mlx_audio/vad/models/smart_turn/smart_turn.py", "Model", ["_prepare_audio_array", "prepare_input_features"],
+                         {"log_mel_spectrogram": R["whisper"].log_mel_spectrogram})
+    pc = types.SimpleNamespace(sampling_rate=16000, max_audio_seconds=2, n_fft=400, hop_length=160, n_mels=80, normalize_audio=True)
+    me = types.SimpleNamespace(config=types.SimpleNamespace(processor_config=pc), dtype=mx.float32, _resample=lambda a, s, t: a)
+    me._prepare_audio_array = lambda audio, sample_rate=None: st._prepare_audio_array(me, audio, sample_rate=sample_rate)
+    for name, n in (("short", 20000), ("long", 40000)):
+        x = synth(507, n) + 0.05
+        g[f"smart|{name}|x"], g[f"smart|{name}|y"] = x, A(st.prepare_input_features(me, x))
+    # LFM2 audio preprocessor (sts/models/lfm_audio/processor.py:34-140), dither 0
+    lf = extract("mlx_audio/sts/models/lfm_audio/processor.py", ["AudioPreprocessor"], {"PreprocessorConfig": object})
+    pcfg = types.SimpleNamespace(sample_rate=16000, normalize="per_feature", window_size=0.025, window_stride=0.01, window="hann",
+                                 features=128, n_fft=512, log=True, dither=0.0, preemph=0.97)
+    x = np.stack([synth(508, 16000 + 53), 0.2 * synth(509, 16000 + 53)])
+    g["lfm2|x"], g["lfm2|y"] = x, A(lf.AudioPreprocessor(pcfg)(mx.array(x)))
+    g["lfm2|y1d"] = A(lf.AudioPreprocessor(pcfg)(mx.array(x[1])))
+    # LFM2 detokenizer iSTFT (sts/models/lfm_audio/detokenizer.py:468-507), n_fft 1280 / hop 320
+    dt = extract_methods("mlx_audio/sts/models/lfm_audio/detokenizer.py", "LFM2AudioDetokenizer", ["_istft"])
+    rng = np.random.default_rng(16)
+    mag = np.exp(0.5 * rng.standard_normal((2, 9, 641))).astype(np.float32)
+    ph = rng.uniform(-np.pi, np.pi, mag.shape).astype(np.float32)
+    w = A(dsp.hanning(1280, True))
+    me = types.SimpleNamespace(n_fft=1280, hop_length=320, window=mx.array(w))
+    g["lfm2|mag"], g["lfm2|phase"], g["lfm2|w"], g["lfm2|wave"] = mag, ph, w, A(dt._istft(me, mx.array(mag), mx.array(ph)))
+    # MossFormer2-SE chunk (sts/models/mossformer2_se/model.py:396-428): stft(center=False) -> (F, T) planes -> ISTFTCache.istft
+    x = (synth(510, 9600, 48000) * 8000.0).astype(np.float32)
+    w = dsp.hamming(1920, periodic=False)
+    sc = dsp.stft(mx.array(x), 1920, 384, 1920, w, center=False)
+    re, im = A(mx.real(sc).T), A(mx.imag(sc).T)
+    g["moss|x"], g["moss|re"], g["moss|im"] = x, re, im
+    cache = dsp.ISTFTCache()
+    g["moss|y"] = A(cache.istft(mx.array(re).reshape(1, *re.shape), mx.array(im).reshape(1, *im.shape), 1920, 384, 1920, w,
+                                center=False, audio_length=9600))[0]
+    np.savez_compressed(os.path.join(OUT, "refshim_variants.npz"), **g)
+
+
 def main():
     mx, R = _load_reference()
+    if "--variants-only" in sys.argv:
+        variants_goldens(mx, R)
+        return
     if "--hift-only" in sys.argv:
         hift_goldens(mx, R)
         return
@@ -380,6 +483,7 @@ def main():
     hift_goldens(mx, R)
     kaldi_goldens(mx, R)
     post_goldens(mx, R)
+    variants_goldens(mx, R)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

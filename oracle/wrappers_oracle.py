@@ -406,3 +406,160 @@ def funasr_apply_cmvn(features, cmvn_mean=None, cmvn_istd=None):  # funasr/audio
 def whisper_mel_segment(mel, seek, segment_size, n_frames=3000, dtype=np.float16):  # whisper/whisper.py:990-996
     seg = np.asarray(mel)[seek: seek + segment_size]
     return whisper_pad_or_trim(seg, n_frames, axis=-2).astype(dtype)
+
+
+# -- the remaining parameter variants of SURVEY §8a row a12 ---------------------------------------------------------------
+def glmasr_preprocess_audio(audio, n_mels=128):  # stt/models/glmasr/glmasr.py:547-589: Whisper-128 chain, (1, T, M)
+    a = np.asarray(audio, F32)
+    if a.ndim == 3:  # already features (:569-570)
+        return a
+    return whisper_log_mel(a, n_mels)[None]
+
+
+def smart_turn_prepare_audio(audio, max_audio_seconds=8, sampling_rate=16000, normalize_audio=True):  # smart_turn.py:158-201
+    a = np.asarray(audio, F32)
+    max_samples = max_audio_seconds * sampling_rate
+    if a.shape[0] > max_samples:
+        a = a[-max_samples:]  # keeps the END of the turn
+    elif a.shape[0] < max_samples:
+        a = np.pad(a, (max_samples - a.shape[0], 0), mode="constant")  # LEFT zero padding
+    if normalize_audio and a.size > 0:
+        mean, std = float(a.mean()), float(a.std())
+        a = (a - mean) / max(std, 1e-7)
+    return a.astype(F32, copy=False)
+
+
+def smart_turn_features(audio, n_mels=80, max_audio_seconds=8, sampling_rate=16000, hop_length=160, normalize_audio=True):
+    """smart_turn.py:203-229 -> (n_mels, target_frames)"""
+    mel = whisper_log_mel(smart_turn_prepare_audio(audio, max_audio_seconds, sampling_rate, normalize_audio), n_mels)
+    target = max_audio_seconds * sampling_rate // hop_length
+    if mel.shape[0] > target:
+        mel = mel[-target:]
+    elif mel.shape[0] < target:
+        mel = np.pad(mel, [(target - mel.shape[0], 0), (0, 0)])
+    return mel.T.astype(F32)
+
+
+def s3gen_mel(y, n_fft=1920, num_mels=80, sampling_rate=24000, hop_size=480, win_size=1920, fmin=0, fmax=8000):
+    """codec/models/s3gen/mel.py:25-100: manual reflect pad (n_fft-hop)/2, center=False, magnitude, ln(max 1e-5), (B, M, T)"""
+    a = np.asarray(y, F32)
+    if a.ndim == 1:
+        a = a[None]
+    pad = (n_fft - hop_size) // 2
+    fb = D.mel_filters(sampling_rate, n_fft, num_mels, fmin, fmax, "slaney", "slaney")
+    out = []
+    for s in a:
+        if pad:
+            s = np.concatenate([s[1 : pad + 1][::-1], s, s[-(pad + 1) : -1][::-1]])
+        spec = D.stft(s, window="hann", n_fft=n_fft, hop_length=hop_size, win_length=win_size, center=False)
+        out.append((np.abs(spec).astype(F32) @ fb.T).T)
+    return np.log(np.maximum(np.stack(out), F32(1e-5))).astype(F32)
+
+
+def indextts_log_mel(audio, sample_rate=24000, n_mels=100, n_fft=1024, hop_length=256, padding=0):
+    """tts/models/indextts/mel.py:6-37: symmetric "hann", hop forwarded, NO frame drop, magnitude, HTK, ln(max 1e-5), (1, T, M)"""
+    spec = D.stft(_rpad(audio, padding), window="hann", n_fft=n_fft, hop_length=hop_length, win_length=n_fft)
+    fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=n_mels, norm=None, mel_scale="htk")
+    return np.log(np.maximum(np.abs(spec).astype(F32) @ fb.T, F32(1e-5)))[None].astype(F32)
+
+
+def spark_mel(audio, sample_rate=16000, n_mels=128, n_fft=1024, f_min=10, f_max=None, hop_length=320, win_length=640, padding=0):
+    """tts/models/spark/bicodec.py:20-49: periodic Hann-640 right-padded to 1024 by dsp.stft, magnitude, no log, (1, T, M)"""
+    w = D.hanning(win_length + 1)[:-1]
+    spec = D.stft(_rpad(audio, padding), window=w, win_length=win_length, hop_length=hop_length, n_fft=n_fft)
+    fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=n_mels, f_min=f_min, f_max=f_max, norm="slaney",
+                       mel_scale="slaney")
+    return (np.abs(spec).astype(F32) @ fb.T)[None].astype(F32)
+
+
+@dataclass
+class VoiceEncConfig:  # tts/models/chatterbox/voice_encoder/config.py (the fields melspectrogram reads)
+    num_mels: int = 40
+    sample_rate: int = 16000
+    n_fft: int = 400
+    hop_size: int = 160
+    win_size: int = 400
+    fmax: int = 8000
+    fmin: int = 0
+    mel_power: float = 2.0
+    mel_type: str = "amp"
+    normalized_mels: bool = False
+    stft_magnitude_min: float = 1e-4
+
+
+def chatterbox_ve_melspectrogram(wav, hp: VoiceEncConfig):  # tts/models/chatterbox/voice_encoder/melspec.py:13-77
+    a = np.asarray(wav, F32)
+    was_1d = a.ndim == 1
+    if was_1d:
+        a = a[None]
+    spec = np.stack([D.stft(r, window="hann", n_fft=hp.n_fft, hop_length=hp.hop_size, win_length=hp.win_size) for r in a])
+    mag = np.abs(spec).astype(F32)
+    if hp.mel_power != 1.0:
+        mag = (mag ** F32(hp.mel_power)).astype(F32)
+    fb = D.mel_filters(hp.sample_rate, hp.n_fft, hp.num_mels, hp.fmin, hp.fmax, "slaney", "slaney")
+    mel = np.transpose(mag @ fb.T, [0, 2, 1])
+    if hp.mel_type == "db":
+        mel = F32(20) * np.log10(np.maximum(mel, F32(hp.stft_magnitude_min)))
+    if hp.normalized_mels:
+        min_level_db = 20 * math.log10(hp.stft_magnitude_min)
+        mel = (mel - F32(min_level_db)) / F32(-min_level_db + 15)
+    mel = mel.astype(F32)
+    return mel[0] if was_1d else mel
+
+
+def lfm2_preprocess(audio, sample_rate=16000, features=128, n_fft=512, window_size=0.025, window_stride=0.01, window="hann",
+                    preemph=0.97, log=True, normalize="per_feature"):
+    """sts/models/lfm_audio/processor.py:61-140 with dither = 0: pre-emphasis, CONSTANT centre padding, power, Slaney/slaney,
+    ln(x + 5.96e-8), mean / Bessel std over the first len // hop frames applied to ALL frames; (B, T, M) or (T, M)"""
+    a = np.asarray(audio, F32)
+    single = a.ndim == 1
+    if single:
+        a = a[None]
+    hop, win = int(sample_rate * window_stride), int(sample_rate * window_size)
+    fb = D.mel_filters(sample_rate, n_fft, features, 0.0, sample_rate // 2, "slaney", "slaney")
+    out = []
+    for w in a:
+        if preemph > 0:
+            w = np.concatenate([w[:1], w[1:] - F32(preemph) * w[:-1]]).astype(F32)
+        spec = D.stft(w, n_fft=n_fft, hop_length=hop, win_length=win, window=window, center=True, pad_mode="constant")
+        mel = (np.abs(spec) ** 2).astype(F32) @ fb.T
+        if log:
+            mel = np.log(mel + F32(5.96e-8))
+        if normalize == "per_feature":
+            n = min(len(w) // hop, mel.shape[0])
+            v = mel[:n]
+            mean = v.mean(axis=0, keepdims=True, dtype=F32)
+            var = ((v - mean) ** 2).sum(axis=0, keepdims=True, dtype=F32) / F32(n - 1)
+            mel = (mel - mean) / (np.sqrt(var) + F32(1e-5))
+        out.append(mel.astype(F32))
+    f = np.stack(out)
+    return f[0] if single else f
+
+
+def lfm2_detokenizer_istft(mag, phase, n_fft=1280, hop_length=320, window=None):
+    """sts/models/lfm_audio/detokenizer.py:468-507: per item istft(center=False, normalized=True), then the "same" trim of
+    (n_fft - hop) / 2 samples at both ends; mag, phase: (B, T, F) -> (B, T * hop)"""
+    mag, phase = np.asarray(mag, F32), np.asarray(phase, F32)
+    S = (mag * np.cos(phase) + 1j * (mag * np.sin(phase))).astype(np.complex64)
+    pad = (n_fft - hop_length) // 2
+    out = []
+    for s in S:
+        y = D.istft(s.T, hop_length=hop_length, win_length=n_fft, window=window, center=False, normalized=True)
+        out.append(y[pad:-pad] if pad > 0 else y)
+    return np.stack(out).astype(F32)
+
+
+def soprano_istft_head(x_lin, n_fft, hop_length):  # tts/models/soprano/decoder.py:22-49: the Vocos head, output (1, samples)
+    return vocos_istft_head(x_lin, n_fft, hop_length)[None, :]
+
+
+def mossformer2_chunk_stft(audio_segment, fft_len=1920, win_inc=384, win_len=1920, window=None):
+    """sts/models/mossformer2_se/model.py:396-406: positional dsp.stft(center=False), returned as (F, T) real / imag planes"""
+    s = D.stft(np.asarray(audio_segment, F32), fft_len, win_inc, win_len, window, center=False)
+    return np.ascontiguousarray(s.real.T), np.ascontiguousarray(s.imag.T)
+
+
+def mossformer2_chunk_istft(real, imag, fft_len=1920, win_inc=384, win_len=1920, window=None, chunk_length=None):
+    """model.py:415-428: ISTFTCache.istft on a batch of one, center=False, audio_length=chunk_length -> (samples,)"""
+    return D.ISTFTCache().istft(np.asarray(real, F32)[None], np.asarray(imag, F32)[None], fft_len, win_inc, win_len,
+                                window, center=False, audio_length=chunk_length)[0]

@@ -712,3 +712,76 @@ def test_fast_logmel_800_and_1024x320(n_fft, hop, win, n_mels, sr, kind):
         S = np.square(S) if kind == "power" else S
         ref = np.log(np.maximum((S.astype(np.float32) @ fb.T).astype(np.float32), np.float32(1e-5)))
         assert y[i].shape == ref.shape and np.abs(y[i] - ref).max() <= 1e-4 * np.log(10) * 4
+
+
+# ---- the remaining thin dsp callers ---------------------------------------------------
+def test_variant_wrappers_parity(golden):
+    from mlx_audio_plus_b200.codec.models.s3gen.mel import mel_spectrogram as s3gen_mel
+    from mlx_audio_plus_b200.stt.models.glmasr.glmasr import preprocess_audio
+    from mlx_audio_plus_b200.tts.models.chatterbox.voice_encoder.config import VoiceEncConfig
+    from mlx_audio_plus_b200.tts.models.chatterbox.voice_encoder.melspec import melspectrogram
+    from mlx_audio_plus_b200.tts.models.indextts.mel import log_mel_spectrogram as indextts_mel
+    from mlx_audio_plus_b200.tts.models.soprano.decoder import ISTFTHead as SopranoHead
+    from mlx_audio_plus_b200.tts.models.spark.bicodec import mel_spectrogram as spark_mel
+    from mlx_audio_plus_b200.vad.models.smart_turn.smart_turn import ProcessorConfig, prepare_input_features
+
+    g = golden("variants")
+
+    def close(y, ref, atol):
+        y = host(y)
+        assert y.shape == ref.shape, (y.shape, ref.shape)
+        assert np.abs(y - ref).max() <= atol, np.abs(y - ref).max()
+
+    for put in (dev, np.asarray):  # torch CUDA in / out, and the NumPy (host-buffer) entry
+        close(s3gen_mel(put(g["s3gen|x"])), g["s3gen|y"], 1e-4)
+        close(indextts_mel(put(g["indextts|x"])), g["indextts|y"], 1e-4)
+        close(spark_mel(put(g["spark|x"])), g["spark|y"], 2e-5 * np.abs(g["spark|y"]).max())
+        close(melspectrogram(put(g["ve|x"]), VoiceEncConfig()), g["ve|amp"], 2e-5 * np.abs(g["ve|amp"]).max())
+        close(preprocess_audio(put(g["glmasr|x"])), g["glmasr|y"], 1e-4)
+    close(s3gen_mel(dev(g["s3gen|x"][1])), g["s3gen|y1d"], 1e-4)
+    close(indextts_mel(dev(g["indextts|x"]), padding=500), g["indextts|ypad"], 1e-4)
+    close(melspectrogram(dev(g["ve|x"][0])), g["ve|amp1d"], 2e-5 * np.abs(g["ve|amp"]).max())
+    close(melspectrogram(dev(g["ve|x"]), VoiceEncConfig(mel_power=1.0, mel_type="db", normalized_mels=True)), g["ve|db_norm"], 1e-4)
+    close(melspectrogram(dev(g["ve|x"]), VoiceEncConfig(mel_type="db")), g["ve|db"], 20 * 1e-4)  # 20 log10: 20 x the log-mel bound
+    with pytest.raises(NotImplementedError):
+        melspectrogram(dev(g["ve|x"]), VoiceEncConfig(mel_power=1.5))
+    assert_wave_close(SopranoHead(8, 2048, 512)(dev(g["soprano|head_in"])), g["soprano|head_out"])
+    y3 = dev(g["glmasr|y"])
+    assert preprocess_audio(y3) is y3  # 3-D input is taken as features (glmasr.py:569-570)
+    pc = ProcessorConfig(max_audio_seconds=2)
+    for n in ("short", "long"):
+        close(prepare_input_features(dev(g[f"smart|{n}|x"]), pc), g[f"smart|{n}|y"], 2e-4)  # torch mean / std of the waveform
+        close(prepare_input_features(g[f"smart|{n}|x"], pc), g[f"smart|{n}|y"], 1e-4)
+
+
+def test_lfm2_and_mossformer_parity(golden):
+    from mlx_audio_plus_b200.dsp import hamming
+    from mlx_audio_plus_b200.sts.models.lfm_audio.detokenizer import istft_same
+    from mlx_audio_plus_b200.sts.models.lfm_audio.processor import AudioPreprocessor, PreprocessorConfig
+    from mlx_audio_plus_b200.sts.models.mossformer2_se.model import chunk_istft, chunk_stft
+
+    g = golden("variants")
+    pre = AudioPreprocessor(PreprocessorConfig(dither=0.0))
+    for put in (dev, np.asarray):
+        y = host(pre(put(g["lfm2|x"])))
+        assert y.shape == g["lfm2|y"].shape and np.abs(y - g["lfm2|y"]).max() <= 5e-4  # normalised: the Parakeet bound
+    y1 = host(pre(dev(g["lfm2|x"][1])))
+    assert y1.shape == g["lfm2|y1d"].shape and np.abs(y1 - g["lfm2|y1d"]).max() <= 5e-4
+    # the statistic covers the first len // hop frames only: it must differ from the all-frames normalisation
+    ref_all = W.sortformer_mel  # noqa: F841  (same chain with all-frame statistics; see test_other_frontends_parity)
+    raw = host(AudioPreprocessor(PreprocessorConfig(dither=0.0, normalize="none"))(dev(g["lfm2|x"])))
+    n = g["lfm2|x"].shape[1] // 160
+    mean = raw[:, :n].mean(axis=1, keepdims=True, dtype=np.float64)
+    std = raw[:, :n].astype(np.float64).std(axis=1, keepdims=True, ddof=1) + 1e-5
+    assert np.abs((raw - mean) / std - host(pre(dev(g["lfm2|x"])))).max() <= 5e-4
+    yd = host(pre.__class__(PreprocessorConfig())(dev(g["lfm2|x"])))  # default dither 1e-5: same features to ~1e-2
+    assert yd.shape == g["lfm2|y"].shape and np.isfinite(yd).all()
+    for put in (dev, np.asarray):
+        assert_wave_close(istft_same(put(g["lfm2|mag"]), put(g["lfm2|phase"]), g["lfm2|w"], 1280, 320), g["lfm2|wave"])
+    w = hamming(1920, periodic=False)
+    re, im = chunk_stft(dev(g["moss|x"]), window=w)
+    assert tuple(re.shape) == (961, 21)
+    assert_stft_close(torch.complex(re, im), (g["moss|re"] + 1j * g["moss|im"]).astype(np.complex64))
+    assert_wave_close(chunk_istft(dev(g["moss|re"]), dev(g["moss|im"]), window=w, chunk_length=9600), g["moss|y"])
+    re_h, im_h = chunk_stft(g["moss|x"])  # NumPy in, default window
+    assert_wave_close(chunk_istft(re_h, im_h, chunk_length=9600), g["moss|y"])  # mask of ones: the reference's own round trip
