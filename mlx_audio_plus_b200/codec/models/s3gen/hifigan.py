@@ -11,8 +11,13 @@ and strips n_fft//2 samples from both ends (543-545).  Both directions process t
 inverse forms clip(mag) * (cos p, sin p) inside the iSTFT kernel (dsp.istft_polar)."""
 from __future__ import annotations
 
-from ....dsp import istft_polar
+from ....dsp import hanning, istft_polar
 from ....dsp import stft as _stft
+
+
+def hann_window_periodic(size: int):
+    """hifigan.py:13-19: 0.5 (1 - cos(2 pi n / size)) evaluated in float64 per tap — dsp.hanning(size, periodic=True)."""
+    return hanning(size, True)
 
 
 def stft(x, n_fft: int, hop_length: int, window):

@@ -286,6 +286,21 @@ def variants_goldens(mx, R):
     cache = dsp.ISTFTCache()
     g["moss|y"] = A(cache.istft(mx.array(re).reshape(1, *re.shape), mx.array(im).reshape(1, *im.shape), 1920, 384, 1920, w,
                                 center=False, audio_length=9600))[0]
+    # Chatterbox-Turbo HiFT (tts/models/chatterbox_turbo/models/s3gen/hifigan.py:418-537): un-centred _stft, S3Gen-style _istft
+    ct = extract_methods("mlx_audio/tts/models/chatterbox_turbo/models/s3gen/hifigan.py", "HiFTGenerator", ["_stft", "_istft"],
+                         {"Tuple": tuple})
+    w16 = A(dsp.hanning(16, True))
+    me = types.SimpleNamespace(istft_params={"n_fft": 16, "hop_len": 4}, stft_window=mx.array(w16))
+    x = np.stack([synth(511, 1203, 24000), 0.4 * synth(512, 1203, 24000)])
+    re, im = ct._stft(me, mx.array(x))
+    g["cturbo|x"], g["cturbo|re"], g["cturbo|im"] = x, A(re), A(im)
+    re, im = ct._stft(me, mx.array(x[:, :9]))  # shorter than n_fft: one zero-extended frame
+    g["cturbo|short|re"], g["cturbo|short|im"] = A(re), A(im)
+    rng = np.random.default_rng(17)
+    mag = np.exp(rng.normal(0, 1.5, (2, 9, 120))).astype(np.float32)
+    mag[0, 3, 4] = 300.0
+    ph = rng.uniform(-np.pi, np.pi, mag.shape).astype(np.float32)
+    g["cturbo|mag"], g["cturbo|phase"], g["cturbo|y"] = mag, ph, A(ct._istft(me, mx.array(mag), mx.array(ph)))
     np.savez_compressed(os.path.join(OUT, "refshim_variants.npz"), **g)
 
 

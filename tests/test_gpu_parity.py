@@ -785,3 +785,24 @@ def test_lfm2_and_mossformer_parity(golden):
     assert_wave_close(chunk_istft(dev(g["moss|re"]), dev(g["moss|im"]), window=w, chunk_length=9600), g["moss|y"])
     re_h, im_h = chunk_stft(g["moss|x"])  # NumPy in, default window
     assert_wave_close(chunk_istft(re_h, im_h, chunk_length=9600), g["moss|y"])  # mask of ones: the reference's own round trip
+
+
+def test_chatterbox_turbo_and_cosyvoice2_hift_parity(golden):
+    from mlx_audio_plus_b200.tts.models.chatterbox_turbo.models.s3gen import hifigan as CT
+    from mlx_audio_plus_b200.tts.models.cosyvoice2 import hifigan as C2
+
+    g = golden("variants")
+    w = CT.hann_window_periodic(16)
+    np.testing.assert_array_equal(np.asarray(w), O.hanning(16, True))
+    for put in (dev, np.asarray):
+        re, im = CT.stft(put(g["cturbo|x"]), 16, 4, w)
+        assert np.abs(host(re) - g["cturbo|re"]).max() <= 1e-5 * np.abs(g["cturbo|re"]).max()
+        assert np.abs(host(im) - g["cturbo|im"]).max() <= 1e-5 * np.abs(g["cturbo|re"]).max()
+        re, im = CT.stft(put(g["cturbo|x"][:, :9]), 16, 4, w)  # shorter than n_fft: one zero-extended frame
+        assert tuple(re.shape) == (2, 9, 1) and np.abs(host(re) - g["cturbo|short|re"]).max() <= 1e-5
+        assert np.abs(host(im) - g["cturbo|short|im"]).max() <= 1e-5
+        assert_wave_close(CT.istft(put(g["cturbo|mag"]), put(g["cturbo|phase"]), 16, 4, w), g["cturbo|y"])
+    h = golden("hift")  # CosyVoice2 forwards to the S3Gen pair
+    re, im = C2.stft(dev(h["n16|x"]), 16, 4, C2.hann_window_periodic(16))
+    assert np.abs(host(re) - h["n16|hift_s3gen|re"]).max() <= 1e-5 * np.abs(h["n16|hift_s3gen|re"]).max()
+    assert_wave_close(C2.istft(dev(h["n16|mag"]), dev(h["n16|phase"]), 16, 4, C2.hann_window_periodic(16)), h["n16|hift_s3gen|y"])
