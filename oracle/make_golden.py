@@ -301,6 +301,11 @@ def variants_goldens(mx, R):
     mag[0, 3, 4] = 300.0
     ph = rng.uniform(-np.pi, np.pi, mag.shape).astype(np.float32)
     g["cturbo|mag"], g["cturbo|phase"], g["cturbo|y"] = mag, ph, A(ct._istft(me, mx.array(mag), mx.array(ph)))
+    # CAMPPlus x-vector front-end (codec/models/s3gen/xvector.py:12-150)
+    xv = extract("mlx_audio/codec/models/s3gen/xvector.py", ["_povey_window", "_next_power_of_2", "kaldi_fbank"])
+    x = synth(513, 16000 + 123) + 0.02
+    g["xvector|x"], g["xvector|y"] = x, A(xv.kaldi_fbank(mx.array(x)))
+    g["xvector|y40"] = A(xv.kaldi_fbank(mx.array(x[None, :4000]), num_mel_bins=40))
     np.savez_compressed(os.path.join(OUT, "refshim_variants.npz"), **g)
 
 

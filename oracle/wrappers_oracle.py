@@ -563,3 +563,25 @@ def mossformer2_chunk_istft(real, imag, fft_len=1920, win_inc=384, win_len=1920,
     """model.py:415-428: ISTFTCache.istft on a batch of one, center=False, audio_length=chunk_length -> (samples,)"""
     return D.ISTFTCache().istft(np.asarray(real, F32)[None], np.asarray(imag, F32)[None], fft_len, win_inc, win_len,
                                 window, center=False, audio_length=chunk_length)[0]
+
+
+def s3gen_xvector_fbank(audio, sample_rate=16000, num_mel_bins=80, frame_length=25.0, frame_shift=10.0):
+    """codec/models/s3gen/xvector.py:38-150 (CAMPPlus front-end): snip-edges framing, per-frame DC removal and pre-emphasis
+    0.97, float32 Povey window, zero-extension to the next power of two, power, dsp.mel_filters HTK from 20 Hz WITHOUT
+    normalisation, ln(max(., float32 eps)); a signal shorter than one window gives one zero-extended frame."""
+    x = np.asarray(audio, F32).squeeze()
+    size, shift = int(sample_rate * frame_length / 1000), int(sample_rate * frame_shift / 1000)
+    n_fft = 1 if size <= 1 else 1 << (size - 1).bit_length()
+    m = (x.shape[0] - size) // shift + 1
+    if m < 1:  # :77-78 then mx.take clamps nothing: the reference's gather of a short signal is restated as zero extension
+        m = 1
+        x = np.concatenate([x, np.zeros(size - x.shape[0], F32)])
+    fr = np.lib.stride_tricks.as_strided(x, shape=(m, size), strides=(4 * shift, 4)).astype(F32)
+    fr = fr - fr.mean(axis=1, keepdims=True, dtype=F32)
+    fr = np.concatenate([fr[:, :1], fr[:, 1:] - F32(0.97) * fr[:, :-1]], axis=1).astype(F32)
+    k = np.arange(size).astype(F32)
+    w = np.power(F32(0.5) - F32(0.5) * np.cos(F32(2) * F32(np.pi) * k / F32(size - 1)), F32(0.85)).astype(F32)
+    spec = np.abs(np.fft.rfft((fr * w).astype(F32), n=n_fft, axis=1).astype(np.complex64)) ** F32(2.0)
+    fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=num_mel_bins, f_min=20.0, f_max=sample_rate / 2, norm=None,
+                       mel_scale="htk")
+    return np.log(np.maximum(spec.astype(F32) @ fb.T, F32(1.1920929e-07))).astype(F32)

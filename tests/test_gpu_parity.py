@@ -806,3 +806,45 @@ def test_chatterbox_turbo_and_cosyvoice2_hift_parity(golden):
     re, im = C2.stft(dev(h["n16|x"]), 16, 4, C2.hann_window_periodic(16))
     assert np.abs(host(re) - h["n16|hift_s3gen|re"]).max() <= 1e-5 * np.abs(h["n16|hift_s3gen|re"]).max()
     assert_wave_close(C2.istft(dev(h["n16|mag"]), dev(h["n16|phase"]), 16, 4, C2.hann_window_periodic(16)), h["n16|hift_s3gen|y"])
+
+
+def _xvector_fbank_f64(x, num_mel_bins=80):
+    """float64 evaluation of the xvector.py:38-150 chain (float32 window and filterbank values, float64 arithmetic)"""
+    x = np.asarray(x, np.float64).squeeze()
+    m = (x.shape[0] - 400) // 160 + 1
+    fr = np.lib.stride_tricks.as_strided(x, shape=(m, 400), strides=(8 * 160, 8)).copy()
+    fr -= fr.mean(axis=1, keepdims=True)
+    fr = np.concatenate([fr[:, :1], fr[:, 1:] - np.float64(np.float32(0.97)) * fr[:, :-1]], axis=1)
+    k = np.arange(400).astype(np.float32)
+    w = np.power(np.float32(0.5) - np.float32(0.5) * np.cos(np.float32(2) * np.float32(np.pi) * k / np.float32(399)), np.float32(0.85))
+    p = np.abs(np.fft.rfft(fr * w.astype(np.float64), n=512, axis=1)) ** 2
+    fb = O.mel_filters(16000, 512, num_mel_bins, 20.0, 8000.0, None, "htk").astype(np.float64)
+    return np.log(np.maximum(p @ fb.T, 1.1920929e-07))
+
+
+def test_xvector_fbank_parity(golden):
+    """CAMPPlus front-end.  Pre-emphasis and DC removal leave the lowest mel bins ~1e5 below the strongest ones, so their
+    float32 FFT round-off is ~1e-4 relative whatever the implementation (the reference fixture itself is 6e-5 off the float64
+    evaluation there).  Bounds: 1e-4 in log units on the bins within e^-9 of the strongest one; on ALL bins 2e-3 in log units
+    and, in the linear domain, 1e-5 of the frame's peak mel energy against both the fixture and the float64 evaluation."""
+    from mlx_audio_plus_b200.codec.models.s3gen.xvector import kaldi_fbank
+
+    g = golden("variants")
+    truth = _xvector_fbank_f64(g["xvector|x"])
+
+    def lin_err(y, ref):
+        return (np.abs(np.exp(y.astype(np.float64)) - np.exp(ref.astype(np.float64))) / np.exp(ref).max(axis=1, keepdims=True)).max()
+
+    strong = g["xvector|y"] > g["xvector|y"].max() - 9.0  # within e^-9 of the strongest bin
+    for put in (dev, np.asarray):
+        y = host(kaldi_fbank(put(g["xvector|x"])))
+        assert y.shape == g["xvector|y"].shape
+        assert np.abs(y - g["xvector|y"])[strong].max() <= 1e-4
+        assert np.abs(y - g["xvector|y"]).max() <= 2e-3
+        assert lin_err(y, g["xvector|y"]) <= 1e-5 and lin_err(y, truth) <= 1e-5, (lin_err(y, g["xvector|y"]), lin_err(y, truth))
+    y = host(kaldi_fbank(dev(g["xvector|x"][None, :4000]), num_mel_bins=40))
+    t40 = _xvector_fbank_f64(g["xvector|x"][:4000], 40)
+    assert y.shape == g["xvector|y40"].shape and np.abs(y - g["xvector|y40"]).max() <= 2e-3 and lin_err(y, t40) <= 1e-5
+    short = g["xvector|x"][:250]  # shorter than one window: one zero-extended frame (xvector.py:77-78, 103-112)
+    ys = host(kaldi_fbank(dev(short)))
+    assert ys.shape == (1, 80) and lin_err(ys, W.s3gen_xvector_fbank(short)) <= 1e-5
