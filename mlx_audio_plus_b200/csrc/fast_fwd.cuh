@@ -400,6 +400,14 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
 // ---- stage 1 of one tile: warp = residue n2 (RPW of them per warp), lane = frame -----------------------------------
 // `preemph` != 0 with a RAW sample tile (flag at xs[-4]): y[n] = x[n] - a*x[n-1] is applied here, on the way in.
 // PREK: 0 = the kernel instance never pre-emphasises (no code for it), 1 / -1 = decided at run time.
+#ifndef B2A_X_CTAB
+#define B2A_X_CTAB 0  // experiment: stage-1 window / inter-stage twiddle broadcasts from the constant bank (LDC) instead of shared memory
+#endif
+#if B2A_X_CTAB
+__constant__ float2 c_win2[1024];
+__constant__ float2 c_tw1[1024];
+#endif
+
 template <class C, int PREK>
 __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const float2* s_win2, const float2* s_tw1, int warp,
                                             int lane, float preemph) {
@@ -426,14 +434,19 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
         x0 = regs::psub(x0, regs::pmul(make_float2(q0, x0.x), make_float2(preemph, preemph)));
         x1 = regs::psub(x1, regs::pmul(make_float2(q1, x1.x), make_float2(preemph, preemph)));
       }
+#if B2A_X_CTAB
+      const float2 wa = c_win2[n2 * N1 + n1], wc = c_win2[n2 * N1 + n1 + 1];
+      const float4 w = make_float4(wa.x, wa.y, wc.x, wc.y);
+#else
       const float4 w = wb4[n1 / 2];
+#endif
       v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
       v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
     });
     Dft<N1>::run(v);
     const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
     float2* eb = E + lane * C::EP + n2;
-#if B2A_X_TWPF > 0
+#if B2A_X_TWPF > 0 && !B2A_X_CTAB
     // inter-stage twiddles: software-pipelined broadcast loads, TWD pairs ahead of their use (pinned with volatile asm:
     // left alone, ptxas issues each LDS.128 right in front of its FMUL2 and every pair waits out a shared-memory latency;
     // measured -1 %)
@@ -446,7 +459,10 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
       constexpr int k1 = 2 * decltype(I_)::value;
       constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
       constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
-#if B2A_X_TWPF > 0
+#if B2A_X_CTAB
+      const float2 ta = c_tw1[n2 * N1 + k1], tc = c_tw1[n2 * N1 + k1 + 1];
+      const float4 t = make_float4(ta.x, ta.y, tc.x, tc.y);
+#elif B2A_X_TWPF > 0
       if constexpr (k1 / 2 + TWD < N1 / 2) tq[k1 / 2 + TWD] = lds128_at<16 * (k1 / 2 + TWD)>(tb_sa);
       const float4 t = tq[k1 / 2];
 #else
@@ -1093,6 +1109,10 @@ int launch_stft_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   static SmemAttrOnce attr;
   if (attr.need(plan->device, smem))
     B2A_CUDA(cudaFuncSetAttribute(fast_stft_kernel<C, PREK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#if B2A_X_CTAB
+  B2A_CUDA(cudaMemcpyToSymbolAsync(c_win2, p.win2, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
+  B2A_CUDA(cudaMemcpyToSymbolAsync(c_tw1, p.tw1, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
+#endif
   fast_stft_kernel<C, PREK><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
@@ -1126,6 +1146,10 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   static SmemAttrOnce attr;
   if (attr.need(plan->device, smem))
     B2A_CUDA(cudaFuncSetAttribute(fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#if B2A_X_CTAB
+  B2A_CUDA(cudaMemcpyToSymbolAsync(c_win2, p.win2, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
+  B2A_CUDA(cudaMemcpyToSymbolAsync(c_tw1, p.tw1, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
+#endif
   fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT><<<grid, C::THREADS, smem, st>>>(p);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
