@@ -51,4 +51,11 @@ def log_mel_spectrogram(x, args: PreprocessArgs):
         log_kind=L.LOG_LN, guard_kind=L.GUARD_ADD, guard_eps=1e-5,
         norm_kind=L.NORM_PER_FEATURE if args.normalize == "per_feature" else L.NORM_GLOBAL,
         norm_ddof=0, norm_eps=1e-5)
-    return emit(ing, out)  # (1, T, M) for a 1-D input, (B, T, M) for a batch
+    res = emit(ing, out)  # (1, T, M) for a 1-D input, (B, T, M) for a batch
+    # audio.py:78 returns in the INPUT dtype (parakeet.py:184,227 may hand bfloat16).  The arithmetic here stays float32
+    # throughout (the reference rounds the power spectrum to the input dtype before the mel product, audio.py:58); only
+    # the result is cast.
+    od = ing.orig_dtype
+    if od is not None and ing.family == "torch" and od != res.dtype and od.is_floating_point:
+        res = res.to(od)
+    return res

@@ -362,6 +362,19 @@ def test_parakeet_parity(golden):
     x = g["parakeet|x"].astype(np.float64)
 
 
+def test_parakeet_returns_the_input_dtype(golden):
+    """parakeet/audio.py:40,78: the features come back in the dtype of the waveform (bfloat16 from parakeet.py:184,227)."""
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram
+
+    pa = PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5)
+    x = dev(golden("models")["parakeet|x"])
+    xb = x.to(torch.bfloat16)
+    yb = log_mel_spectrogram(xb, pa)
+    assert yb.dtype == torch.bfloat16 and tuple(yb.shape) == (1, 151, 80)
+    assert torch.equal(yb, log_mel_spectrogram(xb.float(), pa).to(torch.bfloat16))  # float32 arithmetic, one final cast
+    assert log_mel_spectrogram(x, pa).dtype == torch.float32
+
+
 def test_other_frontends_parity(golden):
     from mlx_audio_plus_b200.codec.models.s3tokenizer.utils import log_mel_spectrogram as s3_mel
     from mlx_audio_plus_b200.codec.models.s3tokenizer.utils import log_mel_spectrogram_compat as s3_compat
