@@ -51,8 +51,10 @@ def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0, *, dtype="flo
     """Whisper log-mel features, shape (T, n_mels) float32 (reference audio.py:44-85).
     Extension: dtype="float16" / "bfloat16" writes the encoder's input dtype straight from the fused kernel — the
     `.astype(self.dtype)` of whisper/whisper.py:994-996 without a second pass, bit-identical to casting the float32 result."""
-    if isinstance(audio, str):
-        raise NotImplementedError("file decoding (load_audio) is outside the DSP hot path; pass a waveform array")
+    if isinstance(audio, str):  # audio.py:68-69 `load_audio(audio)`: 16-bit PCM WAVE here, other containers need a decoder
+        from ...utils import load_audio
+
+        audio = load_audio(audio)
     ing, was_1d = as_batch(audio)
     fb = mel_filters(SAMPLE_RATE, N_FFT, n_mels, norm="slaney", mel_scale=None)
     out = run_frontend(

@@ -132,10 +132,31 @@ def resample_audio(audio, orig_sr: int, target_sr: int):
     return _run(audio, int(target_sr) // g, int(orig_sr) // g, mono=False)
 
 
+def read_wav_pcm16(file):
+    """Host-side container parse for the one format that needs no codec: RIFF / WAVE with 16-bit integer PCM — what
+    audio_io.read yields for it through miniaudio (interleaved int16, audio_io.py:250-262).  -> ((n,) or (n, channels) int16,
+    sample_rate).  Anything else (mp3, flac, m4a, other sample widths) needs a decoder and stays upstream of the path."""
+    import wave
+
+    try:
+        with wave.open(file, "rb") as w:
+            ch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+            if width != 2 or w.getcomptype() != "NONE":
+                raise NotImplementedError(f"b200audio: only 16-bit PCM WAVE is parsed here (sample width {width} bytes)")
+            data = w.readframes(n)
+    except wave.Error as e:
+        raise NotImplementedError(f"b200audio: not a PCM WAVE file ({e}); decode it upstream and pass pcm= / sample_rate=")
+    pcm = np.frombuffer(data, dtype="<i2").copy()  # writable: torch.from_numpy wraps it downstream
+    return (pcm.reshape(-1, ch) if ch > 1 else pcm), int(rate)
+
+
 def load_audio(file=None, sr: int = SAMPLE_RATE, from_stdin=False, dtype=None, *, pcm=None, sample_rate=None):
     """stt/utils.py:32-57 from the decoder's output on: ``pcm`` is what audio_io.read decodes — interleaved int16 of shape
     (n,) or (n, channels) (or float samples already divided by 32768) — at ``sample_rate``.  int16 / 32768 -> resample to
-    ``sr`` if the rates differ -> mean over channels, float32 mono, in one kernel.  Decoding a file is upstream of the path."""
+    ``sr`` if the rates differ -> mean over channels, float32 mono, in one kernel.  A 16-bit PCM WAVE path (or file object)
+    is parsed on the host (read_wav_pcm16); every other container needs a decoder, which is upstream of the path."""
+    if pcm is None and file is not None and not from_stdin:
+        pcm, sample_rate = read_wav_pcm16(file)
     if pcm is None:
         raise NotImplementedError("b200audio: file decoding (miniaudio / ffmpeg) is upstream of the DSP path; pass pcm= and "
                                   "sample_rate= (audio_io.read's output)")

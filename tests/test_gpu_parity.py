@@ -506,6 +506,31 @@ def test_load_audio_resample_parity(orig, target, ch, kind, n):
         assert np.abs(y2 - r2).max() <= 1e-5 * max(np.abs(r2).max(), 1e-3)
 
 
+def test_load_audio_and_whisper_from_a_pcm16_wave_file(tmp_path):
+    """stt/utils.py:32-57 / whisper/audio.py:68-69 with a path: host parse of the container, then the same kernels."""
+    import wave
+
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+    from mlx_audio_plus_b200.stt.utils import load_audio
+    from oracle import pre_oracle as P
+
+    rng = np.random.default_rng(8)
+    pcm = (synth(40, 44100 * 2, 44100)[:, None] * np.array([9000.0, 5000.0])[None] + rng.normal(0, 50, (88200, 2))).astype(np.int16)
+    path = str(tmp_path / "clip.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(pcm.astype("<i2").tobytes())
+    a = load_audio(path)
+    b = load_audio(pcm=pcm, sample_rate=44100)
+    assert a.shape == (32000,) and np.array_equal(host(a), host(b))
+    ref = P.load_audio_from_pcm(pcm, 44100, 16000)
+    assert np.abs(host(a) - ref).max() <= 1e-5 * np.abs(ref).max()
+    m = host(log_mel_spectrogram(path, n_mels=80))
+    assert m.shape == (200, 80) and np.abs(m - W.whisper_log_mel(host(a), 80)).max() <= 1e-4
+
+
 def test_resample_batch_matches_loop():
     from mlx_audio_plus_b200.stt.utils import _run
 

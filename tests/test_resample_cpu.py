@@ -59,8 +59,37 @@ def test_load_audio_oracle_follows_reference_steps():
                                          + (pcm[:, 1].astype(np.float64) / 32768).astype(np.float32)) / np.float32(2))
 
 
-def test_load_audio_needs_decoded_pcm():
-    from mlx_audio_plus_b200.stt.utils import load_audio
+def _write_wav(path, pcm, rate, width=2):
+    import wave
 
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1 if pcm.ndim == 1 else pcm.shape[1])
+        w.setsampwidth(width)
+        w.setframerate(rate)
+        w.writeframes(pcm.astype("<i2").tobytes() if width == 2 else bytes(pcm.size * width))
+
+
+def test_load_audio_needs_decoded_pcm_unless_pcm16_wave(tmp_path):
+    """Only the codec-free container is parsed on the host (16-bit PCM WAVE -> the interleaved int16 audio_io.read yields,
+    audio_io.py:250-262); anything else must arrive decoded (pcm= / sample_rate=)."""
+    from mlx_audio_plus_b200.stt.utils import load_audio, read_wav_pcm16
+
+    rng = np.random.default_rng(3)
+    mono = rng.integers(-32768, 32767, 1234, dtype=np.int16)
+    stereo = rng.integers(-32768, 32767, (777, 2), dtype=np.int16)
+    _write_wav(tmp_path / "m.wav", mono, 16000)
+    _write_wav(tmp_path / "s.wav", stereo, 44100)
+    pcm, sr = read_wav_pcm16(str(tmp_path / "m.wav"))
+    assert sr == 16000 and pcm.dtype == np.int16 and np.array_equal(pcm, mono)
+    pcm, sr = read_wav_pcm16(str(tmp_path / "s.wav"))
+    assert sr == 44100 and pcm.shape == (777, 2) and np.array_equal(pcm, stereo)
+    (tmp_path / "clip.mp3").write_bytes(b"ID3\x03\x00" + bytes(64))
     with pytest.raises(NotImplementedError):
-        load_audio("clip.wav")
+        load_audio(str(tmp_path / "clip.mp3"))
+    _write_wav(tmp_path / "w24.wav", mono, 16000, width=3)
+    with pytest.raises(NotImplementedError):
+        load_audio(str(tmp_path / "w24.wav"))
+    with pytest.raises(FileNotFoundError):
+        load_audio(str(tmp_path / "missing.wav"))
+    with pytest.raises(NotImplementedError):
+        load_audio(None)
