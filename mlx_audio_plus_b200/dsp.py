@@ -224,9 +224,6 @@ class ISTFTCache:
             raise ValueError("ISTFTCache.istft: window / spectrum do not match n_fft")
         plan = cached_plan(IstftPlan, _device_index(re), w, n_fft=int(n_fft), hop=int(hop_length), center=bool(center),
                            normalized=True, div_clamp=True, trim_tail=False)
-        # keep the reference's cache bookkeeping observable (keys only; values are built lazily on request)
-        T = int(re.data.shape[2])
-        self.position_cache.setdefault((T, int(n_fft), int(hop_length)), None) if False else None
         out = plan.run(re, imag=im, length=audio_length)
         return emit(re, out)
 
