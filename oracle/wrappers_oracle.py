@@ -585,3 +585,56 @@ def s3gen_xvector_fbank(audio, sample_rate=16000, num_mel_bins=80, frame_length=
     fb = D.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=num_mel_bins, f_min=20.0, f_max=sample_rate / 2, norm=None,
                        mel_scale="htk")
     return np.log(np.maximum(spec.astype(F32) @ fb.T, F32(1.1920929e-07))).astype(F32)
+
+
+# -- Hugging Face WhisperFeatureExtractor, the third-party front-end of Qwen3-ASR / Qwen3-ForcedAligner --------------------------
+#    (mlx_audio/stt/models/qwen3_asr/qwen3_asr.py:800-846; transformers/models/whisper/feature_extraction_whisper.py)
+def hf_mel_filter_bank(num_frequency_bins, num_mel_filters, min_frequency, max_frequency, sampling_rate):
+    """transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney"), float64, (bins, mels)"""
+    def hz_to_mel(f):
+        f = np.asarray(f, np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) * (27.0 / np.log(6.4)), 3.0 * f / 200.0)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
+
+    ff = mel_to_hz(np.linspace(hz_to_mel(min_frequency), hz_to_mel(max_frequency), num_mel_filters + 2))
+    fft = np.linspace(0, sampling_rate // 2, num_frequency_bins)
+    d = np.diff(ff)
+    sl = ff[None, :] - fft[:, None]
+    fb = np.maximum(0.0, np.minimum(-sl[:, :-2] / d[:-1], sl[:, 2:] / d[1:]))
+    return fb * (2.0 / (ff[2 : num_mel_filters + 2] - ff[:num_mel_filters]))[None, :]
+
+
+def hf_whisper_features(clips, feature_size=128, padding="longest", max_length=480000, truncation=False, do_normalize=False,
+                        n_fft=400, hop=160, sampling_rate=16000):
+    """clips: list of 1-D waveforms -> (features (B, M, T), attention_mask (B, T) int32).  Follows __call__ (pad /
+    truncate / optional zero-mean-unit-variance), _torch_extract_fbank_features (periodic Hann, reflect-centred STFT, power,
+    last frame dropped, log10(clamp 1e-10), PER-CLIP max - 8, (x + 4) / 4) and the mask rescale (::hop, minus one when ragged)."""
+    clips = [np.asarray(c, F32) for c in clips]
+    if truncation:
+        clips = [c[:max_length] for c in clips]
+    target = max(len(c) for c in clips) if padding == "longest" else max_length
+    x = np.zeros((len(clips), target), F32)
+    mask = np.zeros((len(clips), target), np.int32)
+    for i, c in enumerate(clips):
+        x[i, : len(c)], mask[i, : len(c)] = c, 1
+    if do_normalize:
+        for i, c in enumerate(clips):
+            n = len(c)
+            v = (x[i] - x[i, :n].mean()) / np.sqrt(x[i, :n].var() + 1e-7)
+            v[n:] = 0.0
+            x[i] = v
+    fb = hf_mel_filter_bank(1 + n_fft // 2, feature_size, 0.0, 8000.0, sampling_rate).astype(F32)
+    w = D.hanning(n_fft, True)  # torch.hann_window(n_fft): periodic
+    out = []
+    for row in x:
+        p = (np.abs(D.stft(row, window=w, n_fft=n_fft, hop_length=hop)[:-1]) ** 2).astype(F32)
+        y = np.log10(np.maximum(fb.T @ p.T, F32(1e-10)))
+        y = np.maximum(y, y.max() - F32(8.0))
+        out.append(((y + F32(4.0)) / F32(4.0)).astype(F32))
+    m = mask[:, ::hop]
+    if target % hop:
+        m = m[:, :-1]
+    return np.stack(out), m

@@ -886,3 +886,42 @@ def test_xvector_fbank_parity(golden):
     short = g["xvector|x"][:250]  # shorter than one window: one zero-extended frame (xvector.py:77-78, 103-112)
     ys = host(kaldi_fbank(dev(short)))
     assert ys.shape == (1, 80) and lin_err(ys, W.s3gen_xvector_fbank(short)) <= 1e-5
+
+
+def test_hf_whisper_feature_extractor_parity():
+    """Qwen3-ASR / Qwen3-ForcedAligner features (qwen3_asr.py:800-846): the drop-in against the real transformers
+    WhisperFeatureExtractor's output (tests/golden/hf_whisper_fe.npz), with the reference's own call arguments."""
+    import os
+
+    from mlx_audio_plus_b200.stt.models.qwen3_asr.feature_extractor import WhisperFeatureExtractor
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hf_whisper_fe.npz"))
+    fe = WhisperFeatureExtractor(feature_size=128)
+    np.testing.assert_array_equal(fe.mel_filters, g["fb128"])
+    kw = dict(sampling_rate=16000, return_attention_mask=True, truncation=False, padding=True, return_tensors="np")
+    o = fe(g["one|x"], **kw)
+    assert o["input_features"].dtype == np.float32 and o["input_features"].shape == (1, 128, 200)
+    assert np.abs(o["input_features"] - g["one|features"]).max() <= 1e-4
+    np.testing.assert_array_equal(o["attention_mask"], g["one|mask"])
+    o = fe([g["batch|a"], g["batch|b"], g["batch|c"]], **kw)
+    assert np.abs(o["input_features"] - g["batch|features"]).max() <= 1e-4
+    np.testing.assert_array_equal(o["attention_mask"], g["batch|mask"])
+    o = fe(g["one|x"], sampling_rate=16000, return_tensors="np", max_length=48000)
+    assert set(o) == {"input_features"} and np.abs(o["input_features"] - g["default|features"]).max() <= 1e-4
+    o = fe(np.concatenate([g["one|x"], g["one|x"]]), sampling_rate=16000, return_tensors="np", max_length=48000,
+           return_attention_mask=True, do_normalize=True)
+    assert np.abs(o["input_features"] - g["trunc_norm|features"]).max() <= 1e-4
+    np.testing.assert_array_equal(o["attention_mask"], g["trunc_norm|mask"])
+    t = fe(dev(g["one|x"]), sampling_rate=16000, padding=True, truncation=False, return_tensors="cuda")["input_features"]
+    assert t.is_cuda and np.abs(host(t) - g["one|features"]).max() <= 1e-4
+    with pytest.raises(ValueError):
+        fe(g["one|x"], sampling_rate=8000)
+    # rectangular 2-D batches (NumPy and torch CUDA) take the copy-free path: same rows as clip-by-clip calls
+    xb = np.stack([g["batch|a"], 0.5 * g["batch|a"][::-1].copy()])
+    ob = fe(xb, **kw)
+    for i in range(2):
+        oi = fe(xb[i], **kw)
+        np.testing.assert_array_equal(ob["input_features"][i], oi["input_features"][0])
+    od = fe(dev(xb), sampling_rate=16000, max_length=48000, return_attention_mask=True, return_tensors="cuda")  # padded to 3 s
+    assert tuple(od["input_features"].shape) == (2, 128, 300) and int(od["attention_mask"].sum()) == 2 * 150
+    np.testing.assert_array_equal(host(od["input_features"])[0], fe(xb[0], sampling_rate=16000, max_length=48000)["input_features"][0])
