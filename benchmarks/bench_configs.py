@@ -205,6 +205,53 @@ def main():
                     "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
         del mel, feats
         torch.cuda.empty_cache()
+    if want("V"):
+        # SURVEY 8a row a12 callers and the Hugging Face extractor of Qwen3-ASR: (M, T)-layout / run-time-table instances
+        from mlx_audio_plus_b200._post import cmvn_utterance
+        from mlx_audio_plus_b200.codec.models.s3gen.mel import mel_spectrogram as s3gen_mel
+        from mlx_audio_plus_b200.codec.models.s3tokenizer.utils import log_mel_spectrogram_compat as s3_compat
+        from mlx_audio_plus_b200.sts.models.lfm_audio.processor import AudioPreprocessor, PreprocessorConfig
+        from mlx_audio_plus_b200.stt.models.qwen3_asr.feature_extractor import WhisperFeatureExtractor
+        from mlx_audio_plus_b200.tts.models.spark.bicodec import mel_spectrogram as spark_mel
+        x = synth(1024, 480000, 16000, 1243)
+        fe = WhisperFeatureExtractor(feature_size=128)
+        lfm = AudioPreprocessor(PreprocessorConfig(dither=0.0))
+        cases = [
+            ("V qwen3-asr HF WhisperFeatureExtractor 1024 x 30 s -> (B,128,3000)", "fast_logmel_400x160 (run-time tables, MT)",
+             lambda: fe(x, sampling_rate=16000, padding=True, truncation=False, return_attention_mask=True,
+                        return_tensors="cuda")["input_features"]),
+            ("V s3tokenizer compat 1024 x 30 s -> (B,128,3000), one max over the batch", "fast_logmel_400x160 (run-time tables, MT)",
+             lambda: s3_compat(x, 128)),
+            ("V lfm2 preprocessor 1024 x 30 s -> (B,3001,128), valid-frame statistics", "fast_logmel_512x160 + normalise",
+             lambda: lfm(x)),
+            ("V spark mel 1024 x 30 s (1024/320, 128 mel, magnitude)", "fast_logmel_1024x320", lambda: spark_mel(x)),
+        ]
+        for name, kern, fn in cases:
+            out = fn()
+            ms = timeit(fn, a.steps)
+            by = x.numel() * 4 + out.numel() * out.element_size()
+            res.append({"config": name, "kernel": kern, "batch": 1024, "ms": ms, "audio_hours_per_s": 1024 * 30 / 3600.0 / (ms * 1e-3),
+                        "algorithmic_GBps": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(),
+                        "out_shape": list(out.shape)})
+        del x
+        torch.cuda.empty_cache()
+        x24 = synth(1024, 240000, 24000, 1244)
+        out = s3gen_mel(x24)
+        ms = timeit(lambda: s3gen_mel(x24), a.steps)
+        by = x24.numel() * 4 + out.numel() * 4
+        res.append({"config": "V s3gen mel 1024 x 10 s (1920/480, 80 mel) -> (B,80,T)", "kernel": "frontend_generic_kernel", "batch": 1024, "ms": ms,
+                    "audio_hours_per_s": 1024 * 10 / 3600.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+        del x24
+        feats = torch.randn((64, 60000, 560), device="cuda")  # 64 x 1 h of LFR features
+        out = cmvn_utterance(feats)
+        ms = timeit(lambda: cmvn_utterance(feats), a.steps)
+        by = feats.numel() * 4 * 3  # read for the statistics, read + write for the apply pass
+        res.append({"config": "V funasr per-utterance CMVN, 64 x 1 h of (T/6,560)", "kernel": "cmvn_stats_kernel + cmvn_apply_kernel", "batch": 64,
+                    "ms": ms, "audio_hours_per_s": 64.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+        del feats
+        torch.cuda.empty_cache()
     for r in res:
         print(json.dumps(r), flush=True)
     if a.out:

@@ -103,39 +103,84 @@ __global__ void __launch_bounds__(256) lfr_kernel(const float* __restrict__ in, 
 // per-utterance CMVN (funasr/audio.py:160-164): mean / std over the frames of each feature column (mx.std: ddof 0),
 // (x - mean) / (std + eps).  Pass 1: per-column sum and sum of squares in float64 (one atomicAdd pair per block and column);
 // pass 2: apply.  stats: [batch][cols][2] doubles, zeroed by the caller side of the ABI function.
+// Both passes: a block owns a slab of rows, a thread owns V adjacent columns (V = 4: 16-byte loads when the rows allow it)
+// and walks the slab row by row, so a warp reads one contiguous run per row.
+template <int V>
+struct CmvnVec;
+template <>
+struct CmvnVec<1> {
+  using T = float;
+  static __device__ __forceinline__ void get(const T& v, float* e) { e[0] = v; }
+  static __device__ __forceinline__ T make(const float* e) { return e[0]; }
+};
+template <>
+struct CmvnVec<4> {
+  using T = float4;
+  static __device__ __forceinline__ void get(const T& v, float* e) { e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w; }
+  static __device__ __forceinline__ T make(const float* e) { return make_float4(e[0], e[1], e[2], e[3]); }
+};
+
+template <int V>
 __global__ void __launch_bounds__(256) cmvn_stats_kernel(const float* __restrict__ x, int64_t clip_stride, int64_t rows, int cols, double* stats) {
-  const float* src = x + (int64_t)blockIdx.y * clip_stride;
+  using T = typename CmvnVec<V>::T;
+  const T* src = reinterpret_cast<const T*>(x + (int64_t)blockIdx.y * clip_stride);
   double* st = stats + (int64_t)blockIdx.y * cols * 2;
-  // a block owns a contiguous slab of rows; thread t walks columns t, t + 256, ... of that slab
+  const int cv = cols / V;  // columns in units of V
   const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
+  if (r1 <= r0) return;
+  for (int c = threadIdx.x; c < cv; c += blockDim.x) {
+    double s1[V], s2[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s1[k] = s2[k] = 0.0;
+#pragma unroll 4
     for (int64_t r = r0; r < r1; ++r) {
-      const double v = (double)__ldg(src + r * cols + c);
-      s1 += v;
-      s2 += v * v;
+      float e[V];
+      CmvnVec<V>::get(__ldg(src + r * cv + c), e);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const double v = (double)e[k];
+        s1[k] += v;
+        s2[k] += v * v;
+      }
     }
-    if (r1 > r0) {
-      atomicAdd(st + 2 * c, s1);
-      atomicAdd(st + 2 * c + 1, s2);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      atomicAdd(st + 2 * (c * V + k), s1[k]);
+      atomicAdd(st + 2 * (c * V + k) + 1, s2[k]);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t clip_stride, int64_t rows, int cols,
+// (x - mean) / (std + eps) keeps the reference's true division; mean and std + eps are formed once per thread and column
+template <int V>
+__global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* x, float* out, int64_t clip_stride, int64_t rows, int cols,
                                                           const double* stats, float eps) {
-  const float* src = x + (int64_t)blockIdx.y * clip_stride;
-  float* dst = out + (int64_t)blockIdx.y * clip_stride;
+  using T = typename CmvnVec<V>::T;
+  const T* src = reinterpret_cast<const T*>(x + (int64_t)blockIdx.y * clip_stride);
+  T* dst = reinterpret_cast<T*>(out + (int64_t)blockIdx.y * clip_stride);
   const double* st = stats + (int64_t)blockIdx.y * cols * 2;
-  const int64_t total = rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cols);
-    const double mean = st[2 * c] / (double)rows;
-    double var = st[2 * c + 1] / (double)rows - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float m = (float)mean, sd = (float)sqrt(var) + eps;
-    dst[i] = (__ldg(src + i) - m) / sd;
+  const int cv = cols / V;
+  const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (int c = threadIdx.x; c < cv; c += blockDim.x) {
+    float m[V], sd[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const double mean = st[2 * (c * V + k)] / (double)rows;
+      double var = st[2 * (c * V + k) + 1] / (double)rows - mean * mean;
+      if (var < 0.0) var = 0.0;
+      m[k] = (float)mean;
+      sd[k] = (float)sqrt(var) + eps;
+    }
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; ++r) {
+      float e[V];
+      CmvnVec<V>::get(src[r * cv + c], e);  // plain load: x and out may alias
+#pragma unroll
+      for (int k = 0; k < V; ++k) e[k] = (e[k] - m[k]) / sd[k];
+      dst[r * cv + c] = CmvnVec<V>::make(e);
+    }
   }
 }
 
@@ -171,13 +216,20 @@ int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cs = clip_stride ? clip_stride : rows * cols;
   B2A_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)cols * batch, st));
-  int64_t gx = (rows + 63) / 64;
-  if (gx > 148 * 4) gx = 148 * 4;
-  cmvn_stats_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, st>>>(in, cs, rows, cols, stats_ws);
-  B2A_CUDA(cudaGetLastError());
-  int64_t ga = (rows * cols + 255) / 256;
-  if (ga > 148 * 16) ga = 148 * 16;
-  cmvn_apply_kernel<<<dim3((unsigned)ga, (unsigned)batch), 256, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
+  const bool vec = cols % 4 == 0 && cs % 4 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  const int cv = vec ? cols / 4 : cols;
+  const int threads = cv >= 256 ? 256 : ((cv + 31) / 32) * 32;  // whole warps, no idle warps on narrow feature rows
+  const int64_t slab = 64 * (256 / threads);                    // rows per block: ~16 K (row, column-unit) pairs
+  int64_t gx = (rows + slab - 1) / slab;
+  if (gx > 148 * 16) gx = 148 * 16;
+  const dim3 grid((unsigned)gx, (unsigned)batch);
+  if (vec) {
+    cmvn_stats_kernel<4><<<grid, threads, 0, st>>>(in, cs, rows, cols, stats_ws);
+    cmvn_apply_kernel<4><<<grid, threads, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
+  } else {
+    cmvn_stats_kernel<1><<<grid, threads, 0, st>>>(in, cs, rows, cols, stats_ws);
+    cmvn_apply_kernel<1><<<grid, threads, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
+  }
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }

@@ -558,6 +558,11 @@ def test_funasr_frontend_lfr_cmvn_parity(golden):
         assert u.shape == g["funasr|lfr_cmvn_utt"].shape and np.abs(u - g["funasr|lfr_cmvn_utt"]).max() <= 5e-5
     ub = host(FA.apply_cmvn(dev(np.stack([g["funasr|lfr"], 2 * g["funasr|lfr"] + 1]))))
     assert np.abs(ub[1] - ub[0]).max() <= 5e-5  # (x - mean) / std is invariant under x -> 2x + 1
+    for cols in (80, 81, 7):  # narrow rows (whole-warp blocks) and the scalar path (width not a multiple of 4)
+        xr = np.random.default_rng(cols).standard_normal((3, 1000, cols)).astype(np.float32) * 3 + 1
+        ur = host(FA.apply_cmvn(dev(xr)))
+        ref = (xr - xr.mean(axis=1, keepdims=True, dtype=np.float64)) / (xr.std(axis=1, keepdims=True, dtype=np.float64) + 1e-6)
+        assert ur.shape == xr.shape and np.abs(ur - ref).max() <= 5e-6 * np.abs(ref).max()
     fused = host(FA.preprocess_audio(dev(g["funasr|x"]), cmvn_mean=g["funasr|cmvn_mean"], cmvn_istd=g["funasr|cmvn_istd"]))
     assert fused.shape == g["funasr|lfr_cmvn"].shape
     assert np.abs(fused - g["funasr|lfr_cmvn"]).max() <= 1e-3 * 1.5  # log-mel tolerance times the largest istd (1.5)
