@@ -713,9 +713,10 @@ __device__ __forceinline__ void store_quad(void* base, int64_t quad_index, const
 template <class C, bool LAYOUT_TM, bool WANT_SUMS, class MS, int SPECK, int PREK, int ODT = B2A_DTYPE_F32>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(const FastParams p) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
-  constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh); requires the (T, M) layout
-  static_assert(!SPEC || (LAYOUT_TM && MS::NW == C::WARPS && MS::F == C::F && MS::M % 4 == 0),
-                "mel spec / kernel variant mismatch");
+  constexpr bool SPEC = MS::M > 0;  // mel structure baked into code (mel_gen.cuh)
+  static_assert(!SPEC || (MS::NW == C::WARPS && MS::F == C::F && MS::M % 4 == 0), "mel spec / kernel variant mismatch");
+  // (M, T) output of a generated-mel kernel: float32, no per-feature sums (lane == frame in its write-out phase)
+  static_assert(!SPEC || LAYOUT_TM || (!WANT_SUMS && ODT == B2A_DTYPE_F32), "generated-mel (M, T) variant: float32, no sums");
   // SPEC path staging tile Y[frame][YP]: YP/4 odd -> the STS.128 of phase A and the LDS.128 of phase B are
   // both bank-conflict free
   constexpr int YP = SPEC ? (((MS::M / 4) & 1) ? MS::M : MS::M + 4) : 4;
@@ -826,7 +827,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     const int64_t obase = (int64_t)pclip * p.out_clip_stride + (int64_t)ptile * C::FT * MS::M;
     char* const orow = reinterpret_cast<char*>(p.out) + obase * (ODT == B2A_DTYPE_F32 ? 4 : 2);
     const float4* const yb = reinterpret_cast<const float4*>(Y) + lane;
-    if (lane < QL) {
+    if constexpr (SPEC && !LAYOUT_TM) {  // lane == frame, warp == rows m, m + WARPS, ...: one 128-byte column per row
+      if (lane < pnf) {
+        float* const ob = p.out + (int64_t)pclip * p.out_clip_stride + (int64_t)ptile * C::FT + lane;
+#pragma unroll 2
+        for (int m = warp; m < MS::M; m += C::WARPS) {
+          const float a = fmaxf(Y[m * 32 + lane] + guard_add, guard_floor);
+          const float y = use_log ? lg2_approx(a) : a;
+          const float v = fmaf(y, y_mul, y_add);
+          ob[(int64_t)m * p.frame_count] = v;
+          lmax = fmaxf(lmax, v);
+          lmin = fminf(lmin, v);
+        }
+      }
+    } else if (lane < QL) {
 #pragma unroll 1
       for (int f = warp; f < pnf; f += C::WARPS) {
         float4 v = yb[f * (YP / 4)];
@@ -940,11 +954,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         // one STS.128 per finished row quad, as inline PTX with the row offset as an immediate: written as a C++ store,
         // the last quad of every warp's branch is tail-merged into a register-addressed store of unknown alignment and
         // split into four conflicting scalar STS (+120 shared-memory wavefronts per tile)
-        const unsigned yl_sa = (unsigned)__cvta_generic_to_shared(Y + lane * YP);
+        // (M, T) output: the staging tile is transposed, Y[m][frame] at pitch 32 — four scalar stores per quad (the same
+        // four wavefronts as the STS.128), and the write-out phase reads and stores whole 128-byte columns
+        const unsigned yl_sa = (unsigned)__cvta_generic_to_shared(LAYOUT_TM ? Y + lane * YP : Y + lane);
         MS::template run<C>(warp, pr, [&](auto M_, float a0, float a1, float a2, float a3) {
           constexpr int m = decltype(M_)::value;
-          asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(yl_sa), "n"(4 * (m / 4) * 4), "f"(a0), "f"(a1), "f"(a2),
-                       "f"(a3));
+          if constexpr (LAYOUT_TM) {
+            asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(yl_sa), "n"(4 * (m / 4) * 4), "f"(a0), "f"(a1), "f"(a2),
+                         "f"(a3));
+          } else {
+            asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(yl_sa), "n"(128 * m), "f"(a0));
+            asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(yl_sa), "n"(128 * (m + 1)), "f"(a1));
+            asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(yl_sa), "n"(128 * (m + 2)), "f"(a2));
+            asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(yl_sa), "n"(128 * (m + 3)), "f"(a3));
+          }
         });
       }
       prev_clip = clip_i;  // phase B of this tile runs after the next barrier, next to stage 1 of the next tile
@@ -1191,6 +1214,13 @@ struct SpecList;
 #define B2A_LAUNCH(IDX, MS, SUMS_OK, SPECK, PREK)                                                        \
   case IDX:                                                                                              \
     if (p.spec_kind != SPECK || (PREK == 0 && p.preemph != 0.0f)) break;                                 \
+    if (p.out_layout != B2A_LAYOUT_TM) { /* (M, T) rows: S3Tokenizer, Voxtral-RT — the 400/160 family */ \
+      if constexpr (C::N == 400) {                                                                       \
+        if (!sums && p.out_dtype == B2A_DTYPE_F32)                                                       \
+          return launch_variant<C, false, false, MS, SPECK, PREK>(plan, p, st);                         \
+      }                                                                                                  \
+      break;                                                                                             \
+    }                                                                                                    \
     if constexpr (C::N == 400) { /* 16-bit feature output: the encoder-facing 400/160 family */          \
       if (!sums && p.out_dtype == B2A_DTYPE_F16)                                                         \
         return launch_variant<C, true, false, MS, SPECK, PREK, B2A_DTYPE_F16>(plan, p, st);             \
@@ -1230,7 +1260,7 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     set_error("16-bit feature output needs a 400/160 generated-mel kernel, (T, M) layout, 16-byte aligned rows, no normalisation");
     return B2A_ERR_UNSUPPORTED;
   }
-  if (tm && vec_ok && fs->spec > 0 && !getenv("B2A_NO_MELSPEC")) {  // named filterbank: mel structure compiled into the kernel
+  if (fs->spec > 0 && !getenv("B2A_NO_MELSPEC") && ((tm && vec_ok) || (!tm && !sums && p.out_dtype == B2A_DTYPE_F32 && C::N == 400))) {  // named filterbank: mel structure compiled into the kernel
     const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, st);
     if (rc != 1) return rc;
   }
