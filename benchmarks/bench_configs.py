@@ -217,10 +217,10 @@ def main():
         fe = WhisperFeatureExtractor(feature_size=128)
         lfm = AudioPreprocessor(PreprocessorConfig(dither=0.0))
         cases = [
-            ("V qwen3-asr HF WhisperFeatureExtractor 1024 x 30 s -> (B,128,3000)", "fast_logmel_400x160 (run-time tables, MT)",
+            ("V qwen3-asr HF WhisperFeatureExtractor 1024 x 30 s -> (B,128,3000)", "fast_logmel_400x160 (generated mel, (M,T) write-out)",
              lambda: fe(x, sampling_rate=16000, padding=True, truncation=False, return_attention_mask=True,
                         return_tensors="cuda")["input_features"]),
-            ("V s3tokenizer compat 1024 x 30 s -> (B,128,3000), one max over the batch", "fast_logmel_400x160 (run-time tables, MT)",
+            ("V s3tokenizer compat 1024 x 30 s -> (B,128,3000), one max over the batch", "fast_logmel_400x160 (generated mel, (M,T) write-out)",
              lambda: s3_compat(x, 128)),
             ("V lfm2 preprocessor 1024 x 30 s -> (B,3001,128), valid-frame statistics", "fast_logmel_512x160 + normalise",
              lambda: lfm(x)),

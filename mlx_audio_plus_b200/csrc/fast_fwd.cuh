@@ -1200,7 +1200,8 @@ bool spec_matches(const b2a_plan* plan) {
 // of the wrapper that uses it, pre-emphasis compiled in — any other combination takes the run-time-table kernel)
 #define B2A_SPECS_400(X)                                                                                    \
   X(1, melgen::MelSpec_whisper80, false, B2A_SPEC_POWER, 0) X(2, melgen::MelSpec_whisper128, false, B2A_SPEC_POWER, 0) \
-  X(3, melgen::MelSpec_funasr80, false, B2A_SPEC_POWER, 0)
+  X(3, melgen::MelSpec_funasr80, false, B2A_SPEC_POWER, 0) X(4, melgen::MelSpec_hf_whisper80, false, B2A_SPEC_POWER, 0) \
+  X(5, melgen::MelSpec_hf_whisper128, false, B2A_SPEC_POWER, 0)
 #define B2A_SPECS_512(X)                                                                                     \
   X(1, melgen::MelSpec_parakeet80, true, B2A_SPEC_POWER, 1) X(2, melgen::MelSpec_parakeet128, true, B2A_SPEC_POWER, 1) \
   X(3, melgen::MelSpec_nemo_slaney80, true, B2A_SPEC_POWER, 1) X(4, melgen::MelSpec_nemo_slaney128, true, B2A_SPEC_POWER, 1)

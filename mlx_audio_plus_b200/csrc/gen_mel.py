@@ -42,6 +42,11 @@ SPECS = [
     ("vocos100", 24000, 1024, 100, 0.0, 0.0, 0, 1, 16),
     # Qwen3-TTS speaker mel (qwen3_tts.py:33-90: slaney/slaney, f_max 12000 == sr/2)
     ("qwen3tts128", 24000, 1024, 128, 0.0, 12000.0, 1, 0, 16),
+    # Hugging Face WhisperFeatureExtractor (Qwen3-ASR / Qwen3-ForcedAligner, qwen3_asr.py:800-846): transformers'
+    # mel_filter_bank(norm="slaney", mel_scale="slaney") evaluated in float64 and rounded once — NOT bit-identical to
+    # dsp.mel_filters' float32 arithmetic, hence its own specs (filterbank from _hf_filterbank below)
+    ("hf_whisper80", 16000, 400, 80, 0.0, 8000.0, 1, 0, 10),
+    ("hf_whisper128", 16000, 400, 128, 0.0, 8000.0, 1, 0, 10),
 ]
 
 
@@ -81,9 +86,36 @@ def _filterbank(lib, sr, n_fft, M, fmin, fmax, norm, htk):
     return [[buf[m * F + f] for f in range(F)] for m in range(M)], F
 
 
+def _hf_filterbank(sr, n_fft, M, fmin, fmax):
+    """transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney") in float64, rounded to float32 — the same
+    restatement as stt/models/qwen3_asr/feature_extractor.py::mel_filter_bank_slaney (pinned against transformers itself in
+    tests/test_oracle_golden.py); rows = mel filters."""
+    import numpy as np
+
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) * (27.0 / np.log(6.4)), 3.0 * f / 200.0)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
+
+    F = n_fft // 2 + 1
+    ff = mel_to_hz(np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), M + 2))
+    fft = np.linspace(0, sr // 2, F)
+    d = np.diff(ff)
+    sl = np.expand_dims(ff, 0) - np.expand_dims(fft, 1)
+    fb = np.maximum(np.zeros(1), np.minimum(-sl[:, :-2] / d[:-1], sl[:, 2:] / d[1:]))
+    fb = (fb * np.expand_dims(2.0 / (ff[2 : M + 2] - ff[:M]), 0)).astype(np.float32).T  # (M, F)
+    return [[float(v) for v in row] for row in fb], F
+
+
 def _emit_spec(lib, spec):
     name, sr, n_fft, M, fmin, fmax, norm, htk, NW = spec
-    fb, F = _filterbank(lib, sr, n_fft, M, fmin, fmax, norm, htk)
+    if name.startswith("hf_"):
+        fb, F = _hf_filterbank(sr, n_fft, M, fmin, fmax)
+    else:
+        fb, F = _filterbank(lib, sr, n_fft, M, fmin, fmax, norm, htk)
     start, length = [], []
     for m in range(M):
         nz = [f for f in range(F) if fb[m][f] != 0.0]

@@ -124,32 +124,27 @@ class WhisperFeatureExtractor:
             dev = torch.device("cuda", torch.cuda.current_device())
         else:
             raise L.B2AError("b200audio: no CUDA device — this library has no CPU fallback")
+        len_t = torch.tensor(lengths, dtype=torch.int64, device=dev)
         if two_d:  # a rectangular batch: no per-clip copies
             t = raw_speech if _is_torch(raw_speech) else torch.from_numpy(np.ascontiguousarray(raw_speech, dtype=np.float32))
             t = t.to(device=dev, dtype=torch.float32)
-            n = lengths[0]
-            if n == target:
+            if lengths[0] == target:
                 batch = t.contiguous()
-                mask = torch.ones((len(clips), target), dtype=torch.int32, device=dev)
             else:
                 batch = torch.full((len(clips), target), float(self.padding_value), dtype=torch.float32, device=dev)
-                mask = torch.zeros((len(clips), target), dtype=torch.int32, device=dev)
-                batch[:, :n] = t
-                mask[:, :n] = 1
+                batch[:, : lengths[0]] = t
         else:
             batch = torch.full((len(clips), target), float(self.padding_value), dtype=torch.float32, device=dev)
-            mask = torch.zeros((len(clips), target), dtype=torch.int32, device=dev)
             for i, (c, n) in enumerate(zip(clips, lengths)):
                 t = c if _is_torch(c) else torch.from_numpy(np.ascontiguousarray(np.asarray(c, dtype=np.float32)))
                 batch[i, :n] = t[:n].to(device=dev, dtype=torch.float32)
-                mask[i, :n] = 1
         if do_normalize:  # zero_mean_unit_var_norm over the valid samples, padding back to padding_value
-            valid = mask.to(torch.float32)
+            valid_b = torch.arange(target, device=dev)[None, :] < len_t[:, None]
+            valid = valid_b.to(torch.float32)
             cnt = valid.sum(1, keepdim=True)
             mean = (batch * valid).sum(1, keepdim=True) / cnt
             var = (((batch - mean) * valid) ** 2).sum(1, keepdim=True) / cnt
-            batch = torch.where(mask.bool(), (batch - mean) / torch.sqrt(var + 1e-7),
-                                torch.full_like(batch, float(self.padding_value)))
+            batch = torch.where(valid_b, (batch - mean) / torch.sqrt(var + 1e-7), torch.full_like(batch, float(self.padding_value)))
         if self.dither != 0.0:
             batch = batch + self.dither * torch.randn_like(batch)
         ing, _ = as_batch(batch)
@@ -160,7 +155,9 @@ class WhisperFeatureExtractor:
             affine_add=4.0, affine_div=4.0, out_layout=L.LAYOUT_MT)  # (B, n_mels, T)
         out = {"input_features": feats}
         if return_attention_mask if return_attention_mask is not None else self.return_attention_mask:
-            m = mask[:, :: self.hop_length]
+            # the sample-level mask sampled every hop samples (attention_mask[:, ::hop]), built at frame resolution directly
+            starts = torch.arange(0, target, self.hop_length, device=dev)
+            m = (starts[None, :] < len_t[:, None]).to(torch.int32)
             if target % self.hop_length != 0:  # L // hop + 1 frames minus the dropped one
                 m = m[:, :-1]
             out["attention_mask"] = m.contiguous()
