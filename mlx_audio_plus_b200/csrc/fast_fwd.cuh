@@ -763,9 +763,22 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   if (threadIdx.x == 0) s_cur_clip = -1;
 
   // tile walk: tile = clip_i * tiles_per_clip + tile_i advances by gridDim.x without a division per tile
+  // With per-feature sums a CTA walks a CONTIGUOUS run of tiles instead (same static balance): its float64 sums are flushed
+  // when it changes clip, and the strided walk changes clip at every tile once a batch has more clips than CTAs
+  // (1024 x 30 s of Parakeet-80 features: 3.16 -> 2.37 ms; LFM2-128: 4.79 -> 3.11 ms).
   const int tpc = p.tiles_per_clip;
-  const int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
+  int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
   int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
+  int64_t run_left = 0;  // contiguous walk: tiles this CTA still owns (including the current one)
+  if constexpr (WANT_SUMS) {
+    const int64_t total = (int64_t)p.batch * tpc, q = total / gridDim.x, r = total % gridDim.x;
+    const int64_t g0 = (int64_t)blockIdx.x * q + ((int64_t)blockIdx.x < r ? (int64_t)blockIdx.x : r);
+    run_left = q + ((int64_t)blockIdx.x < r ? 1 : 0);
+    clip_i = run_left > 0 ? (int)(g0 / tpc) : p.batch;
+    tile_i = run_left > 0 ? (int)(g0 - (int64_t)clip_i * tpc) : 0;
+    step_c = 0;
+    step_t = 1;
+  }
   if (PREFETCH && clip_i < p.batch) fill_tile<C, PREK>(p, xs, fc, clip_i, tile_i);
 
   const float guard_add = p.guard_add, guard_floor = p.guard_floor, y_mul = p.y_mul, y_add = p.y_add;
@@ -841,6 +854,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         }
       }
     } else if (lane < QL) {
+      // per-feature sums: float32 partials over this warp's (at most four) frames of the tile, folded into the float64
+      // accumulators once per tile — the float64 pipe is the slow one here (per value it doubled the kernel's time)
+      float s1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
       for (int f = warp; f < pnf; f += C::WARPS) {
         float4 v = yb[f * (YP / 4)];
@@ -851,8 +867,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
           const float y = use_log ? lg2_approx(a) : a;
           e[c] = fmaf(y, y_mul, y_add);
           if (WANT_SUMS) {
-            d1[c % NS] += (double)e[c];
-            d2[c % NS] += (double)e[c] * (double)e[c];
+            s1[c] += e[c];
+            s2[c] = fmaf(e[c], e[c], s2[c]);
           }
         }
         store_quad<ODT>(orow, f * (MS::M / 4) + lane, v);
@@ -860,6 +876,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         lmin = fmin3(lmin, v.x, v.y);
         lmax = fmax3(lmax, v.z, v.w);
         lmin = fmin3(lmin, v.z, v.w);
+      }
+      if (WANT_SUMS) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          d1[c % NS] += (double)s1[c];
+          d2[c % NS] += (double)s2[c];
+        }
       }
     }
     if (want_max) {  // one REDUX each on order-preserving integer keys instead of ten dependent shuffles
@@ -900,6 +923,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       ntile -= tpc;
       ++nclip;
     }
+    if constexpr (WANT_SUMS) {
+      if (--run_left <= 0) nclip = p.batch;  // end of this CTA's run
+    }
 
     if (!PREFETCH) {
       __syncthreads();  // previous tile's mel phase has finished reading P (which shares xs' memory)
@@ -936,6 +962,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         t2 -= tpc;
         ++c2;
       }
+      if (WANT_SUMS && run_left <= 1) c2 = p.batch;  // contiguous walk: nothing of this CTA's beyond the next tile
       prefetch_span_l2<C>(p, c2, t2);
     }
 
