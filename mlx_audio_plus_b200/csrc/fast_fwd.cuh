@@ -400,6 +400,9 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
 // ---- stage 1 of one tile: warp = residue n2 (RPW of them per warp), lane = frame -----------------------------------
 // `preemph` != 0 with a RAW sample tile (flag at xs[-4]): y[n] = x[n] - a*x[n-1] is applied here, on the way in.
 // PREK: 0 = the kernel instance never pre-emphasises (no code for it), 1 / -1 = decided at run time.
+#ifndef B2A_X_CONTIG
+#define B2A_X_CONTIG 0  // experiment: contiguous tile runs for every fast_logmel instance (default: only with per-feature sums)
+#endif
 #ifndef B2A_X_CTAB
 #define B2A_X_CTAB 0  // experiment: stage-1 window / inter-stage twiddle broadcasts from the constant bank (LDC) instead of shared memory
 #endif
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
   int step_c = (int)(gridDim.x / (unsigned)tpc), step_t = (int)(gridDim.x - (unsigned)step_c * (unsigned)tpc);
   int clip_i = (int)(blockIdx.x / (unsigned)tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * (unsigned)tpc);
   int64_t run_left = 0;  // contiguous walk: tiles this CTA still owns (including the current one)
-  if constexpr (WANT_SUMS) {
+  if constexpr (WANT_SUMS || B2A_X_CONTIG) {
     const int64_t total = (int64_t)p.batch * tpc, q = total / gridDim.x, r = total % gridDim.x;
     const int64_t g0 = (int64_t)blockIdx.x * q + ((int64_t)blockIdx.x < r ? (int64_t)blockIdx.x : r);
     run_left = q + ((int64_t)blockIdx.x < r ? 1 : 0);
@@ -923,7 +926,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       ntile -= tpc;
       ++nclip;
     }
-    if constexpr (WANT_SUMS) {
+    if constexpr (WANT_SUMS || B2A_X_CONTIG) {
       if (--run_left <= 0) nclip = p.batch;  // end of this CTA's run
     }
 
@@ -962,7 +965,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
         t2 -= tpc;
         ++c2;
       }
-      if (WANT_SUMS && run_left <= 1) c2 = p.batch;  // contiguous walk: nothing of this CTA's beyond the next tile
+      if ((WANT_SUMS || B2A_X_CONTIG) && run_left <= 1) c2 = p.batch;  // contiguous walk: nothing of this CTA's beyond the next tile
       prefetch_span_l2<C>(p, c2, t2);
     }
 
