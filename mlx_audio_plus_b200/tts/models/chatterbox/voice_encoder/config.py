@@ -1,22 +1,25 @@
-"""The fields of mlx_audio/tts/models/chatterbox/voice_encoder/config.py that the mel front-end reads."""
+"""The mel front-end's view of the voice-encoder configuration (reference: tts/models/chatterbox/voice_encoder/config.py).
+
+`melspectrogram` reads these eleven attributes and nothing else, so the reference's own `VoiceEncConfig` instance (which also
+carries the LSTM's sizes) can be passed unchanged; this class exists for callers that only need the features."""
+from __future__ import annotations
+
 from dataclasses import dataclass
 
 
-@dataclass
+@dataclass(frozen=True)
 class VoiceEncConfig:
-    num_mels: int = 40
+    # framing / transform
     sample_rate: int = 16000
-    speaker_embed_size: int = 256
-    ve_hidden_size: int = 256
     n_fft: int = 400
-    hop_size: int = 160
     win_size: int = 400
-    fmax: int = 8000
+    hop_size: int = 160
+    # filterbank
+    num_mels: int = 40
     fmin: int = 0
-    preemphasis: float = 0.0
-    mel_power: float = 2.0
-    mel_type: str = "amp"
-    normalized_mels: bool = False
-    ve_partial_frames: int = 160
-    ve_final_relu: bool = True
+    fmax: int = 8000
+    # compression
+    mel_power: float = 2.0          # |X| ** mel_power before the filterbank (1.0 or 2.0 on the fused path)
+    mel_type: str = "amp"           # "amp": linear mel energies; "db": 20 log10(max(mel, stft_magnitude_min))
     stft_magnitude_min: float = 1e-4
+    normalized_mels: bool = False   # (mel - min_db) / (15 - min_db) with min_db = 20 log10(stft_magnitude_min)
