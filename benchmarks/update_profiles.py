@@ -98,7 +98,9 @@ def main():
             "algorithmic_bytes_per_clip": 3456000, "source": f"profiles/{r}_fast_logmel_400x160_ncu_full.json"}},
             open(os.path.join(P, "traffic.json"), "w"), indent=1)
     # the other kernels of the path: same summary per capture
-    for tag, what in (("fast_logmel_512", "C3 Parakeet 16 x 1 h (benchmarks/bench_configs.py --only C3)"),
+    for tag, what in (("fast_logmel_400_mt", "Hugging Face extractor of Qwen3-ASR, 1024 x 30 s -> (B, 128, 3000): generated mel hf_whisper128, (M, T) "
+                       "write-out (benchmarks/bench_configs.py --only V)"),
+                      ("fast_logmel_512", "C3 Parakeet 16 x 1 h (benchmarks/bench_configs.py --only C3)"),
                       ("fast_logmel_1024", "C5 Vocos mel forward B=8192 (benchmarks/bench_configs.py --only C5)"),
                       ("fast_istft_1024", "C5 Vocos iSTFT head B=1024 (benchmarks/bench_configs.py --only C5)"),
                       ("istft_small", "C4 Kokoro iSTFT B=1024 (benchmarks/bench_configs.py --only C4)"),
