@@ -232,6 +232,9 @@ int b2a_rows_pad_cast(const float* in, int64_t in_clip_stride, int64_t row_begin
                       int64_t rows_out, int32_t out_dtype, int32_t batch, void* stream);
 int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_mels, int32_t lfr_m, int32_t lfr_n,
             const float* cmvn_shift, const float* cmvn_scale, float* out, int64_t out_clip_stride, int32_t batch, void* stream);
+/* (batch, rows, cols) float32 -> (batch, cols, rows_out) with zero columns from `rows` on: the (B, n_mels, T_padded) layout of
+ * vad/models/sortformer/sortformer.py:112-118 (`pad_to`) from (B, T, n_mels) features, one pass. */
+int b2a_transpose_pad(const float* in, float* out, int64_t rows, int32_t cols, int64_t rows_out, int32_t batch, void* stream);
 /* per-utterance CMVN, funasr/audio.py:160-164: out = (x - mean_t) / (std_t + eps) per feature column, mx.std (ddof 0);
  * x, out: (batch, rows, cols) float32 (may alias); stats_ws: device scratch of 2 * cols * batch doubles. */
 int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t rows, int32_t cols, float eps, double* stats_ws,

@@ -60,6 +60,19 @@ def rows_pad_cast(x, row_begin: int, rows_valid: int, rows_out: int, dtype="floa
     return _back(x, out[0] if one else out)
 
 
+def transpose_pad(features, rows_out: int = None):
+    """(B, T, M) -> (B, M, rows_out) float32 with zeros behind column T (Sortformer pad_to, sortformer.py:112-118), one pass"""
+    import torch
+
+    t = _to_cuda_f32(features)
+    B, T, M = t.shape
+    rows_out = T if rows_out is None else int(rows_out)
+    out = torch.empty((B, M, rows_out), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        L.check(L.lib.b2a_transpose_pad(t.data_ptr(), out.data_ptr(), T, M, rows_out, B, _stream()))
+    return _back(features, out)
+
+
 def cmvn_utterance(features, eps: float = 1e-6):
     """(x - mean) / (std + eps) over the frames of every feature column (funasr/audio.py:160-164); (T, M) or (B, T, M)"""
     import torch

@@ -184,6 +184,31 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* x, float* 
   }
 }
 
+// (rows, cols) -> (cols, rows_out) per clip through a 32 x 33 shared-memory tile; columns rows .. rows_out-1 of the output are
+// zeros (Sortformer's pad_to, sortformer.py:112-118: the (B, n_mels, T_padded) layout its encoder reads).
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int cols,
+                                                            int64_t rows_out) {
+  __shared__ float tile[32][33];
+  const float* src = in + (int64_t)blockIdx.z * rows * cols;
+  float* dst = out + (int64_t)blockIdx.z * cols * rows_out;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t r = r0 + ty + 8 * k;
+    const int c = c0 + tx;
+    tile[ty + 8 * k][tx] = (r < rows && c < cols) ? __ldg(src + r * cols + c) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows_out) dst[(int64_t)c * rows_out + r] = tile[tx][ty + 8 * k];
+  }
+}
+
 }  // namespace
 }  // namespace b2a
 
@@ -230,6 +255,17 @@ int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t
     cmvn_stats_kernel<1><<<grid, threads, 0, st>>>(in, cs, rows, cols, stats_ws);
     cmvn_apply_kernel<1><<<grid, threads, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
   }
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int b2a_transpose_pad(const float* in, float* out, int64_t rows, int32_t cols, int64_t rows_out, int32_t batch, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0 || rows_out < rows || batch <= 0 || batch > 65535 || (cols + 31) / 32 > 65535) {
+    set_error("transpose_pad: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  const dim3 grid((unsigned)((rows_out + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
+  transpose_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, rows_out);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }

@@ -930,3 +930,16 @@ def test_hf_whisper_feature_extractor_parity():
     od = fe(dev(xb), sampling_rate=16000, max_length=48000, return_attention_mask=True, return_tensors="cuda")  # padded to 3 s
     assert tuple(od["input_features"].shape) == (2, 128, 300) and int(od["attention_mask"].sum()) == 2 * 150
     np.testing.assert_array_equal(host(od["input_features"])[0], fe(xb[0], sampling_rate=16000, max_length=48000)["input_features"][0])
+
+
+def test_transpose_pad_kernel_bit_exact():
+    """csrc/post.cu transpose_pad_kernel: (B, T, M) -> (B, M, T_padded), zeros behind column T (Sortformer pad_to)."""
+    from mlx_audio_plus_b200._post import transpose_pad
+
+    rng = np.random.default_rng(5)
+    for B, T, M, Tp in ((2, 57, 80, 64), (1, 1, 3, 1), (3, 301, 128, 304), (2, 64, 33, 64)):
+        x = rng.standard_normal((B, T, M)).astype(np.float32)
+        ref = np.zeros((B, M, Tp), np.float32)
+        ref[:, :, :T] = np.swapaxes(x, 1, 2)
+        np.testing.assert_array_equal(host(transpose_pad(dev(x), Tp)), ref)
+        np.testing.assert_array_equal(np.asarray(transpose_pad(x, Tp)), ref)
