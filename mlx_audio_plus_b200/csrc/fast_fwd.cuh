@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <stdlib.h>
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -151,6 +152,13 @@ struct Cfg {
     const int u = N1 - r;
     return (N1 / 2 + u) * CP + (NC - k - u) / N1;
   }
+  // stage-1 constant tables in tensor memory (window + inter-stage twiddles, 4 * N1 columns per role): each warp owns
+  // RPW roles; warps w, w + 4, ... share a lane quadrant and take successive column blocks.  The allocation is a power of two
+  // and every resident CTA needs its own.
+  static constexpr int TM_PER_WARP = 4 * N1 * RPW;
+  static constexpr int TM_NEED = TM_PER_WARP * ((WARPS + 3) / 4);
+  static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
+  static constexpr bool TM_OK = N1 % 4 == 0 && TM_NEED <= 512 && TM_COLS * MIN_BLOCKS <= 512;
   static_assert(N1 % 2 == 0 && N2 % WARPS == 0, "role split");
   static_assert(EP % 2 == 1 && CP >= N2, "odd frame pitch; columns do not overlap");
   static_assert(HOP % (2 * N2) == 0, "hop must be a multiple of 2*N2");
@@ -193,6 +201,65 @@ __device__ __forceinline__ float4 lds128_at(unsigned base) {  // pinned (volatil
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- warp-uniform constant tables in TENSOR MEMORY ------------------------------------------------------------------
+// Window taps, inter-stage twiddles and post-twiddles are the same for every lane of a warp (lane == frame), and a warp
+// keeps its role for the whole kernel: each warp parks its tables once in its own TMEM columns (replicated over the 32
+// lanes of its quadrant) and reads them back with tcgen05.ld (SASS LDTM) — a datapath of its own, so the ~520 broadcast
+// LDS wavefronts per tile (20 % of the kernel's shared-memory traffic, the pipe that limits it) disappear from the
+// shared-memory pipe (microbenchmark scratch/r2/ubench_tmem.cu: 2 x LDS.64 + LDS.128 broadcast 6.0 cycles per group and
+// SM, 2 x LDS.64 + LDTM.x4 4.0).  tcgen05.wait::ld waits for ALL of the thread's outstanding loads: the loaded registers
+// are passed through the wait statement ("+f") so that no use can be scheduled in front of it.
+template <int N>
+__device__ __forceinline__ void tm_ld(uint32_t taddr, float* r) {
+  static_assert(N == 4 || N == 8, "chunk");
+  if constexpr (N == 8)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(taddr));
+  else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tm_wait(float* r) {
+  if constexpr (N == 8)
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]));
+  else
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]));
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+// allocation: one warp allocates NCOLS columns (power of two >= 32) and publishes the base address through shared memory
+template <int NCOLS>
+__device__ __forceinline__ uint32_t tm_alloc(uint32_t* s_slot, int warp) {
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_slot)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  return *reinterpret_cast<volatile uint32_t*>(s_slot);
+}
+template <int NCOLS>
+__device__ __forceinline__ void tm_free(uint32_t base, int warp) {  // every warp of the CTA has finished its TMEM reads
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(NCOLS));
+}
+// this warp's table columns: lanes of quadrant warp % 4, column block warp / 4 of `cols_per_warp` columns
+__device__ __forceinline__ uint32_t tm_warp_base(uint32_t base, int warp, int cols_per_warp) {
+  return base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * cols_per_warp);
+}
+// parks n float2 constants (same values in every lane) at column `taddr`; n even
+__device__ __forceinline__ void tm_store_table(uint32_t taddr, const float2* __restrict__ src, int n) {
+  for (int j = 0; j < n; j += 2) {
+    const float2 a = __ldg(src + j), b = __ldg(src + j + 1);
+    tm_st4(taddr + 2 * j, a.x, a.y, b.x, b.y);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
 // non-negative floats order like signed ints, negative floats order inversely as unsigned ints.
@@ -259,7 +326,8 @@ struct FillCtx {
 
 // Copies the tile's sample span into shared memory (rows of HOP samples at pitch P).
 template <class C, int PREK>
-__device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const FillCtx<C>& fc, int clip_i, int tile_i) {
+__device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const FillCtx<C>& fc, int clip_i, int tile_i,
+                                          unsigned dst_off = 0) {  // dst_off: byte offset of `xs` from the buffer fc was set up for
   // Interior tiles are copied RAW with cp.async (asynchronous: the copy of the next tile overlaps stage 2 / mel).  With
   // pre-emphasis the filter y[n] = x[n] - a*x[n-1] is then applied by stage 1 as it reads (separately rounded multiply
   // and subtract, bit-exact vs the reference's `x[1:] - a*x[:-1]`); the one sample in front of the span goes to
@@ -271,11 +339,11 @@ __device__ __forceinline__ void fill_tile(const FastParams& p, float* xs, const 
     if (fc.active) {
 #pragma unroll
       for (int i = 0; i < FillCtx<C>::ITERS - 1; ++i)
-        cp_async8(fc.dst + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
+        cp_async8(fc.dst + dst_off + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
     }
     if (fc.last_ok) {
       constexpr int i = FillCtx<C>::ITERS - 1;
-      cp_async8(fc.dst + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
+      cp_async8(fc.dst + dst_off + 4u * (unsigned)(i * FillCtx<C>::RPI * C::P), src + i * FillCtx<C>::RPI * C::HOP);
     }
     if (threadIdx.x == 0) {
       reinterpret_cast<int*>(xs)[-4] = raw_pre ? 1 : 0;
@@ -403,6 +471,9 @@ struct Smem {  // section offsets in float4 units from the 16-byte aligned dynam
 #ifndef B2A_X_CONTIG
 #define B2A_X_CONTIG 0  // experiment: contiguous tile runs for every fast_logmel instance (default: only with per-feature sums)
 #endif
+#ifndef B2A_X_TMC
+#define B2A_X_TMC 1  // stage-1 window / twiddle tables from tensor memory (0: shared-memory broadcasts) in fast_logmel_kernel
+#endif
 #ifndef B2A_X_CTAB
 #define B2A_X_CTAB 0  // experiment: stage-1 window / inter-stage twiddle broadcasts from the constant bank (LDC) instead of shared memory
 #endif
@@ -411,10 +482,13 @@ __constant__ float2 c_win2[1024];
 __constant__ float2 c_tw1[1024];
 #endif
 
-template <class C, int PREK>
+// TMC: window taps and inter-stage twiddles come from this warp's tensor-memory columns `tmc` — per role 2 * N1 window
+// columns then 2 * N1 twiddle columns — instead of shared-memory broadcasts (s_win2 / s_tw1 unused).
+template <class C, int PREK, bool TMC = false>
 __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const float2* s_win2, const float2* s_tw1, int warp,
-                                            int lane, float preemph) {
+                                            int lane, float preemph, uint32_t tmc = 0) {
   constexpr int N1 = C::N1, N2 = C::N2;
+  static_assert(!TMC || N1 % 4 == 0, "tensor-memory tables are read in chunks of four constants");
   const bool pre = PREK != 0 && preemph != 0.0f && reinterpret_cast<const int*>(xs)[-4] != 0;
 #pragma unroll 1
   for (int rr = 0; rr < C::RPW; ++rr) {
@@ -425,8 +499,16 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
     // the sample in front of a pair sits one float back — or, for the first pair of a row (n2 == 0 and column 0),
     // behind the row padding: P - HOP + 1 floats back
     const int back0 = n2 == 0 ? C::P - C::HOP + 1 : 1;
+    [[maybe_unused]] float tmw[2][8];  // TMC: two chunks of four constants in flight
+    [[maybe_unused]] const uint32_t tm_role = tmc + (uint32_t)(rr * 4 * N1);
+    if constexpr (TMC) tm_ld<8>(tm_role, tmw[0]);
     static_for<0, N1 / 2>([&](auto I_) {
       constexpr int n1 = 2 * decltype(I_)::value;
+      if constexpr (TMC && n1 % 4 == 0) {  // chunk n1 / 4 has landed; start the next one (after the last window chunk: twiddle chunk 0)
+        constexpr int c = n1 / 4;
+        tm_wait<8>(tmw[c & 1]);
+        tm_ld<8>(tm_role + 8 * (c + 1), tmw[(c + 1) & 1]);
+      }
       constexpr int off0 = (n1 / C::K) * C::P + (n1 % C::K) * 2 * N2;
       constexpr int off1 = ((n1 + 1) / C::K) * C::P + ((n1 + 1) % C::K) * 2 * N2;
       float2 x0 = *reinterpret_cast<const float2*>(xb + off0);
@@ -441,7 +523,13 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
       const float2 wa = c_win2[n2 * N1 + n1], wc = c_win2[n2 * N1 + n1 + 1];
       const float4 w = make_float4(wa.x, wa.y, wc.x, wc.y);
 #else
-      const float4 w = wb4[n1 / 2];
+      float4 w;
+      if constexpr (TMC) {
+        const float* t = tmw[(n1 / 4) & 1] + (n1 % 4) * 2;
+        w = make_float4(t[0], t[1], t[2], t[3]);
+      } else {
+        w = wb4[n1 / 2];
+      }
 #endif
       v[n1] = regs::pmul(x0, make_float2(w.x, w.y));
       v[n1 + 1] = regs::pmul(x1, make_float2(w.z, w.w));
@@ -449,6 +537,25 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
     Dft<N1>::run(v);
     const float4* tb4 = reinterpret_cast<const float4*>(s_tw1 + n2 * N1);
     float2* eb = E + lane * C::EP + n2;
+    if constexpr (TMC) {  // twiddle chunk c sits in tmw[(N1 / 4 + c) & 1] (chunk 0 was requested with the last window chunk)
+      static_for<0, N1 / 2>([&](auto I_) {
+        constexpr int k1 = 2 * decltype(I_)::value;
+        constexpr int slot0 = (k1 <= N1 / 2) ? k1 : (3 * N1 / 2 - k1);
+        constexpr int slot1 = (k1 + 1 <= N1 / 2) ? (k1 + 1) : (3 * N1 / 2 - (k1 + 1));
+        constexpr int c = N1 / 4 + k1 / 4;
+        if constexpr (k1 % 4 == 0) {
+          tm_wait<8>(tmw[c & 1]);
+          if constexpr (k1 + 4 < N1) tm_ld<8>(tm_role + 8 * (c + 1), tmw[(c + 1) & 1]);
+        }
+        const float* t = tmw[c & 1] + (k1 % 4) * 2;
+        float2 y0 = v[k1];
+        if constexpr (k1 > 0) y0 = regs::cmul(y0, make_float2(t[0], t[1]));
+        const float2 y1 = regs::cmul(v[k1 + 1], make_float2(t[2], t[3]));
+        eb[slot0 * C::CP] = y0;
+        eb[slot1 * C::CP] = y1;
+      });
+      continue;
+    }
 #if B2A_X_TWPF > 0 && !B2A_X_CTAB
     // inter-stage twiddles: software-pipelined broadcast loads, TWD pairs ahead of their use (pinned with volatile asm:
     // left alone, ptxas issues each LDS.128 right in front of its FMUL2 and every pair waits out a shared-memory latency;
@@ -485,11 +592,25 @@ __device__ __forceinline__ void stage1_tile(const float* xs, float2* E, const fl
 // only its output bins differ (slots [0, N2/2) -> N1*(s+1), slots [N2/2, N2) -> N1/2 + N1*(s - N2/2)).
 // INPLACE: the power tile overwrites this frame's exchange row (Cfg::sig); otherwise it goes to Pw in natural bin order.
 // CPLX (with INPLACE): the spectrum itself, one complex value per slot (fast_stft_kernel).
-template <class C, bool INPLACE, bool CPLX = false>
+// TMC: the unit's N2 post-twiddles come from tensor-memory columns `tmc` (2 * N2 of them) instead of shared memory.
+template <class C, bool INPLACE, bool CPLX = false, bool TMC = false>
 __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* s_twp, int warp, int lane, bool pw_only,
-                                            float spec_eps) {
+                                            float spec_eps, uint32_t tmc = 0) {
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC;
   constexpr bool SPEC = INPLACE;
+  constexpr int NQ2 = N2 / 2;  // post-twiddle quads (two twiddles each); TMC reads them in chunks of two quads
+  [[maybe_unused]] float tmp[2][8];
+  [[maybe_unused]] auto tm_chunk_ld = [&](auto C_) {
+    constexpr int c = decltype(C_)::value;
+    if constexpr (2 * c + 1 < NQ2) tm_ld<8>(tmc + 8 * c, tmp[c & 1]);
+    else if constexpr (2 * c < NQ2) tm_ld<4>(tmc + 8 * c, tmp[c & 1]);
+  };
+  [[maybe_unused]] auto tm_chunk_wait = [&](auto C_) {
+    constexpr int c = decltype(C_)::value;
+    if constexpr (2 * c + 1 < NQ2) tm_wait<8>(tmp[c & 1]);
+    else tm_wait<4>(tmp[c & 1]);
+  };
+  if constexpr (TMC) tm_chunk_ld(std::integral_constant<int, 0>{});
 #ifndef B2A_NO_UREMAP
   // unit 0 (the longest: DC / Nyquist + register permutation) goes to the highest warp id — the scheduler favours
   // high warp ids, so the longest unit is not also the last one served (measured: -0.3 %)
@@ -543,10 +664,25 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
     });
   }
   // post-twiddles: broadcast loads issued TWD2 pairs ahead of their use (pinned), like the inter-stage twiddles of stage 1
-  constexpr int TWD2 = B2A_X_TWPF2 < N2 / 2 ? B2A_X_TWPF2 : N2 / 2;
+  constexpr int TWD2 = TMC ? 0 : (B2A_X_TWPF2 < N2 / 2 ? B2A_X_TWPF2 : N2 / 2);
   const unsigned tw_sa = (unsigned)__cvta_generic_to_shared(s_twp + u * 2 * N2);
   float4 tw4[N2 / 2];
   static_for<0, TWD2>([&](auto I_) { tw4[decltype(I_)::value] = lds128_at<16 * decltype(I_)::value>(tw_sa); });
+  // quad q of the post-twiddles: from the pipelined shared-memory loads, or from the tensor-memory chunk q / 2
+  auto twq = [&](auto Q_) -> float4 {
+    constexpr int q = decltype(Q_)::value;
+    if constexpr (TMC) {
+      if constexpr (q % 2 == 0) {
+        tm_chunk_wait(std::integral_constant<int, q / 2>{});
+        tm_chunk_ld(std::integral_constant<int, q / 2 + 1>{});
+      }
+      const float* t = tmp[(q / 2) & 1] + (q % 2) * 4;
+      return make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+      if constexpr (q + TWD2 < N2 / 2) tw4[q + TWD2] = lds128_at<16 * (q + TWD2)>(tw_sa);
+      return tw4[q];
+    }
+  };
   // slot s holds the bin pair (k, Nc - k): natural layout -> k = kb + N1*s; in-place layout -> Cfg::sig
   float* const plo = SPEC ? pr + 2 * (u * C::CP) : pr + kb_lo;
   float* const mlo = SPEC ? pr + 2 * ((N1 / 2 + u) * C::CP) : pr + (NC - kb_lo);
@@ -558,8 +694,7 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
     float2* const cm = E + lane * C::EP + (N1 / 2 + u) * C::CP;
     static_for<0, N2 / 2>([&](auto I_) {
       constexpr int k2 = 2 * decltype(I_)::value;
-      if constexpr (k2 / 2 + TWD2 < N2 / 2) tw4[k2 / 2 + TWD2] = lds128_at<16 * (k2 / 2 + TWD2)>(tw_sa);
-      const float4 t = tw4[k2 / 2];
+      const float4 t = twq(std::integral_constant<int, k2 / 2>{});
       float2 xk, xm;
       post_pair_c(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), xk, xm);
       ck[k2] = xk;
@@ -576,8 +711,7 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   }
   static_for<0, N2 / 2>([&](auto I_) {
     constexpr int k2 = 2 * decltype(I_)::value;
-    if constexpr (k2 / 2 + TWD2 < N2 / 2) tw4[k2 / 2 + TWD2] = lds128_at<16 * (k2 / 2 + TWD2)>(tw_sa);
-    const float4 t = tw4[k2 / 2];
+    const float4 t = twq(std::integral_constant<int, k2 / 2>{});
     float pk, pm;
     post_pair(A[k2], B[N2 - 1 - k2], make_float2(t.x, t.y), pk, pm);
     emit((k2 < N2 / 2 ? plo : phi) + SK * k2, pk);
@@ -753,6 +887,18 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     s_win2[i] = p.win2[i];
     s_tw1[i] = p.tw1[i];
     s_twp[i] = p.twp[i];
+  }
+  constexpr bool TMC = B2A_X_TMC && C::TM_OK;
+  __shared__ uint32_t s_tm_slot;
+  uint32_t tm_base = 0, tmc = 0;
+  if constexpr (TMC) {
+    tm_base = tm_alloc<C::TM_COLS>(&s_tm_slot, warp);
+    tmc = tm_warp_base(tm_base, warp, C::TM_PER_WARP);
+    for (int rr = 0; rr < C::RPW; ++rr) {
+      const int n2 = warp * C::RPW + rr;
+      tm_store_table(tmc + rr * 4 * N1, p.win2 + n2 * N1, N1);
+      tm_store_table(tmc + rr * 4 * N1 + 2 * N1, p.tw1 + n2 * N1, N1);
+    }
   }
   if (!SPEC) {
     for (int i = threadIdx.x; i < G * 8; i += C::THREADS) s_start[i] = p.mel_start[i];
@@ -952,7 +1098,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
       __syncthreads();
     }
     // ---- stage 1 ----------------------------------------------------------------------------------------
-    stage1_tile<C, PREK>(xs, E, s_win2, s_tw1, warp, lane, p.preemph);
+    stage1_tile<C, PREK, TMC>(xs, E, s_win2, s_tw1, warp, lane, p.preemph, tmc);
     __syncthreads();  // E complete, xs free
     tick(1);
     fold_red();  // the per-warp max / min of the rows phase B has just written
@@ -1056,7 +1202,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) fast_logmel_kernel(
     if (prev >= 0)
       for (int i = threadIdx.x; i < 2 * M; i += C::THREADS) atomicAdd(p.feat_sums + (int64_t)prev * 2 * M + i, s_sums[i]);
   }
+  if constexpr (TMC) tm_free<C::TM_COLS>(tm_base, warp);
 }
+
+#include "fast_ws.cuh"  // warp-specialised two-tile pipeline kernels (fast_logmel_ws_kernel, fast_logmel_ws_tma_kernel)
 
 // ---- fast_stft_kernel: the complex spectrum itself (dsp.stft, dsp.py:92-141) through the same fill / stage 1 / stage 2.
 // Stage 2 leaves X[frame][sig(k)] in place in the exchange buffer; the copy-out makes every row of the (T, F) complex64
@@ -1208,6 +1357,82 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   return B2A_OK;
 }
 
+// B2A_WS (A/B runs; read once): 0 = write-out-phase kernel (fast_logmel_kernel), 1 = warp-specialised TMA kernel,
+// 2 (default) = single-group TMA kernel
+inline int ws_mode() {
+  static const int v = [] {
+    const char* e = getenv("B2A_WS");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
+// cuTensorMapEncodeTiled through the runtime (the library links only the static CUDA runtime, not libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// B2A_TMA_OUT=0: warps write the rows themselves (phase B) instead of the TMA (A/B runs); read once
+inline bool tma_out_enabled() {
+  static const int v = [] {
+    const char* e = getenv("B2A_TMA_OUT");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+template <class C, class MS, int SPECK, int ODT>
+int launch_ws(b2a_plan* plan, FastParams& p, cudaStream_t st) {
+  const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count);
+  if (grid < 1) grid = 1;
+  if constexpr (ODT == B2A_DTYPE_F32 && MS::M % 32 == 0) {
+    EncodeTiledFn enc = tma_out_enabled() ? encode_tiled_fn() : nullptr;
+    // (instantiated for the max-type guard of the Whisper family; an additive guard takes the kernel below)
+    if (enc && p.guard_add == 0.0f && p.frame_count < ((int64_t)1 << 31) && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.out_clip_stride % 4 == 0) {
+      // output as a 4-D tensor (feature within a box, frame, box, clip): one box of the map is the whole staging tile —
+      // n_mels / 32 sub-tiles of 32 frames x 32 features (128 bytes, the swizzle span), sub-tile after sub-tile in shared memory
+      CUtensorMap map;
+      const cuuint64_t gdim[4] = {32, (cuuint64_t)p.frame_count, (cuuint64_t)(MS::M / 32), (cuuint64_t)p.batch};
+      const cuuint64_t gstride[3] = {(cuuint64_t)MS::M * 4, 128, (cuuint64_t)p.out_clip_stride * 4};
+      const cuuint32_t box[4] = {32, 32, (cuuint32_t)(MS::M / 32), 1}, estr[4] = {1, 1, 1, 1};
+      if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        if (ws_mode() != 1) {  // single-group kernel with the TMA write-out (the default)
+          using S1 = SmemT<C, MS::M>;
+          constexpr size_t smem1 = (size_t)16 * S1::END + 16;
+          int per_sm = (int)((227 * 1024) / (smem1 + 1024));
+          per_sm = std::max(1, std::min(per_sm, C::MIN_BLOCKS));
+          const int grid1 = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm));
+          static SmemAttrOnce attr1;
+          if (attr1.need(plan->device, smem1))
+            B2A_CUDA(cudaFuncSetAttribute(fast_logmel_tma_kernel<C, MS, SPECK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+          fast_logmel_tma_kernel<C, MS, SPECK, true><<<grid1, C::THREADS, smem1, st>>>(p, map);
+          B2A_CUDA(cudaGetLastError());
+          return B2A_OK;
+        }
+        using S = SmemWST<C, MS::M>;
+        constexpr size_t smem = (size_t)16 * S::END + 16;
+        static_assert(smem <= 226 * 1024, "warp-specialised TMA kernel: shared memory");
+        static SmemAttrOnce attr;
+        if (attr.need(plan->device, smem))
+          B2A_CUDA(cudaFuncSetAttribute(fast_logmel_ws_tma_kernel<C, MS, SPECK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fast_logmel_ws_tma_kernel<C, MS, SPECK, true><<<grid, 2 * C::THREADS, smem, st>>>(p, map);
+        B2A_CUDA(cudaGetLastError());
+        return B2A_OK;
+      }
+    }
+  }
+  return 1;  // no TMA instance for this call: the caller takes the write-out-phase kernel
+}
+
 // does the plan's filterbank equal the generated spec bit for bit?
 template <class MS>
 bool spec_matches(const b2a_plan* plan) {
@@ -1251,6 +1476,12 @@ struct SpecList;
           return launch_variant<C, false, false, MS, SPECK, PREK>(plan, p, st);                         \
       }                                                                                                  \
       break;                                                                                             \
+    }                                                                                                    \
+    if constexpr (C::N == 400 && PREK == 0 && MS::M % 32 == 0) { /* epilogue in the mel phase + TMA write-out (fast_ws.cuh) */ \
+      if (!sums && p.out_dtype == B2A_DTYPE_F32 && ws_mode() != 0) {                                     \
+        const int rc = launch_ws<C, MS, SPECK, B2A_DTYPE_F32>(plan, p, st);                              \
+        if (rc != 1) return rc;                                                                          \
+      }                                                                                                  \
     }                                                                                                    \
     if constexpr (C::N == 400) { /* 16-bit feature output: the encoder-facing 400/160 family */          \
       if (!sums && p.out_dtype == B2A_DTYPE_F16)                                                         \

@@ -141,32 +141,68 @@ def _emit_spec(lib, spec):
         bins = max(start[m] + length[m] for m in live) - min(start[m] for m in live)
         return sum(length[m] for m in rows) + bins + 1
 
-    cost = [quad_cost(q) for q in range(NQ)]
-    total = sum(cost)
-    # optimal contiguous partition (minimise the heaviest warp): DP over (quads, warps)
-    pre = [0]
-    for c in cost:
-        pre.append(pre[-1] + c)
-    INF = float("inf")
-    best = [[INF] * (NW + 1) for _ in range(NQ + 1)]
-    cut = [[0] * (NW + 1) for _ in range(NQ + 1)]
-    best[0][0] = 0
-    for w in range(1, NW + 1):
-        for q in range(NQ + 1):
-            for j in range(q + 1):
-                v = max(best[j][w - 1], pre[q] - pre[j])
-                if v < best[q][w]:
-                    best[q][w], cut[q][w] = v, j
-    bounds = [NQ]
-    q = NQ
-    for w in range(NW, 0, -1):
-        q = cut[q][w]
-        bounds.append(q)
-    bounds = bounds[::-1]
+    def partition(NP, extra):
+        """optimal contiguous partition of the row quads into NP parts (minimise the heaviest part): DP over (quads, parts)"""
+        cost = [quad_cost(q) + extra for q in range(NQ)]
+        pre = [0]
+        for c in cost:
+            pre.append(pre[-1] + c)
+        INF = float("inf")
+        best = [[INF] * (NP + 1) for _ in range(NQ + 1)]
+        cut = [[0] * (NP + 1) for _ in range(NQ + 1)]
+        best[0][0] = 0
+        for w in range(1, NP + 1):
+            for q in range(NQ + 1):
+                for j in range(q + 1):
+                    v = max(best[j][w - 1], pre[q] - pre[j])
+                    if v < best[q][w]:
+                        best[q][w], cut[q][w] = v, j
+        bounds = [NQ]
+        q = NQ
+        for w in range(NP, 0, -1):
+            q = cut[q][w]
+            bounds.append(q)
+        bounds = bounds[::-1]
+        return bounds, [sum(cost[bounds[w]:bounds[w + 1]]) for w in range(NP)]
+
+    def emit_run(o, fn, NP, bounds, ret_range=False):
+        o.append("  template <class C, class Emit4>")
+        o.append(f"  static __device__ __forceinline__ {'int' if ret_range else 'void'} {fn}(int warp, const float* __restrict__ pr, Emit4&& emit4) {{")
+        if ret_range:
+            o.append("    int range = 0;  // first quad | (end quad << 8) of the part")
+        o.append("    switch (warp) {")
+        for w in range(NP):
+            m0, m1 = 4 * bounds[w], 4 * bounds[w + 1]
+            o.append(f"      case {w}: {{  // rows [{m0}, {m1})")
+            if m1 > m0:
+                rows = list(range(m0, m1))
+                o.append("        float " + ", ".join(f"a{m} = 0.0f" for m in rows) + ";")
+                live = [m for m in rows if length[m] > 0]
+                if live:
+                    k0 = min(start[m] for m in live)
+                    k1 = max(start[m] + length[m] for m in live)
+                    for k in range(k0, k1):
+                        users = [m for m in live if start[m] <= k < start[m] + length[m] and fb[m][k] != 0.0]
+                        if not users:
+                            continue
+                        stmts = " ".join(f"a{m} = fmaf(p, {_hexf(fb[m][k])}, a{m});" for m in users)
+                        o.append(f"        {{ const float p = pr[2 * C::sig({k})]; {stmts} }}")
+                for m in range(m0, m1, 4):
+                    o.append(f"        emit4(std::integral_constant<int, {m}>{{}}, a{m}, a{m + 1}, a{m + 2}, a{m + 3});")
+            if ret_range:
+                o.append(f"        range = {bounds[w]} | ({bounds[w + 1]} << 8);")
+            o.append("      } break;")
+        o.append("      default: break;")
+        o.append("    }")
+        if ret_range:
+            o.append("    return range;")
+        o.append("  }")
+
+    bounds, wcost = partition(NW, 0)
     o = []
     o.append(f"// {name}: sr={sr} n_fft={n_fft} n_mels={M} f_min={fmin} f_max={fmax or sr / 2} "
              f"norm={'slaney' if norm else 'none'} scale={'htk' if htk else 'slaney'}; {nnz} taps; "
-             f"warp costs {[sum(cost[bounds[w]:bounds[w + 1]]) for w in range(NW)]}")
+             f"warp costs {wcost}")
     o.append(f"struct MelSpec_{name} {{")
     o.append(f"  static constexpr int M = {M}, F = {F}, NW = {NW}, NNZ = {nnz}, N_FFT = {n_fft};")
     o.append(f"  static constexpr const char* kName = \"{name}\";")
@@ -175,31 +211,7 @@ def _emit_spec(lib, spec):
     o.append(f"  static constexpr unsigned kWBits[{max(nnz, 1)}] = {{{', '.join('0x%08xu' % b for b in wbits) or '0u'}}};")
     o.append("  // lane == frame: `pr` is this lane's power row inside the exchange buffer (bin k at float 2 * C::sig(k));")
     o.append("  // emit4(integral_constant<m0>, a0..a3) per row quad")
-    o.append("  template <class C, class Emit4>")
-    o.append("  static __device__ __forceinline__ void run(int warp, const float* __restrict__ pr, Emit4&& emit4) {")
-    o.append("    switch (warp) {")
-    for w in range(NW):
-        m0, m1 = 4 * bounds[w], 4 * bounds[w + 1]
-        o.append(f"      case {w}: {{  // rows [{m0}, {m1})")
-        if m1 > m0:
-            rows = list(range(m0, m1))
-            o.append("        float " + ", ".join(f"a{m} = 0.0f" for m in rows) + ";")
-            live = [m for m in rows if length[m] > 0]
-            if live:
-                k0 = min(start[m] for m in live)
-                k1 = max(start[m] + length[m] for m in live)
-                for k in range(k0, k1):
-                    users = [m for m in live if start[m] <= k < start[m] + length[m] and fb[m][k] != 0.0]
-                    if not users:
-                        continue
-                    stmts = " ".join(f"a{m} = fmaf(p, {_hexf(fb[m][k])}, a{m});" for m in users)
-                    o.append(f"        {{ const float p = pr[2 * C::sig({k})]; {stmts} }}")
-            for m in range(m0, m1, 4):
-                o.append(f"        emit4(std::integral_constant<int, {m}>{{}}, a{m}, a{m + 1}, a{m + 2}, a{m + 3});")
-        o.append("      } break;")
-    o.append("      default: break;")
-    o.append("    }")
-    o.append("  }")
+    emit_run(o, "run", NW, bounds)
     o.append("};")
     return "\n".join(o)
 
