@@ -122,6 +122,8 @@ typedef struct b2a_frontend_desc {
   int32_t out_dtype;
 } b2a_frontend_desc;
 
+enum { B2A_PCM_F32 = 0, B2A_PCM_I16 = 1 }; /* sample formats (b2a_forward_args.audio_kind, b2a_resample_args.in_kind) */
+
 /* Arguments of one forward launch over `batch` equal-length clips.
  * Long-form frame-range sharding: a rank that owns frames [frame_begin, frame_begin+frame_count)
  * of a signal of GLOBAL length `length` passes a slice whose first element is global sample
@@ -141,9 +143,13 @@ typedef struct b2a_forward_args {
   int64_t out_clip_stride; /* elements (float32, or complex64 for SPEC_COMPLEX) between clips; 0 = dense */
   float* clip_max;       /* optional [batch] float: running max of y before clamp (device); NULL = internal */
   double* feat_sums;     /* optional [batch][2*n_mels] double: sum, sum of squares per mel (device) */
-  void* workspace;       /* device scratch of b2a_frontend_workspace_bytes() or NULL to let the plan own it */
+  void* workspace;       /* device scratch of b2a_frontend_call_workspace_bytes() or NULL to let the plan own it */
   size_t workspace_bytes;
   uint64_t seed;         /* dither stream (used only when desc.dither != 0) */
+  int32_t audio_kind;    /* B2A_PCM_F32 (0, default): float32 samples.  B2A_PCM_I16: `audio` points at int16 PCM as a decoder
+                          * delivers it (audio_io.py:258-262: float32 = int16 / 32768, exact) — b2a_frontend_forward_host only:
+                          * half the host-to-device bytes, converted on the device in front of the fused kernel. */
+  int32_t reserved0;
 } b2a_forward_args;
 
 typedef struct b2a_plan b2a_plan;
@@ -179,6 +185,11 @@ int b2a_frontend_create(const b2a_frontend_desc* desc, const float* h_window,
 int b2a_plan_destroy(b2a_plan* plan);
 int b2a_frontend_out_frames(const b2a_plan* plan, int64_t length, int64_t* frames /* after drop_last */);
 size_t b2a_frontend_workspace_bytes(const b2a_plan* plan, int32_t batch);
+/* Scratch ONE call needs (statistics + per-tile minima for these args).  A call whose args->workspace has at least this
+ * many bytes touches nothing of the plan's own scratch, so one plan may serve concurrent streams / threads (each with its
+ * own workspace; partial() and finalize() of one call share it).  With a smaller or NULL workspace the plan's scratch
+ * is used and calls on one plan must not overlap. */
+size_t b2a_frontend_call_workspace_bytes(const b2a_plan* plan, const b2a_forward_args* args);
 /* forward = partial + finalize (clamp / normalise) in one stream-ordered call */
 int b2a_frontend_forward(b2a_plan* plan, const b2a_forward_args* args, void* stream);
 /* split form for frame-range sharding: partial() leaves un-clamped / un-normalised values in `out`
@@ -204,7 +215,6 @@ const char* b2a_plan_kernel_name(const b2a_plan* plan);
  * handed over as h_taps[j][phase] = h_padded[phase + j * up], taps_per_phase = ceil(len(h_padded) / up);
  * pre_remove = resample_poly's n_pre_remove.  Output sample n = sum_j taps[j][t % up] * x_edge[t / up - j], t = (n + pre_remove) * down. */
 typedef struct b2a_resampler b2a_resampler;
-enum { B2A_PCM_F32 = 0, B2A_PCM_I16 = 1 };
 typedef struct b2a_resample_args {
   const void* in;          /* device: (batch, n_in, channels) interleaved float32 or int16 */
   float* out;              /* device: (batch, n_out) when mono, else (batch, n_out, channels) */

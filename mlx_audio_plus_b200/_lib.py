@@ -50,6 +50,7 @@ class ForwardArgs(C.Structure):
         ("sample_offset", C.c_int64), ("frame_begin", C.c_int64), ("frame_count", C.c_int64),
         ("out", C.c_void_p), ("out_clip_stride", C.c_int64), ("clip_max", C.c_void_p),
         ("feat_sums", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("seed", C.c_uint64),
+        ("audio_kind", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -94,6 +95,7 @@ SYMBOLS = {
     "b2a_plan_destroy": (C.c_int, [C.c_void_p]),
     "b2a_frontend_out_frames": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "b2a_frontend_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "b2a_frontend_call_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(ForwardArgs)]),
     "b2a_frontend_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
     "b2a_frontend_partial": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
     "b2a_frontend_finalize": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_int64, C.c_void_p]),

@@ -133,6 +133,20 @@ struct StatPtrs {
   double* feat_sums;
 };
 
+int stats_tile_frames(const b2a_plan* p, const b2a_forward_args* a) {
+  int tf = p->family == KF_FAST ? 32 : generic_tile_frames(p, a);
+  return tf > 0 ? tf : 2;
+}
+size_t tilemin_count(const b2a_plan* p, const b2a_forward_args* a) {
+  const int tf = stats_tile_frames(p, a);
+  const size_t tiles = (size_t)a->batch * (size_t)((a->frame_count + tf - 1) / tf);
+  return tiles > 0 ? tiles : 1;
+}
+// a caller-owned workspace of this size makes the call independent of the plan's own scratch (re-entrant plans)
+size_t call_ws_bytes(const b2a_plan* p, const b2a_forward_args* a) {
+  return stats_bytes(p, a->batch) + ((tilemin_count(p, a) * sizeof(float) + 15) & ~(size_t)15);
+}
+
 int resolve_args(const b2a_plan* p, const b2a_forward_args* in, b2a_forward_args* a) {
   *a = *in;
   if (!in->audio || !in->out || in->batch <= 0) {
@@ -161,12 +175,12 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s, int slot =
   const bool need_sums = d.norm_kind != B2A_NORM_NONE;
   s->clip_max = s->tile_min = nullptr;
   s->feat_sums = nullptr;
-  s->tile_frames = p->family == KF_FAST ? 32 : generic_tile_frames(p, a);
-  if (s->tile_frames <= 0) s->tile_frames = 2;
+  s->tile_frames = stats_tile_frames(p, a);
   if (!need_max && !need_sums && !a->clip_max && !a->feat_sums) return B2A_OK;
   char* base;
   const size_t need = stats_bytes(p, a->batch);
-  if (a->workspace && a->workspace_bytes >= need) {
+  const bool own_ws = a->workspace && a->workspace_bytes >= need;
+  if (own_ws) {
     base = (char*)a->workspace;
   } else {
     int rc = ensure_ws(p, need);
@@ -174,9 +188,10 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s, int slot =
     base = (char*)p->d_ws;
   }
   s->clip_max = (float*)base;
-  {
-    const size_t tiles = (size_t)a->batch * (size_t)((a->frame_count + s->tile_frames - 1) / s->tile_frames);
-    int rc = ensure_tilemin(p, slot, tiles > 0 ? tiles : 1);
+  if (a->workspace && a->workspace_bytes >= call_ws_bytes(p, a)) {
+    s->tile_min = (float*)((char*)a->workspace + need);  // the whole call runs on the caller's scratch
+  } else {
+    int rc = ensure_tilemin(p, slot, tilemin_count(p, a));
     if (rc) return rc;
     s->tile_min = p->d_tilemin[slot];
   }
@@ -352,8 +367,22 @@ size_t b2a_frontend_workspace_bytes(const b2a_plan* p, int32_t batch) {
   return stats_bytes(p, batch);
 }
 
+size_t b2a_frontend_call_workspace_bytes(const b2a_plan* p, const b2a_forward_args* in) {
+  if (!p || p->kind != PLAN_FRONTEND || !in) return 0;
+  b2a_forward_args a;
+  if (resolve_args(p, in, &a)) return 0;
+  return call_ws_bytes(p, &a);
+}
+
+static int reject_pcm16(const b2a_forward_args* in) {
+  if (in->audio_kind == B2A_PCM_F32) return B2A_OK;
+  set_error("audio_kind %d: int16 PCM input is taken by b2a_frontend_forward_host only (device entries read float32)", in->audio_kind);
+  return B2A_ERR_UNSUPPORTED;
+}
+
 int b2a_frontend_partial(b2a_plan* p, const b2a_forward_args* in, void* stream) {
   if (!p || p->kind != PLAN_FRONTEND || !in) return B2A_ERR_INVALID_ARG;
+  if (int prc = reject_pcm16(in)) return prc;
   b2a_forward_args a;
   int rc = resolve_args(p, in, &a);
   if (rc) return rc;
@@ -375,6 +404,7 @@ int b2a_frontend_finalize(b2a_plan* p, const b2a_forward_args* in, int64_t globa
 
 int b2a_frontend_forward(b2a_plan* p, const b2a_forward_args* in, void* stream) {
   if (!p || p->kind != PLAN_FRONTEND || !in) return B2A_ERR_INVALID_ARG;
+  if (int prc = reject_pcm16(in)) return prc;
   b2a_forward_args a;
   int rc = resolve_args(p, in, &a);
   if (rc) return rc;
@@ -387,11 +417,30 @@ int b2a_frontend_forward(b2a_plan* p, const b2a_forward_args* in, void* stream) 
 
 int b2a_frontend_dump_frames(b2a_plan* p, const b2a_forward_args* in, int apply_window, void* stream) {
   if (!p || p->kind != PLAN_FRONTEND || !in) return B2A_ERR_INVALID_ARG;
+  if (int prc = reject_pcm16(in)) return prc;
   b2a_forward_args a;
   int rc = resolve_args(p, in, &a);
   if (rc) return rc;
   // dump ignores drop_last bookkeeping beyond what resolve_args applied
   return dump_frames(p, &a, apply_window, (cudaStream_t)stream);
+}
+
+// int16 PCM -> float32 / 32768 (audio_io.py:258-262; exact), 8 samples per thread; n8 = groups of eight, then the tail
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t n8 = n / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 v = reinterpret_cast<const int4*>(in)[i];
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = (float)(short)(w[k] & 0xffff) * (1.0f / 32768.0f);
+      f[2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+    }
+    reinterpret_cast<float4*>(out)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - 8 * n8)) out[8 * n8 + threadIdx.x] = (float)in[8 * n8 + threadIdx.x] * (1.0f / 32768.0f);
 }
 
 // ---- host-buffer pipeline: chunks of clips, two streams, H2D / compute / D2H overlapped -----------------
@@ -433,15 +482,38 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
     if ((size_t)chunk * per_clip_bytes > cap) chunk = (int)std::max<size_t>(1, cap / per_clip_bytes);
     if (a.batch >= 16 && chunk > (a.batch + 7) / 8) chunk = (a.batch + 7) / 8;
   }
-  if ((rc = ensure_stage(p, (size_t)chunk * in_per_clip * 4, (size_t)chunk * out_per_clip * out_elem))) return rc;
+  const bool pcm16 = a.audio_kind == B2A_PCM_I16;
+  if (a.audio_kind != B2A_PCM_F32 && !pcm16) {
+    set_error("forward_host: audio_kind %d", a.audio_kind);
+    return B2A_ERR_INVALID_ARG;
+  }
+  // int16 input: the PCM lands behind the float32 area of the staging buffer (16-byte aligned) and is converted in place
+  const size_t f32_bytes = ((size_t)chunk * in_per_clip * 4 + 15) & ~(size_t)15;
+  if ((rc = ensure_stage(p, f32_bytes + (pcm16 ? (size_t)chunk * in_per_clip * 2 : 0), (size_t)chunk * out_per_clip * out_elem))) return rc;
   // per-stream statistic scratch
   const size_t sb = stats_bytes(p, chunk);
   if ((rc = ensure_ws(p, 2 * sb))) return rc;
+  // the chunk loop as a lambda: whatever it returns, BOTH streams are drained before this call returns — asynchronous copies
+  // must never still be writing into the caller's buffers after an error return
+  auto run_chunks = [&]() -> int {
   int idx = 0;
   for (int c0 = 0; c0 < a.batch; c0 += chunk, ++idx) {
     const int nb = std::min(chunk, a.batch - c0);
     const int s = idx & 1;
     cudaStream_t st = p->host_streams[s];
+    if (pcm16) {
+      const int16_t* hsrc = reinterpret_cast<const int16_t*>(a.audio) + (int64_t)c0 * a.clip_stride;
+      int16_t* d16 = reinterpret_cast<int16_t*>((char*)p->d_stage_in[s] + f32_bytes);
+      if (a.clip_stride == in_per_clip) {
+        B2A_CUDA(cudaMemcpyAsync(d16, hsrc, (size_t)nb * in_per_clip * 2, cudaMemcpyHostToDevice, st));
+      } else {
+        B2A_CUDA(cudaMemcpy2DAsync(d16, (size_t)in_per_clip * 2, hsrc, (size_t)a.clip_stride * 2, (size_t)in_per_clip * 2, nb,
+                                   cudaMemcpyHostToDevice, st));
+      }
+      const int64_t n = (int64_t)nb * in_per_clip;
+      pcm16_to_f32_kernel<<<(unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, 4096), 256, 0, st>>>(d16, (float*)p->d_stage_in[s], n);
+      B2A_CUDA(cudaGetLastError());
+    } else {
     const float* hsrc = a.audio + (int64_t)c0 * a.clip_stride;
     if (a.clip_stride == in_per_clip) {
       B2A_CUDA(cudaMemcpyAsync(p->d_stage_in[s], hsrc, (size_t)nb * in_per_clip * 4, cudaMemcpyHostToDevice, st));
@@ -449,7 +521,9 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
       B2A_CUDA(cudaMemcpy2DAsync(p->d_stage_in[s], (size_t)in_per_clip * 4, hsrc, (size_t)a.clip_stride * 4,
                                  (size_t)in_per_clip * 4, nb, cudaMemcpyHostToDevice, st));
     }
+    }
     b2a_forward_args c = a;
+    c.audio_kind = B2A_PCM_F32;
     c.audio = (const float*)p->d_stage_in[s];
     c.clip_stride = in_per_clip;
     c.batch = nb;
@@ -473,8 +547,13 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
                                  (size_t)out_per_clip * out_elem, nb, cudaMemcpyDeviceToHost, st));
     }
   }
-  B2A_CUDA(cudaStreamSynchronize(p->host_streams[0]));
-  B2A_CUDA(cudaStreamSynchronize(p->host_streams[1]));
+  return B2A_OK;
+  };
+  rc = run_chunks();
+  const cudaError_t e0 = cudaStreamSynchronize(p->host_streams[0]), e1 = cudaStreamSynchronize(p->host_streams[1]);
+  if (rc) return rc;
+  B2A_CUDA(e0);
+  B2A_CUDA(e1);
   return B2A_OK;
 }
 
@@ -494,25 +573,28 @@ int b2a_istft_out_len(const b2a_plan* p, int64_t num_frames, int64_t length, int
   return B2A_OK;
 }
 
-int b2a_istft_inverse(b2a_plan* p, const b2a_inverse_args* a, void* stream) {
+// argument checks shared by the device and the host entry point
+static int check_inverse_args(const b2a_plan* p, const b2a_inverse_args* a, const char* who) {
   if (!p || p->kind != PLAN_ISTFT || !a || !a->spec || !a->out || a->batch <= 0 || a->num_frames <= 0) {
-    set_error("istft_inverse: invalid argument");
+    set_error("%s: invalid argument", who);
     return B2A_ERR_INVALID_ARG;
   }
   if (p->id.input_form == B2A_ISTFT_INPUT_POLAR && !a->spec_imag) {
-    set_error("istft_inverse: the polar input form needs the phase plane in spec_imag");
+    set_error("%s: the polar input form needs the phase plane in spec_imag", who);
     return B2A_ERR_INVALID_ARG;
   }
+  return B2A_OK;
+}
+
+int b2a_istft_inverse(b2a_plan* p, const b2a_inverse_args* a, void* stream) {
+  if (int vrc = check_inverse_args(p, a, "istft_inverse")) return vrc;
   if (p->family == KF_SMALL) return small_istft(p, a, (cudaStream_t)stream);
   if (p->family == KF_FAST) return fast_istft(p, a, (cudaStream_t)stream);
   return generic_istft(p, a, (cudaStream_t)stream);
 }
 
 int b2a_istft_inverse_host(b2a_plan* p, const b2a_inverse_args* in) {
-  if (!p || p->kind != PLAN_ISTFT || !in || !in->spec || !in->out || in->batch <= 0 || in->num_frames <= 0) {
-    set_error("istft_inverse_host: invalid argument");
-    return B2A_ERR_INVALID_ARG;
-  }
+  if (int vrc = check_inverse_args(p, in, "istft_inverse_host")) return vrc;
   const int F = p->n_freqs;
   const int64_t T = in->num_frames;
   int64_t out_len;
@@ -529,6 +611,7 @@ int b2a_istft_inverse_host(b2a_plan* p, const b2a_inverse_args* in) {
   if ((size_t)chunk * per_clip_bytes > cap) chunk = (int)std::max<size_t>(1, cap / per_clip_bytes);
   if (in->batch >= 16 && chunk > (in->batch + 7) / 8) chunk = (in->batch + 7) / 8;
   if ((rc = ensure_stage(p, (size_t)chunk * in_per_clip * 8, (size_t)chunk * std::max<int64_t>(out_len, 1) * 4))) return rc;
+  auto run_chunks = [&]() -> int {  // both streams are drained below whatever this returns
   int idx = 0;
   for (int c0 = 0; c0 < in->batch; c0 += chunk, ++idx) {
     const int nb = std::min(chunk, in->batch - c0);
@@ -558,8 +641,13 @@ int b2a_istft_inverse_host(b2a_plan* p, const b2a_inverse_args* in) {
       B2A_CUDA(cudaMemcpy2DAsync((char*)in->out + (size_t)c0 * out_stride * 4, (size_t)out_stride * 4, p->d_stage_out[s],
                                  (size_t)out_len * 4, (size_t)out_len * 4, nb, cudaMemcpyDeviceToHost, st));
   }
-  B2A_CUDA(cudaStreamSynchronize(p->host_streams[0]));
-  B2A_CUDA(cudaStreamSynchronize(p->host_streams[1]));
+  return B2A_OK;
+  };
+  rc = run_chunks();
+  const cudaError_t e0 = cudaStreamSynchronize(p->host_streams[0]), e1 = cudaStreamSynchronize(p->host_streams[1]);
+  if (rc) return rc;
+  B2A_CUDA(e0);
+  B2A_CUDA(e1);
   return B2A_OK;
 }
 

@@ -99,7 +99,8 @@ int launch_const_rows(const b2a_plan* plan, const b2a_forward_args* a, int64_t r
 // call, and the reflected tail must not reach back into the signal.
 int64_t fast_const_row0(const b2a_plan* plan, const b2a_forward_args* a) {
   const b2a_frontend_desc& d = plan->fd;
-  if (plan->family != KF_FAST || getenv("B2A_NO_PAD_SKIP")) return -1;
+  static const bool no_pad_skip = getenv("B2A_NO_PAD_SKIP") != nullptr;  // development toggle, read once
+  if (plan->family != KF_FAST || no_pad_skip) return -1;
   const int64_t pc = d.center ? d.n_fft / 2 : 0;
   const bool tail_ok = !d.center || d.pad_mode == B2A_PAD_CONSTANT || a->length - pc - 1 >= a->valid_length;
   if (!(a->pad_value == 0.0f && d.preemph == 0.0f && d.n_mels > 0 && d.norm_kind == B2A_NORM_NONE && a->feat_sums == nullptr && tail_ok &&

@@ -1335,7 +1335,8 @@ constexpr int spec_yp() {
 template <class C, bool TM, bool SUMS, class MS, int SPECK = -1, int PREK = -1, int ODT = B2A_DTYPE_F32>
 int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   size_t smem = smem_bytes<C, spec_yp<MS>()>(p.mel_groups, p.mel_wg_count);
-  if (getenv("B2A_SMEM_PAD")) smem += (size_t)atoi(getenv("B2A_SMEM_PAD"));  // profiling aid: lowers the CTAs / SM
+  static const size_t smem_pad = getenv("B2A_SMEM_PAD") ? (size_t)atoi(getenv("B2A_SMEM_PAD")) : 0;  // profiling aid (read once): lowers the CTAs / SM
+  smem += smem_pad;
   if (smem > 226 * 1024) {
     set_error("fast kernel: %zu bytes of shared memory needed", smem);
     return B2A_ERR_UNSUPPORTED;
@@ -1522,7 +1523,8 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     set_error("16-bit feature output needs a 400/160 generated-mel kernel, (T, M) layout, 16-byte aligned rows, no normalisation");
     return B2A_ERR_UNSUPPORTED;
   }
-  if (fs->spec > 0 && !getenv("B2A_NO_MELSPEC") && ((tm && vec_ok) || (!tm && !sums && p.out_dtype == B2A_DTYPE_F32 && C::N == 400))) {  // named filterbank: mel structure compiled into the kernel
+  static const bool no_melspec = getenv("B2A_NO_MELSPEC") != nullptr;  // development toggle, read once
+  if (fs->spec > 0 && !no_melspec && ((tm && vec_ok) || (!tm && !sums && p.out_dtype == B2A_DTYPE_F32 && C::N == 400))) {  // named filterbank: mel structure compiled into the kernel
     const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, st);
     if (rc != 1) return rc;
   }

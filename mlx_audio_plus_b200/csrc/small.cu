@@ -229,6 +229,8 @@ bool small_stft_supported(const b2a_plan* plan) {
   const b2a_frontend_desc& d = plan->fd;
   if (getenv("B2A_FORCE_GENERIC")) return false;
   if (d.frame_dc || d.frame_preemph != 0.0f || d.dither != 0.0f || d.frame_len != 0) return false;
+  // stft_small_kernel writes plain (T, F) complex rows: anything else a descriptor may ask for goes to the generic kernel
+  if (d.out_layout != B2A_LAYOUT_TM || d.clamp_kind != B2A_CLAMP_NONE || d.norm_kind != B2A_NORM_NONE || d.preemph != 0.0f) return false;
   return (d.n_fft == 20 || d.n_fft == 16) && d.n_mels == 0 && d.spec_kind == B2A_SPEC_COMPLEX;
 }
 

@@ -242,6 +242,10 @@ def compute_deltas_kaldi(specgram, win_length: int = 5, mode: str = "edge"):
     dsp.py:439-483 (a Python loop over time steps there, one launch here)."""
     if win_length < 3:
         raise ValueError(f"win_length should be >= 3, got {win_length}")  # dsp.py:456-457
+    if win_length % 2 == 0:
+        # the reference multiplies a win_length-wide slice by 2 * ((win_length - 1) // 2) + 1 weights (dsp.py:473-480): for an
+        # even win_length the shapes do not broadcast and it raises; same exception type here instead of a silent n = (w-1)//2
+        raise ValueError(f"win_length should be odd, got {win_length}: shapes ({win_length},) and ({win_length - 1},) cannot be broadcast")
     ing = ingest(specgram, "float32")
     shape = tuple(int(v) for v in ing.data.shape)
     cols = shape[-1]
@@ -358,7 +362,8 @@ def compute_fbank_kaldi(waveform, sample_rate: int = 48000, win_len: int = 1920,
             cat = np.concatenate
         if pad > 0:
             left = flip(x[1 : pad + 1])
-            right = flip(x[num_samples - pad :]) if pad > 1 else flip(x[1:])
+            # waveform[-1 : -pad - 1 : -1]: a signal shorter than `pad` contributes ALL of its samples, reversed
+            right = flip(x[max(num_samples - pad, 0) :]) if pad > 1 else flip(x[1:])
             x = cat([left, x, right])
         else:
             x = cat([x[-pad:], flip(x)])

@@ -27,6 +27,9 @@ def _current_device_and_stream(device=None):
 class _PlanBase:
     def __init__(self):
         self._h = C.c_void_p()
+        # the *_host entry points stage through plan-owned device buffers and streams: one host call per plan at a time
+        self._host_lock = threading.Lock()
+        self._tls = threading.local()
 
     def close(self):
         if self._h:
@@ -126,6 +129,7 @@ class FrontendPlan(_PlanBase):
                 a = self._args(x.data_ptr(), Lx, length, Lx, B, out.data_ptr(), pad_value=pad_value, frame_count=T)
                 a.seed = int(seed)
                 if T > 0:
+                    ws = self._call_workspace(a, ing.device)  # noqa: F841  (kept alive until the launch is enqueued)
                     L.check(L.lib.b2a_frontend_forward(self._h, C.byref(a), C.c_void_p(st)))
             return out
         _current_device_and_stream()  # fail loudly without a GPU
@@ -135,8 +139,49 @@ class FrontendPlan(_PlanBase):
         a = self._args(x.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value, frame_count=T)
         a.seed = int(seed)
         if T > 0:
-            L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
+            with self._host_lock:
+                L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
         return out
+
+    def run_host_pcm16(self, pcm, out=None, *, length=None, pad_value=0.0):
+        """Host int16 PCM (B, L) as a decoder delivers it (audio_io.py:258-262: float32 = int16 / 32768) -> features on the
+        host, through ONE pipelined b2a_frontend_forward_host call: half the host-to-device bytes of the float32 entry, and
+        with out_dtype float16 (what whisper.py:990-996 casts its segments to) half the device-to-host bytes too.
+        `pcm` / `out` may be pinned (torch) buffers viewed as NumPy arrays."""
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.dtype != np.int16 or pcm.ndim != 2:
+            raise TypeError("run_host_pcm16 takes a (batch, samples) int16 array")
+        _current_device_and_stream()
+        B, Lx = int(pcm.shape[0]), int(pcm.shape[1])
+        length = Lx if length is None else int(length)
+        T = self.out_frames(length)
+        shape = self.out_shape(B, T)
+        if self.out_dtype == "bfloat16":
+            raise TypeError("bfloat16 features need a torch CUDA input (NumPy has no bfloat16)")
+        if out is None:
+            out = np.empty(shape, dtype=np.dtype(self.out_dtype))
+        a = self._args(pcm.ctypes.data, Lx, length, Lx, B, out.ctypes.data, pad_value=pad_value, frame_count=T)
+        a.audio_kind = L.PCM_I16
+        if T > 0:
+            with self._host_lock:
+                L.check(L.lib.b2a_frontend_forward_host(self._h, C.byref(a)))
+        return out
+
+    def _call_workspace(self, a, device):
+        """Per-call device scratch (clip maxima, per-feature sums, per-tile minima) from torch's caching allocator on the
+        caller's current stream: the plan object is shared by every caller on the device (cached_plan), and with its own
+        scratch two streams / threads running a clamping or normalising front-end would race on the statistics.  The
+        allocator recycles the block in stream order, so it may be dropped as soon as the launch is enqueued."""
+        if self.desc.clamp_kind == L.CLAMP_NONE and self.desc.norm_kind == L.NORM_NONE and not a.clip_max and not a.feat_sums:
+            return None
+        import torch
+
+        n = int(L.lib.b2a_frontend_call_workspace_bytes(self._h, C.byref(a)))
+        if n <= 0:
+            return None
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), n
+        return ws
 
     # -- split form for frame-range sharding (SURVEY §8e) ------------------------------------------------
     def stats_tensors(self, batch, device):
@@ -159,15 +204,19 @@ class FrontendPlan(_PlanBase):
                        pad_value=pad_value, sample_offset=int(sample_offset), frame_begin=int(frame_begin),
                        frame_count=int(frame_count), clip_max=clip_max.data_ptr(), feat_sums=feat_sums.data_ptr())
         st = torch.cuda.current_stream(x_cuda.device).cuda_stream
-        L.check(L.lib.b2a_frontend_partial(self._h, C.byref(a), C.c_void_p(st)))
-        self._last_partial = a
+        with torch.cuda.device(x_cuda.device):
+            ws = self._call_workspace(a, x_cuda.device)
+            L.check(L.lib.b2a_frontend_partial(self._h, C.byref(a), C.c_void_p(st)))
+        # the call's context (arguments + its scratch, which finalize() reads the per-tile minima from): per thread, never
+        # on the shared plan object
+        self._tls.last_partial = (a, ws)
         return out
 
     def finalize(self, out, clip_max, feat_sums, *, global_frames):
-        """Clamp / normalise `out` in place with the (all-reduced) statistics."""
+        """Clamp / normalise `out` in place with the (all-reduced) statistics of this thread's last partial() call."""
         import torch
 
-        a = self._last_partial
+        a, _ws = self._tls.last_partial
         a.out, a.clip_max, a.feat_sums = out.data_ptr(), clip_max.data_ptr(), feat_sums.data_ptr()
         st = torch.cuda.current_stream(out.device).cuda_stream
         L.check(L.lib.b2a_frontend_finalize(self._h, C.byref(a), int(global_frames), C.c_void_p(st)))
@@ -234,7 +283,8 @@ class IstftPlan(_PlanBase):
         out = np.empty((B, n_out), dtype=np.float32)
         a.spec, a.spec_imag, a.out = x.ctypes.data, (imag.data.ctypes.data if imag is not None else None), out.ctypes.data
         if n_out > 0:
-            L.check(L.lib.b2a_istft_inverse_host(self._h, C.byref(a)))
+            with self._host_lock:
+                L.check(L.lib.b2a_istft_inverse_host(self._h, C.byref(a)))
         return out
 
 
@@ -254,10 +304,37 @@ def _device_index(ing: Ingested = None) -> int:
     return torch.cuda.current_device()
 
 
+_FP_CACHE = OrderedDict()  # (data pointer, shape, strides, dtype) of a READ-ONLY array -> (owner kept alive, fingerprint)
+_FP_MAX = 64
+
+
+def _fingerprint(arr):
+    """Content key of a window / filterbank array.  The wrappers pass the same lru-cached, read-only tables (or views of
+    them) on every call — dsp.hanning / dsp.mel_filters cache like the reference's do — so the ~100 KB filterbank is
+    hashed once per table, not once per call.  Writable arrays may change under the same address and are hashed every time."""
+    if arr is None:
+        return None
+    if isinstance(arr, np.ndarray) and not arr.flags.writeable:
+        k = (arr.__array_interface__["data"][0], arr.shape, arr.strides, arr.dtype.str)
+        with _CACHE_LOCK:
+            ent = _FP_CACHE.get(k)
+            if ent is not None:
+                _FP_CACHE.move_to_end(k)
+                return ent[1]
+    else:
+        k = None
+    a = np.ascontiguousarray(arr, dtype=np.float32)
+    fp = (a.shape, hash(a.tobytes()), float(a.sum(dtype=np.float64)))
+    if k is not None:
+        with _CACHE_LOCK:
+            _FP_CACHE[k] = (arr, fp)  # holding the array keeps its address from being reused while the entry lives
+            while len(_FP_CACHE) > _FP_MAX:
+                _FP_CACHE.popitem(last=False)
+    return fp
+
+
 def cached_plan(cls, dev_index: int, window: np.ndarray, filterbank=None, **kw):
-    window = np.ascontiguousarray(window, dtype=np.float32)
-    key = (cls.__name__, dev_index, tuple(sorted(kw.items())), window.tobytes(),
-           None if filterbank is None else (filterbank.shape, filterbank.tobytes()))
+    key = (cls.__name__, dev_index, tuple(sorted(kw.items())), _fingerprint(window), _fingerprint(filterbank))
     with _CACHE_LOCK:
         plan = _CACHE.get(key)
         if plan is not None:
@@ -265,6 +342,7 @@ def cached_plan(cls, dev_index: int, window: np.ndarray, filterbank=None, **kw):
             return plan
     import torch
 
+    window = np.ascontiguousarray(window, dtype=np.float32)
     with torch.cuda.device(dev_index):
         plan = cls(window=window, filterbank=filterbank, **kw) if filterbank is not None or cls is FrontendPlan \
             else cls(window=window, **kw)

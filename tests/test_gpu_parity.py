@@ -298,6 +298,21 @@ def test_kaldi_fbank_and_deltas_parity(golden, where):
         assert d.shape == g[key].shape and np.abs(d - g[key]).max() <= 1e-5 * np.abs(g[key]).max()
 
 
+@pytest.mark.parametrize("where", ["cuda", "numpy"])
+def test_kaldi_snip_edges_false_short_input(where):
+    """snip_edges=False with a signal SHORTER than the reflect pad (dsp.py:511-521): `waveform[-1 : -pad - 1 : -1]` keeps the
+    whole reversed signal (a negative start would keep only its tail).  180 samples, pad 192: the padded signal (539 samples)
+    still holds the one 512-sample frame, so the reference's strided view stays inside its buffer."""
+    from mlx_audio_plus_b200 import dsp
+
+    x = (synth(403, 180, 16000) * 8000.0).astype(np.float32)
+    kw = dict(sample_rate=16000, win_len=512, win_inc=128, num_mels=40, win_type="rectangular", preemphasis=0.5, snip_edges=False)
+    ref = W.kaldi_fbank(x, **kw)
+    y = host(dsp.compute_fbank_kaldi(dev(x) if where == "cuda" else x, dither=0.0, **kw))
+    assert y.shape == ref.shape == (1, 40)
+    assert np.abs(y - ref).max() <= 2e-4
+
+
 def test_kaldi_dither_is_seeded_noise_of_the_right_size():
     """dither != 0 cannot match MLX's generator; it must be reproducible per seed, differ across seeds, and perturb
     the frames like N(0, dither^2): on silence the mean frame energy after the Hamming window is dither^2 * sum(w^2)
