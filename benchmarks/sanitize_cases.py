@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Smallest case of every kernel family, for `compute-sanitizer --tool memcheck|racecheck|synccheck python benchmarks/sanitize_cases.py`
+(logs committed under profiles/).  Each case is checked against the oracle as well, so a clean sanitizer run is also a
+correct run."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from oracle import dsp_oracle as O  # noqa: E402
+from oracle import wrappers_oracle as W  # noqa: E402
+from oracle.make_golden import synth  # noqa: E402
+
+
+def main():
+    from mlx_audio_plus_b200 import dsp
+    from mlx_audio_plus_b200._post import lfr, rows_pad_cast
+    from mlx_audio_plus_b200.codec.models.s3gen.mel import mel_spectrogram as s3gen_mel
+    from mlx_audio_plus_b200.codec.models.vocos.mel import log_mel_spectrogram as vocos_mel
+    from mlx_audio_plus_b200.codec.models.vocos.vocos import ISTFTHead
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram as parakeet_mel
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram as whisper_mel
+    from mlx_audio_plus_b200.stt.utils import load_audio
+    from mlx_audio_plus_b200.tts.models.kokoro.istftnet import MLXSTFT
+
+    only = set(sys.argv[1:])
+    done = []
+
+    def case(name, fn):
+        if only and name not in only:
+            return
+        fn()
+        torch.cuda.synchronize()
+        done.append(name)
+
+    x = synth(1, 16000 * 2 + 77)
+    xd = torch.from_numpy(x).cuda()
+    x[9000:14000] = 0  # the clamp fix-up rewrites these tiles
+
+    def k1_400():
+        for m in (80, 128):
+            y = whisper_mel(torch.from_numpy(x).cuda(), n_mels=m)
+            assert np.abs(y.cpu().numpy() - W.whisper_log_mel(x, m)).max() <= 1e-4
+        y = whisper_mel(torch.from_numpy(x).cuda(), n_mels=128, padding=48000, dtype="float16")  # const rows + 16-bit epilogue
+        assert y.shape[0] == (len(x) + 48000) // 160
+
+    def k1_512():
+        pa = PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5)
+        y = parakeet_mel(xd, pa)
+        ref = W.parakeet_log_mel(xd.cpu().numpy(), W.PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5))
+        assert np.abs(y.cpu().numpy() - ref).max() <= 5e-4
+
+    def k1_1024():
+        x24 = torch.from_numpy(synth(2, 24000)).cuda()
+        y = vocos_mel(x24)
+        assert np.abs(y.cpu().numpy() - W.vocos_log_mel(x24.cpu().numpy())).max() <= 1e-4
+
+    def k1c_stft():
+        for n_fft, hop in ((400, 160), (512, 160), (1024, 256), (800, 200), (1024, 320)):
+            s = dsp.stft(xd, n_fft, hop, window=O.hanning(n_fft))
+            r = O.stft(xd.cpu().numpy(), n_fft, hop, window=O.hanning(n_fft))
+            assert np.linalg.norm(s.cpu().numpy() - r) <= 2e-6 * np.linalg.norm(r)
+
+    def k2_generic():
+        s = dsp.stft(xd, 320, 80, window=O.hanning(320))
+        r = O.stft(xd.cpu().numpy(), 320, 80, window=O.hanning(320))
+        assert np.linalg.norm(s.cpu().numpy() - r) <= 2e-6 * np.linalg.norm(r)
+        x24 = synth(3, 24000)
+        y = s3gen_mel(torch.from_numpy(x24).cuda()[None])
+        assert np.abs(y.cpu().numpy() - W.s3gen_mel(x24[None])).max() <= 1e-4
+
+    def k3_istft():
+        rng = np.random.default_rng(3)
+        for n_fft, hop, T in ((1024, 256, 9), (1280, 320, 7), (2048, 512, 6), (1920, 384, 5), (320, 80, 11)):
+            spec = (rng.standard_normal((n_fft // 2 + 1, T)) + 1j * rng.standard_normal((n_fft // 2 + 1, T))).astype(np.complex64)
+            w = dsp.istft(torch.from_numpy(spec).cuda(), hop_length=hop, win_length=n_fft, window=O.hanning(n_fft))
+            r = O.istft(spec, hop_length=hop, win_length=n_fft, window=O.hanning(n_fft))
+            assert np.abs(w.cpu().numpy() - r).max() <= 1e-5 * np.abs(r).max()
+        xl = rng.standard_normal((1, 9, 1026)).astype(np.float32)
+        yh = ISTFTHead(512, 1024, 256)(torch.from_numpy(xl).cuda())
+        rh = W.vocos_istft_head(xl, 1024, 256)
+        assert np.abs(np.asarray(yh.cpu()).reshape(-1) - np.asarray(rh).reshape(-1)).max() <= 1e-5 * np.abs(rh).max()
+
+    def k4_small():
+        rng = np.random.default_rng(4)
+        mag = np.exp(0.5 * rng.standard_normal((2, 11, 301))).astype(np.float32)
+        ph = np.sin(rng.standard_normal((2, 11, 301))).astype(np.float32)
+        st = MLXSTFT(20, 5, 20)
+        y = st.inverse(torch.from_numpy(mag).cuda(), torch.from_numpy(ph).cuda())
+        r = W.kokoro_inverse(mag, ph)
+        assert np.abs(y.cpu().numpy() - r).max() <= 1e-5 * np.abs(r).max()
+        m2, p2 = st.transform(torch.from_numpy(synth(5, 1500)).cuda())
+        rm, rp = W.kokoro_transform(synth(5, 1500))
+        assert np.abs(m2.cpu().numpy() - rm).max() <= 1e-4 * np.abs(rm).max()
+
+    def k5_resample():
+        rng = np.random.default_rng(5)
+        pcm = (rng.standard_normal((4411, 2)) * 3000).astype(np.int16)
+        y = load_audio(pcm=torch.from_numpy(pcm).cuda(), sample_rate=44100, sr=16000)
+        from oracle import pre_oracle as P
+        r = P.load_audio_from_pcm(pcm, 44100, 16000)
+        assert np.abs(y.cpu().numpy() - r).max() <= 1e-5 * np.abs(r).max()
+
+    def k6_post():
+        mel = torch.randn((2, 300, 128), device="cuda")
+        seg = rows_pad_cast(mel, 100, 150, 256, "float16")
+        assert tuple(seg.shape) == (2, 256, 128) and float(seg[:, 200:].abs().max()) == 0.0
+        f = torch.randn((1, 100, 80), device="cuda")
+        o = lfr(f, 7, 6, None, None)
+        assert np.array_equal(o[0].cpu().numpy(), W.funasr_apply_lfr(f[0].cpu().numpy(), 7, 6))
+
+    for name, fn in (("k1_400", k1_400), ("k1_512", k1_512), ("k1_1024", k1_1024), ("k1c_stft", k1c_stft), ("k2_generic", k2_generic),
+                     ("k3_istft", k3_istft), ("k4_small", k4_small), ("k5_resample", k5_resample), ("k6_post", k6_post)):
+        case(name, fn)
+    print("sanitize cases ok:", " ".join(done))
+
+
+if __name__ == "__main__":
+    main()

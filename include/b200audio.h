@@ -268,6 +268,8 @@ typedef struct b2a_istft_desc {
                          (kokoro/istftnet.py:500-512, s3gen/hifigan.py:480-485, cosyvoice3/hifigan.py:447-452) */
   float mag_clip_max; /* POLAR: magnitude is clipped to <= this (1e2 in the HiFT heads); <= 0 = no upper clip */
   int32_t mag_clip_min_zero; /* POLAR: 1 = clip magnitude to >= 0 (cosyvoice3/hifigan.py:447 a_min=0.0) */
+  int32_t mag_log;    /* POLAR: 1 = the magnitude plane holds LOG-magnitudes, mag = exp(a) before the clip — the Vocos / Soprano
+                         iSTFT head `clip(exp(x), max=1e2)` (codec/models/vocos/vocos.py:129-130, soprano/decoder.py:36-37) */
 } b2a_istft_desc;
 
 typedef struct b2a_inverse_args {

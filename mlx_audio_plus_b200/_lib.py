@@ -59,6 +59,7 @@ class IstftDesc(C.Structure):
         ("n_fft", C.c_int32), ("hop", C.c_int32), ("window_len", C.c_int32), ("center", C.c_int32),
         ("norm_kind", C.c_int32), ("div_kind", C.c_int32), ("trim_tail", C.c_int32),
         ("div_eps", C.c_float), ("input_form", C.c_int32), ("mag_clip_max", C.c_float), ("mag_clip_min_zero", C.c_int32),
+        ("mag_log", C.c_int32),
     ]
 
 

@@ -79,15 +79,51 @@ struct PolarSpec {
   int polar;          // 1: (a, b) = (magnitude, phase) -> clip(a) * (cos b, sin b)
   float clip_max;     // <= 0: none
   int clip_min_zero;
+  int log_mag;        // 1: a holds ln(magnitude): exp first (Vocos / Soprano head)
 };
 #ifdef __CUDACC__
+__device__ __forceinline__ float lg2_approx(float x) {  // MUFU.LG2: the fused kernels' logarithm (base change folded into the affine FFMA)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// sin and cos of one float32 argument, both within 1.2 ulp of 1 (max abs error 7e-8, checked against float64 over
+// |x| <= 1e5): three-term Cody-Waite reduction by pi/2 (hi / mid / lo of pi/2, one FMA each), then the degree-7 / degree-8
+// minimax polynomials on [-pi/4, pi/4] and a quadrant swap — ~25 instructions where libdevice's sincosf, which carries
+// the Payne-Hanek path for huge arguments inline, costs ~100 (the polar iSTFT kernels evaluate one per spectrum bin:
+// C4, 270 M of them, 1.32 -> see DESIGN).  Arguments beyond 65536 rad (and NaN / inf) take libdevice's path.
+__device__ __forceinline__ void sincos_cw(float x, float* sn, float* cs) {
+  if (!(fabsf(x) <= 65536.0f)) {
+    sincosf(x, sn, cs);
+    return;
+  }
+  const float q = rintf(x * 0.636619747f);
+  float r = fmaf(-q, 0x1.921fb6p+0f, x);
+  r = fmaf(-q, -0x1.777a5cp-25f, r);
+  r = fmaf(-q, -0x1.ee59dap-50f, r);
+  const float r2 = r * r;
+  float s = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+  s = fmaf(s, r2, -1.66666546e-1f);
+  s = fmaf(s * r2, r, r);
+  float c = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+  c = fmaf(c, r2, 4.16666457e-2f);
+  c = fmaf(c, r2, -0.5f);
+  c = fmaf(c, r2, 1.0f);
+  const int k = (int)q;
+  const float a = (k & 1) ? c : s, b = (k & 1) ? s : c;
+  *sn = (k & 2) ? -a : a;
+  *cs = ((k + 1) & 2) ? -b : b;
+}
+
 __device__ __forceinline__ float2 polar_to_complex(const PolarSpec& ps, float2 v) {
   if (!ps.polar) return v;
   float m = v.x;
+  if (ps.log_mag) m = expf(m);
   if (ps.clip_max > 0.0f) m = fminf(m, ps.clip_max);
   if (ps.clip_min_zero) m = fmaxf(m, 0.0f);
   float s, c;
-  sincosf(v.y, &s, &c);  // full-range accurate version (the reference uses libm-grade cos / sin)
+  sincos_cw(v.y, &s, &c);  // libm-grade accuracy (the reference uses float32 cos / sin)
   return make_float2(m * c, m * s);
 }
 #endif
@@ -96,8 +132,38 @@ inline PolarSpec make_polar_spec(const b2a_istft_desc& d) {
   ps.polar = d.input_form == B2A_ISTFT_INPUT_POLAR;
   ps.clip_max = d.mag_clip_max;
   ps.clip_min_zero = d.mag_clip_min_zero;
+  ps.log_mag = d.mag_log;
   return ps;
 }
+// Epilogue constants of the fused log-mel kernels: a = max(x + guard_add, guard_floor); y = (use_log ? log2(a) : a) * y_mul + y_add
+// (log base change and the affine map folded into one FFMA).  ONE definition: the kernels, the constant-row fill and the
+// clamp fix-up's fill of unwritten (all-silent) tiles must produce bit-identical values.
+struct EpilogueConsts {
+  float guard_add, guard_floor, y_mul, y_add;
+  int use_log;
+};
+inline EpilogueConsts epilogue_consts(const b2a_frontend_desc& d) {
+  EpilogueConsts e;
+  e.guard_add = d.guard_kind == B2A_GUARD_ADD ? d.guard_eps : 0.0f;
+  e.guard_floor = d.guard_kind == B2A_GUARD_MAX ? d.guard_eps : -INFINITY;
+  e.use_log = d.log_kind != B2A_LOG_NONE;
+  const double lscale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521 : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942 : 1.0);
+  if (d.affine_div != 0.0f) {  // ((log2(a) * lscale) + add) / div
+    e.y_mul = (float)(lscale / (double)d.affine_div);
+    e.y_add = (float)((double)d.affine_add / (double)d.affine_div);
+  } else {
+    e.y_mul = (float)lscale;
+    e.y_add = 0.0f;
+  }
+  return e;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ float epilogue_of_zero(const EpilogueConsts& e) {  // the value every mel bin of a silent frame gets
+  const float a = fmaxf(0.0f + e.guard_add, e.guard_floor);
+  return fmaf(e.use_log ? lg2_approx(a) : a, e.y_mul, e.y_add);
+}
+#endif
+
 inline float istft_div_eps(const b2a_istft_desc& d) { return d.div_eps > 0.0f ? d.div_eps : 1e-10f; }
 
 struct MelCsr {  // filterbank rows as contiguous runs of non-zero taps
@@ -160,6 +226,7 @@ int fast_frontend_init(b2a_plan* plan);
 void fast_frontend_destroy(b2a_plan* plan);
 bool fast_frontend_out16_ok(const b2a_plan* plan);
 int64_t fast_const_row0(const b2a_plan* plan, const b2a_forward_args* a);
+bool fast_skip_floor_tiles(const b2a_plan* plan);
 int fast_const_rows_finalize(const b2a_plan* plan, const b2a_forward_args* a, int64_t row0, float* clip_max, cudaStream_t st);
 int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);

@@ -56,18 +56,13 @@ __global__ void const_fold_max_kernel(float* clip_max, int batch, ConstRows cr) 
 }
 
 ConstRows make_const_rows(const b2a_frontend_desc& d) {
+  const EpilogueConsts ec = epilogue_consts(d);
   ConstRows cr;
-  cr.guard_add = d.guard_kind == B2A_GUARD_ADD ? d.guard_eps : 0.0f;
-  cr.guard_floor = d.guard_kind == B2A_GUARD_MAX ? d.guard_eps : -INFINITY;
-  cr.use_log = d.log_kind != B2A_LOG_NONE;
-  const double lscale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521 : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942 : 1.0);
-  if (d.affine_div != 0.0f) {
-    cr.y_mul = (float)(lscale / (double)d.affine_div);
-    cr.y_add = (float)((double)d.affine_add / (double)d.affine_div);
-  } else {
-    cr.y_mul = (float)lscale;
-    cr.y_add = 0.0f;
-  }
+  cr.guard_add = ec.guard_add;
+  cr.guard_floor = ec.guard_floor;
+  cr.use_log = ec.use_log;
+  cr.y_mul = ec.y_mul;
+  cr.y_add = ec.y_add;
   cr.floor_mode = 0;
   cr.floor_delta = cr.floor_fixed = 0.0f;
   return cr;
@@ -92,6 +87,15 @@ int launch_const_rows(const b2a_plan* plan, const b2a_forward_args* a, int64_t r
 }
 
 }  // namespace
+
+// May fast_logmel_tma_kernel leave all-silent tiles unwritten (tile_min = -inf) for the clamp fix-up to fill?  Only when a
+// clamp fix-up is certain to follow and writes float32 (T, M) rows.  A pure function of the plan: partial and finalize agree.
+bool fast_skip_floor_tiles(const b2a_plan* plan) {
+  const b2a_frontend_desc& d = plan->fd;
+  static const bool off = getenv("B2A_NO_TILE_SKIP") != nullptr;  // development toggle, read once
+  return !off && plan->family == KF_FAST && d.clamp_kind != B2A_CLAMP_NONE && d.norm_kind == B2A_NORM_NONE && d.n_mels > 0 &&
+         d.out_layout == B2A_LAYOUT_TM && d.out_dtype == B2A_DTYPE_F32 && d.guard_kind == B2A_GUARD_MAX && d.n_mels % 4 == 0;
+}
 
 // First row of the trailing block of all-padding frames that is filled instead of transformed (a multiple of the 32-frame
 // tile), or -1.  A pure function of the plan and the call's arguments: the partial and the finalize step both derive it.
@@ -278,17 +282,14 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.spec_kind = d.spec_kind;
   p.spec_eps = d.spec_kind == B2A_SPEC_SQRT_POWER_EPS ? d.spec_eps : 0.0f;
   p.n_mels = d.n_mels;
-  p.guard_add = d.guard_kind == B2A_GUARD_ADD ? d.guard_eps : 0.0f;
-  p.guard_floor = d.guard_kind == B2A_GUARD_MAX ? d.guard_eps : -INFINITY;
-  p.use_log = d.log_kind != B2A_LOG_NONE;
-  const double lscale = d.log_kind == B2A_LOG_LOG10 ? 0.30102999566398119521 : (d.log_kind == B2A_LOG_LN ? 0.69314718055994530942 : 1.0);
-  if (d.affine_div != 0.0f) {  // ((log2(a) * lscale) + add) / div
-    p.y_mul = (float)(lscale / (double)d.affine_div);
-    p.y_add = (float)((double)d.affine_add / (double)d.affine_div);
-  } else {
-    p.y_mul = (float)lscale;
-    p.y_add = 0.0f;
-  }
+  const EpilogueConsts ec = epilogue_consts(d);
+  p.guard_add = ec.guard_add;
+  p.guard_floor = ec.guard_floor;
+  p.use_log = ec.use_log;
+  p.y_mul = ec.y_mul;
+  p.y_add = ec.y_add;
+  // all-silent tiles are left to the clamp fix-up (which then writes them once) whenever a clamp follows
+  p.skip_floor_tiles = fast_skip_floor_tiles(plan) ? 1 : 0;
   p.out_layout = d.out_layout;
   p.out_dtype = d.out_dtype;
   p.out = reinterpret_cast<float*>(a->out);

@@ -73,6 +73,8 @@ struct FastParams {
   int mel_groups, mel_wg_count;
   int tiles_per_clip;
   int tile_min_pitch;  // tiles per clip in the tile_min table (>= tiles_per_clip when trailing all-padding tiles are skipped)
+  int skip_floor_tiles;  // 1: a tile whose every value is the guard-floor constant (digital silence) is NOT stored; its
+                         // tile_min entry is -inf and the clamp fix-up writes max(c, floor) there (fast_logmel_tma_kernel)
   long long* dbg_clk;  // profiling aid (B2A_CLOCKS=file): per CTA, cycles accumulated per phase [8] (thread 0's view)
 };
 
@@ -188,11 +190,6 @@ __device__ __forceinline__ int float_key(float f) {
   return b ^ ((b >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 template <int BYTE_OFF>
 __device__ __forceinline__ float4 lds128_at(unsigned base) {  // pinned (volatile) broadcast load: keeps its place in program order
   float4 v;

@@ -122,10 +122,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
       const int64_t stepT = (int64_t)N1 * T, jumpT = (int64_t)(kb_hi - kb_lo) * T;
       int64_t oa = (int64_t)clip_i * p.clip_stride + t + (int64_t)kb_lo * T;
       int64_t ob = (int64_t)clip_i * p.clip_stride + t + (int64_t)(NC - kb_lo) * T;
+      // (magnitude / phase planes are converted after ALL loads of the unit are in flight: a conversion per load site put
+      // its range-reduction branch between consecutive loads and serialised them)
       auto load_at = [&](int64_t i) -> float2 {
         if (!live) return make_float2(0.0f, 0.0f);
-        if (POLAR) return polar_to_complex(p.polar, make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)));
-        return planar ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
+        return (POLAR || planar) ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
       };
       float2 xa[N2], xb[N2];
       static_for<0, N2>([&](auto S_) {
@@ -142,7 +143,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
       float2 dc = make_float2(0.0f, 0.0f);
       if (u == 0) {  // Im(DC), Im(Nyquist) are ignored (irfft)
         const int64_t o0 = (int64_t)clip_i * p.clip_stride + t;
-        dc = make_float2(load_at(o0).x, load_at(o0 + (int64_t)NC * T).x);
+        float2 x0 = load_at(o0), xn = load_at(o0 + (int64_t)NC * T);
+        if (POLAR && live) {
+          x0 = polar_to_complex(p.polar, x0);
+          xn = polar_to_complex(p.polar, xn);
+        }
+        dc = make_float2(x0.x, xn.x);
+      }
+      if (POLAR && live) {
+#pragma unroll
+        for (int s = 0; s < N2; ++s) {
+          xa[s] = polar_to_complex(p.polar, xa[s]);
+          xb[s] = polar_to_complex(p.polar, xb[s]);
+        }
       }
       const float4* tp4 = reinterpret_cast<const float4*>(s_twp + u * N2);
       // Hermitian unpacking of one slot; the two results land in DIFFERENT registers for unit 0 (whose columns 0 and

@@ -447,6 +447,8 @@ struct FinParams {
   int stats_affine;  // 1: clip_max / tile_min were recorded AFTER the affine map (fast kernels)
   int tile_min_pitch;  // tiles per clip in the tile_min table (tiles_per_clip may be cut short: constant padding rows)
   int out_dtype;     // B2A_DTYPE_*: 16-bit features (fast 400/160 kernels, (T, M) layout): the floor is cast the same way
+  int fill_unwritten;  // 1: tiles with tile_min == -inf were NOT stored by the fused kernel (all-silent: every value is the
+  EpilogueConsts ec;   //    epilogue's constant for zero power) — the fix-up writes max(c, floor) there
 };
 
 // B2A_CLAMP_BATCH_MAX: one max over the whole batch (s3tokenizer/utils.py:131) -> broadcast into clip_max
@@ -487,11 +489,35 @@ __global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
       floor_out = p.apply_affine ? (floor_cmp + p.affine_add) / p.affine_div : floor_cmp;
     }
   }
-  if (!(p.tile_min[(int64_t)clip_i * p.tile_min_pitch + tile] < floor_cmp)) return;
+  const float tmin = p.tile_min[(int64_t)clip_i * p.tile_min_pitch + tile];
+  const bool unwritten = p.fill_unwritten && tmin == -INFINITY;
+  if (!unwritten && !(tmin < floor_cmp)) return;
   float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
   const int M = p.n_mels;
   const int64_t f0 = (int64_t)tile * p.tile_frames;
   const int nf = (int)min((int64_t)p.tile_frames, p.frames - f0);
+  if (p.out_dtype == B2A_DTYPE_F32 && p.out_layout == B2A_LAYOUT_TM && (reinterpret_cast<uintptr_t>(o + f0 * M) & 15) == 0 && (M & 3) == 0) {
+    // float32 (T, M) rows of a tile are one contiguous, 16-byte aligned block: float4 sweeps
+    float4* t4 = reinterpret_cast<float4*>(o + f0 * M);
+    const int n4 = nf * M / 4;
+    if (unwritten) {  // the tile was never stored: every element is max(c, floor) — one write pass, no read
+      const float v = fmaxf(epilogue_of_zero(p.ec), floor_out);
+      const float4 v4 = make_float4(v, v, v, v);
+      for (int i = lane; i < n4; i += 32) t4[i] = v4;
+    } else {
+      for (int i = lane; i < n4; i += 32) {
+        float4 v = t4[i];
+        if (v.x < floor_out || v.y < floor_out || v.z < floor_out || v.w < floor_out) {  // (a NaN stays a NaN)
+          v.x = v.x < floor_out ? floor_out : v.x;
+          v.y = v.y < floor_out ? floor_out : v.y;
+          v.z = v.z < floor_out ? floor_out : v.z;
+          v.w = v.w < floor_out ? floor_out : v.w;
+          t4[i] = v;
+        }
+      }
+    }
+    return;
+  }
   if (p.out_dtype == B2A_DTYPE_F16) {  // cast(max(y, floor)) == max(cast(y), cast(floor)): the cast is monotone
     __half* t = reinterpret_cast<__half*>(p.out) + (int64_t)clip_i * p.out_clip_stride + f0 * M;
     const __half fl = __float2half_rn(floor_out);
@@ -504,9 +530,10 @@ __global__ void __launch_bounds__(256) clamp_fixup_kernel(const FinParams p) {
       if (__hlt(t[i], fl)) t[i] = fl;
   } else if (p.out_layout == B2A_LAYOUT_TM) {
     float* t = o + f0 * M;
+    const float cfill = unwritten ? fmaxf(epilogue_of_zero(p.ec), floor_out) : 0.0f;
     for (int i = lane; i < nf * M; i += 32) {
-      const float v = t[i];
-      if (v < floor_out) t[i] = floor_out;
+      const float v = unwritten ? cfill : t[i];
+      if (unwritten || v < floor_out) t[i] = unwritten ? cfill : floor_out;
     }
   } else {
     for (int i = lane; i < nf * M; i += 32) {
@@ -906,6 +933,8 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   p.feat_sums = feat_sums;
   p.stats_affine = plan->family == KF_FAST ? 1 : 0;
   p.out_dtype = d.out_dtype;
+  p.fill_unwritten = fast_skip_floor_tiles(plan) ? 1 : 0;
+  p.ec = epilogue_consts(d);
   if (d.clamp_kind != B2A_CLAMP_NONE) {
     if (d.clamp_kind == B2A_CLAMP_BATCH_MAX) {
       batch_max_kernel<<<1, 256, 0, st>>>(clip_max, a->batch);

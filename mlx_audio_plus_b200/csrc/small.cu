@@ -56,7 +56,12 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
     for (int k = 0; k < F; ++k) {
       X[k] = live ? make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T), __ldg(p.spec_im + base + (int64_t)k * p.T))
                   : make_float2(0.f, 0.f);
-      if (POLAR) X[k] = live ? polar_to_complex(p.polar, X[k]) : X[k];
+    }
+    // magnitude / phase -> complex in a SECOND pass: with the conversion (and its range-reduction branch) inside the load
+    // loop the 2 * F loads were issued one bin at a time, each waiting out an HBM round trip (C4: 1.32 ms, see DESIGN)
+    if (POLAR && live) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) X[k] = polar_to_complex(p.polar, X[k]);
     }
   }
   X[0].y = 0.f;   // irfft ignores Im(DC) and Im(Nyquist)

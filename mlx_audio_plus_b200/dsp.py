@@ -141,12 +141,17 @@ def istft(x, hop_length=None, win_length=None, window="hann", center=True, lengt
 
 
 def istft_polar(magnitude, phase, n_fft, hop_length, window, *, center=True, normalized=False, div_clamp=False,
-                div_eps=0.0, trim_tail=True, length=None, mag_clip_max=0.0, mag_clip_min_zero=False):
+                div_eps=0.0, trim_tail=True, length=None, mag_clip_max=0.0, mag_clip_min_zero=False, mag_log=False,
+                clip_stride=0):
     """iSTFT of a spectrum given as (magnitude, phase) planes of shape (B, F, T): the fused form of the
     `mag*cos(phase) + 1j*mag*sin(phase)` -> istft sequences in kokoro/istftnet.py:500-519, s3gen/hifigan.py:480-549
     and cosyvoice3/hifigan.py:447-499 — clip, cos / sin, inverse FFT, window, overlap-add and envelope division run
-    in ONE kernel; the complex spectrum never exists in HBM.  Not a reference name: the model-local drop-ins call it."""
+    in ONE kernel; the complex spectrum never exists in HBM.  Not a reference name: the model-local drop-ins call it.
+    `mag_log`: the magnitude plane holds log-magnitudes (`clip(exp(x), max=1e2)` of the Vocos head, vocos.py:129-130);
+    `clip_stride`: elements between clips when the two planes are halves of one (B, 2F, T) device buffer."""
     m, ph = ingest(magnitude, "float32"), ingest(phase, "float32")
+    if clip_stride and _is_strided_pair(magnitude, phase):  # views into one buffer: no copies, explicit clip stride
+        m.data, ph.data = magnitude, phase
     if m.data.ndim != 3 or tuple(m.data.shape) != tuple(ph.data.shape):
         raise ValueError("istft_polar expects magnitude / phase of identical shape (batch, freq, time)")
     if m.on_device != ph.on_device:
@@ -157,8 +162,18 @@ def istft_polar(magnitude, phase, n_fft, hop_length, window, *, center=True, nor
     plan = cached_plan(IstftPlan, _device_index(m), w, n_fft=int(n_fft), hop=int(hop_length), center=bool(center),
                        normalized=bool(normalized), div_clamp=bool(div_clamp), trim_tail=bool(trim_tail),
                        div_eps=float(div_eps), polar=True, mag_clip_max=float(mag_clip_max),
-                       mag_clip_min_zero=bool(mag_clip_min_zero))
-    return emit(m, plan.run(m, imag=ph, length=length))
+                       mag_clip_min_zero=bool(mag_clip_min_zero), mag_log=bool(mag_log))
+    return emit(m, plan.run(m, imag=ph, length=length, clip_stride=int(clip_stride)))
+
+
+def _is_strided_pair(a, b):
+    """Two float32 CUDA views of shape (B, F, T) whose (F, T) planes are dense: usable with an explicit clip stride."""
+    if type(a).__module__.split(".")[0] != "torch" or not (a.is_cuda and b.is_cuda):
+        return False
+    import torch
+
+    ok = lambda t: t.dtype == torch.float32 and t.ndim == 3 and t.stride(2) == 1 and t.stride(1) == t.shape[2]  # noqa: E731
+    return ok(a) and ok(b) and a.stride(0) == b.stride(0)
 
 
 @lru_cache(maxsize=None)

@@ -239,7 +239,7 @@ class FrontendPlan(_PlanBase):
 
 class IstftPlan(_PlanBase):
     def __init__(self, *, n_fft, hop, window, center=True, normalized=False, div_clamp=False, trim_tail=True,
-                 div_eps=0.0, polar=False, mag_clip_max=0.0, mag_clip_min_zero=False):
+                 div_eps=0.0, polar=False, mag_clip_max=0.0, mag_clip_min_zero=False, mag_log=False):
         super().__init__()
         window = np.ascontiguousarray(window, dtype=np.float32)
         d = L.IstftDesc()
@@ -250,6 +250,7 @@ class IstftPlan(_PlanBase):
         d.div_eps = float(div_eps)
         d.input_form = L.ISTFT_INPUT_POLAR if polar else L.ISTFT_INPUT_COMPLEX
         d.mag_clip_max, d.mag_clip_min_zero = float(mag_clip_max), int(bool(mag_clip_min_zero))
+        d.mag_log = int(bool(mag_log))
         self.desc = d
         self.n_fft, self.hop, self.n_freqs = int(n_fft), int(hop), n_fft // 2 + 1
         L.check(L.lib.b2a_istft_create(C.byref(d), window.ctypes.data_as(C.c_void_p), C.byref(self._h)))
@@ -259,15 +260,16 @@ class IstftPlan(_PlanBase):
         L.check(L.lib.b2a_istft_out_len(self._h, int(num_frames), -1 if length is None else int(length), C.byref(n)))
         return n.value
 
-    def run(self, ing: Ingested, imag: Ingested = None, *, length=None):
-        """ing.data: (B, F, T) complex64 — or float32 real plane with `imag` the imaginary plane."""
+    def run(self, ing: Ingested, imag: Ingested = None, *, length=None, clip_stride=0):
+        """ing.data: (B, F, T) complex64 — or float32 real plane with `imag` the imaginary plane.  `clip_stride` (elements
+        between clips; 0 = dense F * T) lets the two planes be halves of one (B, 2F, T) buffer."""
         x = ing.data
         B, F, T = (int(s) for s in x.shape)
         if F != self.n_freqs:
             raise ValueError(f"istft: {F} frequency bins do not match n_fft={self.n_fft} (needs {self.n_freqs})")
         n_out = self.out_len(T, length)
         a = L.InverseArgs()
-        a.clip_stride, a.num_frames, a.batch = 0, T, B
+        a.clip_stride, a.num_frames, a.batch = int(clip_stride), T, B
         a.length, a.out_clip_stride = (-1 if length is None else int(length)), 0
         if ing.on_device:
             import torch

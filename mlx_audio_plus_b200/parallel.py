@@ -102,13 +102,24 @@ def long_form_features(plan, signal_slice, shard: FrameShard, *, length: int, gl
 
 
 def gather_features(local, group=None):
-    """Optional all-gather of equally shaped feature shards along the frame/clip axis (reported separately from
-    throughput: the path itself needs no collective)."""
+    """Optional all-gather of feature shards along the frame / clip axis (axis 0) to every rank (reported separately from
+    throughput: the path itself needs no collective).  Frame ranges differ by at most one frame between ranks, so the
+    shard lengths are exchanged first and shorter shards travel zero-padded to the longest."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
-    parts = [torch.empty_like(local) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts, dim=0)
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    top = max(counts)
+    send = local.contiguous()
+    if send.shape[0] < top:
+        pad = torch.zeros((top - send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        send = torch.cat([send, pad], dim=0)
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)

@@ -353,6 +353,36 @@ def test_whisper_parity(golden):
     assert tuple(y30.shape) == (3100, 80)  # stt/tests/test_models.py contract: (N_FRAMES+100, n_mels)
 
 
+def test_whisper_all_silent_tiles_are_written_once_by_the_fixup():
+    """Digital silence covering whole 32-frame tiles: the fused kernel does not store such a tile (every value is the
+    epilogue's constant for zero power) and the clamp fix-up writes max(c, floor) there.  Against the oracle, and the
+    output buffer is poisoned first so an unwritten element cannot pass.  Cases: silence in the middle, at both ends, a
+    clip that is silent throughout (floor = c - 2: the constant itself survives), and a batch mixing them."""
+    from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
+
+    n = 16000 * 12
+    clips = []
+    for i, (a, b) in enumerate(((40000, 120000), (0, 70000), (100000, n), (0, n), (5117, 5117 + 160 * 40))):
+        x = synth(700 + i, n) * (0.3 + 0.2 * i)
+        x[a:b] = 0.0
+        clips.append(x)
+    xb = np.stack(clips)
+    torch.empty((5, 1200, 128), device="cuda").fill_(float("nan"))  # poison what the allocator hands out next
+    torch.cuda.synchronize()
+    yb = host(log_mel_spectrogram(dev(xb), n_mels=128))
+    assert np.isfinite(yb).all()
+    for i in range(5):
+        ref = W.whisper_log_mel(xb[i], 128)
+        assert np.abs(yb[i] - ref).max() <= 1e-4, i
+        torch.empty((1200, 128), device="cuda").fill_(float("nan"))
+        one = host(log_mel_spectrogram(dev(xb[i]), n_mels=128))
+        np.testing.assert_array_equal(one, yb[i])
+    assert np.all(yb[3] == yb[3][0, 0]) and abs(float(yb[3][0, 0]) - (-10.0 + 4.0) / 4.0) <= 1e-6  # silent clip: log10(1e-10)
+    y80 = host(log_mel_spectrogram(dev(xb), n_mels=80))  # the other generated instances of the family
+    for i in range(5):
+        assert np.abs(y80[i] - W.whisper_log_mel(xb[i], 80)).max() <= 1e-4
+
+
 def test_whisper_batch_per_clip_max():
     from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
 
@@ -373,8 +403,39 @@ def test_parakeet_parity(golden):
     pa2 = PreprocessArgs(16000, "all_features", 0.025, 0.01, "hamming", 64, 512, 0.0, pad_to=30000, pad_value=0.0, preemph=0.0)
     y2 = host(log_mel_spectrogram(dev(g["parakeet|x"]), pa2))
     assert np.abs(y2 - g["parakeet|global"]).max() <= 5e-4
-    # fp64-truth check: kernel error vs float64 pipeline <= 2x the float32 oracle's
-    x = g["parakeet|x"].astype(np.float64)
+
+
+def _parakeet_float64_truth(x, n_fft=512, hop=160, win=400, n_mels=80, preemph=0.97):
+    """parakeet/audio.py:39-78 evaluated in float64 end to end (the filterbank keeps its float32 VALUES: it is data)."""
+    from oracle import dsp_oracle as D
+
+    x = np.asarray(x, np.float64)
+    y = np.concatenate([x[:1], x[1:] - preemph * x[:-1]])
+    fr = y[D.frame_indices(len(y), n_fft, hop, True, "reflect")]
+    w = D._fit_window(D.hanning(win), n_fft).astype(np.float64)
+    p = np.abs(np.fft.rfft(fr * w, axis=1)) ** 2
+    fb = D.mel_filters(16000, n_fft, n_mels, norm="per_feature", mel_scale=None).astype(np.float64)
+    m = np.log(p @ fb.T + 1e-5)
+    return ((m - m.mean(0)) / (m.std(0) + 1e-5))[None]
+
+
+@pytest.mark.parametrize("seed,n", [(0, 24000), (3, 160000), (9, 480000)])
+def test_parakeet_error_against_float64_truth(golden, seed, n):
+    """err(kernel, float64 truth) <= 2 x err(float32 oracle, float64 truth) — the kernel is a float32
+    implementation of the same chain and may not be materially worse than the reference's own float32 arithmetic."""
+    from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram
+
+    x = golden("models")["parakeet|x"] if seed == 0 else synth(seed, n) * 0.7
+    pa = PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5)
+    truth = _parakeet_float64_truth(x)
+    ref = W.parakeet_log_mel(x, W.PreprocessArgs(16000, "per_feature", 0.025, 0.01, "hann", 80, 512, 1e-5)).astype(np.float64)
+    y = host(log_mel_spectrogram(dev(x), pa)).astype(np.float64)
+    assert y.shape == truth.shape == ref.shape
+    e_kernel, e_oracle = np.abs(y - truth), np.abs(ref - truth)
+    assert e_kernel.max() <= 2.0 * e_oracle.max() + 1e-6, (e_kernel.max(), e_oracle.max())
+    # (the oracle's FFT is NumPy's float64 transform rounded once — more accurate than MLX's single-precision pocketfft,
+    # so the max bound above is already tighter than the same test against MLX; the RMS gets an absolute bound)
+    assert np.sqrt((e_kernel ** 2).mean()) <= 1e-5
 
 
 def test_parakeet_returns_the_input_dtype(golden):
@@ -490,6 +551,62 @@ def test_c3_one_hour_file_full_size_vs_oracle():
         "sample_rate", "normalize", "window_size", "window_stride", "window", "features", "n_fft", "dither")}))
     assert ref.shape == (1, 360001, 80)
     assert np.abs(y.cpu().numpy() - ref).max() <= 5e-4
+
+
+def test_c4_full_batch_kokoro_istft_1024_items():
+    """BASELINE configs[3] at full size (B = 1024 x (11, 24 001) magnitude / phase, n_fft 20, hop 5): sampled items against the
+    oracle's MLXSTFT.inverse (<= 1e-5 of the peak), the batched launch bit-identical to single-item launches, and the
+    size-independent round trip transform(inverse(.)) -> inverse == identity on the waveform (Hann-20 / hop 5 is COLA)."""
+    from mlx_audio_plus_b200.tts.models.kokoro.istftnet import MLXSTFT
+
+    B, T = 1024, 24001
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    mag = torch.exp(0.5 * torch.randn((B, 11, T), generator=g, device="cuda")).clamp(max=1e2)
+    ph = torch.sin(torch.randn((B, 11, T), generator=g, device="cuda"))  # Kokoro: phase = sin(.) (istftnet.py:805)
+    st = MLXSTFT(filter_length=20, hop_length=5, win_length=20)
+    y = st.inverse(mag, ph)
+    assert tuple(y.shape) == (B, 1, 120000) and bool(torch.isfinite(y).all())
+    for i in (0, 5, B // 2, B - 1):
+        ref = W.kokoro_inverse(mag[i : i + 1].cpu().numpy(), ph[i : i + 1].cpu().numpy())
+        assert np.abs(y[i].cpu().numpy() - ref[0]).max() <= 1e-5 * np.abs(ref).max()
+        assert torch.equal(st.inverse(mag[i : i + 1].clone(), ph[i : i + 1].clone())[0], y[i])
+    m2, p2 = st.transform(y[:64, 0])  # a waveform that IS an iSTFT output survives stft -> istft
+    y2 = st.inverse(m2, p2)
+    assert float((y2[:, 0, 40:-40] - y[:64, 0, 40:-40]).abs().max()) <= 2e-5 * float(y[:64].abs().max())
+
+
+def test_c5_full_batch_vocos_forward_8192_and_inverse_1024():
+    """BASELINE configs[4] at full size: forward mel on B = 8192 x 5 s (sampled clips vs the oracle <= 1e-4, batched ==
+    alone bit for bit) and the iSTFT head's inverse on B = 1024 x (513, 468) (sampled items vs the oracle <= 1e-5 of the
+    peak, batched == alone, 119 552 samples per item as codec/tests/test_vocos.py:61-73 pins)."""
+    from mlx_audio_plus_b200.codec.models.vocos.mel import log_mel_spectrogram
+    from mlx_audio_plus_b200.dsp import hanning, istft
+
+    free, _ = torch.cuda.mem_get_info()
+    B = 8192 if free > 20e9 else 1024
+    x = _bench_like_batch(B, 120000, 24000, 1238)
+    y = log_mel_spectrogram(x)
+    assert tuple(y.shape) == (B, 468, 100) and bool(torch.isfinite(y).all())
+    for i in (0, 3, B // 2 + 1, B - 1):
+        ref = W.vocos_log_mel(x[i].cpu().numpy())[0]
+        assert np.abs(y[i].cpu().numpy() - ref).max() <= 1e-4
+        assert torch.equal(log_mel_spectrogram(x[i : i + 1].clone())[0], y[i])
+    del x, y
+    Bi = 1024
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    mag = torch.exp(0.5 * torch.randn((Bi, 513, 468), generator=g, device="cuda")).clamp(max=1e2)
+    ph = torch.randn((Bi, 513, 468), generator=g, device="cuda")
+    spec = torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)).contiguous()
+    del mag, ph
+    w = hanning(1024)
+    out = istft(spec, window=w, hop_length=256, win_length=1024)
+    assert tuple(out.shape) == (Bi, 119552)
+    for i in (0, 17, Bi - 1):
+        ref = O.istft(spec[i].cpu().numpy(), window=O.hanning(1024), hop_length=256, win_length=1024)
+        assert np.abs(out[i].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+        assert torch.equal(istft(spec[i].clone(), window=w, hop_length=256, win_length=1024), out[i])
 
 
 # ---- the step in front of the path: PCM -> resample -> mono (stt/utils.py:21-57) -------------------------------

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mlx_audio_plus_b200.parallel import clip_shard, frame_shards, num_frames, reduce_stats
+from mlx_audio_plus_b200.parallel import clip_shard, frame_shards, gather_features, num_frames, reduce_stats
 from oracle import dsp_oracle as D
 from oracle import wrappers_oracle as W
 from oracle.make_golden import synth
@@ -71,7 +71,9 @@ def _worker(rank, world, port, q):
         partw = (np.maximum(raww, mx.item() - np.float32(8.0)) + np.float32(4.0)) / np.float32(4.0)
         # ---- clip sharding ----------------------------------------------------------------------------------
         c0, c1 = clip_shard(7, world, rank)
-        q.put((rank, sh.frame_begin, part, shw.frame_begin, partw, (c0, c1)))
+        # ---- ragged all-gather of the shards (frame counts differ by one between the ranks) -------------------
+        full = gather_features(torch.from_numpy(np.ascontiguousarray(part))).numpy()
+        q.put((rank, sh.frame_begin, part, shw.frame_begin, partw, (c0, c1), full))
     finally:
         dist.destroy_process_group()
 
@@ -99,6 +101,9 @@ def test_frame_range_sharding_world2_gloo():
     gotw = np.concatenate([r[4] for r in res])
     assert gotw.shape == refw.shape and np.abs(gotw - refw).max() <= 1e-5
     assert [r[5] for r in res] == [(0, 4), (4, 7)]
+    assert res[0][2].shape[0] != res[1][2].shape[0]  # 251 frames over 2 ranks: ragged
+    for r in res:  # every rank ends up with the whole feature matrix
+        np.testing.assert_array_equal(r[6], got)
 
 
 @pytest.mark.parametrize("L,n_fft,hop,center,pre", [(57600, 512, 160, True, True), (48000, 400, 160, True, False),
