@@ -532,15 +532,17 @@ def run_parakeet_frames(ctx, steps, warmup, e2e_steps=0):
     xs = ctx.synth(1, sh.sample_hi - sh.sample_lo, SR, 1236)[0]
     group = None
 
+    obuf = torch.empty(plan.out_shape(1, sh.frame_count), dtype=torch.float32, device=ctx.dev)
+
     def step():
-        return long_form_features(plan, xs, sh, length=HOUR_LEN, global_frames=T, group=group)
+        return long_form_features(plan, xs, sh, length=HOUR_LEN, global_frames=T, group=group, out=obuf)
 
     y = step()
     assert tuple(y.shape) == (sh.frame_count, 80) and bool(torch.isfinite(y).all())
     ms = ctx.timed(step, steps, warmup)
     res = {"ms_per_step": ms, "value": 1.0 / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name,
            "shard": "frames", "frames_per_rank": sh.frame_count, "halo_samples": 512 - 160 + 1, "global_frames": T,
-           "collective": "all_reduce(SUM, 160 float64) + all_reduce(MAX, 1 float32) per step (NCCL)" if ctx.world > 1 else "none (1 rank)",
+           "collective": "one all_reduce(SUM, 160 float64) per step (NCCL)" if ctx.world > 1 else "none (1 rank)",
            "api": "parallel.long_form_features (partial -> reduce_stats -> finalize)", "gpu_launches_per_step": 3,
            "roofline": ctx.roofline(w, 1.0 / ctx.world, ms) | {"note": "whole step (2 launches + normalise sweep + all-reduce); one file is latency-bound, see parakeet_64x1h"}}
     if e2e_steps and ctx.world == 1:

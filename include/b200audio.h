@@ -245,6 +245,14 @@ int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_m
 /* (batch, rows, cols) float32 -> (batch, cols, rows_out) with zero columns from `rows` on: the (B, n_mels, T_padded) layout of
  * vad/models/sortformer/sortformer.py:112-118 (`pad_to`) from (B, T, n_mels) features, one pass. */
 int b2a_transpose_pad(const float* in, float* out, int64_t rows, int32_t cols, int64_t rows_out, int32_t batch, void* stream);
+/* Row-wise zero-mean / unit-variance of waveforms (rows, cols): (x - mean) / den over the first valid[row] samples (device int64
+ * array, or NULL = all), pad_value behind them.  den_kind 0: sqrt(var + eps) (transformers zero_mean_unit_var_norm: the Qwen3-ASR
+ * extractor's do_normalize); 1: max(std, eps) (vad/models/smart_turn/smart_turn.py:196-199).  ddof 0, float64 accumulation. */
+int b2a_rows_normalize(const float* in, float* out, int64_t rows, int64_t cols, const int64_t* valid, int32_t den_kind, float eps,
+                       float pad_value, void* stream);
+/* Phase unwrap along the last axis of (rows, cols) float32 (tts/models/kokoro/istftnet.py:418-452 mlx_unwrap, discont >= period / 2):
+ * one pass, float32 prefix sum of the 2 pi corrections. */
+int b2a_unwrap(const float* in, float* out, int64_t rows, int64_t cols, float discont, float period, void* stream);
 /* per-utterance CMVN, funasr/audio.py:160-164: out = (x - mean_t) / (std_t + eps) per feature column, mx.std (ddof 0);
  * x, out: (batch, rows, cols) float32 (may alias); stats_ws: device scratch of 2 * cols * batch doubles. */
 int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t rows, int32_t cols, float eps, double* stats_ws,

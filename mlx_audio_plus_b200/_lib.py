@@ -117,6 +117,8 @@ SYMBOLS = {
     "b2a_lfr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "b2a_transpose_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "b2a_rows_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
+    "b2a_unwrap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "b2a_cmvn_utterance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_int32,
                                      C.c_void_p]),
     "b2a_measure_fp32_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),

@@ -112,3 +112,45 @@ def lfr(features, lfr_m: int, lfr_n: int, cmvn_shift=None, cmvn_scale=None):
         L.check(L.lib.b2a_lfr(t.data_ptr(), T * M, T, M, int(lfr_m), int(lfr_n), sh.data_ptr() if sh is not None else None,
                               sc.data_ptr() if sc is not None else None, out.data_ptr(), 0, B, _stream()))
     return _back(features, out[0] if one else out)
+
+
+def rows_normalize(x, valid=None, *, den_kind: int = 0, eps: float = 1e-7, pad_value: float = 0.0):
+    """Row-wise zero-mean / unit-variance of waveforms, one launch: x (L,) or (B, L) float32 -> same shape.  `valid`: per-row
+    sample counts (the rest of a row becomes `pad_value`).  den_kind 0 = sqrt(var + eps) (transformers' zero_mean_unit_var_norm),
+    1 = max(std, eps) (smart_turn.py:196-199)."""
+    import torch
+
+    t = _to_cuda_f32(x)
+    one = t.ndim == 1
+    if one:
+        t = t[None]
+    B, n = t.shape
+    out = torch.empty_like(t)
+    v = None
+    if valid is not None:
+        v = torch.as_tensor(valid, dtype=torch.int64, device=t.device).contiguous()
+    if n > 0:
+        with torch.cuda.device(t.device):
+            L.check(L.lib.b2a_rows_normalize(t.data_ptr(), out.data_ptr(), B, n, v.data_ptr() if v is not None else None, int(den_kind),
+                                             float(eps), float(pad_value), _stream()))
+    return _back(x, out[0] if one else out)
+
+
+def unwrap(p, discont: float, period: float, axis: int = -1):
+    """Phase unwrap along `axis` (kokoro/istftnet.py:418-452), one launch over rows of the last axis."""
+    import torch
+
+    t = _to_cuda_f32(p)
+    moved = axis not in (-1, t.ndim - 1)
+    if moved:
+        t = t.movedim(axis, -1).contiguous()
+    shape = t.shape
+    n = int(shape[-1]) if t.ndim else 0
+    out = torch.empty_like(t)
+    rows = t.numel() // n if n else 0
+    if rows > 0:
+        with torch.cuda.device(t.device):
+            L.check(L.lib.b2a_unwrap(t.data_ptr(), out.data_ptr(), rows, n, float(discont), float(period), _stream()))
+    if moved:
+        out = out.movedim(-1, axis)
+    return _back(p, out)

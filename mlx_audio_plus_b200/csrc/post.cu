@@ -210,6 +210,99 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
 }
 
 }  // namespace
+
+// ---- waveform-side helpers of the drop-ins (one launch each instead of a chain of eager array ops) -----------------
+// block-wide sum of one double per thread (blockDim.x a multiple of 32, <= 1024); every thread gets the total
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// Row-wise zero-mean / unit-variance of waveforms (B, L): out = (x - mean) / den over the first `valid[b]` samples (all L
+// when valid == nullptr), `pad_value` behind them.  den_kind 0: sqrt(var + eps) — transformers' zero_mean_unit_var_norm
+// (the Qwen3-ASR extractor's do_normalize); 1: max(std, eps) — smart_turn.py:196-199.  Population variance (ddof 0), mean
+// and centred sum of squares accumulated in float64 (two sweeps over a row that stays in L2), one CTA per row.
+__global__ void __launch_bounds__(512) rows_normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t cols,
+                                                              const int64_t* __restrict__ valid, int den_kind, float eps, float pad_value) {
+  __shared__ double red[32];
+  const float* x = in + (int64_t)blockIdx.x * cols;
+  float* o = out + (int64_t)blockIdx.x * cols;
+  int64_t n = valid ? valid[blockIdx.x] : cols;
+  n = n < 0 ? 0 : (n > cols ? cols : n);
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+  const double cnt = n > 0 ? (double)n : 1.0;
+  const float mean = (float)(block_sum(s, red) / cnt);
+  double q = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = x[i] - mean;
+    q += (double)d * (double)d;
+  }
+  const float var = (float)(block_sum(q, red) / cnt);
+  const float den = den_kind == 0 ? sqrtf(var + eps) : fmaxf(sqrtf(var), eps);
+  for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) o[i] = i < n ? __fdiv_rn(x[i] - mean, den) : pad_value;
+}
+
+// Phase unwrap along the last axis (kokoro/istftnet.py:418-452, numpy.unwrap's algorithm in float32): out[t] = p[t] +
+// cumsum(corr)[t], corr[t] = wrap(p[t] - p[t-1]) - (p[t] - p[t-1]) where |p[t] - p[t-1]| >= discont, else 0.
+// One CTA per row; 4 consecutive samples per thread and sweep, block-wide inclusive scan of the thread sums (warp shuffles),
+// running carry across sweeps.  (The reference's cumsum is a float32 prefix sum whose rounding depends on the evaluation
+// order; this one associates per thread / warp / sweep — same magnitude of rounding error, not the same bits.)
+__device__ __forceinline__ float unwrap_corr(float cur, float prev, float discont, float period) {
+  const float hi = 0.5f * period, lo = -0.5f * period;
+  const float dd = __fsub_rn(cur, prev);
+  float ddmod = __fsub_rn(dd, __fmul_rn(period, floorf(__fdiv_rn(__fsub_rn(dd, lo), period))));
+  if (fabsf(__fsub_rn(dd, hi)) < 1e-10f && dd > 0.0f) ddmod = hi;
+  return fabsf(dd) < discont ? 0.0f : __fsub_rn(ddmod, dd);
+}
+
+__global__ void __launch_bounds__(256) unwrap_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t cols, float discont,
+                                                          float period) {
+  __shared__ float wsum[8];
+  __shared__ float s_carry;
+  const float* p = in + (int64_t)blockIdx.x * cols;
+  float* o = out + (int64_t)blockIdx.x * cols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0.0f;
+  __syncthreads();
+  for (int64_t base = 0; base < cols; base += 1024) {
+    const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+    float v[4], c[4];
+    float prev = (i0 > 0 && i0 - 1 < cols) ? p[i0 - 1] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = i0 + k;
+      v[k] = i < cols ? p[i] : 0.0f;
+      c[k] = (i > 0 && i < cols) ? unwrap_corr(v[k], prev, discont, period) : 0.0f;
+      prev = v[k];
+    }
+    c[1] += c[0];
+    c[2] += c[1];
+    c[3] += c[2];
+    float incl = c[3];  // inclusive scan of the thread totals across the warp, then across the 8 warps
+    for (int d = 1; d < 32; d <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    float off = s_carry;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    const float excl = off + (incl - c[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < cols) o[i0 + k] = v[k] + (excl + c[k]);
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = off + incl;
+    __syncthreads();
+  }
+}
+
 }  // namespace b2a
 
 using namespace b2a;
@@ -255,6 +348,27 @@ int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t
     cmvn_stats_kernel<1><<<grid, threads, 0, st>>>(in, cs, rows, cols, stats_ws);
     cmvn_apply_kernel<1><<<grid, threads, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
   }
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int b2a_rows_normalize(const float* in, float* out, int64_t rows, int64_t cols, const int64_t* valid, int32_t den_kind, float eps,
+                       float pad_value, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0 || rows > 2147483647LL || (den_kind != 0 && den_kind != 1)) {
+    set_error("rows_normalize: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  rows_normalize_kernel<<<(unsigned)rows, 512, 0, (cudaStream_t)stream>>>(in, out, cols, valid, den_kind, eps, pad_value);
+  B2A_CUDA(cudaGetLastError());
+  return B2A_OK;
+}
+
+int b2a_unwrap(const float* in, float* out, int64_t rows, int64_t cols, float discont, float period, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0 || rows > 2147483647LL || !(period > 0.0f)) {
+    set_error("unwrap: invalid argument");
+    return B2A_ERR_INVALID_ARG;
+  }
+  unwrap_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(in, out, cols, discont, period);
   B2A_CUDA(cudaGetLastError());
   return B2A_OK;
 }

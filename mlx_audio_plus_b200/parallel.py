@@ -69,33 +69,42 @@ def frame_shards(length: int, n_fft: int, hop: int, world: int, *, center: bool 
     return out
 
 
-def reduce_stats(clip_max, feat_sums, group=None):
+def reduce_stats(clip_max, feat_sums, group=None, *, need_max=True, need_sums=True):
     """All-reduce the cross-frame statistics of a frame-sharded signal (MAX for the clip maximum, SUM for the
-    per-feature sums).  Works on torch CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    per-feature sums).  Works on torch CUDA tensors (NCCL) and CPU tensors (gloo).  `need_max` / `need_sums` skip the
+    exchange a plan does not use (a clamping front-end needs only the maximum, a normalising one only the sums): one
+    collective per step instead of two — a frame-sharded step is latency-bound."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return clip_max, feat_sums
-    dist.all_reduce(clip_max, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(feat_sums, op=dist.ReduceOp.SUM, group=group)
+    if need_max:
+        dist.all_reduce(clip_max, op=dist.ReduceOp.MAX, group=group)
+    if need_sums:
+        dist.all_reduce(feat_sums, op=dist.ReduceOp.SUM, group=group)
     return clip_max, feat_sums
 
 
 def long_form_features(plan, signal_slice, shard: FrameShard, *, length: int, global_frames: int, group=None,
-                       valid_length=None, pad_value=0.0):
+                       valid_length=None, pad_value=0.0, out=None):
     """One rank's part of a frame-sharded long-form featurisation.  `signal_slice` is the torch CUDA tensor
     holding samples [shard.sample_lo, shard.sample_hi) (1-D).  Returns this rank's (frames, n_out) features,
-    clamped / normalised with the GLOBAL statistics."""
+    clamped / normalised with the GLOBAL statistics (whole-file statistics as parakeet/audio.py:66-69 and
+    whisper/audio.py:83 compute them).  `out`: optional preallocated (1, frames, n_out) float32 buffer."""
     import torch
 
+    from . import _lib as L
+
     x = signal_slice.reshape(1, -1).contiguous()
-    out = torch.empty(plan.out_shape(1, shard.frame_count), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(plan.out_shape(1, shard.frame_count), dtype=torch.float32, device=x.device)
     clip_max, feat_sums = plan.stats_tensors(1, x.device)
     if shard.frame_count > 0:
         plan.partial(x, out, clip_max, feat_sums, length=length, sample_offset=shard.sample_lo,
                      frame_begin=shard.frame_begin, frame_count=shard.frame_count, valid_length=valid_length,
                      pad_value=pad_value)
-    reduce_stats(clip_max, feat_sums, group)
+    reduce_stats(clip_max, feat_sums, group, need_max=plan.desc.clamp_kind != L.CLAMP_NONE,
+                 need_sums=plan.desc.norm_kind != L.NORM_NONE)
     if shard.frame_count > 0:
         plan.finalize(out, clip_max, feat_sums, global_frames=global_frames)
     return out[0]

@@ -138,13 +138,10 @@ class WhisperFeatureExtractor:
             for i, (c, n) in enumerate(zip(clips, lengths)):
                 t = c if _is_torch(c) else torch.from_numpy(np.ascontiguousarray(np.asarray(c, dtype=np.float32)))
                 batch[i, :n] = t[:n].to(device=dev, dtype=torch.float32)
-        if do_normalize:  # zero_mean_unit_var_norm over the valid samples, padding back to padding_value
-            valid_b = torch.arange(target, device=dev)[None, :] < len_t[:, None]
-            valid = valid_b.to(torch.float32)
-            cnt = valid.sum(1, keepdim=True)
-            mean = (batch * valid).sum(1, keepdim=True) / cnt
-            var = (((batch - mean) * valid) ** 2).sum(1, keepdim=True) / cnt
-            batch = torch.where(valid_b, (batch - mean) / torch.sqrt(var + 1e-7), torch.full_like(batch, float(self.padding_value)))
+        if do_normalize:  # zero_mean_unit_var_norm over the valid samples, padding back to padding_value: one launch
+            from ...._post import rows_normalize
+
+            batch = rows_normalize(batch, len_t, den_kind=0, eps=1e-7, pad_value=float(self.padding_value))
         if self.dither != 0.0:
             batch = batch + self.dither * torch.randn_like(batch)
         ing, _ = as_batch(batch)

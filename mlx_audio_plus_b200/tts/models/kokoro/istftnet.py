@@ -31,17 +31,14 @@ def mlx_unwrap(p, discont=None, axis=-1, period=2 * math.pi):
         discont = period / 2
     discont = max(discont, period / 2)
     hi, lo = period / 2, -period / 2
+    if _is_torch(p) and p.is_cuda:  # one kernel (csrc/post.cu unwrap_rows_kernel) instead of seven eager passes over (B, F, T)
+        from ...._post import unwrap
+
+        return unwrap(p, discont, period, axis)
     if _is_torch(p):
         import torch
 
-        dd = torch.diff(p, dim=axis)
-        ddmod = dd - period * torch.floor((dd - lo) / period)
-        ddmod = torch.where((torch.abs(dd - hi) < 1e-10) & (dd > 0), torch.full_like(dd, hi), ddmod)
-        corr = torch.where(torch.abs(dd) < discont, torch.zeros_like(dd), ddmod - dd)
-        shape = list(corr.shape)
-        shape[axis] = 1
-        corr = torch.cat([torch.zeros(shape, dtype=corr.dtype, device=corr.device), corr], dim=axis)
-        return p + torch.cumsum(corr, dim=axis)
+        return torch.from_numpy(mlx_unwrap(p.detach().numpy(), discont, axis, period))
     p = np.asarray(p, dtype=np.float32)
     dd = np.diff(p, axis=axis).astype(np.float32)
     ddmod = (dd - np.float32(period) * np.floor((dd - np.float32(lo)) / np.float32(period))).astype(np.float32)

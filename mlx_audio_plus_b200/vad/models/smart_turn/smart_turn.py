@@ -36,9 +36,10 @@ def prepare_audio_array(audio, config: ProcessorConfig = ProcessorConfig()):
             a = a[-max_samples:]
         elif a.shape[0] < max_samples:
             a = torch.nn.functional.pad(a, (max_samples - a.shape[0], 0))
-        if config.normalize_audio and a.numel() > 0:
-            std, mean = torch.std_mean(a, correction=0)
-            a = (a - mean) / torch.clamp(std, min=1e-7)
+        if config.normalize_audio and a.numel() > 0:  # (a - mean) / max(std, 1e-7), smart_turn.py:196-199: one launch
+            from ...._post import rows_normalize
+
+            a = rows_normalize(a.contiguous(), den_kind=1, eps=1e-7)
         return a.contiguous()
     a = np.asarray(audio.detach().numpy() if _is_torch(audio) else audio, dtype=np.float32)
     if a.ndim != 1:

@@ -11,7 +11,7 @@ for spec in "$@"; do
   if [ "$filt" != "-" ]; then
     env B2A_LIB="$PWD/$lib" $envs timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$filt" 2>&1 | tail -3
   fi
-  env B2A_LIB="$PWD/$lib" $envs timeout 90 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  env B2A_LIB="$PWD/$lib" $envs timeout 90 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
   echo "rc=$?"; tail -3 gpurun_out/ab_$tag.err
   python -c "import json;d=json.load(open('gpurun_out/ab_$tag.json'));print('ms/step %.3f kernel_ms %.3f frac %.3f'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac']))"
 done
