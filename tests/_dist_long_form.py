@@ -50,9 +50,12 @@ def main():
         res["whisper"] = gather_features(yw)
         # ---- clip sharding: each rank featurises its clips, no collective on the data path ---------------------
         clips = np.stack([synth(300 + i, 48000) * (0.2 + 0.1 * i) for i in range(7)])
-        c0, c1 = clip_shard(7, world, rank)
+        c0, c1 = clip_shard(7, world, rank)  # 7 clips: ragged over 2 / 4 ranks, and rank 7 of 8 owns NO clip
         from mlx_audio_plus_b200.stt.models.whisper.audio import log_mel_spectrogram
-        yc = log_mel_spectrogram(torch.from_numpy(clips[c0:c1]).to(dev), n_mels=80)
+        if c1 > c0:
+            yc = log_mel_spectrogram(torch.from_numpy(clips[c0:c1]).to(dev), n_mels=80)
+        else:
+            yc = torch.empty((0, 300, 80), dtype=torch.float32, device=dev)
         res["clips"] = gather_features(yc)
         torch.cuda.synchronize()
         if rank == 0:

@@ -39,7 +39,8 @@ def _launch(world, out_path, length):
         except subprocess.TimeoutExpired:
             for q in procs:
                 q.kill()
-            raise
+            tails = [(q.communicate()[0] or "")[-1500:] for q in procs]
+            raise AssertionError("multi-GPU worker timed out:\n" + "\n-----\n".join(tails))
         logs.append(out)
     for r, p in enumerate(procs):
         assert p.returncode == 0, f"rank {r} failed:\n{logs[r][-3000:]}"
