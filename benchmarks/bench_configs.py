@@ -252,6 +252,51 @@ def main():
                     "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
         del feats
         torch.cuda.empty_cache()
+    if want("G"):
+        # shapes the generic (any-n_fft) kernels serve: S3Gen mel 1920/480, Soprano head 2048/512, LFM2 detokenizer 1280/320,
+        # MossFormer2-SE chunk stft / istft 1920/384, Kaldi fbank (512-point after zero extension) — SURVEY 8a rows a10 / a12
+        from mlx_audio_plus_b200.codec.models.s3gen.mel import mel_spectrogram as s3gen_mel
+        from mlx_audio_plus_b200.dsp import compute_fbank_kaldi
+        from mlx_audio_plus_b200.sts.models.lfm_audio.detokenizer import istft_same
+        from mlx_audio_plus_b200.tts.models.soprano.decoder import ISTFTHead as SopranoHead
+        g = torch.Generator(device="cuda")
+        g.manual_seed(21)
+
+        def rec(name, kern, fn, in_bytes, secs):
+            out = fn()
+            ms = timeit(fn, a.steps)
+            by = in_bytes + out.numel() * out.element_size()
+            res.append({"config": name, "kernel": kern, "ms": ms, "audio_hours_per_s": secs / 3600.0 / (ms * 1e-3),
+                        "algorithmic_GBps": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)})
+
+        x24 = synth(1024, 240000, 24000, 1244)
+        rec("G s3gen mel 1024 x 10 s (1920/480, 80 mel) -> (B,80,T)", "forward 1920/480", lambda: s3gen_mel(x24), x24.numel() * 4, 1024 * 10)
+        del x24
+        xl = torch.randn((64, 469, 2050), generator=g, device="cuda") * 0.5
+        sh = SopranoHead(512, 2048, 512)
+        rec("G soprano head 64 x (469, 2050) -> 2048/512 istft", "inverse 2048/512 (polar, log-magnitude)", lambda: sh(xl)[0], xl.numel() * 4, 64 * 468 * 512 / 32000)
+        del xl
+        mag = torch.exp(0.3 * torch.randn((256, 375, 641), generator=g, device="cuda"))
+        ph = torch.randn((256, 375, 641), generator=g, device="cuda")
+        w = torch.hann_window(1280, device="cuda")
+        rec("G lfm2 detokenizer 256 x (375, 641) -> 1280/320 istft", "inverse 1280/320 (polar)", lambda: istft_same(mag, ph, w, 1280, 320), 2 * mag.numel() * 4, 256 * 375 * 320 / 24000)
+        del mag, ph
+        x48 = synth(256, 480000, 48000, 1245)
+        from mlx_audio_plus_b200.dsp import ISTFTCache, hamming, stft
+        wm = hamming(1920, periodic=False)
+        rec("G mossformer stft 256 x 10 s (1920/384, complex)", "forward 1920/384 complex", lambda: stft(x48, 1920, 384, 1920, wm, center=False), x48.numel() * 4, 2560)
+        spec = stft(x48, 1920, 384, 1920, wm, center=False)  # (B, T, F)
+        re, im = spec.real.transpose(1, 2).contiguous(), spec.imag.transpose(1, 2).contiguous()
+        del spec
+        cache = ISTFTCache()
+        rec("G mossformer ISTFTCache.istft 256 x (961, 1246) planes (1920/384)", "inverse 1920/384 (planar)",
+            lambda: cache.istft(re, im, 1920, 384, 1920, wm, center=False, audio_length=480000), 2 * re.numel() * 4, 2560)
+        del re, im
+        x16 = synth(1, 16000 * 3600, 16000, 1246)[0] * 8000.0  # compute_fbank_kaldi takes ONE waveform (dsp.py:607-608)
+        rec("G kaldi fbank 1 h (400/160 -> 512-point, 80 mel, povey)", "forward kaldi 512",
+            lambda: compute_fbank_kaldi(x16, sample_rate=16000, win_len=400, win_inc=160, num_mels=80, win_type="povey", dither=0.0), x16.numel() * 4, 3600)
+        del x16
+        torch.cuda.empty_cache()
     for r in res:
         print(json.dumps(r), flush=True)
     if a.out:

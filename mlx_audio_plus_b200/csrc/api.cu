@@ -11,6 +11,11 @@ using namespace b2a;
 
 namespace {
 
+// Radix plan of the generic shared-memory FFT (csrc/generic.cu run_fft).  Powers of two first — so that the product of the
+// radices already applied stays a power of two and the pass index is a mask, not a modulo — split into ceil(e / 5) passes of
+// near-equal radix <= 32; then 15, 25, 5, 3 and the remaining primes <= 31.  A trailing 2 / 4 merges with a 3 / 5 into one
+// 6 / 10 / 12 / 20 pass (register codelets for all of them: fft_regs.cuh).  1920 = 16 x 8 x 15, 2048 = 16 x 16 x 8,
+// 1280 = 16 x 16 x 5, 512 = 32 x 16, 320 = 16 x 20.
 int factorize(int n, int* radix, int* nstages) {
   int cnt = 0;
   auto push = [&](int r) -> bool {
@@ -18,13 +23,31 @@ int factorize(int n, int* radix, int* nstages) {
     radix[cnt++] = r;
     return true;
   };
-  while (n % 4 == 0) { if (!push(4)) return -1; n /= 4; }
-  while (n % 2 == 0) { if (!push(2)) return -1; n /= 2; }
-  while (n % 3 == 0) { if (!push(3)) return -1; n /= 3; }
+  int e = 0;
+  while (n % 2 == 0) { n /= 2; ++e; }
+  if (e > 0) {
+    const int passes = (e + 4) / 5, base = e / passes, rem = e % passes;
+    for (int i = 0; i < passes; ++i)
+      if (!push(1 << (base + (i < rem ? 1 : 0)))) return -1;
+  }
+  const int first_odd = cnt;
+  while (n % 15 == 0) { if (!push(15)) return -1; n /= 15; }
+  while (n % 25 == 0) { if (!push(25)) return -1; n /= 25; }
   while (n % 5 == 0) { if (!push(5)) return -1; n /= 5; }
+  while (n % 3 == 0) { if (!push(3)) return -1; n /= 3; }
   for (int p = 7; p <= kMaxGenericRadix && n > 1; p += 2)
     while (n % p == 0) { if (!push(p)) return -1; n /= p; }
   if (n != 1) return -1;
+  // merge the smallest power-of-two pass (the last one) with the first 3 / 5 pass when the product has a codelet
+  if (first_odd > 0 && first_odd < cnt) {
+    const int a = radix[first_odd - 1], b = radix[first_odd];
+    if ((a == 2 || a == 4) && (b == 3 || b == 5)) {
+      radix[first_odd - 1] = a * b;
+      for (int i = first_odd; i + 1 < cnt; ++i) radix[i] = radix[i + 1];
+      --cnt;
+      // the merged (non power of two) pass must come after every power-of-two pass: it already does (it was the last of them)
+    }
+  }
   if (cnt == 0) { radix[cnt++] = 1; }
   *nstages = cnt;
   return 0;

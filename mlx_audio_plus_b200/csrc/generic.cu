@@ -20,12 +20,13 @@
 #include <curand_kernel.h>
 
 #include "common.cuh"
+#include "fft_regs.cuh"
 
 namespace b2a {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 
 struct FftDesc {
   int n;
@@ -39,77 +40,51 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
+// Shared-memory FFT buffers are SKEWED: element e of a sequence lives at e + (e >> 4) (one float2 of padding per 16), sequences
+// are seq_pitch(n) float2 apart.  The first Stockham pass writes R consecutive outputs per thread, i.e. the lanes of a warp
+// store at a stride of R float2 — with R = 16 that is one bank pair for the whole warp (16-way conflicts on every store);
+// the skew turns every power-of-two stride into an odd one.
+__host__ __device__ __forceinline__ int skew(int e) { return e + (e >> 4); }
+__host__ __device__ __forceinline__ int seq_pitch(int n) { return n + (n >> 4) + 1; }
+
+// Exact idx / d for idx * d-independent small operands (idx < 2^20, d < 2^12): one multiply-high instead of a division sequence
+__device__ __forceinline__ int fast_div(int idx, int d, unsigned magic) {
+  (void)d;
+  return (int)__umulhi((unsigned)idx, magic);
+}
+__host__ __device__ inline unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+
 // One Stockham pass of radix R over `count` independent length-n sequences laid out back to back.
-// src/dst: [count][n] float2.  tw: W_n^k table.  Ns = product of the radices already applied.
-template <int R>
-__device__ __forceinline__ void butterfly(float2* v);
-
-template <>
-__device__ __forceinline__ void butterfly<2>(float2* v) {
-  float2 a = v[0], b = v[1];
-  v[0] = cadd(a, b);
-  v[1] = csub(a, b);
-}
-template <>
-__device__ __forceinline__ void butterfly<3>(float2* v) {
-  const float s = 0.86602540378443864676f;
-  float2 t1 = cadd(v[1], v[2]);
-  float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
-  float2 d = csub(v[1], v[2]);
-  float2 t3 = make_float2(s * d.y, -s * d.x);  // -i * s * d
-  v[0] = cadd(v[0], t1);
-  v[1] = cadd(t2, t3);
-  v[2] = csub(t2, t3);
-}
-template <>
-__device__ __forceinline__ void butterfly<4>(float2* v) {
-  float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
-  float2 c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
-  float2 md = make_float2(d.y, -d.x);  // -i * d
-  v[0] = cadd(a, c);
-  v[2] = csub(a, c);
-  v[1] = cadd(b, md);
-  v[3] = csub(b, md);
-}
-template <>
-__device__ __forceinline__ void butterfly<5>(float2* v) {
-  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-  float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
-  float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
-  float2 x0 = v[0];
-  v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
-  float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
-  float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
-  // -i * (s1 b1 + s2 b2),  -i * (s2 b1 - s1 b2)
-  float2 q1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
-  float2 q2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
-  v[1] = cadd(p1, q1);
-  v[4] = csub(p1, q1);
-  v[2] = cadd(p2, q2);
-  v[3] = csub(p2, q2);
-}
-
+// src / dst: [count][n] float2.  tw: W_n^k table (SHARED memory: the generic kernels stage it once per CTA — read from global
+// memory it put an L2 round trip into every butterfly).  Ns = product of the radices already applied.  The radix-R butterfly is
+// the register codelet of fft_regs.cuh (2, 3, 4, 5 hand written; 6, 8, 10, 12, 15, 16, 20, 25, 32 composed at compile time), so a
+// 1920-point transform is three passes (16 x 8 x 15) instead of six (4 x 4 x 4 x 2 x 3 x 5), 2048 is 16 x 16 x 8.
 template <int R>
 __device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ src, float2* __restrict__ dst,
                                                     const float2* __restrict__ tw, int n, int Ns, int count) {
   const int nb = n / R;            // butterflies per sequence
   const int tstep = n / (Ns * R);  // twiddle index stride
-  for (int idx = threadIdx.x; idx < count * nb; idx += blockDim.x) {
-    const int seq = idx / nb, j = idx - seq * nb;
-    const int k = j % Ns;
-    const float2* s = src + (size_t)seq * n;
+  const unsigned nb_magic = div_magic(nb);
+  const bool ns_pow2 = (Ns & (Ns - 1)) == 0;
+  const int total = count * nb;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int seq = nb > 1 ? fast_div(idx, nb, nb_magic) : idx;
+    const int j = idx - seq * nb;
+    const int k = ns_pow2 ? (j & (Ns - 1)) : (j % Ns);
+    const float2* sp = src + (size_t)seq * seq_pitch(n);
     float2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float2 x = s[j + r * nb];
-      if (r > 0) x = cmul(x, tw[k * r * tstep]);  // k*r < Ns*R  =>  index < n
-      v[r] = x;
-    }
-    butterfly<R>(v);
-    float2* d = dst + (size_t)seq * n + (j - k) * R + k;
+    for (int r = 0; r < R; ++r) v[r] = sp[skew(j + r * nb)];
+    if (Ns > 1) {  // first pass: k == 0, every twiddle is 1
+      const int kt = k * tstep;
 #pragma unroll
-    for (int r = 0; r < R; ++r) d[r * Ns] = v[r];
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[kt * r]);  // k * r < Ns * R  =>  index < n
+    }
+    regs::Dft<R>::run(v);
+    float2* d = dst + (size_t)seq * seq_pitch(n);
+    const int o0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[skew(o0 + r * Ns)] = v[r];
   }
 }
 
@@ -122,23 +97,24 @@ __device__ __forceinline__ void stockham_pass_any(const float2* __restrict__ src
   for (int idx = threadIdx.x; idx < count * nb; idx += blockDim.x) {
     const int seq = idx / nb, j = idx - seq * nb;
     const int k = j % Ns;
-    const float2* s = src + (size_t)seq * n;
+    const float2* sp = src + (size_t)seq * seq_pitch(n);
     float2 v[kMaxGenericRadix];
     for (int r = 0; r < R; ++r) {
-      float2 x = s[j + r * nb];
+      float2 x = sp[skew(j + r * nb)];
       if (r > 0) x = cmul(x, tw[k * r * tstep]);  // k*r < Ns*R  =>  index < n
       v[r] = x;
     }
-    float2* d = dst + (size_t)seq * n + (j - k) * R + k;
+    float2* d = dst + (size_t)seq * seq_pitch(n);
+    const int o0 = (j - k) * R + k;
     for (int q = 0; q < R; ++q) {
       float2 acc = v[0];
       for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(v[r], tw[((q * r) % R) * rstep]));
-      d[q * Ns] = acc;
+      d[skew(o0 + q * Ns)] = acc;
     }
   }
 }
 
-// Runs all passes; returns the buffer holding the result.  All threads must call.
+// Runs all passes; returns the buffer holding the result.  All threads must call.  `tw` lives in shared memory.
 __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2* tw, int count) {
   int Ns = 1;
   float2 *src = a, *dst = b;
@@ -149,6 +125,15 @@ __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2
       case 3: stockham_pass_fixed<3>(src, dst, tw, fd.n, Ns, count); break;
       case 4: stockham_pass_fixed<4>(src, dst, tw, fd.n, Ns, count); break;
       case 5: stockham_pass_fixed<5>(src, dst, tw, fd.n, Ns, count); break;
+      case 6: stockham_pass_fixed<6>(src, dst, tw, fd.n, Ns, count); break;
+      case 8: stockham_pass_fixed<8>(src, dst, tw, fd.n, Ns, count); break;
+      case 10: stockham_pass_fixed<10>(src, dst, tw, fd.n, Ns, count); break;
+      case 12: stockham_pass_fixed<12>(src, dst, tw, fd.n, Ns, count); break;
+      case 15: stockham_pass_fixed<15>(src, dst, tw, fd.n, Ns, count); break;
+      case 16: stockham_pass_fixed<16>(src, dst, tw, fd.n, Ns, count); break;
+      case 20: stockham_pass_fixed<20>(src, dst, tw, fd.n, Ns, count); break;
+      case 25: stockham_pass_fixed<25>(src, dst, tw, fd.n, Ns, count); break;
+      case 32: stockham_pass_fixed<32>(src, dst, tw, fd.n, Ns, count); break;
       default: stockham_pass_any(src, dst, tw, fd.n, Ns, count, R); break;
     }
     __syncthreads();
@@ -158,6 +143,12 @@ __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2
     dst = t;
   }
   return src;
+}
+
+// the twiddle table into shared memory, once per CTA (n float2 behind the kernel's other buffers)
+__device__ __forceinline__ void stage_twiddles(float2* tw_s, const float2* __restrict__ tw_g, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tw_s[i] = tw_g[i];
+  __syncthreads();
 }
 
 // Fire-and-forget float max (no read-back, so the issuing warp never waits on an HBM round trip):
@@ -210,14 +201,17 @@ __device__ __forceinline__ float fetch_sample(const FwdParams& p, const float* c
   return x;
 }
 
-__global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.n_fft, hop = p.hop, F = p.n_freqs, FT = p.frames_per_tile, PAIRS = FT / 2;
   const int span = (FT - 1) * hop + N;
+  const int NP = seq_pitch(N);  // skewed sequence pitch of the FFT buffers
   float2* bufA = reinterpret_cast<float2*>(smem_raw);
-  float2* bufB = bufA + (size_t)PAIRS * N;
-  float* xs = reinterpret_cast<float*>(bufB + (size_t)PAIRS * N);
+  float2* bufB = bufA + (size_t)PAIRS * NP;
+  float* xs = reinterpret_cast<float*>(bufB + (size_t)PAIRS * NP);
+  float2* tw_s = reinterpret_cast<float2*>(xs + ((span + 3) & ~3));  // [N] twiddles, staged once per CTA
   __shared__ float red_max[kThreads / 32], red_min[kThreads / 32];
+  if (!p.dump_frames) stage_twiddles(tw_s, p.tw, N);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -273,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
           a += p.dither * g.x;
           b += p.dither * g.y;
         }
-        bufA[i] = make_float2(a, b);
+        bufA[(size_t)pr * NP + skew(k)] = make_float2(a, b);
       }
       __syncthreads();
       float2* means = reinterpret_cast<float2*>(xs);  // the sample span is consumed: reuse it for the frame means
@@ -282,7 +276,7 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
         for (int pr = warp; pr < PAIRS; pr += nw) {
           float sa = 0.0f, sb = 0.0f;
           for (int k = lane; k < W; k += 32) {
-            const float2 v = bufA[(size_t)pr * N + k];
+            const float2 v = bufA[(size_t)pr * NP + skew(k)];
             sa += v.x;
             sb += v.y;
           }
@@ -300,10 +294,10 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
         float2 v = make_float2(0.0f, 0.0f);
         if (k < W) {
           const float2 m = p.frame_dc ? means[pr] : make_float2(0.0f, 0.0f);
-          const float2 x = bufA[i];
+          const float2 x = bufA[(size_t)pr * NP + skew(k)];
           v = make_float2(x.x - m.x, x.y - m.y);
           if (pe != 0.0f && k > 0) {  // separately rounded multiply and subtract, as the reference's array expression
-            const float2 xp = bufA[i - 1];
+            const float2 xp = bufA[(size_t)pr * NP + skew(k - 1)];
             v.x = __fsub_rn(v.x, __fmul_rn(pe, xp.x - m.x));
             v.y = __fsub_rn(v.y, __fmul_rn(pe, xp.y - m.y));
           }
@@ -311,10 +305,10 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
           v.x *= w;
           v.y *= w;
         }
-        bufB[i] = v;
+        bufB[(size_t)pr * NP + skew(k)] = v;
       }
       __syncthreads();
-      Z = run_fft(p.fft, bufB, bufA, p.tw, PAIRS);
+      Z = run_fft(p.fft, bufB, bufA, tw_s, PAIRS);
     } else {
       for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
         const int pr = i / N, k = i - pr * N;
@@ -322,10 +316,10 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
         const int fa = 2 * pr, fb = 2 * pr + 1;
         const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
         const float b = fb < nf ? xs[fb * hop + k] * w : 0.0f;
-        bufA[i] = make_float2(a, b);
+        bufA[(size_t)pr * NP + skew(k)] = make_float2(a, b);
       }
       __syncthreads();
-      Z = run_fft(p.fft, bufA, bufB, p.tw, PAIRS);
+      Z = run_fft(p.fft, bufA, bufB, tw_s, PAIRS);
     }
     float2* other = (Z == bufA) ? bufB : bufA;
 
@@ -334,8 +328,8 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
       float2* o = reinterpret_cast<float2*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * F;
       for (int i = threadIdx.x; i < nf * F; i += blockDim.x) {
         const int f = i / F, k = i - f * F;
-        const float2* z = Z + (size_t)(f >> 1) * N;
-        const float2 zk = z[k], zm = z[k == 0 ? 0 : N - k];
+        const float2* z = Z + (size_t)(f >> 1) * NP;
+        const float2 zk = z[skew(k)], zm = z[k == 0 ? 0 : skew(N - k)];
         float2 X;
         if ((f & 1) == 0) X = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         else X = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
@@ -349,8 +343,8 @@ __global__ void __launch_bounds__(kThreads) frontend_generic_kernel(const FwdPar
       const int f = i / F, k = i - f * F;
       float v = 0.0f;
       if (f < nf) {
-        const float2* z = Z + (size_t)(f >> 1) * N;
-        const float2 zk = z[k], zm = z[k == 0 ? 0 : N - k];
+        const float2* z = Z + (size_t)(f >> 1) * NP;
+        const float2 zk = z[skew(k)], zm = z[k == 0 ? 0 : skew(N - k)];
         float re, im;
         if ((f & 1) == 0) { re = 0.5f * (zk.x + zm.x); im = 0.5f * (zk.y - zm.y); }
         else { re = 0.5f * (zk.y + zm.y); im = 0.5f * (zm.x - zk.x); }
@@ -665,78 +659,113 @@ struct InvParams {
   float div_eps;
 };
 
-__global__ void __launch_bounds__(kThreads) istft_generic_kernel(const InvParams p) {
+// A CTA owns a contiguous range of S = frames_adv * hop OUTPUT samples and keeps their overlap-add sums in shared memory.
+// It inverse-transforms the frames that touch the range, a few pairs per round (two Hermitian spectra per complex FFT), in
+// ASCENDING frame order, and after every round each thread adds the round's windowed samples into the sums it owns — frame by
+// frame, so every output sample accumulates its frames in exactly the order of the reference's scatter-add (dsp.py:193-204).
+// Round 1 kept every windowed frame of the tile in shared memory instead (N floats per frame): with N = 1920 that left room for
+// 4 new frames per tile next to the 5 it had to recompute from its neighbours; the sums need hop floats per frame.
+__global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.n_fft, hop = p.hop, F = p.n_freqs;
+  const int NP = seq_pitch(N);  // skewed sequence pitch of the FFT buffers
   float2* bufA = reinterpret_cast<float2*>(smem_raw);
-  float2* bufB = bufA + (size_t)p.pairs_chunk * N;
-  float* Y = reinterpret_cast<float*>(bufB + (size_t)p.pairs_chunk * N);  // [frames_cap][N] windowed frames
+  float2* bufB = bufA + (size_t)p.pairs_chunk * NP;
+  float2* tw_s = bufB + (size_t)p.pairs_chunk * NP;         // [N] twiddles
+  float* win_s = reinterpret_cast<float*>(tw_s + N);        // [N] window
+  float* acc = win_s + N;                                    // [frames_adv * hop] overlap-add sums of the tile
   const float invN = 1.0f / (float)N;
-  const int64_t S = (int64_t)p.frames_adv * hop;
+  const int S = p.frames_adv * hop;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) win_s[i] = p.window[i];
+  stage_twiddles(tw_s, p.tw, N);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int clip_i = (int)(tile / p.tiles_per_clip);
     const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
     const int64_t j0 = (int64_t)tile_i * S;                   // first output index of this tile
-    const int64_t j1 = min(j0 + S, p.out_len);
+    const int64_t j1 = min(j0 + (int64_t)S, p.out_len);
+    const int s_tile = (int)(j1 - j0);
     const int64_t n0 = p.out_start + j0, n1 = p.out_start + j1;  // OLA coordinates [n0, n1)
     // frames touching [n0, n1): t*hop <= n1-1  and  t*hop + N - 1 >= n0
     int64_t t_lo = n0 - N + 1 <= 0 ? 0 : (n0 - N + 1 + hop - 1) / hop;
     int64_t t_hi = (n1 - 1) / hop;
     if (t_hi > p.T - 1) t_hi = p.T - 1;
     const int nfr = (int)(t_hi - t_lo + 1);
+    for (int i = threadIdx.x; i < s_tile; i += blockDim.x) acc[i] = 0.0f;
+    // (the first round's barrier below orders these stores before the first accumulation)
 
     for (int c0 = 0; c0 < nfr; c0 += 2 * p.pairs_chunk) {
       const int cf = min(2 * p.pairs_chunk, nfr - c0);  // frames in this round
       const int cp = (cf + 1) / 2;
       // load + pack: Z[k] = conj(Xa[k] + i Xb[k]) over the full Hermitian-extended spectrum, so that
-      // FFT(Z) = conj(N * (xa + i xb))
-      for (int i = threadIdx.x; i < cp * N; i += blockDim.x) {
-        const int pr = i / N, k = i - pr * N;
-        const int kk = k < F ? k : N - k;  // source bin (N even or odd: bins > N/2 mirror)
-        const bool mir = k >= F;
-        float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-        const int fa = c0 + 2 * pr, fb = fa + 1;
-        const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo;
-        if (fa < c0 + cf)
-          xa = p.spec ? p.spec[base + fa] : polar_to_complex(p.polar, make_float2(p.spec_re[base + fa], p.spec_im[base + fa]));
-        if (fb < c0 + cf)
-          xb = p.spec ? p.spec[base + fb] : polar_to_complex(p.polar, make_float2(p.spec_re[base + fb], p.spec_im[base + fb]));
-        // irfft ignores Im(DC) and, for even N, Im(Nyquist)
-        if (kk == 0 || (2 * kk == N)) { xa.y = 0.f; xb.y = 0.f; }
-        if (mir) { xa.y = -xa.y; xb.y = -xb.y; }
-        // z = xa + i xb ; store conj(z)
-        bufA[i] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
+      // FFT(Z) = conj(N * (xa + i xb)).  A thread owns a BIN and walks the round's frame pairs: the frames of a bin are
+      // adjacent in the (B, F, T) layout, so its loads fall into one or two 32-byte sectors (with bin-major threads every
+      // 4- or 8-byte load opened a sector of its own and the load phase, latency-bound, was most of the kernel), and each
+      // spectrum element is read once — the mirrored half of the extended spectrum is written from the same registers.
+      for (int kk = threadIdx.x; kk < F; kk += blockDim.x) {
+        const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0;
+        const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
+        const int km = (kk == 0 || 2 * kk == N) ? -1 : N - kk;  // mirrored position (bins > N/2), none for DC / Nyquist
+#pragma unroll 4
+        for (int pr = 0; pr < cp; ++pr) {
+          const int fa = 2 * pr, fb = fa + 1;
+          float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
+          if (p.spec) {
+            xa = p.spec[base + fa];
+            if (fb < cf) xb = p.spec[base + fb];
+          } else {  // all loads of the pair in flight before the (branchy) polar conversion
+            xa = make_float2(p.spec_re[base + fa], p.spec_im[base + fa]);
+            if (fb < cf) xb = make_float2(p.spec_re[base + fb], p.spec_im[base + fb]);
+            if (p.polar.polar) {
+              xa = polar_to_complex(p.polar, xa);
+              if (fb < cf) xb = polar_to_complex(p.polar, xb);
+            }
+          }
+          if (real_bin) { xa.y = 0.f; xb.y = 0.f; }
+          // z = xa + i xb ; store conj(z).  Mirrored bin: conj(xa) + i conj(xb)
+          bufA[(size_t)pr * NP + skew(kk)] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
+          if (km >= 0) bufA[(size_t)pr * NP + skew(km)] = make_float2(xa.x + xb.y, -(xb.x - xa.y));
+        }
       }
       __syncthreads();
-      float2* Z = run_fft(p.fft, bufA, bufB, p.tw, cp);
-      for (int i = threadIdx.x; i < cf * N; i += blockDim.x) {
-        const int f = i / N, k = i - f * N;
-        const float2 z = Z[(size_t)(f >> 1) * N + k];
-        const float v = ((f & 1) == 0 ? z.x : -z.y) * invN;
-        Y[(size_t)(c0 + f) * N + k] = v * p.window[k];
+      const float2* Z = run_fft(p.fft, bufA, bufB, tw_s, cp);
+      // accumulate: a thread owns output samples; for each it walks the round's frames in ascending order
+      const int64_t first = (t_lo + c0) * hop - n0;  // tile-relative position of sample 0 of the round's first frame
+      int lo = first < 0 ? 0 : (int)first;
+      int64_t hi64 = first + (int64_t)(cf - 1) * hop + N;
+      const int hi = hi64 > s_tile ? s_tile : (int)hi64;
+      for (int n = lo + threadIdx.x; n < hi; n += blockDim.x) {
+        float sum = acc[n];
+        int k = n - (int)first;  // sample index within frame f = 0; decreases by hop per frame
+        for (int f = 0; f < cf; ++f, k -= hop) {
+          if (k >= 0 && k < N) {
+            const float2 z = Z[(size_t)(f >> 1) * NP + skew(k)];
+            sum += (((f & 1) == 0 ? z.x : -z.y) * invN) * win_s[k];
+          }
+        }
+        acc[n] = sum;
       }
       __syncthreads();
     }
-    // gather overlap-add, ascending frame order
+    // envelope (position only, ascending frame order) and the division
     float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-      const int64_t n = p.out_start + j;
+    for (int i = threadIdx.x; i < s_tile; i += blockDim.x) {
+      const int64_t n = n0 + i;
       int64_t ta = n - N + 1 <= 0 ? 0 : (n - N + 1 + hop - 1) / hop;
       int64_t tb = n / hop;
       if (tb > p.T - 1) tb = p.T - 1;
-      float num = 0.f, den = 0.f;
-      for (int64_t t = ta; t <= tb; ++t) {
-        const int k = (int)(n - t * hop);
-        num += Y[(size_t)(t - t_lo) * N + k];
-        const float w = p.window[k];
+      float den = 0.f;
+      int k = (int)(n - ta * hop);
+      for (int64_t t = ta; t <= tb; ++t, k -= hop) {
+        const float w = win_s[k];
         den += p.norm_sq ? w * w : w;
       }
+      const float num = acc[i];
       float r;
       if (p.div_clamp) r = num / fmaxf(den, p.div_eps);
       else r = den > p.div_eps ? num / den : num;
-      o[j] = r;
+      o[j0 + i] = r;
     }
     __syncthreads();
   }
@@ -757,18 +786,22 @@ size_t generic_smem_limit(const b2a_plan* plan) {
   return 200 * 1024;
 }
 
+// dynamic shared memory of frontend_generic_kernel: sample span (padded to 16 bytes), two FFT buffers, twiddle table
+static size_t fwd_smem_bytes(int ft, int N, int hop) {
+  const size_t span = (size_t)(ft - 1) * hop + N;
+  return (size_t)4 * ((span + 3) & ~(size_t)3) + (size_t)16 * (ft / 2) * seq_pitch(N) + (size_t)8 * N;
+}
+
 static int choose_frames_per_tile(int N, int hop, size_t budget, int max_ft) {
   int best = 0;
-  for (int ft = 2; ft <= max_ft; ft += 2) {
-    size_t bytes = (size_t)4 * ((size_t)(ft - 1) * hop + N) + (size_t)16 * (ft / 2) * N;
-    if (bytes <= budget) best = ft;
-  }
+  for (int ft = 2; ft <= max_ft; ft += 2)
+    if (fwd_smem_bytes(ft, N, hop) <= budget) best = ft;
   return best;
 }
 
 int generic_tile_frames(const b2a_plan* plan, const b2a_forward_args* a) {
   const b2a_frontend_desc& d = plan->fd;
-  int ft = choose_frames_per_tile(d.n_fft, d.hop, 96 * 1024, 64);
+  int ft = choose_frames_per_tile(d.n_fft, d.hop, 200 * 1024, 64);
   if (ft == 0) ft = choose_frames_per_tile(d.n_fft, d.hop, generic_smem_limit(plan), 2);
   if (ft == 0) return 0;
   // small inputs: shrink tiles so that the grid still covers the SMs
@@ -830,7 +863,7 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   }
   p.frames_per_tile = ft;
   p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
-  const size_t smem = (size_t)4 * ((size_t)(ft - 1) * d.hop + d.n_fft) + (size_t)16 * (ft / 2) * d.n_fft;
+  const size_t smem = fwd_smem_bytes(ft, d.n_fft, d.hop);
   B2A_CUDA(cudaFuncSetAttribute(frontend_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -870,7 +903,7 @@ int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cud
   if (ft == 0) ft = 2;
   p.frames_per_tile = ft;
   p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
-  const size_t smem = (size_t)4 * ((size_t)(ft - 1) * d.hop + d.n_fft) + (size_t)16 * (ft / 2) * d.n_fft;
+  const size_t smem = fwd_smem_bytes(ft, d.n_fft, d.hop);
   B2A_CUDA(cudaFuncSetAttribute(frontend_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * 2);
@@ -995,17 +1028,22 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.fft = make_fft_desc(plan);
   if (len <= 0) return B2A_OK;
   const int ov = (N + hop - 1) / hop;  // frames overlapping one sample (upper bound)
-  // pick frames_adv so that Y + FFT buffers fit in ~100 KB (up to the hard limit for huge N)
-  int pairs_chunk = N <= 256 ? 8 : (N <= 1024 ? 2 : 1);
-  size_t fft_bytes = (size_t)16 * pairs_chunk * N;
+  // a few pairs per FFT round (enough butterflies for the CTA), then as many new frames per tile as ~100 KB hold (two CTAs per
+  // SM); every tile re-transforms the ov - 1 frames it shares with its left neighbour, so larger tiles waste less
+  int pairs_chunk = 4096 / N;
+  pairs_chunk = pairs_chunk < 1 ? 1 : (pairs_chunk > 16 ? 16 : pairs_chunk);
+  auto smem_for = [&](int pc, int adv) { return (size_t)16 * pc * seq_pitch(N) + (size_t)8 * N + (size_t)4 * N + (size_t)4 * adv * hop + 16; };
   int adv = 0;
-  for (int cand = 1; cand <= 256; cand *= 2) {
-    size_t bytes = fft_bytes + (size_t)4 * N * (cand + ov);
-    if (bytes <= 100 * 1024) adv = cand;
+  for (int cand = 1; cand <= 1024; cand *= 2)
+    if (smem_for(pairs_chunk, cand) <= 200 * 1024 && cand * hop <= (1 << 20)) adv = cand;
+  if (adv < 4 * ov) {  // large transforms: one CTA per SM, all of its shared memory
+    for (int cand = adv > 0 ? adv : 1; cand <= 1024; cand *= 2)
+      if (smem_for(pairs_chunk, cand) <= generic_smem_limit(plan)) adv = cand;
   }
   if (adv == 0) {
+    pairs_chunk = 1;
     adv = 1;
-    if (fft_bytes + (size_t)4 * N * (adv + ov) > generic_smem_limit(plan)) {
+    if (smem_for(1, 1) > generic_smem_limit(plan)) {
       set_error("n_fft=%d / hop=%d too large for the generic iSTFT kernel", N, hop);
       return B2A_ERR_UNSUPPORTED;
     }
@@ -1017,7 +1055,7 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.pairs_chunk = pairs_chunk;
   const int64_t S = (int64_t)adv * hop;
   p.tiles_per_clip = (int)((len + S - 1) / S);
-  const size_t smem = fft_bytes + (size_t)4 * N * p.frames_cap;
+  const size_t smem = smem_for(pairs_chunk, adv);
   B2A_CUDA(cudaFuncSetAttribute(istft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
