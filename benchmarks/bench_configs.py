@@ -158,12 +158,15 @@ def main():
             r = {"config": f"R load_audio {nm}", "kernel": "resample_kernel", "batch": 1, "samples": n, "ms": ms,
                  "audio_hours_per_s": secs / 3600.0 / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
                  "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak(), "out_shape": list(out.shape)}
-            try:
+            try:  # the reference's own call (stt/utils.py:21-29: scipy.signal.resample_poly per channel, then the channel mean)
                 import time
-                from oracle import pre_oracle as P
-                sub = pcm[: orig * 60].cpu().numpy()
+                from math import gcd
+
+                from scipy.signal import resample_poly
+                sub = pcm[: orig * 60].cpu().numpy().astype(np.float32) / 32768.0
+                g_ = gcd(orig, 16000)
                 t0 = time.perf_counter()
-                P.load_audio_from_pcm(sub, orig, 16000)
+                resample_poly(sub, 16000 // g_, orig // g_, axis=0, padtype="edge").mean(axis=1)
                 r["scipy_cpu_1core_audio_hours_per_s"] = (60 / 3600.0) / (time.perf_counter() - t0)
             except Exception as e:  # noqa: BLE001
                 r["scipy_cpu_1core_audio_hours_per_s"] = str(e)

@@ -12,8 +12,8 @@ for k,v in d['workloads'].items():
     print(k, 'ms %.3f value %.0f bound %s binding_frac %.3f hbm_frac %.3f e2e %s cpu %s' % (v['ms_per_step'], v['value'], v['roofline']['bound'], v['roofline']['binding_frac'], v['roofline']['frac'], v.get('e2e',{}).get('value'), (v.get('cpu_baseline') or {}).get('value')))
 print(d['variants']); print(d['e2e_api'])
 P
-timeout 300 python benchmarks/sanitize_cases.py > gpurun_out/a_sanitize_plain.log 2>&1; echo "sanitize plain rc=$?"; tail -3 gpurun_out/a_sanitize_plain.log
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python benchmarks/sanitize_cases.py > gpurun_out/a_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/a_memcheck.log
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python benchmarks/sanitize_cases.py k1_400 k1_512 k1c_stft k3_istft k4_small > gpurun_out/a_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/a_racecheck.log
+timeout 300 python tests/sanitize_cases.py > gpurun_out/a_sanitize_plain.log 2>&1; echo "sanitize plain rc=$?"; tail -3 gpurun_out/a_sanitize_plain.log
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/sanitize_cases.py > gpurun_out/a_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/a_memcheck.log
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python tests/sanitize_cases.py k1_400 k1_512 k1c_stft k3_istft k4_small > gpurun_out/a_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/a_racecheck.log
 CMD="python bench.py --clips 512 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/a_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/a_launches.csv $CMD > gpurun_out/a_ncu_l.log 2>&1; echo "ncu list rc=$?"

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""Smallest case of every kernel family, for `compute-sanitizer --tool memcheck|racecheck|synccheck python benchmarks/sanitize_cases.py`
-(logs committed under profiles/).  Each case is checked against the oracle as well, so a clean sanitizer run is also a
-correct run."""
+"""Smallest case of every kernel family, for `compute-sanitizer --tool memcheck|racecheck|synccheck python tests/sanitize_cases.py`
+(SURVEY 5).  Each case is checked against the oracle as well, so a clean sanitizer run is also a correct run.
+Round 2: compute-sanitizer is CLOSED on this GPU pool (the wrapper exits 86 with "compute-sanitizer is closed on this pool and
+stays closed", profiles/r02_compute_sanitizer.txt), so the committed evidence is this script's plain run plus what stands in for
+memcheck in the suite: outputs allocated from poisoned (NaN-filled) memory where a kernel may skip stores
+(test_whisper_all_silent_tiles...), ragged / edge lengths for every kernel family, and bit-identical batched-vs-single launches."""
 import os
 import sys
 
