@@ -55,6 +55,9 @@ class WhisperFeatureExtractor:
         self.n_samples = chunk_length * sampling_rate
         self.nb_max_frames = self.n_samples // hop_length
         self.mel_filters = mel_filter_bank_slaney(1 + n_fft // 2, feature_size, 0.0, 8000.0, sampling_rate)
+        # (n_mels, F) float32, made once and read-only: the plan cache fingerprints a read-only table once, not per call
+        self._fb = np.ascontiguousarray(self.mel_filters.T, dtype=np.float32)
+        self._fb.setflags(write=False)
 
     # -- transformers' SequenceFeatureExtractor.pad for one float feature per time step ------------------------------------
     def _pad(self, clips, padding, max_length, truncation, pad_to_multiple_of):
@@ -146,7 +149,7 @@ class WhisperFeatureExtractor:
             batch = batch + self.dither * torch.randn_like(batch)
         ing, _ = as_batch(batch)
         feats = run_frontend(
-            ing, hanning(self.n_fft, True), np.ascontiguousarray(self.mel_filters.T, dtype=np.float32), n_fft=self.n_fft,
+            ing, hanning(self.n_fft, True), self._fb, n_fft=self.n_fft,
             hop=self.hop_length, center=True, pad_mode="reflect", drop_last=True, spec_kind=L.SPEC_POWER,
             log_kind=L.LOG_LOG10, guard_kind=L.GUARD_MAX, guard_eps=1e-10, clamp_kind=L.CLAMP_CLIP_MAX, clamp_value=8.0,
             affine_add=4.0, affine_div=4.0, out_layout=L.LAYOUT_MT)  # (B, n_mels, T)
