@@ -52,8 +52,9 @@ WORKLOADS = {
     "vocos_mel": dict(unit="5 s clip", sec=5.0, bytes=1424 * VOC_T, flops=30800.0 * VOC_T, units=8192, cpu="vocos_mel"),
     "vocos_istft": dict(unit="5 s item, (513, 468) complex64", sec=119552 / 24000.0, bytes=5128 * VOC_T, flops=27900.0 * VOC_T, units=1024, cpu="vocos_istft"),
 }
-# kernels of ours launched per step (profiles/r02_launches_summary.csv lists them by name)
-LAUNCHES = {"whisper128_30s": 3, "whisper80_30s": 3, "parakeet_1h": 3, "parakeet_64x1h": 3, "kokoro_istft": 1, "vocos_mel": 1, "vocos_istft": 1}
+# kernels of ours per step when the library's counter is unavailable (bench.py reads b2a_launch_count() around every timed loop;
+# profiles/r02_launches_summary.csv lists the kernels by name).  The clamping Whisper forward is ONE cooperative launch.
+LAUNCHES = {"whisper128_30s": 1, "whisper80_30s": 1, "parakeet_1h": 3, "parakeet_64x1h": 3, "kokoro_istft": 1, "vocos_mel": 1, "vocos_istft": 1}
 
 
 def synth_clip_np(i: int, n: int = CLIP_LEN, sr: int = SR) -> np.ndarray:
@@ -328,15 +329,20 @@ class Ctx:
 
     def timed(self, fn, steps, warmup=3, collective=True):
         """ms per step: `warmup` untimed steps, then exactly `steps` steps between two CUDA events on the launch stream,
-        bracketed by barrier + synchronize on both sides; max over ranks."""
+        bracketed by barrier + synchronize on both sides; max over ranks.  The library's own launch counter is read on both
+        sides of the timed loop: `self.last_launches` = kernels of ours launched inside the timed region (this rank)."""
+        from mlx_audio_plus_b200 import _lib as L
+
         for _ in range(warmup):
             fn()
         self.barrier() if collective else self.torch.cuda.synchronize()
         e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        n0 = int(L.lib.b2a_launch_count())
         e0.record(self.stream)
         for _ in range(steps):
             fn()
         e1.record(self.stream)
+        self.last_launches = int(L.lib.b2a_launch_count()) - n0
         self.barrier() if collective else self.torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         return self.max_over_ranks(ms) if collective else ms
@@ -449,7 +455,7 @@ def run_whisper(ctx, name, B, steps, warmup, *, e2e_steps=0, silence_frac=0.0, p
         L.check(L.lib.b2a_frontend_partial(plan._h, C.byref(args), ctx.sp))
 
     ms = ctx.timed(step, steps, warmup)
-    res = {"ms_per_step": ms, "units_per_rank": B, "kernel": plan.kernel_name, "frames_per_clip": T}
+    res = {"ms_per_step": ms, "units_per_rank": B, "kernel": plan.kernel_name, "frames_per_clip": T, "gpu_launches": ctx.last_launches}
     if kernel_alone:  # dominant kernel alone (init_stats + fused kernel, no finalize), same stream, CUDA events
         res["kernel_ms"] = ctx.timed(step_partial, steps, 1, collective=False)
         step()  # leave finalized features in `out` (partial() alone skips the clamp)
@@ -540,10 +546,10 @@ def run_parakeet_frames(ctx, steps, warmup, e2e_steps=0):
     y = step()
     assert tuple(y.shape) == (sh.frame_count, 80) and bool(torch.isfinite(y).all())
     ms = ctx.timed(step, steps, warmup)
-    res = {"ms_per_step": ms, "value": 1.0 / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name,
+    res = {"ms_per_step": ms, "value": 1.0 / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name, "gpu_launches": ctx.last_launches,
            "shard": "frames", "frames_per_rank": sh.frame_count, "halo_samples": 512 - 160 + 1, "global_frames": T,
            "collective": "one all_reduce(SUM, 160 float64) per step (NCCL)" if ctx.world > 1 else "none (1 rank)",
-           "api": "parallel.long_form_features (partial -> reduce_stats -> finalize)", "gpu_launches_per_step": 3,
+           "api": "parallel.long_form_features (partial -> reduce_stats -> finalize)",
            "roofline": ctx.roofline(w, 1.0 / ctx.world, ms) | {"note": "whole step (2 launches + normalise sweep + all-reduce); one file is latency-bound, see parakeet_64x1h"}}
     if e2e_steps and ctx.world == 1:
         from mlx_audio_plus_b200.stt.models.parakeet.audio import PreprocessArgs, log_mel_spectrogram
@@ -570,9 +576,10 @@ def run_parakeet_batch(ctx, B, steps, warmup):
     out = torch.empty((B, T, 80), dtype=torch.float32, device=ctx.dev)
     args = plan._args(x.data_ptr(), HOUR_LEN, HOUR_LEN, HOUR_LEN, B, out.data_ptr())
     ms = ctx.timed(lambda: L.check(L.lib.b2a_frontend_forward(plan._h, C.byref(args), ctx.sp)), steps, warmup)
+    nl = ctx.last_launches
     kms = ctx.timed(lambda: L.check(L.lib.b2a_frontend_partial(plan._h, C.byref(args), ctx.sp)), steps, 1, collective=False)
     res = {"ms_per_step": ms, "value": ctx.world * B / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name,
-           "units_per_rank": B, "shard": "clips", "gpu_launches_per_step": 3,
+           "units_per_rank": B, "shard": "clips", "gpu_launches": nl,
            "roofline": ctx.roofline(w, B, kms) | {"step_binding_frac_incl_normalise_sweep": None}}
     r = res["roofline"]
     r["step_binding_frac_incl_normalise_sweep"] = r["binding_frac"] * kms / ms
@@ -597,7 +604,7 @@ def run_vocos_mel(ctx, B, steps, warmup, e2e_steps=0):
     args = plan._args(x.data_ptr(), VOC_LEN, VOC_LEN, VOC_LEN, B, out.data_ptr())
     ms = ctx.timed(lambda: L.check(L.lib.b2a_frontend_forward(plan._h, C.byref(args), ctx.sp)), steps, warmup)
     res = {"ms_per_step": ms, "value": ctx.world * B * 5.0 / 3600.0 / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name,
-           "units_per_rank": B, "shard": "clips", "gpu_launches_per_step": 1, "roofline": ctx.roofline(w, B, ms)}
+           "units_per_rank": B, "shard": "clips", "gpu_launches": ctx.last_launches, "roofline": ctx.roofline(w, B, ms)}
     if e2e_steps:
         hx = torch.empty((B, VOC_LEN), dtype=torch.float32, pin_memory=True)
         hx.copy_(x)
@@ -647,7 +654,18 @@ def run_istft(ctx, name, B, steps, warmup, e2e_steps=0):
     sec_unit = w["sec"]
     res = {"ms_per_step": ms, "value": ctx.world * B * sec_unit / 3600.0 / (ms * 1e-3), "unit": "audio-hours/s", "kernel": plan.kernel_name,
            "units_per_rank": B, "shard": "clips", "input_form": "magnitude / phase planes" if polar else "complex64",
-           "gpu_launches_per_step": 1, "roofline": ctx.roofline(w, B, ms)}
+           "gpu_launches": ctx.last_launches, "roofline": ctx.roofline(w, B, ms)}
+    if name == "kokoro_istft":  # the same spectra as ONE complex64 tensor (round 1's C4 figure): what the cos / sin inside the kernel cost
+        planc = IstftPlan(n_fft=20, hop=5, window=np.asarray(hanning(21)[:-1]), center=True)
+        spec = torch.complex(hold[0] * torch.cos(hold[1]), hold[0] * torch.sin(hold[1])).contiguous()
+        ac = L.InverseArgs()
+        ac.spec, ac.spec_imag = spec.data_ptr(), None
+        ac.clip_stride, ac.num_frames, ac.batch, ac.length, ac.out_clip_stride, ac.out = 0, T, B, -1, 0, out.data_ptr()
+        msc = ctx.timed(lambda: L.check(L.lib.b2a_istft_inverse(planc._h, C.byref(ac), ctx.sp)), steps, warmup)
+        res["complex_input"] = {"ms_per_step": msc, "hbm_frac": float(w["bytes"]) * B / (msc * 1e-3) / 1e9 / ctx.peak,
+                                "note": "same items handed over as complex64 (mag * exp(i phase) formed beforehand)"}
+        L.check(L.lib.b2a_istft_inverse(plan._h, C.byref(a), ctx.sp))  # `out` holds the polar result again (checked below)
+        del spec, planc
     if e2e_steps:
         hs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in hold]
         for h, t in zip(hs, hold):
@@ -703,9 +721,16 @@ def run_api(ctx):
     e1.record()
     torch.cuda.synchronize()
     res["c1_us_per_call_back_to_back_device"] = e0.elapsed_time(e1) / 200 * 1e3  # launch-rate bound: wrapper + 3 launches
+    # the same clip with 128 mels: a grid this small takes the single cooperative launch (statistics, grid barrier and clamp
+    # fix-up inside the fused kernel) instead of init_stats + kernel + fix-up
+    from mlx_audio_plus_b200 import _lib as L
+    n0 = int(L.lib.b2a_launch_count())
+    res["c1_128mel_latency_us_torch_cuda_in"] = lat(lambda: log_mel_spectrogram(xd, n_mels=128))
+    res["c1_128mel_launches_per_call"] = (int(L.lib.b2a_launch_count()) - n0) / 220.0
     res["c1_audio_hours_per_s_back_to_back"] = 30.0 / 3600.0 / (res["c1_us_per_call_back_to_back_device"] * 1e-6)
     # per-clip loop (how the reference batches: dsp.py:131 is 1-D only) vs one batched call, host NumPy arrays, 128 mels
     xs = np.stack([synth_clip_np(i) for i in range(64)])
+    log_mel_spectrogram(xs[0], n_mels=128)  # plan + staging buffers of the host path exist before the clock starts
     t0 = time.perf_counter()
     for i in range(64):
         log_mel_spectrogram(xs[i], n_mels=128)
@@ -781,7 +806,7 @@ def main():
         return hi - lo
 
     sampler = ClockSampler(ctx.local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("B2A_BENCH_NO_SAMPLER"):  # (development: A/B of the sampler's own perturbation)
         sampler.start()
         time.sleep(0.25)
 
@@ -814,7 +839,7 @@ def main():
                    "l2_policy": "inputs + outputs per step far exceed the 126 MB L2 at N <= 8 (headline: 14.2 GB / N per rank)",
                    "kernel": h["kernel"]},
         "roofline": h["roofline"], "cpu_baseline": cpu.get(w["cpu"]), "e2e": h.get("e2e"),
-        "gpu_launches": LAUNCHES[name] * a.steps, "clocks": clocks,
+        "gpu_launches": h.get("gpu_launches", LAUNCHES[name] * a.steps), "clocks": clocks,
     }
     if "e2e_i16_f16" in h:
         line["e2e_i16_f16"] = h["e2e_i16_f16"]

@@ -158,6 +158,7 @@ typedef struct b2a_plan b2a_plan;
 int b2a_version(void);
 const char* b2a_last_error(void);
 int b2a_device_count(void); /* 0 when no CUDA device / driver: compute calls will fail loudly */
+unsigned long long b2a_launch_count(void); /* kernels this library has launched in this process (all plans, all streams) */
 
 /* ---- host-side tables (no GPU needed) ------------------------------------------------------------
  * b2a_window: dsp.py:33-79 — float64 cosine evaluated per tap, rounded to float32.

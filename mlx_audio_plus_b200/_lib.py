@@ -93,6 +93,7 @@ SYMBOLS = {
     "b2a_frame_source_index": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "b2a_istft_geometry": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b2a_frontend_create": (C.c_int, [C.POINTER(FrontendDesc), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2a_launch_count": (C.c_ulonglong, []),
     "b2a_plan_destroy": (C.c_int, [C.c_void_p]),
     "b2a_frontend_out_frames": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "b2a_frontend_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),

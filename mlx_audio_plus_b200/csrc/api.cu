@@ -9,6 +9,12 @@
 
 using namespace b2a;
 
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+namespace b2a {
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace b2a
+
 namespace {
 
 // Radix plan of the generic shared-memory FFT (csrc/generic.cu run_fft).  Powers of two first — so that the product of the
@@ -152,6 +158,7 @@ size_t stats_bytes(const b2a_plan* p, int batch) {
 struct StatPtrs {
   float* clip_max;
   float* tile_min;
+  float* tile_max;  // fast family: [tiles] behind tile_min
   int tile_frames;
   double* feat_sums;
 };
@@ -160,11 +167,13 @@ int stats_tile_frames(const b2a_plan* p, const b2a_forward_args* a) {
   int tf = p->family == KF_FAST ? 32 : generic_tile_frames(p, a);
   return tf > 0 ? tf : 2;
 }
-size_t tilemin_count(const b2a_plan* p, const b2a_forward_args* a) {
+size_t tile_count(const b2a_plan* p, const b2a_forward_args* a) {
   const int tf = stats_tile_frames(p, a);
   const size_t tiles = (size_t)a->batch * (size_t)((a->frame_count + tf - 1) / tf);
   return tiles > 0 ? tiles : 1;
 }
+// floats of per-tile statistics a call needs: minima, and for the fast family maxima behind them (single-launch forward)
+size_t tilemin_count(const b2a_plan* p, const b2a_forward_args* a) { return tile_count(p, a) * (p->family == KF_FAST ? 2 : 1); }
 // a caller-owned workspace of this size makes the call independent of the plan's own scratch (re-entrant plans)
 size_t call_ws_bytes(const b2a_plan* p, const b2a_forward_args* a) {
   return stats_bytes(p, a->batch) + ((tilemin_count(p, a) * sizeof(float) + 15) & ~(size_t)15);
@@ -196,7 +205,7 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s, int slot =
   const b2a_frontend_desc& d = p->fd;
   const bool need_max = d.clamp_kind != B2A_CLAMP_NONE;
   const bool need_sums = d.norm_kind != B2A_NORM_NONE;
-  s->clip_max = s->tile_min = nullptr;
+  s->clip_max = s->tile_min = s->tile_max = nullptr;
   s->feat_sums = nullptr;
   s->tile_frames = stats_tile_frames(p, a);
   if (!need_max && !need_sums && !a->clip_max && !a->feat_sums) return B2A_OK;
@@ -218,6 +227,7 @@ int locate_stats(b2a_plan* p, const b2a_forward_args* a, StatPtrs* s, int slot =
     if (rc) return rc;
     s->tile_min = p->d_tilemin[slot];
   }
+  s->tile_max = p->family == KF_FAST ? s->tile_min + tile_count(p, a) : nullptr;
   size_t off = ((size_t)a->batch * 2 * sizeof(float) + 15) & ~(size_t)15;
   s->feat_sums = (double*)(base + off);
   if (a->clip_max) s->clip_max = a->clip_max;  // caller-visible (sharded) statistics
@@ -241,6 +251,8 @@ int partial_impl(b2a_plan* p, const b2a_forward_args* a, const StatPtrs& s, cuda
 }  // namespace
 
 extern "C" {
+
+unsigned long long b2a_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int b2a_frontend_create(const b2a_frontend_desc* d, const float* h_window, const float* h_fb, b2a_plan** out) {
   if (!d || !h_window || !out) {
@@ -433,6 +445,11 @@ int b2a_frontend_forward(b2a_plan* p, const b2a_forward_args* in, void* stream) 
   if (rc) return rc;
   StatPtrs s;
   if ((rc = locate_stats(p, &a, &s))) return rc;
+  if (p->family == KF_FAST && a.frame_count > 0 && s.tile_max) {
+    // per-clip clamp on the TMA kernel: statistics, grid-wide barrier and fix-up in ONE cooperative launch (1 = not applicable)
+    rc = fast_frontend_fused(p, &a, s.tile_min, s.tile_max, a.clip_max ? s.clip_max : nullptr, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   if ((rc = partial_impl(p, &a, s, (cudaStream_t)stream, true))) return rc;
   if (a.frame_count == 0) return B2A_OK;
   return frontend_finalize(p, &a, a.frame_count, s.clip_max, s.tile_min, s.tile_frames, s.feat_sums, (cudaStream_t)stream);
@@ -535,7 +552,7 @@ int b2a_frontend_forward_host(b2a_plan* p, const b2a_forward_args* in) {
       }
       const int64_t n = (int64_t)nb * in_per_clip;
       pcm16_to_f32_kernel<<<(unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, 4096), 256, 0, st>>>(d16, (float*)p->d_stage_in[s], n);
-      B2A_CUDA(cudaGetLastError());
+      B2A_LAUNCHED();
     } else {
     const float* hsrc = a.audio + (int64_t)c0 * a.clip_stride;
     if (a.clip_stride == in_per_clip) {

@@ -33,6 +33,14 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return b2a::cuda_fail(_e, #call);  \
   } while (0)
 
+// every kernel launch of the library is counted (b2a_launch_count: bench.py's `gpu_launches` is a measurement, not a claim)
+void note_launch();
+#define B2A_LAUNCHED()                 \
+  do {                                 \
+    b2a::note_launch();                \
+    B2A_CUDA(cudaGetLastError());      \
+  } while (0)
+
 constexpr int kMaxStages = 12;
 constexpr int kMaxGenericRadix = 32;
 
@@ -227,6 +235,8 @@ void fast_frontend_destroy(b2a_plan* plan);
 bool fast_frontend_out16_ok(const b2a_plan* plan);
 int64_t fast_const_row0(const b2a_plan* plan, const b2a_forward_args* a);
 bool fast_skip_floor_tiles(const b2a_plan* plan);
+// the whole clamping forward in one cooperative launch (fast_logmel_tma_kernel<..., FUSED>); returns 1 when not applicable
+int fast_frontend_fused(b2a_plan* plan, const b2a_forward_args* a, float* tile_min, float* tile_max, float* clip_max_out, cudaStream_t st);
 int fast_const_rows_finalize(const b2a_plan* plan, const b2a_forward_args* a, int64_t row0, float* clip_max, cudaStream_t st);
 int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
                           double* feat_sums, cudaStream_t st);

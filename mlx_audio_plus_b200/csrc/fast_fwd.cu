@@ -82,7 +82,7 @@ int launch_const_rows(const b2a_plan* plan, const b2a_forward_args* a, int64_t r
     const_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(a->out), stride, row0, rows, d.n_mels, cr, clip_max);
   else
     const_rows_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(a->out), stride, row0, rows, d.n_mels, cr, clip_max);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -260,11 +260,10 @@ void fast_frontend_destroy(b2a_plan* plan) {
   plan->fast = nullptr;
 }
 
-int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
-                          double* feat_sums, cudaStream_t st) {
+// launch parameters common to the partial step and the single-launch forward
+static void fill_fast_params(const b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min, double* feat_sums, FastParams& p) {
   const b2a_frontend_desc& d = plan->fd;
-  FastState* fs = reinterpret_cast<FastState*>(plan->fast);
-  FastParams p;
+  const FastState* fs = reinterpret_cast<const FastState*>(plan->fast);
   memset(&p, 0, sizeof(p));
   p.audio = a->audio;
   p.clip_stride = a->clip_stride;
@@ -307,6 +306,14 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
   p.mel_wg_count = fs->wg_count;
   p.tiles_per_clip = (int)((a->frame_count + 31) / 32);
   p.tile_min_pitch = p.tiles_per_clip;
+}
+
+int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip_max, float* tile_min,
+                          double* feat_sums, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  FastState* fs = reinterpret_cast<FastState*>(plan->fast);
+  FastParams p;
+  fill_fast_params(plan, a, clip_max, tile_min, feat_sums, p);
   // Trailing frames that see only virtual zero padding are constant rows (fast_const_row0): transform the frames that
   // touch the signal, rounded up to a tile, and fill the rest — here when there is no clamp, in the finalize step otherwise.
   const int64_t const_row0 = fast_const_row0(plan, a);
@@ -336,7 +343,7 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
       rc = launch_const_rows(plan, a, const_row0, cr, clip_max, st);
     } else {  // the rows are written by the finalize step (max(c, floor), one pass); their value counts for the clip max
       const_fold_max_kernel<<<(a->batch + 255) / 256, 256, 0, st>>>(clip_max, a->batch, cr);
-      B2A_CUDA(cudaGetLastError());
+      B2A_LAUNCHED();
     }
   }
   if (clk_path && rc == B2A_OK) {  // debugging only: synchronises the stream
@@ -356,6 +363,27 @@ int fast_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* clip
     }
   }
   return rc;
+}
+
+// The whole clamping forward in ONE cooperative launch of the TMA kernel: per-tile maxima instead of atomics on an initialised
+// clip_max, a grid-wide barrier, the clamp fix-up by the same CTAs.  Applies to the per-clip clamp of the 400/160 generated-mel
+// float32 (T, M) instances without constant padding rows and with at most 512 tiles per clip (a CTA reduces a clip's tile
+// maxima and fixes its tiles by itself: long files keep the three-launch path, whose fix-up spreads a clip over the grid).
+// Returns 1 when it does not apply (or the grid cannot be launched cooperatively): the caller takes the three-launch path.
+int fast_frontend_fused(b2a_plan* plan, const b2a_forward_args* a, float* tile_min, float* tile_max, float* clip_max_out, cudaStream_t st) {
+  const b2a_frontend_desc& d = plan->fd;
+  FastState* fs = reinterpret_cast<FastState*>(plan->fast);
+  static const bool off = getenv("B2A_NO_FUSED_FORWARD") != nullptr;  // development toggle, read once
+  if (off || !fs || fs->variant != 1 || fs->spec <= 0 || d.clamp_kind != B2A_CLAMP_CLIP_MAX || !fast_skip_floor_tiles(plan) ||
+      a->feat_sums != nullptr || fast_const_row0(plan, a) >= 0 || !tile_min || !tile_max)
+    return 1;
+  const int64_t tpc = (a->frame_count + 31) / 32;
+  if (tpc > 512 || a->batch * tpc >= ((int64_t)1 << 31)) return 1;
+  FastParams p;
+  fill_fast_params(plan, a, clip_max_out, tile_min, nullptr, p);
+  p.tile_max = tile_max;
+  p.clamp_delta = d.affine_div != 0.0f ? d.clamp_value / d.affine_div : d.clamp_value;  // clamp_fixup_kernel: mx - clamp_value / affine_div
+  return fast_launch_400(plan, fs, p, st);
 }
 
 }  // namespace b2a

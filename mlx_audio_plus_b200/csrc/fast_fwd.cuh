@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "fft_regs.cuh"
 #include "mel_gen.cuh"
@@ -73,6 +74,10 @@ struct FastParams {
   int mel_groups, mel_wg_count;
   int tiles_per_clip;
   int tile_min_pitch;  // tiles per clip in the tile_min table (>= tiles_per_clip when trailing all-padding tiles are skipped)
+  // single-launch forward (fast_logmel_tma_kernel<..., FUSED>, cooperative launch): per-tile maxima instead of atomics on an
+  // initialised clip_max, then a grid-wide barrier and the clamp fix-up by the same CTAs (one CTA per clip)
+  float* tile_max;       // [batch][tile_min_pitch]; non-null only in the fused launch
+  float clamp_delta;     // floor = clip max - clamp_delta (affine domain)
   int skip_floor_tiles;  // 1: a tile whose every value is the guard-floor constant (digital silence) is NOT stored; its
                          // tile_min entry is -inf and the clamp fix-up writes max(c, floor) there (fast_logmel_tma_kernel)
   long long* dbg_clk;  // profiling aid (B2A_CLOCKS=file): per CTA, cycles accumulated per phase [8] (thread 0's view)
@@ -1313,7 +1318,7 @@ int launch_stft_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   B2A_CUDA(cudaMemcpyToSymbolAsync(c_tw1, p.tw1, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
 #endif
   fast_stft_kernel<C, PREK><<<grid, C::THREADS, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -1351,7 +1356,7 @@ int launch_variant(b2a_plan* plan, FastParams& p, cudaStream_t st) {
   B2A_CUDA(cudaMemcpyToSymbolAsync(c_tw1, p.tw1, sizeof(float2) * C::NC, 0, cudaMemcpyDeviceToDevice, st));
 #endif
   fast_logmel_kernel<C, TM, SUMS, MS, SPECK, PREK, ODT><<<grid, C::THREADS, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -1403,6 +1408,38 @@ int launch_ws(b2a_plan* plan, FastParams& p, cudaStream_t st) {
       const cuuint32_t box[4] = {32, 32, (cuuint32_t)(MS::M / 32), 1}, estr[4] = {1, 1, 1, 1};
       if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        if (p.tile_max) {  // single launch: cooperative grid (every CTA resident), grid-wide barrier, in-kernel fix-up
+          if (ws_mode() == 1) return 1;
+          using S1 = SmemT<C, MS::M>;
+          constexpr size_t smem1 = (size_t)16 * S1::END + 16;
+          auto kern = fast_logmel_tma_kernel<C, MS, SPECK, true, true>;
+          static SmemAttrOnce attrf;
+          if (attrf.need(plan->device, smem1)) {
+            B2A_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            // a cooperative grid is validated against the occupancy calculator, which assumes the function's preferred carveout:
+            // ask for the largest shared-memory partition (two 90 KB CTAs per SM; the default reported one)
+            B2A_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          }
+          static int resident = -1;  // CTAs of this kernel one SM holds (registers, shared memory, tensor memory)
+          if (resident < 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::THREADS, smem1) != cudaSuccess) n = 0;
+            resident = std::min(n, C::MIN_BLOCKS);
+          }
+          // Measured on B200 / CUDA 12.9: the calculator (and the driver's cooperative-launch check: a 296-CTA grid is refused as
+          // too large) grants this kernel ONE co-resident CTA per SM although ordinary launches run two (ncu: limits 2 / 2) — at
+          // one CTA per SM the kernel is 40 % slower (512 clips: 0.90 vs 0.64 ms).  The single launch is therefore taken only
+          // where every tile has a CTA of its own anyway: small batches, where the two saved launches are what matters.
+          if (resident < 1 || tiles > (int64_t)plan->sm_count * resident) return 1;
+          const int gridf = (int)tiles;
+          void* kargs[2] = {(void*)&p, (void*)&map};
+          if (cudaLaunchCooperativeKernel((const void*)kern, dim3(gridf), dim3(C::THREADS), kargs, smem1, st) != cudaSuccess) {
+            cudaGetLastError();  // not launchable as a cooperative grid here: the caller takes the three-launch path
+            return 1;
+          }
+          note_launch();
+          return B2A_OK;
+        }
         if (ws_mode() != 1) {  // single-group kernel with the TMA write-out (the default)
           using S1 = SmemT<C, MS::M>;
           constexpr size_t smem1 = (size_t)16 * S1::END + 16;
@@ -1411,9 +1448,9 @@ int launch_ws(b2a_plan* plan, FastParams& p, cudaStream_t st) {
           const int grid1 = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm));
           static SmemAttrOnce attr1;
           if (attr1.need(plan->device, smem1))
-            B2A_CUDA(cudaFuncSetAttribute(fast_logmel_tma_kernel<C, MS, SPECK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-          fast_logmel_tma_kernel<C, MS, SPECK, true><<<grid1, C::THREADS, smem1, st>>>(p, map);
-          B2A_CUDA(cudaGetLastError());
+            B2A_CUDA(cudaFuncSetAttribute(fast_logmel_tma_kernel<C, MS, SPECK, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+          fast_logmel_tma_kernel<C, MS, SPECK, true, false><<<grid1, C::THREADS, smem1, st>>>(p, map);
+          B2A_LAUNCHED();
           return B2A_OK;
         }
         using S = SmemWST<C, MS::M>;
@@ -1423,7 +1460,7 @@ int launch_ws(b2a_plan* plan, FastParams& p, cudaStream_t st) {
         if (attr.need(plan->device, smem))
           B2A_CUDA(cudaFuncSetAttribute(fast_logmel_ws_tma_kernel<C, MS, SPECK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fast_logmel_ws_tma_kernel<C, MS, SPECK, true><<<grid, 2 * C::THREADS, smem, st>>>(p, map);
-        B2A_CUDA(cudaGetLastError());
+        B2A_LAUNCHED();
         return B2A_OK;
       }
     }
@@ -1481,6 +1518,7 @@ struct SpecList;
         if (rc != 1) return rc;                                                                          \
       }                                                                                                  \
     }                                                                                                    \
+    if (p.tile_max) return 1; /* a fused (single-launch) request is served by the TMA kernel or not at all */ \
     if constexpr (C::N == 400) { /* 16-bit feature output: the encoder-facing 400/160 family */          \
       if (!sums && p.out_dtype == B2A_DTYPE_F16)                                                         \
         return launch_variant<C, true, false, MS, SPECK, PREK, B2A_DTYPE_F16>(plan, p, st);             \
@@ -1521,6 +1559,10 @@ int launch(b2a_plan* plan, FastState* fs, FastParams& p, cudaStream_t st) {
     return B2A_ERR_UNSUPPORTED;
   }
   static const bool no_melspec = getenv("B2A_NO_MELSPEC") != nullptr;  // development toggle, read once
+  if (p.tile_max) {  // fused single-launch request: generated-mel TMA kernel only
+    if (fs->spec > 0 && !no_melspec && tm && vec_ok && !sums) return SpecList<C>::launch(fs->spec, sums, plan, p, st);
+    return 1;
+  }
   if (fs->spec > 0 && !no_melspec && ((tm && vec_ok) || (!tm && !sums && p.out_dtype == B2A_DTYPE_F32 && C::N == 400))) {  // named filterbank: mel structure compiled into the kernel
     const int rc = SpecList<C>::launch(fs->spec, sums, plan, p, st);
     if (rc != 1) return rc;

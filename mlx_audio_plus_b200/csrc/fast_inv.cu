@@ -315,7 +315,7 @@ int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, plan->sm_count));
   fast_istft_kernel<C, POLAR><<<grid, C::THREADS, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 

@@ -872,7 +872,7 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
   frontend_generic_kernel<<<grid, kThreads, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -909,7 +909,7 @@ int dump_frames(b2a_plan* plan, const b2a_forward_args* a, int apply_window, cud
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * 2);
   if (grid < 1) grid = 1;
   frontend_generic_kernel<<<grid, kThreads, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -920,7 +920,7 @@ int deltas(const float* x, float* out, int64_t rows, int64_t cols, int win_lengt
   if (total <= 0) return B2A_OK;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   deltas_kernel<<<grid, 256, 0, st>>>(x, out, rows, cols, n, denom, edge);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -929,7 +929,7 @@ int init_stats(float* clip_max, double* feat_sums, int batch, int n_mels, cudaSt
   const int n = batch > n_sums ? batch : n_sums;
   if (n <= 0) return B2A_OK;
   init_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(clip_max, feat_sums, batch, n_sums);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -971,11 +971,11 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   if (d.clamp_kind != B2A_CLAMP_NONE) {
     if (d.clamp_kind == B2A_CLAMP_BATCH_MAX) {
       batch_max_kernel<<<1, 256, 0, st>>>(clip_max, a->batch);
-      B2A_CUDA(cudaGetLastError());
+      B2A_LAUNCHED();
     }
     dim3 grid((p.tiles_per_clip + 7) / 8, a->batch);
     clamp_fixup_kernel<<<grid, 256, 0, st>>>(p);
-    B2A_CUDA(cudaGetLastError());
+    B2A_LAUNCHED();
     if (const_row0 >= 0) return fast_const_rows_finalize(plan, a, const_row0, clip_max, st);
     return B2A_OK;
   }
@@ -984,7 +984,7 @@ int frontend_finalize(b2a_plan* plan, const b2a_forward_args* a, int64_t global_
   if (gx < 1) gx = 1;
   dim3 grid(gx, a->batch);
   normalise_kernel<<<grid, 256, 0, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -1064,7 +1064,7 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   int grid = (int)std::min<int64_t>(tiles, (int64_t)plan->sm_count * per_sm);
   if (grid < 1) grid = 1;
   istft_generic_kernel<<<grid, kThreads, smem, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 

@@ -66,7 +66,7 @@ int launch_rows(const float* in, int64_t in_clip_stride, int64_t row_begin, int6
   dim3 grid((unsigned)gx, (unsigned)batch);
   if (vec) rows_pad_cast_kernel<T, 4><<<grid, 256, 0, st>>>(in, in_clip_stride, row_begin, rows_valid, cols, (T*)out, rows_out);
   else rows_pad_cast_kernel<T, 1><<<grid, 256, 0, st>>>(in, in_clip_stride, row_begin, rows_valid, cols, (T*)out, rows_out);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -348,7 +348,7 @@ int b2a_cmvn_utterance(const float* in, float* out, int64_t clip_stride, int64_t
     cmvn_stats_kernel<1><<<grid, threads, 0, st>>>(in, cs, rows, cols, stats_ws);
     cmvn_apply_kernel<1><<<grid, threads, 0, st>>>(in, out, cs, rows, cols, stats_ws, eps);
   }
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -359,7 +359,7 @@ int b2a_rows_normalize(const float* in, float* out, int64_t rows, int64_t cols, 
     return B2A_ERR_INVALID_ARG;
   }
   rows_normalize_kernel<<<(unsigned)rows, 512, 0, (cudaStream_t)stream>>>(in, out, cols, valid, den_kind, eps, pad_value);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -369,7 +369,7 @@ int b2a_unwrap(const float* in, float* out, int64_t rows, int64_t cols, float di
     return B2A_ERR_INVALID_ARG;
   }
   unwrap_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(in, out, cols, discont, period);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -380,7 +380,7 @@ int b2a_transpose_pad(const float* in, float* out, int64_t rows, int32_t cols, i
   }
   const dim3 grid((unsigned)((rows_out + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
   transpose_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, rows_out);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -402,7 +402,7 @@ int b2a_lfr(const float* in, int64_t in_clip_stride, int64_t frames, int32_t n_m
   dim3 grid((unsigned)gx, (unsigned)batch);
   if (vec) lfr_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(in, ics, frames, n_mels, lfr_m, lfr_n, cmvn_shift, cmvn_scale, out, ocs, t_lfr);
   else lfr_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(in, ics, frames, n_mels, lfr_m, lfr_n, cmvn_shift, cmvn_scale, out, ocs, t_lfr);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 

@@ -236,7 +236,7 @@ int launch_resample(const ResampleParams& p, int sm_count, int64_t batch, cudaSt
   if (p.channels == 1) go(resample_kernel<T, 1>);
   else if (p.channels == 2) go(resample_kernel<T, 2>);
   else go(resample_kernel<T, 0>);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -352,7 +352,7 @@ int b2a_resample(b2a_resampler* h, const b2a_resample_args* a, void* stream) {
       if (a->channels == 1) i16 ? go(resample_phase_kernel<int16_t, 1>) : go(resample_phase_kernel<float, 1>);
       else if (a->channels == 2) i16 ? go(resample_phase_kernel<int16_t, 2>) : go(resample_phase_kernel<float, 2>);
       else i16 ? go(resample_phase_kernel<int16_t, 0>) : go(resample_phase_kernel<float, 0>);
-      B2A_CUDA(cudaGetLastError());
+      B2A_LAUNCHED();
       return B2A_OK;
     }
   }

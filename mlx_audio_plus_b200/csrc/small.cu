@@ -226,7 +226,7 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   else if (N == 20) istft_small_kernel<20, false><<<grid, 256, 0, st>>>(p);
   else if (p.polar.polar) istft_small_kernel<16, true><<<grid, 256, 0, st>>>(p);
   else istft_small_kernel<16, false><<<grid, 256, 0, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
@@ -260,7 +260,7 @@ int small_stft(b2a_plan* plan, const b2a_forward_args* a, cudaStream_t st) {
   dim3 grid((unsigned)((a->frame_count + 255) / 256), a->batch);
   if (d.n_fft == 20) stft_small_kernel<20><<<grid, 256, 0, st>>>(p);
   else stft_small_kernel<16><<<grid, 256, 0, st>>>(p);
-  B2A_CUDA(cudaGetLastError());
+  B2A_LAUNCHED();
   return B2A_OK;
 }
 
