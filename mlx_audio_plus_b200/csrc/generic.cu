@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
   float2* tw_s = reinterpret_cast<float2*>(xs + ((span + 3) & ~3));  // [N] twiddles, staged once per CTA
   __shared__ float red_max[kThreads / 32], red_min[kThreads / 32];
   if (!p.dump_frames) stage_twiddles(tw_s, p.tw, N);
+  // index splits of the element-wise loops as multiply-high (operands well below 2^20 / 2^12, see fast_div)
+  const unsigned mg_N = div_magic(N), mg_F = div_magic(F), mg_M = div_magic(p.n_mels > 0 ? p.n_mels : F);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       // then the window (zero beyond W).  Raw frames go to bufA, the finished ones to bufB.
       const int W = p.frame_len > 0 ? p.frame_len : N;
       for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
-        const int pr = i / N, k = i - pr * N;
+        const int pr = N > 1 ? fast_div(i, N, mg_N) : i, k = i - pr * N;
         const int fa = 2 * pr, fb = 2 * pr + 1;
         float a = (fa < nf && k < W) ? xs[fa * hop + k] : 0.0f;
         float b = (fb < nf && k < W) ? xs[fb * hop + k] : 0.0f;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       __syncthreads();
       const float pe = p.frame_preemph;
       for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
-        const int pr = i / N, k = i - pr * N;
+        const int pr = N > 1 ? fast_div(i, N, mg_N) : i, k = i - pr * N;
         float2 v = make_float2(0.0f, 0.0f);
         if (k < W) {
           const float2 m = p.frame_dc ? means[pr] : make_float2(0.0f, 0.0f);
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       Z = run_fft(p.fft, bufB, bufA, tw_s, PAIRS);
     } else {
       for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
-        const int pr = i / N, k = i - pr * N;
+        const int pr = N > 1 ? fast_div(i, N, mg_N) : i, k = i - pr * N;
         const float w = p.window[k];
         const int fa = 2 * pr, fb = 2 * pr + 1;
         const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     if (p.n_mels == 0 && p.spec_kind == B2A_SPEC_COMPLEX) {
       float2* o = reinterpret_cast<float2*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * F;
       for (int i = threadIdx.x; i < nf * F; i += blockDim.x) {
-        const int f = i / F, k = i - f * F;
+        const int f = F > 1 ? fast_div(i, F, mg_F) : i, k = i - f * F;
         const float2* z = Z + (size_t)(f >> 1) * NP;
         const float2 zk = z[skew(k)], zm = z[k == 0 ? 0 : skew(N - k)];
         float2 X;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     }
     float* P = reinterpret_cast<float*>(other);  // [FT][F]
     for (int i = threadIdx.x; i < FT * F; i += blockDim.x) {
-      const int f = i / F, k = i - f * F;
+      const int f = F > 1 ? fast_div(i, F, mg_F) : i, k = i - f * F;
       float v = 0.0f;
       if (f < nf) {
         const float2* z = Z + (size_t)(f >> 1) * NP;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     float* Y = reinterpret_cast<float*>(Z);  // [FT][M]   (M <= F <= N)
     float lmax = -INFINITY, lmin = INFINITY;
     for (int i = threadIdx.x; i < nf * M; i += blockDim.x) {
-      const int f = i / M, m = i - f * M;
+      const int f = M > 1 ? fast_div(i, M, mg_M) : i, m = i - f * M;
       float acc;
       if (p.n_mels > 0) {
         const float* row = P + (size_t)f * F + p.mel_start[m];
