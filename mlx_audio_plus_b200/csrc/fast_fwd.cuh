@@ -195,6 +195,11 @@ __device__ __forceinline__ int float_key(float f) {
   return b ^ ((b >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT-class approximation, flush-to-zero
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int BYTE_OFF>
 __device__ __forceinline__ float4 lds128_at(unsigned base) {  // pinned (volatile) broadcast load: keeps its place in program order
   float4 v;
@@ -636,7 +641,11 @@ __device__ __forceinline__ void stage2_tile(float2* E, float* Pw, const float2* 
   // one value per float2 slot, in the half selected by lane >> 4 (the row pitch is 2 * odd floats, so lanes l and
   // l + 16 would otherwise share a bank)
   float* pr = SPEC ? reinterpret_cast<float*>(E + lane * C::EP) + (lane >> 4) : Pw + lane * C::PP;
-  auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrtf(v + spec_eps); };
+  // magnitude: ONE MUFU instruction (sqrt.approx, <= 2 ulp) — sqrtf() is the IEEE sequence (MUFU.RSQ, two Newton FFMAs, a
+  // denormal slow path behind BSSY / BRA / BSYNC): ~8 instructions and a branch per bin, 513 bins per frame in the 1024 / 256
+  // instance = 19 % of its instructions (ncu source page, profiles/r02_k1_1024_ncu_full.json).  The reference's abs() is a float32
+  // sqrt of float32 squares; the features that follow are held to 1e-4 after a logarithm.
+  auto emit = [&](float* q, float v) { *q = pw_only ? v : sqrt_approx(v + spec_eps); };
   float dc_k = 0.0f, dc_m = 0.0f;
   float2 dc_kc = make_float2(0.f, 0.f), dc_mc = make_float2(0.f, 0.f);
   if (CPLX && u == 0) post_pair_c(A[0], A[0], make_float2(1.0f, 0.0f), dc_kc, dc_mc);

@@ -80,8 +80,12 @@ __device__ __forceinline__ float4 lds128_pinned(unsigned base) {  // volatile: k
   return v;
 }
 
-template <class C, bool POLAR>
+// PLANAR (two float32 planes: real / imaginary, or magnitude / phase with POLAR) is a compile-time variant as well: as a run-time
+// test every one of the 34 loads per thread carried its own branch chain (frame alive? planes or interleaved?) — 547 BRA,
+// 1 313 IADD3 and 1 066 LEA next to 516 LDG per tile on the ncu source page (round 2).
+template <class C, bool POLAR, bool PLANAR>
 __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFastParams p) {
+  static_assert(PLANAR || !POLAR, "magnitude / phase input comes as two planes");
   constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, HOP = C::HOP;
   extern __shared__ float4 smem4[];
   float2* const E = reinterpret_cast<float2*>(smem4);                   // [FT][EP]
@@ -103,7 +107,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
   const int rowA = u, rowB = u != 0 ? N1 - u : N1 / 2;    // E rows (k1) of the unit's two columns
   const int tpc = p.tiles_per_clip;
   const int64_t T = p.T;
-  const bool planar = p.spec == nullptr;
 
 #pragma unroll 1
   for (int64_t tile = blockIdx.x; tile < (int64_t)p.batch * tpc; tile += gridDim.x) {
@@ -117,29 +120,43 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
     // ---- step 1 ---------------------------------------------------------------------------------------
     {
       float2 A[N2], B[N2];  // columns (u, N1-u) in k2 order; swapped domain (x = Im, y = Re)
-      // Running element offsets: bin k of slot s is kb + N1*s, its partner Nc - k; consecutive slots are N1*T
-      // elements apart, so every address is one 64-bit add away from the previous one.
-      const int64_t stepT = (int64_t)N1 * T, jumpT = (int64_t)(kb_hi - kb_lo) * T;
-      int64_t oa = (int64_t)clip_i * p.clip_stride + t + (int64_t)kb_lo * T;
-      int64_t ob = (int64_t)clip_i * p.clip_stride + t + (int64_t)(NC - kb_lo) * T;
+      // Running POINTERS: bin k of slot s is kb + N1*s, its partner Nc - k; consecutive slots are N1*T elements apart, so every
+      // address is one 64-bit add away from the previous one; a dead lane (frame outside the clip) loads nothing (predicated)
       // (magnitude / phase planes are converted after ALL loads of the unit are in flight: a conversion per load site put
       // its range-reduction branch between consecutive loads and serialised them)
-      auto load_at = [&](int64_t i) -> float2 {
-        if (!live) return make_float2(0.0f, 0.0f);
-        return (POLAR || planar) ? make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i)) : __ldg(p.spec + i);
-      };
+      const int64_t stepT = (int64_t)N1 * T, jumpT = (int64_t)(kb_hi - kb_lo) * T;
+      const int64_t oa0 = (int64_t)clip_i * p.clip_stride + (live ? t : 0) + (int64_t)kb_lo * T;
+      const int64_t ob0 = (int64_t)clip_i * p.clip_stride + (live ? t : 0) + (int64_t)(NC - kb_lo) * T;
+      const float2* qa = p.spec + oa0;   // interleaved
+      const float2* qb = p.spec + ob0;
+      const float *ra = p.spec_re + oa0, *ia = p.spec_im + oa0;  // planes
+      const float *rb = p.spec_re + ob0, *ib = p.spec_im + ob0;
+      const float2 zero2 = make_float2(0.0f, 0.0f);
       float2 xa[N2], xb[N2];
       static_for<0, N2>([&](auto S_) {
         constexpr int s = decltype(S_)::value;
         if (s == N2 / 2) {  // unit 0 switches from column 0 to column N1/2 here (jumpT == 0 for the other units)
-          oa += jumpT;
-          ob -= jumpT;
+          if constexpr (PLANAR) {
+            ra += jumpT; ia += jumpT; rb -= jumpT; ib -= jumpT;
+          } else {
+            qa += jumpT; qb -= jumpT;
+          }
         }
-        xa[s] = load_at(oa);
-        xb[s] = load_at(ob);
-        oa += stepT;
-        ob -= stepT;
+        if constexpr (PLANAR) {
+          xa[s] = live ? make_float2(__ldg(ra), __ldg(ia)) : zero2;
+          xb[s] = live ? make_float2(__ldg(rb), __ldg(ib)) : zero2;
+          ra += stepT; ia += stepT; rb -= stepT; ib -= stepT;
+        } else {
+          xa[s] = live ? __ldg(qa) : zero2;
+          xb[s] = live ? __ldg(qb) : zero2;
+          qa += stepT; qb -= stepT;
+        }
       });
+      auto load_at = [&](int64_t i) -> float2 {
+        if (!live) return zero2;
+        if constexpr (PLANAR) return make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i));
+        else return __ldg(p.spec + i);
+      };
       float2 dc = make_float2(0.0f, 0.0f);
       if (u == 0) {  // Im(DC), Im(Nyquist) are ignored (irfft)
         const int64_t o0 = (int64_t)clip_i * p.clip_stride + t;
@@ -254,6 +271,27 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
       const float* y = Yf + (q0 + 1) * (2 * C::EP) + r + 3 * HOP;
       int64_t j0 = (int64_t)tile_i * C::S + 2 * threadIdx.x - p.out_start;
       const float2 rden = *reinterpret_cast<const float2*>(s_rden + r);
+      // interior tile (CTA-uniform): every frame the tile's samples touch exists, the reciprocal envelope table applies, every
+      // output pair is inside the clip's range and 8-byte aligned — the sweep is then loads, adds, one multiply and one store
+      // (the general loop below spends more instructions on its range / edge tests than on the overlap-add: ISETP 1 076, IADD3 821,
+      // BRA 380 against 474 LDS per tile, ncu source page)
+      const int64_t jt0 = (int64_t)tile_i * C::S - p.out_start;
+      const bool interior = t_q0 - 3 >= 0 && t_q0 + C::FA - 1 < Ti && p.rden_ok && p.vec_ok && jt0 >= 0 && jt0 + C::S <= p.out_len;
+      if (interior) {
+        float* oj = o + j0;
+#pragma unroll
+        for (int it = 0; it < (C::S / 2) / C::THREADS; ++it) {
+          const float* yi = y + it * (HPS * 2 * C::EP);
+          float2 num = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 yv = *reinterpret_cast<const float2*>(yi + j * (2 * C::EP - HOP));
+            num.x += yv.x;
+            num.y += yv.y;
+          }
+          *reinterpret_cast<float2*>(oj + it * (2 * C::THREADS)) = make_float2(num.x * rden.x, num.y * rden.y);
+        }
+      } else
 #pragma unroll 1
       for (int it = 0; it < (C::S / 2) / C::THREADS; ++it, y += HPS * 2 * C::EP, j0 += 2 * C::THREADS) {
         const int q = q0 + HPS * it;
@@ -306,15 +344,15 @@ size_t inv_smem_bytes() {
   return sizeof(float2) * ((size_t)C::FT * C::EP + C::WARPS * C::N2 * 3 + C::NC) + sizeof(float) * (C::N + C::HOP) + 16;
 }
 
-template <class C, bool POLAR>
+template <class C, bool POLAR, bool PLANAR>
 int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
   const size_t smem = inv_smem_bytes<C>();
   static SmemAttrOnce attr;
   if (attr.need(plan->device, smem))
-    B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C, POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_CUDA(cudaFuncSetAttribute(fast_istft_kernel<C, POLAR, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)p.batch * p.tiles_per_clip;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, plan->sm_count));
-  fast_istft_kernel<C, POLAR><<<grid, C::THREADS, smem, st>>>(p);
+  fast_istft_kernel<C, POLAR, PLANAR><<<grid, C::THREADS, smem, st>>>(p);
   B2A_LAUNCHED();
   return B2A_OK;
 }
@@ -433,7 +471,8 @@ int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.rden_ok = fs->rden_ok;
   // tiles cover OLA coordinates [0, start + len)
   p.tiles_per_clip = (int)((start + len + C::S - 1) / C::S);
-  return p.polar.polar ? launch_inv<C, true>(plan, p, st) : launch_inv<C, false>(plan, p, st);
+  if (p.polar.polar) return launch_inv<C, true, true>(plan, p, st);
+  return p.spec == nullptr ? launch_inv<C, false, true>(plan, p, st) : launch_inv<C, false, false>(plan, p, st);
 }
 
 }  // namespace b2a
