@@ -101,11 +101,16 @@ __device__ __forceinline__ float lg2_approx(float x) {  // MUFU.LG2: the fused k
 // minimax polynomials on [-pi/4, pi/4] and a quadrant swap — ~25 instructions where libdevice's sincosf, which carries
 // the Payne-Hanek path for huge arguments inline, costs ~100 (the polar iSTFT kernels evaluate one per spectrum bin:
 // C4, 270 M of them, 1.32 -> see DESIGN).  Arguments beyond 65536 rad (and NaN / inf) take libdevice's path.
+__device__ __forceinline__ void sincos_cw_reduced(float x, float* sn, float* cs);
 __device__ __forceinline__ void sincos_cw(float x, float* sn, float* cs) {
   if (!(fabsf(x) <= 65536.0f)) {
     sincosf(x, sn, cs);
     return;
   }
+  sincos_cw_reduced(x, sn, cs);
+}
+// the branch-free part: valid for |x| <= 65536 (callers that test a whole group of arguments at once use it directly)
+__device__ __forceinline__ void sincos_cw_reduced(float x, float* sn, float* cs) {
   const float q = rintf(x * 0.636619747f);
   float r = fmaf(-q, 0x1.921fb6p+0f, x);
   r = fmaf(-q, -0x1.777a5cp-25f, r);

@@ -35,6 +35,8 @@ struct SmallInvParams {
   float div_eps;
 };
 
+__device__ __forceinline__ float num_div(float a, float b) { return a / b; }  // IEEE division, as the general path below
+
 template <int N, bool POLAR>
 __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p) {
   constexpr int NC = N / 2, F = NC + 1, HOP = N / 4;
@@ -45,23 +47,37 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
   const int64_t t = (int64_t)wclip * 29 - 3 + lane;  // frame slot; slots < 0 or >= T contribute nothing
   const bool live = t >= 0 && t < p.T;
 
-  // ---- load the frame's spectrum: lanes are consecutive frames -> coalesced ---------------------------
+  // ---- load the frame's spectrum: lanes are consecutive frames -> coalesced; one running pointer per plane ------
   float2 X[F];
   const int64_t base = (int64_t)clip_i * p.clip_stride + (live ? t : 0);
   if (p.spec) {
+    const float2* q = p.spec + base;
 #pragma unroll
-    for (int k = 0; k < F; ++k) X[k] = live ? __ldg(p.spec + base + (int64_t)k * p.T) : make_float2(0.f, 0.f);
+    for (int k = 0; k < F; ++k, q += p.T) X[k] = live ? __ldg(q) : make_float2(0.f, 0.f);
   } else {
+    const float *qr = p.spec_re + base, *qi = p.spec_im + base;
 #pragma unroll
-    for (int k = 0; k < F; ++k) {
-      X[k] = live ? make_float2(__ldg(p.spec_re + base + (int64_t)k * p.T), __ldg(p.spec_im + base + (int64_t)k * p.T))
-                  : make_float2(0.f, 0.f);
-    }
+    for (int k = 0; k < F; ++k, qr += p.T, qi += p.T) X[k] = live ? make_float2(__ldg(qr), __ldg(qi)) : make_float2(0.f, 0.f);
     // magnitude / phase -> complex in a SECOND pass: with the conversion (and its range-reduction branch) inside the load
     // loop the 2 * F loads were issued one bin at a time, each waiting out an HBM round trip (C4: 1.32 ms, see DESIGN)
     if (POLAR && live) {
+      // the common form (no clipping, plain magnitudes, |phase| <= 65536: Kokoro) is straight-line code — no per-bin
+      // flag tests, no per-bin slow-path branch — so the F independent sin / cos chains interleave
+      float big = 0.0f;
 #pragma unroll
-      for (int k = 0; k < F; ++k) X[k] = polar_to_complex(p.polar, X[k]);
+      for (int k = 0; k < F; ++k) big = fmaxf(big, fabsf(X[k].y));
+      const bool plain = !p.polar.log_mag && !(p.polar.clip_max > 0.0f) && !p.polar.clip_min_zero;
+      if (plain && big <= 65536.0f) {
+#pragma unroll
+        for (int k = 0; k < F; ++k) {
+          float sn, cs;
+          sincos_cw_reduced(X[k].y, &sn, &cs);
+          X[k] = make_float2(X[k].x * cs, X[k].x * sn);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < F; ++k) X[k] = polar_to_complex(p.polar, X[k]);
+      }
     }
   }
   X[0].y = 0.f;   // irfft ignores Im(DC) and Im(Nyquist)
@@ -92,6 +108,26 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
   }
 
   // ---- overlap-add by shuffles, ascending frame order: t-3, t-2, t-1, t ------------------------------------
+  // interior lanes (all four contributing frames exist, the whole hop inside the output range): sums and the envelope of
+  // the four taps in the same order as below, without the per-frame existence tests (88 ISETP per warp on the source page)
+  const bool inner = t - 3 >= 0 && t < p.T && t * HOP - p.out_start >= 0 && t * HOP + HOP - p.out_start <= p.out_len;
+  if (__all_sync(0xffffffffu, inner || lane < 3)) {
+    float* o = p.out + (int64_t)clip_i * p.out_clip_stride + (t * HOP - p.out_start);
+#pragma unroll
+    for (int j = 0; j < HOP; ++j) {
+      const float y3 = __shfl_up_sync(0xffffffffu, y[j + 3 * HOP], 3);
+      const float y2 = __shfl_up_sync(0xffffffffu, y[j + 2 * HOP], 2);
+      const float y1 = __shfl_up_sync(0xffffffffu, y[j + HOP], 1);
+      const float w3 = p.w[j + 3 * HOP], w2 = p.w[j + 2 * HOP], w1 = p.w[j + HOP], w0 = p.w[j];
+      const float n_ = ((0.f + y3) + y2) + y1 + y[j];
+      const float d_ = p.norm_sq ? (((0.f + w3 * w3) + w2 * w2) + w1 * w1) + w0 * w0 : (((0.f + w3) + w2) + w1) + w0;
+      float r;
+      if (p.div_clamp) r = num_div(n_, fmaxf(d_, p.div_eps));
+      else r = d_ > p.div_eps ? num_div(n_, d_) : n_;
+      if (lane >= 3) o[j] = r;
+    }
+    return;
+  }
   float num[HOP], den[HOP];
 #pragma unroll
   for (int j = 0; j < HOP; ++j) {
