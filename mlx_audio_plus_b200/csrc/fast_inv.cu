@@ -26,6 +26,10 @@
 #include "common.cuh"
 #include "fft_regs.cuh"
 
+#ifndef B2A_X_PF
+#define B2A_X_PF 1
+#endif
+
 namespace b2a {
 
 namespace {
@@ -230,6 +234,36 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
       });
     }
     __syncthreads();  // E[frame][k1][n2] complete
+#if B2A_X_PF
+    // The NEXT tile's spectrum rows are pulled into L2 while this tile is transformed: the kernel holds ONE tile per SM (131 KB
+    // exchange buffer, 126 registers), so nothing else keeps the DRAM busy during steps 2 and 3, and the loads at the top of the
+    // next tile otherwise wait out a full DRAM round trip with every warp of the SM stalled on them.
+    {
+      const int64_t ntile = tile + gridDim.x;
+      if (ntile < (int64_t)p.batch * tpc) {
+        const int nclip = (int)(ntile / tpc);
+        const int nti = (int)(ntile - (int64_t)nclip * tpc);
+        int64_t tf = (int64_t)nti * C::FA - C::HALO, tl = tf + C::FT - 1;
+        tf = tf < 0 ? 0 : tf;
+        tl = tl > T - 1 ? T - 1 : tl;
+        if (tl >= tf) {
+          const int64_t nb = (int64_t)nclip * p.clip_stride;
+          for (int k = threadIdx.x; k <= NC; k += C::THREADS) {
+            const int64_t o0 = nb + (int64_t)k * T + tf, o1 = nb + (int64_t)k * T + tl;
+            if constexpr (PLANAR) {
+              for (uintptr_t q = reinterpret_cast<uintptr_t>(p.spec_re + o0) & ~(uintptr_t)127; q <= reinterpret_cast<uintptr_t>(p.spec_re + o1); q += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+              for (uintptr_t q = reinterpret_cast<uintptr_t>(p.spec_im + o0) & ~(uintptr_t)127; q <= reinterpret_cast<uintptr_t>(p.spec_im + o1); q += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            } else {
+              for (uintptr_t q = reinterpret_cast<uintptr_t>(p.spec + o0) & ~(uintptr_t)127; q <= reinterpret_cast<uintptr_t>(p.spec + o1); q += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+          }
+        }
+      }
+    }
+#endif
 
     // ---- step 2 ---------------------------------------------------------------------------------------
     {

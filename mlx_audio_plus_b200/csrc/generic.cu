@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
   __shared__ float red_max[kThreads / 32], red_min[kThreads / 32];
   if (!p.dump_frames) stage_twiddles(tw_s, p.tw, N);
   // index splits of the element-wise loops as multiply-high (operands well below 2^20 / 2^12, see fast_div)
-  const unsigned mg_N = div_magic(N), mg_F = div_magic(F), mg_M = div_magic(p.n_mels > 0 ? p.n_mels : F);
+  const unsigned mg_N = div_magic(N), mg_FT = div_magic(FT);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -227,13 +227,53 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     // ---- stage the sample span (padding / right-pad / pre-emphasis resolved here) -------------------
     const int64_t q0 = t0 * hop;
     const int need = (nf - 1) * hop + N;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) {
-      float v = 0.0f;
-      if (i < need) {
-        const int64_t s = source_index(p.geo, p.pad_mode, q0 + i);
-        if (s >= 0) v = fetch_sample(p, clip, s);
+    // INTERIOR tile (CTA-uniform): every needed sample is a sample of the signal this rank holds — no padding, no reflection,
+    // no virtual right pad — so the span is one linear copy (16-byte loads where the source is aligned).  The general loop
+    // below resolves padding per sample (64-bit index arithmetic and three range tests around every 4-byte load: on the ncu
+    // source page it was 26 % of the S3Gen-mel kernel's time, waiting on its own loads).
+    const int64_t s0 = q0 - p.geo.pad_left;
+    const int64_t s_lim = p.geo.length < p.valid_length ? p.geo.length : p.valid_length;
+    const bool interior = s0 >= (p.preemph != 0.0f ? 1 : 0) && s0 - (p.preemph != 0.0f ? 1 : 0) >= p.sample_offset && s0 + need <= s_lim;
+    if (interior) {
+      const float* src = clip + (s0 - p.sample_offset);
+      if (p.preemph != 0.0f) {
+        for (int i = threadIdx.x; i < need; i += blockDim.x) xs[i] = __fsub_rn(__ldg(src + i), __fmul_rn(p.preemph, __ldg(src + i - 1)));
+      } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* x4 = reinterpret_cast<float4*>(xs);
+        const int n4 = need >> 2;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) x4[i] = __ldg(s4 + i);
+        for (int i = 4 * n4 + threadIdx.x; i < need; i += blockDim.x) xs[i] = __ldg(src + i);
+      } else {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < need; i += blockDim.x) xs[i] = __ldg(src + i);
       }
-      xs[i] = v;
+      for (int i = need + threadIdx.x; i < span; i += blockDim.x) xs[i] = 0.0f;
+    } else {
+      for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        float v = 0.0f;
+        if (i < need) {
+          const int64_t s = source_index(p.geo, p.pad_mode, q0 + i);
+          if (s >= 0) v = fetch_sample(p, clip, s);
+        }
+        xs[i] = v;
+      }
+    }
+    {  // the next tile's samples are pulled into L2 while this tile is transformed (one 128-byte line per thread)
+      const int64_t ntile = tile + gridDim.x;
+      if (ntile < total_tiles) {
+        const int nclip = (int)(ntile / p.tiles_per_clip);
+        const int nti = (int)(ntile - (int64_t)nclip * p.tiles_per_clip);
+        int64_t a0 = (p.frame_begin + (int64_t)nti * FT) * hop - p.geo.pad_left, a1 = a0 + span;
+        a0 = a0 < p.sample_offset ? p.sample_offset : a0;
+        a1 = a1 > s_lim ? s_lim : a1;
+        const float* nsrc = p.audio + (int64_t)nclip * p.clip_stride - p.sample_offset;
+        const uintptr_t l0 = reinterpret_cast<uintptr_t>(nsrc + a0) & ~(uintptr_t)127;
+        if (a1 > a0)
+          for (uintptr_t q = l0 + 128u * threadIdx.x; q < reinterpret_cast<uintptr_t>(nsrc + a1); q += 128u * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      }
     }
     __syncthreads();
 
@@ -312,13 +352,17 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       __syncthreads();
       Z = run_fft(p.fft, bufB, bufA, tw_s, PAIRS);
     } else {
-      for (int i = threadIdx.x; i < PAIRS * N; i += blockDim.x) {
-        const int pr = N > 1 ? fast_div(i, N, mg_N) : i, k = i - pr * N;
-        const float w = p.window[k];
-        const int fa = 2 * pr, fb = 2 * pr + 1;
-        const float a = fa < nf ? xs[fa * hop + k] * w : 0.0f;
-        const float b = fb < nf ? xs[fb * hop + k] * w : 0.0f;
-        bufA[(size_t)pr * NP + skew(k)] = make_float2(a, b);
+      // a thread owns sample positions k and walks the tile's frame pairs: one window tap and one skewed offset per k
+      for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const float w = __ldg(p.window + k);
+        const float* x0 = xs + k;
+        float2* d = bufA + skew(k);
+        for (int pr = 0; pr < PAIRS; ++pr) {
+          const int fa = 2 * pr, fb = 2 * pr + 1;
+          const float a = fa < nf ? x0[fa * hop] * w : 0.0f;
+          const float b = fb < nf ? x0[fb * hop] * w : 0.0f;
+          d[(size_t)pr * NP] = make_float2(a, b);
+        }
       }
       __syncthreads();
       Z = run_fft(p.fft, bufA, bufB, tw_s, PAIRS);
@@ -326,38 +370,46 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     float2* other = (Z == bufA) ? bufB : bufA;
 
     // ---- Hermitian separation ------------------------------------------------------------------------
+    // A thread owns BINS and walks the tile's frame pairs: Z[k] and Z[N-k] are read once for both frames of a pair, the skewed
+    // offsets are computed once per bin, and no element index is split by a division.
     if (p.n_mels == 0 && p.spec_kind == B2A_SPEC_COMPLEX) {
       float2* o = reinterpret_cast<float2*>(p.out) + (int64_t)clip_i * p.out_clip_stride + lt0 * F;
-      for (int i = threadIdx.x; i < nf * F; i += blockDim.x) {
-        const int f = F > 1 ? fast_div(i, F, mg_F) : i, k = i - f * F;
-        const float2* z = Z + (size_t)(f >> 1) * NP;
-        const float2 zk = z[skew(k)], zm = z[k == 0 ? 0 : skew(N - k)];
-        float2 X;
-        if ((f & 1) == 0) X = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        else X = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
-        o[i] = X;
+      for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const float2* zk_p = Z + skew(k);
+        const float2* zm_p = Z + (k == 0 ? 0 : skew(N - k));
+        for (int pr = 0; pr < PAIRS; ++pr) {
+          const int fa = 2 * pr, fb = 2 * pr + 1;
+          if (fa >= nf) break;
+          const float2 zk = zk_p[(size_t)pr * NP], zm = zm_p[(size_t)pr * NP];
+          o[(int64_t)fa * F + k] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+          if (fb < nf) o[(int64_t)fb * F + k] = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+        }
       }
       __syncthreads();
       continue;
     }
     float* P = reinterpret_cast<float*>(other);  // [FT][F]
-    for (int i = threadIdx.x; i < FT * F; i += blockDim.x) {
-      const int f = F > 1 ? fast_div(i, F, mg_F) : i, k = i - f * F;
-      float v = 0.0f;
-      if (f < nf) {
-        const float2* z = Z + (size_t)(f >> 1) * NP;
-        const float2 zk = z[skew(k)], zm = z[k == 0 ? 0 : skew(N - k)];
-        float re, im;
-        if ((f & 1) == 0) { re = 0.5f * (zk.x + zm.x); im = 0.5f * (zk.y - zm.y); }
-        else { re = 0.5f * (zk.y + zm.y); im = 0.5f * (zm.x - zk.x); }
-        const float pw = re * re + im * im;
-        switch (p.spec_kind) {
-          case B2A_SPEC_POWER: v = pw; break;
-          case B2A_SPEC_MAGNITUDE: v = sqrtf(pw); break;
-          default: v = sqrtf(pw + p.spec_eps); break;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      const float2* zk_p = Z + skew(k);
+      const float2* zm_p = Z + (k == 0 ? 0 : skew(N - k));
+      float* pk = P + k;
+      for (int pr = 0; pr < PAIRS; ++pr) {
+        const int fa = 2 * pr, fb = 2 * pr + 1;
+        const float2 zk = zk_p[(size_t)pr * NP], zm = zm_p[(size_t)pr * NP];
+        float va = 0.0f, vb = 0.0f;
+        if (fa < nf) {
+          const float re = 0.5f * (zk.x + zm.x), im = 0.5f * (zk.y - zm.y);
+          const float pw = re * re + im * im;
+          va = p.spec_kind == B2A_SPEC_POWER ? pw : p.spec_kind == B2A_SPEC_MAGNITUDE ? sqrtf(pw) : sqrtf(pw + p.spec_eps);
         }
+        if (fb < nf) {
+          const float re = 0.5f * (zk.y + zm.y), im = 0.5f * (zm.x - zk.x);
+          const float pw = re * re + im * im;
+          vb = p.spec_kind == B2A_SPEC_POWER ? pw : p.spec_kind == B2A_SPEC_MAGNITUDE ? sqrtf(pw) : sqrtf(pw + p.spec_eps);
+        }
+        pk[(size_t)fa * F] = va;
+        pk[(size_t)fb * F] = vb;
       }
-      P[i] = v;
     }
     __syncthreads();
 
@@ -365,14 +417,19 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     const int M = p.n_mels > 0 ? p.n_mels : F;
     float* Y = reinterpret_cast<float*>(Z);  // [FT][M]   (M <= F <= N)
     float lmax = -INFINITY, lmin = INFINITY;
-    for (int i = threadIdx.x; i < nf * M; i += blockDim.x) {
-      const int f = M > 1 ? fast_div(i, M, mg_M) : i, m = i - f * M;
+    // FRAME-fastest items: the lanes that share a mel row read the same weights (one sector per load instead of up to 32) and
+    // walk the power tile at a stride of F floats (F odd for even n_fft: conflict free); with row-fastest items every lane
+    // started its band at a different bin (55 % of the phase's shared-memory wavefronts were bank-conflict replays)
+    for (int i = threadIdx.x; i < FT * M; i += blockDim.x) {
+      const int m = FT > 1 ? fast_div(i, FT, mg_FT) : i, f = i - m * FT;
+      if (f >= nf) continue;
       float acc;
       if (p.n_mels > 0) {
-        const float* row = P + (size_t)f * F + p.mel_start[m];
-        const float* w = p.mel_w + p.mel_off[m];
-        const int len = p.mel_len[m];
+        const float* row = P + (size_t)f * F + __ldg(p.mel_start + m);
+        const float* w = p.mel_w + __ldg(p.mel_off + m);
+        const int len = __ldg(p.mel_len + m);
         acc = 0.0f;
+#pragma unroll 4
         for (int j = 0; j < len; ++j) acc = fmaf(row[j], __ldg(w + j), acc);
       } else {
         acc = P[(size_t)f * F + m];
@@ -384,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       lmax = fmaxf(lmax, acc);
       lmin = fminf(lmin, acc);
       if (p.apply_affine) acc = (acc + p.affine_add) / p.affine_div;
-      Y[i] = acc;
+      Y[f * M + m] = acc;
     }
     if (p.clip_max) {
       for (int o = 16; o > 0; o >>= 1) {
@@ -414,10 +471,13 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       float* ot = o + lt0 * M;
       for (int i = threadIdx.x; i < nf * M; i += blockDim.x) ot[i] = Y[i];
     } else {
-      for (int i = threadIdx.x; i < nf * M; i += blockDim.x) {
-        const int m = i / nf, f = i - m * nf;
-        o[(int64_t)m * p.frame_count + lt0 + f] = Y[f * M + m];
-      }
+      // (M, T): a warp takes 32 / fp feature rows at a time, fp = the tile's frame count rounded up to a power of two —
+      // no per-element division by the run-time frame count (a 40-instruction sequence per stored value)
+      const int fp = nf <= 1 ? 1 : nf <= 2 ? 2 : nf <= 4 ? 4 : nf <= 8 ? 8 : nf <= 16 ? 16 : 32;
+      const int sh = __ffs(fp) - 1, lane = threadIdx.x & 31, rpw = 32 >> sh;
+      const int fl = lane & (fp - 1), rl = lane >> sh;
+      for (int m = (threadIdx.x >> 5) * rpw + rl; m < M; m += (blockDim.x >> 5) * rpw)
+        for (int f = fl; f < nf; f += fp) o[(int64_t)m * p.frame_count + lt0 + f] = Y[f * M + m];
     }
     __syncthreads();
   }
@@ -700,6 +760,22 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
   stage_twiddles(tw_s, p.tw, N);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
+  // tile-relative sample positions stay below 2^20 and hop below 2^12 for every shape the host hands over with fdiv_ok set:
+  // their quotients by the hop are then one multiply-high (fast_div) instead of a 64-bit division sequence per output sample
+  const bool fdiv_ok = hop < 4096 && (int64_t)S + N + (int64_t)(2 * p.pairs_chunk + 2) * hop < (1 << 20);
+  const unsigned mg_hop = div_magic(hop);
+  auto div_hop = [&](int x) -> int { return fdiv_ok ? fast_div(x, hop, mg_hop) : x / hop; };
+  // frames touching a tile's OLA range [n0, n1): t*hop <= n1-1  and  t*hop + N - 1 >= n0
+  auto tile_frames = [&](int64_t tl, int& clip_o, int64_t& tlo_o, int& nfr_o) {
+    clip_o = (int)(tl / p.tiles_per_clip);
+    const int ti = (int)(tl - (int64_t)clip_o * p.tiles_per_clip);
+    const int64_t a0 = (int64_t)ti * S, a1 = min(a0 + (int64_t)S, p.out_len);
+    const int64_t m0 = p.out_start + a0, m1 = p.out_start + a1;
+    tlo_o = m0 - N + 1 <= 0 ? 0 : (m0 - N + 1 + hop - 1) / hop;
+    int64_t th = (m1 - 1) / hop;
+    if (th > p.T - 1) th = p.T - 1;
+    nfr_o = (int)(th - tlo_o + 1);
+  };
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int clip_i = (int)(tile / p.tiles_per_clip);
     const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
@@ -707,11 +783,14 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
     const int64_t j1 = min(j0 + (int64_t)S, p.out_len);
     const int s_tile = (int)(j1 - j0);
     const int64_t n0 = p.out_start + j0, n1 = p.out_start + j1;  // OLA coordinates [n0, n1)
-    // frames touching [n0, n1): t*hop <= n1-1  and  t*hop + N - 1 >= n0
     int64_t t_lo = n0 - N + 1 <= 0 ? 0 : (n0 - N + 1 + hop - 1) / hop;
     int64_t t_hi = (n1 - 1) / hop;
     if (t_hi > p.T - 1) t_hi = p.T - 1;
     const int nfr = (int)(t_hi - t_lo + 1);
+    // the first round of the NEXT tile, for the L2 prefetch issued during this tile's last round
+    int nx_clip = 0, nx_nfr = 0;
+    int64_t nx_tlo = 0;
+    if (tile + gridDim.x < total_tiles) tile_frames(tile + gridDim.x, nx_clip, nx_tlo, nx_nfr);
     for (int i = threadIdx.x; i < s_tile; i += blockDim.x) acc[i] = 0.0f;
     // (the first round's barrier below orders these stores before the first accumulation)
 
@@ -723,8 +802,31 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
       // adjacent in the (B, F, T) layout, so its loads fall into one or two 32-byte sectors (with bin-major threads every
       // 4- or 8-byte load opened a sector of its own and the load phase, latency-bound, was most of the kernel), and each
       // spectrum element is read once — the mirrored half of the extended spectrum is written from the same registers.
+      // what the NEXT round (of this tile, or the first of the CTA's next tile) will read goes to L2 now: the load phase is
+      // latency-bound (every warp of the SM waits on it) and nothing else keeps the DRAM busy during the transform
+      int64_t pf_base = -1;
+      int pf_n = 0;
+      if (c0 + 2 * p.pairs_chunk < nfr) {
+        pf_base = (int64_t)clip_i * p.clip_stride + t_lo + c0 + 2 * p.pairs_chunk;
+        pf_n = min(2 * p.pairs_chunk, nfr - c0 - 2 * p.pairs_chunk);
+      } else if (nx_nfr > 0) {
+        pf_base = (int64_t)nx_clip * p.clip_stride + nx_tlo;
+        pf_n = min(2 * p.pairs_chunk, nx_nfr);
+      }
       for (int kk = threadIdx.x; kk < F; kk += blockDim.x) {
         const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0;
+        if (pf_n > 0) {
+          const int64_t b0 = pf_base + (int64_t)kk * p.T, b1 = b0 + pf_n - 1;
+          if (p.spec) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b1));
+          } else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b1));
+          }
+        }
         const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
         const int km = (kk == 0 || 2 * kk == N) ? -1 : N - kk;  // mirrored position (bins > N/2), none for DC / Nyquist
 #pragma unroll 4
@@ -757,12 +859,15 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
       const int hi = hi64 > s_tile ? s_tile : (int)hi64;
       for (int n = lo + threadIdx.x; n < hi; n += blockDim.x) {
         float sum = acc[n];
-        int k = n - (int)first;  // sample index within frame f = 0; decreases by hop per frame
-        for (int f = 0; f < cf; ++f, k -= hop) {
-          if (k >= 0 && k < N) {
-            const float2 z = Z[(size_t)(f >> 1) * NP + skew(k)];
-            sum += (((f & 1) == 0 ? z.x : -z.y) * invN) * win_s[k];
-          }
+        const int k0 = n - (int)first;  // sample index within the round's frame 0 (>= 0); decreases by hop per frame
+        // the frames that hold this sample: 0 <= k0 - f*hop < N — walked without per-frame range tests
+        const int f_lo = k0 - N + 1 <= 0 ? 0 : div_hop(k0 - N + hop);
+        int f_hi = div_hop(k0);
+        f_hi = f_hi > cf - 1 ? cf - 1 : f_hi;
+        int k = k0 - f_lo * hop;
+        for (int f = f_lo; f <= f_hi; ++f, k -= hop) {
+          const float2 z = Z[(size_t)(f >> 1) * NP + skew(k)];
+          sum += (((f & 1) == 0 ? z.x : -z.y) * invN) * win_s[k];
         }
         acc[n] = sum;
       }
@@ -770,10 +875,19 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
     }
     // envelope (position only, ascending frame order) and the division
     float* o = p.out + (int64_t)clip_i * p.out_clip_stride;
+    const int64_t qn = n0 / hop, cn = n0 - N + hop, qc = cn >= 0 ? cn / hop : 0;
+    const int rn = (int)(n0 - qn * hop), rc = cn >= 0 ? (int)(cn - qc * hop) : 0;
+    const bool fast_idx = fdiv_ok && cn >= 0;  // every sample of the tile has n >= N: both quotients are tile-relative
     for (int i = threadIdx.x; i < s_tile; i += blockDim.x) {
       const int64_t n = n0 + i;
-      int64_t ta = n - N + 1 <= 0 ? 0 : (n - N + 1 + hop - 1) / hop;
-      int64_t tb = n / hop;
+      int64_t ta, tb;
+      if (fast_idx) {
+        ta = qc + fast_div(rc + i, hop, mg_hop);
+        tb = qn + fast_div(rn + i, hop, mg_hop);
+      } else {
+        ta = n - N + 1 <= 0 ? 0 : (n - N + 1 + hop - 1) / hop;
+        tb = n / hop;
+      }
       if (tb > p.T - 1) tb = p.T - 1;
       float den = 0.f;
       int k = (int)(n - ta * hop);
@@ -1059,6 +1173,8 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   // SM); every tile re-transforms the ov - 1 frames it shares with its left neighbour, so larger tiles waste less
   int pairs_chunk = 4096 / N;
   pairs_chunk = pairs_chunk < 1 ? 1 : (pairs_chunk > 16 ? 16 : pairs_chunk);
+  static const int pc_override = getenv("B2A_X_PC") ? atoi(getenv("B2A_X_PC")) : 0;  // development: pairs per FFT round
+  if (pc_override > 0) pairs_chunk = pc_override;
   auto smem_for = [&](int pc, int adv) { return (size_t)16 * pc * seq_pitch(N) + (size_t)8 * N + (size_t)4 * N + (size_t)4 * adv * hop + 16; };
   int adv = 0;
   for (int cand = 1; cand <= 1024; cand *= 2)

@@ -33,7 +33,24 @@ struct SmallInvParams {
   int warps_per_clip;
   PolarSpec polar;
   float div_eps;
+  float rden[8];  // 1 / (full-overlap envelope of output sample j of a hop, summed in ascending frame order)
+  int rden_ok;    // every entry of that envelope lies above the division guard
 };
+
+// sin / cos for |x| <= 1 without range reduction (near-minimax fits, <= 0.6 ulp of 1.0): the phases Kokoro's generator hands to
+// MLXSTFT.inverse are sin(.) of a network output (istftnet.py), i.e. always inside [-1, 1] — 12 instructions per bin instead of 22
+__device__ __forceinline__ void sincos_unit(float x, float* sn, float* cs) {
+  const float r2 = x * x;
+  float s = fmaf(r2, 0x1.27dbb8p-19f, -0x1.9e3becp-13f);
+  s = fmaf(s, r2, 0x1.110d8ap-7f);
+  s = fmaf(s, r2, -0x1.55554ep-3f);
+  *sn = fmaf(s * r2, x, x);
+  float c = fmaf(r2, 0x1.783fa2p-22f, 0x1.88ffdp-16f);
+  c = fmaf(c, r2, -0x1.6bd36p-10f);
+  c = fmaf(c, r2, 0x1.5554c6p-5f);
+  c = fmaf(c, r2, -0x1.fffffep-2f);
+  *cs = fmaf(c, r2, 1.0f);
+}
 
 __device__ __forceinline__ float num_div(float a, float b) { return a / b; }  // IEEE division, as the general path below
 
@@ -67,7 +84,14 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
 #pragma unroll
       for (int k = 0; k < F; ++k) big = fmaxf(big, fabsf(X[k].y));
       const bool plain = !p.polar.log_mag && !(p.polar.clip_max > 0.0f) && !p.polar.clip_min_zero;
-      if (plain && big <= 65536.0f) {
+      if (plain && big <= 1.0f) {
+#pragma unroll
+        for (int k = 0; k < F; ++k) {
+          float sn, cs;
+          sincos_unit(X[k].y, &sn, &cs);
+          X[k] = make_float2(X[k].x * cs, X[k].x * sn);
+        }
+      } else if (plain && big <= 65536.0f) {
 #pragma unroll
         for (int k = 0; k < F; ++k) {
           float sn, cs;
@@ -112,19 +136,38 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
   // the four taps in the same order as below, without the per-frame existence tests (88 ISETP per warp on the source page)
   const bool inner = t - 3 >= 0 && t < p.T && t * HOP - p.out_start >= 0 && t * HOP + HOP - p.out_start <= p.out_len;
   if (__all_sync(0xffffffffu, inner || lane < 3)) {
-    float* o = p.out + (int64_t)clip_i * p.out_clip_stride + (t * HOP - p.out_start);
+    // the warp's 29 hops are ONE contiguous run of the output: results are parked in a per-warp staging row (pitch odd:
+    // conflict free) and leave as coalesced 128-byte stores — a thread storing its own hop writes HOP floats at a stride of
+    // HOP floats, i.e. every store instruction of the warp touches all ~19 sectors of the run
+    constexpr int SP = HOP | 1;
+    __shared__ float s_out[8][32 * SP];
+    float* const so = s_out[threadIdx.x >> 5];
+    const bool rd = p.rden_ok != 0;
 #pragma unroll
     for (int j = 0; j < HOP; ++j) {
       const float y3 = __shfl_up_sync(0xffffffffu, y[j + 3 * HOP], 3);
       const float y2 = __shfl_up_sync(0xffffffffu, y[j + 2 * HOP], 2);
       const float y1 = __shfl_up_sync(0xffffffffu, y[j + HOP], 1);
-      const float w3 = p.w[j + 3 * HOP], w2 = p.w[j + 2 * HOP], w1 = p.w[j + HOP], w0 = p.w[j];
       const float n_ = ((0.f + y3) + y2) + y1 + y[j];
-      const float d_ = p.norm_sq ? (((0.f + w3 * w3) + w2 * w2) + w1 * w1) + w0 * w0 : (((0.f + w3) + w2) + w1) + w0;
       float r;
-      if (p.div_clamp) r = num_div(n_, fmaxf(d_, p.div_eps));
-      else r = d_ > p.div_eps ? num_div(n_, d_) : n_;
-      if (lane >= 3) o[j] = r;
+      if (rd) {
+        // all four frames exist: the envelope is a constant of j; its reciprocal (rounded once from double on the host)
+        // replaces the IEEE division (<= 1 ulp from the quotient), as in the 1024 / 256 kernel
+        r = n_ * p.rden[j];
+      } else {
+        const float w3 = p.w[j + 3 * HOP], w2 = p.w[j + 2 * HOP], w1 = p.w[j + HOP], w0 = p.w[j];
+        const float d_ = p.norm_sq ? (((0.f + w3 * w3) + w2 * w2) + w1 * w1) + w0 * w0 : (((0.f + w3) + w2) + w1) + w0;
+        if (p.div_clamp) r = num_div(n_, fmaxf(d_, p.div_eps));
+        else r = d_ > p.div_eps ? num_div(n_, d_) : n_;
+      }
+      so[lane * SP + j] = r;
+    }
+    __syncwarp();
+    float* const o = p.out + (int64_t)clip_i * p.out_clip_stride + ((int64_t)wclip * 29 * HOP - p.out_start);  // hop of lane 3
+#pragma unroll
+    for (int i0 = 0; i0 < 29 * HOP; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < 29 * HOP) o[i] = so[(3 + i / HOP) * SP + i % HOP];
     }
     return;
   }
@@ -255,6 +298,16 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : len;
   p.out = a->out;
   for (int i = 0; i < 32; ++i) p.w[i] = i < N ? plan->h_window[i] : 0.0f;
+  p.rden_ok = 1;
+  for (int j = 0; j < d.hop; ++j) {  // ascending frame order: the oldest frame contributes tap j + 3 * hop
+    float sum = 0.0f;
+    for (int q = 3; q >= 0; --q) {
+      const float w = p.w[j + q * d.hop];
+      sum += p.norm_sq ? w * w : w;
+    }
+    if (!(sum > p.div_eps)) p.rden_ok = 0;  // guard active: keep the exact division path
+    p.rden[j] = (float)(1.0 / (double)sum);
+  }
   const int64_t slots = a->num_frames + 3;
   p.warps_per_clip = (int)((slots + 28) / 29);
   dim3 grid((p.warps_per_clip + 7) / 8, a->batch);
