@@ -83,6 +83,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--match", default="", help="section G: run only the shapes whose name contains this text")
     a = ap.parse_args()
     res = []
 
@@ -266,6 +267,8 @@ def main():
         g.manual_seed(21)
 
         def rec(name, kern, fn, in_bytes, secs):
+            if a.match and a.match not in name:
+                return
             out = fn()
             ms = timeit(fn, a.steps)
             by = in_bytes + out.numel() * out.element_size()

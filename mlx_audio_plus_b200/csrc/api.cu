@@ -89,6 +89,23 @@ int plan_common_init(b2a_plan* p, int n_fft, int hop, const float* h_window, int
   }
   int rc = upload((void**)&p->d_twiddle, tw.data(), sizeof(float2) * n_fft);
   if (rc) return rc;
+  // per-pass twiddle tables of the generic kernels' Stockham passes (generic.cu: stockham_pass_fixed)
+  std::vector<float2> twp(n_fft > 0 ? n_fft : 1, make_float2(1.0f, 0.0f));
+  {
+    int Ns = 1;
+    for (int s = 0; s < p->nstages; ++s) {
+      const int R = p->radix[s];
+      if (Ns > 1)
+        for (int r = 1; r < R; ++r)
+          for (int k = 0; k < Ns; ++k) {
+            const double a = -2.0 * M_PI * (double)(((int64_t)k * r) % ((int64_t)Ns * R)) / (double)((int64_t)Ns * R);
+            twp[(Ns - 1) + (r - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
+          }
+      Ns *= R;
+    }
+  }
+  rc = upload((void**)&p->d_twiddle_passes, twp.data(), sizeof(float2) * twp.size());
+  if (rc) return rc;
   p->h_window.assign(n_fft, 0.0f);  // zero-extended on the right: dsp.py:114-116 / 180-181
   for (int i = 0; i < window_len; ++i) p->h_window[i] = h_window[i];
   return upload((void**)&p->d_window, p->h_window.data(), sizeof(float) * n_fft);
@@ -368,6 +385,7 @@ int b2a_plan_destroy(b2a_plan* p) {
   if (p->fast && p->kind == PLAN_ISTFT) fast_istft_destroy(p);
   if (p->fast) fast_frontend_destroy(p);
   cudaFree(p->d_twiddle);
+  cudaFree(p->d_twiddle_passes);
   cudaFree(p->d_window);
   cudaFree(p->mel.d_start);
   cudaFree(p->mel.d_len);

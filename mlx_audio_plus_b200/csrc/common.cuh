@@ -200,6 +200,7 @@ struct b2a_plan {
   int device, sm_count;
   // device tables
   float2* d_twiddle;  // W_N^k = exp(-2 pi i k / N), k = 0..N-1 (computed in double)
+  float2* d_twiddle_passes;  // the same roots as per-pass tables [r - 1][k] = W_(Ns R)^(k r), back to back (N - 1 entries, padded to N)
   float* d_window;    // n_fft taps, zero-extended on the right
   std::vector<float> h_window;
   b2a::MelCsr mel;

@@ -32,10 +32,16 @@ struct FftDesc {
   int n;
   int nstages;
   int radix[kMaxStages];
+  const float2* tw_plain;  // W_n^k, k < n, in GLOBAL memory: only the prime-radix pass reads it
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT-class approximation, flush-to-zero
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -52,7 +58,10 @@ __device__ __forceinline__ int fast_div(int idx, int d, unsigned magic) {
   (void)d;
   return (int)__umulhi((unsigned)idx, magic);
 }
-__host__ __device__ inline unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+// ceil(2^32 / d) = floor((2^32 - 1) / d) + 1, in 32-bit arithmetic: written as a 64-bit quotient this was a ~90-instruction
+// library call per thread in every FFT pass (the kernels compute the magic of a pass's butterfly count on the fly) — 6-9 % of
+// the generic kernels' instructions on the ncu source page
+__host__ __device__ inline unsigned div_magic(int d) { return d <= 1 ? 0u : 0xFFFFFFFFu / (unsigned)d + 1u; }
 
 // One Stockham pass of radix R over `count` independent length-n sequences laid out back to back.
 // src / dst: [count][n] float2.  tw: W_n^k table (SHARED memory: the generic kernels stage it once per CTA — read from global
@@ -63,7 +72,6 @@ template <int R>
 __device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ src, float2* __restrict__ dst,
                                                     const float2* __restrict__ tw, int n, int Ns, int count) {
   const int nb = n / R;            // butterflies per sequence
-  const int tstep = n / (Ns * R);  // twiddle index stride
   const unsigned nb_magic = div_magic(nb);
   const bool ns_pow2 = (Ns & (Ns - 1)) == 0;
   const int total = count * nb;
@@ -76,9 +84,12 @@ __device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ s
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = sp[skew(j + r * nb)];
     if (Ns > 1) {  // first pass: k == 0, every twiddle is 1
-      const int kt = k * tstep;
+      // per-pass table [r - 1][k] = W_(Ns R)^(k r): the lanes of a warp (consecutive k) read consecutive entries.  Indexed as
+      // W_n^(k tstep r) in one table of n roots, a warp's loads were strided by tstep * r entries: the twiddle loads were the
+      // bank-conflict replays of the FFT passes (23 % of the forward kernel's shared-memory wavefronts there, 58 % of the inverse's)
+      const float2* t = tw + k;
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[kt * r]);  // k * r < Ns * R  =>  index < n
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], t[(r - 1) * Ns]);
     }
     regs::Dft<R>::run(v);
     float2* d = dst + (size_t)seq * seq_pitch(n);
@@ -101,14 +112,14 @@ __device__ __forceinline__ void stockham_pass_any(const float2* __restrict__ src
     float2 v[kMaxGenericRadix];
     for (int r = 0; r < R; ++r) {
       float2 x = sp[skew(j + r * nb)];
-      if (r > 0) x = cmul(x, tw[k * r * tstep]);  // k*r < Ns*R  =>  index < n
+      if (r > 0) x = cmul(x, __ldg(tw + k * r * tstep));  // k*r < Ns*R  =>  index < n
       v[r] = x;
     }
     float2* d = dst + (size_t)seq * seq_pitch(n);
     const int o0 = (j - k) * R + k;
     for (int q = 0; q < R; ++q) {
       float2 acc = v[0];
-      for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(v[r], tw[((q * r) % R) * rstep]));
+      for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(v[r], __ldg(tw + ((q * r) % R) * rstep)));
       d[skew(o0 + q * Ns)] = acc;
     }
   }
@@ -120,21 +131,22 @@ __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2
   float2 *src = a, *dst = b;
   for (int s = 0; s < fd.nstages; ++s) {
     const int R = fd.radix[s];
+    const float2* tws = tw + (Ns - 1);  // pass tables back to back: sum over earlier passes of (R - 1) * Ns = Ns - 1
     switch (R) {
-      case 2: stockham_pass_fixed<2>(src, dst, tw, fd.n, Ns, count); break;
-      case 3: stockham_pass_fixed<3>(src, dst, tw, fd.n, Ns, count); break;
-      case 4: stockham_pass_fixed<4>(src, dst, tw, fd.n, Ns, count); break;
-      case 5: stockham_pass_fixed<5>(src, dst, tw, fd.n, Ns, count); break;
-      case 6: stockham_pass_fixed<6>(src, dst, tw, fd.n, Ns, count); break;
-      case 8: stockham_pass_fixed<8>(src, dst, tw, fd.n, Ns, count); break;
-      case 10: stockham_pass_fixed<10>(src, dst, tw, fd.n, Ns, count); break;
-      case 12: stockham_pass_fixed<12>(src, dst, tw, fd.n, Ns, count); break;
-      case 15: stockham_pass_fixed<15>(src, dst, tw, fd.n, Ns, count); break;
-      case 16: stockham_pass_fixed<16>(src, dst, tw, fd.n, Ns, count); break;
-      case 20: stockham_pass_fixed<20>(src, dst, tw, fd.n, Ns, count); break;
-      case 25: stockham_pass_fixed<25>(src, dst, tw, fd.n, Ns, count); break;
-      case 32: stockham_pass_fixed<32>(src, dst, tw, fd.n, Ns, count); break;
-      default: stockham_pass_any(src, dst, tw, fd.n, Ns, count, R); break;
+      case 2: stockham_pass_fixed<2>(src, dst, tws, fd.n, Ns, count); break;
+      case 3: stockham_pass_fixed<3>(src, dst, tws, fd.n, Ns, count); break;
+      case 4: stockham_pass_fixed<4>(src, dst, tws, fd.n, Ns, count); break;
+      case 5: stockham_pass_fixed<5>(src, dst, tws, fd.n, Ns, count); break;
+      case 6: stockham_pass_fixed<6>(src, dst, tws, fd.n, Ns, count); break;
+      case 8: stockham_pass_fixed<8>(src, dst, tws, fd.n, Ns, count); break;
+      case 10: stockham_pass_fixed<10>(src, dst, tws, fd.n, Ns, count); break;
+      case 12: stockham_pass_fixed<12>(src, dst, tws, fd.n, Ns, count); break;
+      case 15: stockham_pass_fixed<15>(src, dst, tws, fd.n, Ns, count); break;
+      case 16: stockham_pass_fixed<16>(src, dst, tws, fd.n, Ns, count); break;
+      case 20: stockham_pass_fixed<20>(src, dst, tws, fd.n, Ns, count); break;
+      case 25: stockham_pass_fixed<25>(src, dst, tws, fd.n, Ns, count); break;
+      case 32: stockham_pass_fixed<32>(src, dst, tws, fd.n, Ns, count); break;
+      default: stockham_pass_any(src, dst, fd.tw_plain, fd.n, Ns, count, R); break;
     }
     __syncthreads();
     Ns *= R;
@@ -181,6 +193,7 @@ struct FwdParams {
   const float* window;
   const int *mel_start, *mel_len, *mel_off;
   const float* mel_w;
+  int mel_nnz, mel_smem;  // filterbank taps; 1: the CSR tables are staged in shared memory behind the twiddles
   FftDesc fft;
   int frames_per_tile, tiles_per_clip;
   int dump_frames, dump_windowed;
@@ -211,14 +224,34 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
   float* xs = reinterpret_cast<float*>(bufB + (size_t)PAIRS * NP);
   float2* tw_s = reinterpret_cast<float2*>(xs + ((span + 3) & ~3));  // [N] twiddles, staged once per CTA
   __shared__ float red_max[kThreads / 32], red_min[kThreads / 32];
+  // the CSR filterbank (taps, then start / length / offset per row) once per CTA: read from global memory, the taps put an L1
+  // round trip into every step of the projection's FMA chains (long-scoreboard stalls were half of that phase's samples)
+  float* melw_s = reinterpret_cast<float*>(tw_s + N);
+  int* melm_s = reinterpret_cast<int*>(melw_s + ((p.mel_nnz + 3) & ~3));
+  if (p.mel_smem) {
+    for (int i = threadIdx.x; i < p.mel_nnz; i += blockDim.x) melw_s[i] = p.mel_w[i];
+    for (int i = threadIdx.x; i < p.n_mels; i += blockDim.x) {
+      melm_s[3 * i + 0] = p.mel_start[i];
+      melm_s[3 * i + 1] = p.mel_len[i];
+      melm_s[3 * i + 2] = p.mel_off[i];
+    }
+  }
   if (!p.dump_frames) stage_twiddles(tw_s, p.tw, N);
+  else __syncthreads();
   // index splits of the element-wise loops as multiply-high (operands well below 2^20 / 2^12, see fast_div)
   const unsigned mg_N = div_magic(N), mg_FT = div_magic(FT);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int clip_i = (int)(tile / p.tiles_per_clip);
-    const int tile_i = (int)(tile - (int64_t)clip_i * p.tiles_per_clip);
+  // (clip, tile) of the CTA's tiles are walked incrementally: a 64-bit division per tile and thread (two with the prefetch of
+  // the next tile) was 6 % of the instructions at 8 frames per tile
+  const unsigned tpc = (unsigned)p.tiles_per_clip;
+  const int step_c = (int)(gridDim.x / tpc), step_t = (int)(gridDim.x - (unsigned)step_c * tpc);
+  int clip_i = (int)(blockIdx.x / tpc), tile_i = (int)(blockIdx.x - (unsigned)clip_i * tpc);
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, clip_i += step_c, tile_i += step_t) {
+    if (tile_i >= (int)tpc) {
+      tile_i -= (int)tpc;
+      ++clip_i;
+    }
     const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
     const int64_t lt0 = (int64_t)tile_i * FT;  // local frame index of the tile's first frame
     const int64_t t0 = p.frame_begin + lt0;    // global frame index
@@ -263,8 +296,11 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     {  // the next tile's samples are pulled into L2 while this tile is transformed (one 128-byte line per thread)
       const int64_t ntile = tile + gridDim.x;
       if (ntile < total_tiles) {
-        const int nclip = (int)(ntile / p.tiles_per_clip);
-        const int nti = (int)(ntile - (int64_t)nclip * p.tiles_per_clip);
+        int nclip = clip_i + step_c, nti = tile_i + step_t;
+        if (nti >= (int)tpc) {
+          nti -= (int)tpc;
+          ++nclip;
+        }
         int64_t a0 = (p.frame_begin + (int64_t)nti * FT) * hop - p.geo.pad_left, a1 = a0 + span;
         a0 = a0 < p.sample_offset ? p.sample_offset : a0;
         a1 = a1 > s_lim ? s_lim : a1;
@@ -357,12 +393,10 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
         const float w = __ldg(p.window + k);
         const float* x0 = xs + k;
         float2* d = bufA + skew(k);
-        for (int pr = 0; pr < PAIRS; ++pr) {
-          const int fa = 2 * pr, fb = 2 * pr + 1;
-          const float a = fa < nf ? x0[fa * hop] * w : 0.0f;
-          const float b = fb < nf ? x0[fb * hop] * w : 0.0f;
-          d[(size_t)pr * NP] = make_float2(a, b);
-        }
+        const int full = nf >> 1;  // pairs whose two frames both exist
+#pragma unroll 4
+        for (int pr = 0; pr < full; ++pr, x0 += 2 * hop, d += NP) *d = make_float2(x0[0] * w, x0[hop] * w);
+        for (int pr = full; pr < PAIRS; ++pr, x0 += 2 * hop, d += NP) *d = make_float2(2 * pr < nf ? x0[0] * w : 0.0f, 0.0f);
       }
       __syncthreads();
       Z = run_fft(p.fft, bufA, bufB, tw_s, PAIRS);
@@ -389,6 +423,9 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       continue;
     }
     float* P = reinterpret_cast<float*>(other);  // [FT][F]
+    // magnitude: ONE MUFU instruction (sqrt.approx, <= 2 ulp, as the fused kernels) instead of the IEEE sqrtf sequence with its
+    // denormal slow path behind a branch per bin
+    const float spec_add = p.spec_kind == B2A_SPEC_MAGNITUDE ? 0.0f : p.spec_eps;
     for (int k = threadIdx.x; k < F; k += blockDim.x) {
       const float2* zk_p = Z + skew(k);
       const float2* zm_p = Z + (k == 0 ? 0 : skew(N - k));
@@ -400,12 +437,12 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
         if (fa < nf) {
           const float re = 0.5f * (zk.x + zm.x), im = 0.5f * (zk.y - zm.y);
           const float pw = re * re + im * im;
-          va = p.spec_kind == B2A_SPEC_POWER ? pw : p.spec_kind == B2A_SPEC_MAGNITUDE ? sqrtf(pw) : sqrtf(pw + p.spec_eps);
+          va = p.spec_kind == B2A_SPEC_POWER ? pw : sqrt_approx(pw + spec_add);
         }
         if (fb < nf) {
           const float re = 0.5f * (zk.y + zm.y), im = 0.5f * (zm.x - zk.x);
           const float pw = re * re + im * im;
-          vb = p.spec_kind == B2A_SPEC_POWER ? pw : p.spec_kind == B2A_SPEC_MAGNITUDE ? sqrtf(pw) : sqrtf(pw + p.spec_eps);
+          vb = p.spec_kind == B2A_SPEC_POWER ? pw : sqrt_approx(pw + spec_add);
         }
         pk[(size_t)fa * F] = va;
         pk[(size_t)fb * F] = vb;
@@ -417,23 +454,43 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     const int M = p.n_mels > 0 ? p.n_mels : F;
     float* Y = reinterpret_cast<float*>(Z);  // [FT][M]   (M <= F <= N)
     float lmax = -INFINITY, lmin = INFINITY;
-    // FRAME-fastest items: the lanes that share a mel row read the same weights (one sector per load instead of up to 32) and
-    // walk the power tile at a stride of F floats (F odd for even n_fft: conflict free); with row-fastest items every lane
-    // started its band at a different bin (55 % of the phase's shared-memory wavefronts were bank-conflict replays)
-    for (int i = threadIdx.x; i < FT * M; i += blockDim.x) {
-      const int m = FT > 1 ? fast_div(i, FT, mg_FT) : i, f = i - m * FT;
-      if (f >= nf) continue;
-      float acc;
-      if (p.n_mels > 0) {
-        const float* row = P + (size_t)f * F + __ldg(p.mel_start + m);
-        const float* w = p.mel_w + __ldg(p.mel_off + m);
-        const int len = __ldg(p.mel_len + m);
-        acc = 0.0f;
+    // One item = (mel row, frame), frame fastest, owned by a QUAD of lanes: the four lanes take every fourth tap and fold with
+    // two shuffles.  The quads that share a row read the same taps (one broadcast), walk the power tile at a stride of F floats
+    // (F odd for even n_fft: conflict free), and — what matters at 8 frames per tile — every thread gets the same mix of short
+    // and long rows: with one thread per item the 640 items of an S3Gen tile left three quarters of the CTA idle while the first
+    // 128 threads walked the longest rows (60 taps) after their short ones.
+    // (large tiles of short rows — the Kaldi front-end: 64 frames x 80 rows of 3-12 taps — keep one thread per item)
+    const int items = FT * M, items_pad = (items + 7) & ~7;  // warp-uniform trip count (8 quads per warp): the shuffles need every lane
+    const bool quads = p.n_mels > 0 && items <= 4 * (int)blockDim.x;
+    const int lsh = quads ? 2 : 0, lpi = 1 << lsh;
+    const int quad = threadIdx.x >> lsh, sub = threadIdx.x & (lpi - 1);
+    for (int i = quad; i < items_pad; i += blockDim.x >> lsh) {
+      const int m = FT > 1 ? fast_div(i, FT, mg_FT) : i;
+      const int f = i < items ? i - m * FT : FT;
+      float acc = 0.0f;
+      if (f < nf) {
+        if (p.n_mels > 0) {
+          int start, len, off;
+          const float* w;
+          if (p.mel_smem) {
+            start = melm_s[3 * m], len = melm_s[3 * m + 1], off = melm_s[3 * m + 2];
+            w = melw_s + off;
+          } else {
+            start = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m), off = __ldg(p.mel_off + m);
+            w = p.mel_w + off;
+          }
+          const float* row = P + (size_t)f * F + start;
 #pragma unroll 4
-        for (int j = 0; j < len; ++j) acc = fmaf(row[j], __ldg(w + j), acc);
-      } else {
-        acc = P[(size_t)f * F + m];
+          for (int j = sub; j < len; j += lpi) acc = fmaf(row[j], w[j], acc);
+        } else if (sub == 0) {
+          acc = P[(size_t)f * F + m];
+        }
       }
+      if (quads) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      }
+      if (f >= nf || sub != 0) continue;
       if (p.guard_kind == B2A_GUARD_MAX) acc = fmaxf(acc, p.guard_eps);
       else if (p.guard_kind == B2A_GUARD_ADD) acc = acc + p.guard_eps;
       if (p.log_kind == B2A_LOG_LOG10) acc = log10f(acc);
@@ -813,41 +870,64 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
         pf_base = (int64_t)nx_clip * p.clip_stride + nx_tlo;
         pf_n = min(2 * p.pairs_chunk, nx_nfr);
       }
-      for (int kk = threadIdx.x; kk < F; kk += blockDim.x) {
-        const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0;
+      // up to KB bins per thread and four frames (two pairs) per bin are loaded BEFORE anything is converted or stored: with one
+      // bin at a time a thread waited out one memory round trip per bin and pair group (long-scoreboard stalls were 67 % of
+      // this phase's samples, the phase 42 % of the MossFormer2 inverse)
+      constexpr int KB = 3;
+      for (int kb0 = threadIdx.x; kb0 < F; kb0 += KB * blockDim.x) {
         if (pf_n > 0) {
-          const int64_t b0 = pf_base + (int64_t)kk * p.T, b1 = b0 + pf_n - 1;
-          if (p.spec) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b1));
-          } else {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b1));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b1));
-          }
-        }
-        const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
-        const int km = (kk == 0 || 2 * kk == N) ? -1 : N - kk;  // mirrored position (bins > N/2), none for DC / Nyquist
-#pragma unroll 4
-        for (int pr = 0; pr < cp; ++pr) {
-          const int fa = 2 * pr, fb = fa + 1;
-          float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-          if (p.spec) {
-            xa = p.spec[base + fa];
-            if (fb < cf) xb = p.spec[base + fb];
-          } else {  // all loads of the pair in flight before the (branchy) polar conversion
-            xa = make_float2(p.spec_re[base + fa], p.spec_im[base + fa]);
-            if (fb < cf) xb = make_float2(p.spec_re[base + fb], p.spec_im[base + fb]);
-            if (p.polar.polar) {
-              xa = polar_to_complex(p.polar, xa);
-              if (fb < cf) xb = polar_to_complex(p.polar, xb);
+#pragma unroll
+          for (int b = 0; b < KB; ++b) {
+            const int kk = kb0 + b * blockDim.x;
+            if (kk >= F) break;
+            const int64_t b0 = pf_base + (int64_t)kk * p.T, b1 = b0 + pf_n - 1;
+            if (p.spec) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b1));
+            } else {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b1));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b1));
             }
           }
-          if (real_bin) { xa.y = 0.f; xb.y = 0.f; }
-          // z = xa + i xb ; store conj(z).  Mirrored bin: conj(xa) + i conj(xb)
-          bufA[(size_t)pr * NP + skew(kk)] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
-          if (km >= 0) bufA[(size_t)pr * NP + skew(km)] = make_float2(xa.x + xb.y, -(xb.x - xa.y));
+        }
+        for (int pr0 = 0; pr0 < cp; pr0 += 2) {
+          float2 x[KB][4];
+#pragma unroll
+          for (int b = 0; b < KB; ++b) {
+            const int kk = kb0 + b * blockDim.x;
+            const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0 + 2 * pr0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              x[b][q] = make_float2(0.f, 0.f);
+              if (kk < F && 2 * pr0 + q < cf) {
+                if (p.spec) x[b][q] = p.spec[base + q];
+                else x[b][q] = make_float2(p.spec_re[base + q], p.spec_im[base + q]);
+              }
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < KB; ++b) {
+            const int kk = kb0 + b * blockDim.x;
+            if (kk >= F) break;
+            const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
+            const int km = real_bin ? -1 : N - kk;         // mirrored position (bins > N/2), none for DC / Nyquist
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int pr = pr0 + h;
+              if (pr >= cp) break;
+              float2 xa = x[b][2 * h], xb = x[b][2 * h + 1];
+              if (!p.spec && p.polar.polar) {
+                xa = polar_to_complex(p.polar, xa);
+                if (2 * pr + 1 < cf) xb = polar_to_complex(p.polar, xb);
+              }
+              if (real_bin) { xa.y = 0.f; xb.y = 0.f; }
+              // z = xa + i xb ; store conj(z).  Mirrored bin: conj(xa) + i conj(xb)
+              bufA[(size_t)pr * NP + skew(kk)] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
+              if (km >= 0) bufA[(size_t)pr * NP + skew(km)] = make_float2(xa.x + xb.y, -(xb.x - xa.y));
+            }
+          }
         }
       }
       __syncthreads();
@@ -910,10 +990,17 @@ static FftDesc make_fft_desc(const b2a_plan* plan) {
   d.n = plan->n_fft;
   d.nstages = plan->nstages;
   for (int i = 0; i < kMaxStages; ++i) d.radix[i] = plan->radix[i];
+  d.tw_plain = plan->d_twiddle;
   return d;
 }
 
 }  // namespace
+
+// Tile budget of the generic kernels: dynamic shared memory that still fits the SM's 196 KB shared-memory configuration (1 KB
+// reserved per CTA, ~1 KB static), which leaves 60 KB of L1.  One step further — the 228 KB configuration, 28 KB of L1 — the
+// spectrum loads of the inverse (half a 32-byte sector per bin and round; the next round finds the other half in L1) and the
+// window / filterbank reads start missing: measured 15-25 % slower on every shape (MossFormer2 inverse 7.3 -> 9.1 ms).
+constexpr size_t kTileBudget = 194 * 1024;
 
 size_t generic_smem_limit(const b2a_plan* plan) {
   (void)plan;
@@ -935,7 +1022,9 @@ static int choose_frames_per_tile(int N, int hop, size_t budget, int max_ft) {
 
 int generic_tile_frames(const b2a_plan* plan, const b2a_forward_args* a) {
   const b2a_frontend_desc& d = plan->fd;
-  int ft = choose_frames_per_tile(d.n_fft, d.hop, 200 * 1024, 64);
+  // (the CSR filterbank tables ride in the same budget: at most ~4 * n_fft + 12 * n_mels bytes)
+  const size_t mel_room = d.n_mels > 0 ? (size_t)4 * (plan->mel.nnz + 4) + (size_t)12 * d.n_mels : 0;
+  int ft = choose_frames_per_tile(d.n_fft, d.hop, kTileBudget > mel_room + 32 * 1024 ? kTileBudget - mel_room : kTileBudget, 64);
   if (ft == 0) ft = choose_frames_per_tile(d.n_fft, d.hop, generic_smem_limit(plan), 2);
   if (ft == 0) return 0;
   // small inputs: shrink tiles so that the grid still covers the SMs
@@ -978,7 +1067,7 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   p.clip_max = clip_max;
   p.tile_min = tile_min;
   p.feat_sums = feat_sums;
-  p.tw = plan->d_twiddle;
+  p.tw = plan->d_twiddle_passes;
   p.window = plan->d_window;
   p.mel_start = plan->mel.d_start;
   p.mel_len = plan->mel.d_len;
@@ -997,7 +1086,12 @@ int generic_frontend_partial(b2a_plan* plan, const b2a_forward_args* a, float* c
   }
   p.frames_per_tile = ft;
   p.tiles_per_clip = (int)((a->frame_count + ft - 1) / ft);
-  const size_t smem = fwd_smem_bytes(ft, d.n_fft, d.hop);
+  size_t smem = fwd_smem_bytes(ft, d.n_fft, d.hop);
+  // the CSR filterbank rides behind the twiddles when it fits the slack between the tile budget (200 KB) and the 227 KB a CTA may own
+  p.mel_nnz = d.n_mels > 0 ? plan->mel.nnz : 0;
+  const size_t mel_bytes = d.n_mels > 0 ? (size_t)4 * ((p.mel_nnz + 3) & ~3) + (size_t)12 * d.n_mels : 0;
+  p.mel_smem = d.n_mels > 0 && smem + mel_bytes <= 226 * 1024;
+  if (p.mel_smem) smem += mel_bytes;
   B2A_CUDA(cudaFuncSetAttribute(frontend_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)a->batch * p.tiles_per_clip;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -1164,21 +1258,28 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.out_len = len;
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : len;
   p.out = a->out;
-  p.tw = plan->d_twiddle;
+  p.tw = plan->d_twiddle_passes;
   p.window = plan->d_window;
   p.fft = make_fft_desc(plan);
   if (len <= 0) return B2A_OK;
   const int ov = (N + hop - 1) / hop;  // frames overlapping one sample (upper bound)
-  // a few pairs per FFT round (enough butterflies for the CTA), then as many new frames per tile as ~100 KB hold (two CTAs per
-  // SM); every tile re-transforms the ov - 1 frames it shares with its left neighbour, so larger tiles waste less
-  int pairs_chunk = 4096 / N;
-  pairs_chunk = pairs_chunk < 1 ? 1 : (pairs_chunk > 16 ? 16 : pairs_chunk);
-  static const int pc_override = getenv("B2A_X_PC") ? atoi(getenv("B2A_X_PC")) : 0;  // development: pairs per FFT round
-  if (pc_override > 0) pairs_chunk = pc_override;
+  // pairs per FFT round: enough butterflies for the CTA (a radix-16 pass over two 2048-point pairs is 256 butterflies for 512
+  // threads; four pairs also make a bin's frames of one round a whole 32-byte sector), as long as the tile still advances by
+  // >= 4 * ov frames — every tile re-transforms the ov - 1 frames it shares with its left neighbour.  The tile stays within
+  // kTileBudget (the 196 KB shared-memory configuration).
   auto smem_for = [&](int pc, int adv) { return (size_t)16 * pc * seq_pitch(N) + (size_t)8 * N + (size_t)4 * N + (size_t)4 * adv * hop + 16; };
-  int adv = 0;
-  for (int cand = 1; cand <= 1024; cand *= 2)
-    if (smem_for(pairs_chunk, cand) <= 200 * 1024 && cand * hop <= (1 << 20)) adv = cand;
+  auto adv_for = [&](int pc) {
+    int best = 0;
+    for (int cand = 1; cand <= 1024; cand *= 2)
+      if (smem_for(pc, cand) <= kTileBudget && (int64_t)cand * hop <= (1 << 20)) best = cand;
+    return best;
+  };
+  static const int pc_override = getenv("B2A_X_PC") ? atoi(getenv("B2A_X_PC")) : 0;  // development: pairs per FFT round
+  int pairs_chunk = 8192 / N;
+  pairs_chunk = pairs_chunk < 1 ? 1 : (pairs_chunk > 16 ? 16 : pairs_chunk);
+  if (adv_for(pairs_chunk) < 4 * ov) pairs_chunk = pairs_chunk / 2 < 1 ? 1 : pairs_chunk / 2;
+  if (pc_override > 0) pairs_chunk = pc_override;
+  int adv = adv_for(pairs_chunk);
   if (adv < 4 * ov) {  // large transforms: one CTA per SM, all of its shared memory
     for (int cand = adv > 0 ? adv : 1; cand <= 1024; cand *= 2)
       if (smem_for(pairs_chunk, cand) <= generic_smem_limit(plan)) adv = cand;

@@ -1,7 +1,9 @@
 #!/bin/bash
-# ncu --set full captures (with source) of the two generic kernels on the shapes of bench_configs section G
+# prof_g.sh <name> <kernel regex> <match text> : ncu --set full capture (with source) of one generic-kernel shape of bench_configs section G
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
-G="python benchmarks/bench_configs.py --only G --steps 2"
-$G > gpurun_out/pg_plain.log 2>&1; echo "plain rc=$?"; tail -7 gpurun_out/pg_plain.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:frontend_generic -c 1 -f -o gpurun_out/r02_k2_fwd_1920 $G > gpurun_out/pg_ncu_fwd.log 2>&1; echo "ncu fwd rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:istft_generic -c 1 -f -o gpurun_out/r02_k3b_inv_2048 $G > gpurun_out/pg_ncu_inv.log 2>&1; echo "ncu inv rc=$?"
+while [ $# -ge 3 ]; do
+G="python benchmarks/bench_configs.py --only G --steps 2 --match $3"
+$G > gpurun_out/pg_plain_$1.log 2>&1; echo "plain rc=$?"; tail -2 gpurun_out/pg_plain_$1.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o gpurun_out/$1 $G > gpurun_out/pg_ncu_$1.log 2>&1; echo "ncu $1 rc=$?"
+shift 3
+done
