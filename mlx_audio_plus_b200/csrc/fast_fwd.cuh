@@ -1458,6 +1458,8 @@ int launch_ws(b2a_plan* plan, FastParams& p, cudaStream_t st) {
           static SmemAttrOnce attr1;
           if (attr1.need(plan->device, smem1))
             B2A_CUDA(cudaFuncSetAttribute(fast_logmel_tma_kernel<C, MS, SPECK, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            if (getenv("B2A_X_CARVE_K1"))  // development: shared-memory configuration as a percentage of the largest one
+              B2A_CUDA(cudaFuncSetAttribute(fast_logmel_tma_kernel<C, MS, SPECK, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("B2A_X_CARVE_K1"))));
           fast_logmel_tma_kernel<C, MS, SPECK, true, false><<<grid1, C::THREADS, smem1, st>>>(p, map);
           B2A_LAUNCHED();
           return B2A_OK;

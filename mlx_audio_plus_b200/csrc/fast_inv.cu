@@ -29,6 +29,17 @@
 #ifndef B2A_X_PF
 #define B2A_X_PF 1
 #endif
+// Spectrum loads bypass L1 (ld.global.cg): every sector is read by exactly one warp, and an L1 miss has to hold an L1 line until its
+// data returns — with most of the SM's unified memory carved out as shared memory (28 KB of L1 next to two 89 KB CTAs) the few
+// lines left cap the loads in flight, and the kernels are load-latency bound
+#ifndef B2A_X_LDCG
+#define B2A_X_LDCG 0
+#endif
+#if B2A_X_LDCG
+#define B2A_LD(p) __ldcg(p)
+#else
+#define B2A_LD(p) __ldg(p)
+#endif
 
 namespace b2a {
 
@@ -147,19 +158,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) fast_istft_kernel(const InvFast
           }
         }
         if constexpr (PLANAR) {
-          xa[s] = live ? make_float2(__ldg(ra), __ldg(ia)) : zero2;
-          xb[s] = live ? make_float2(__ldg(rb), __ldg(ib)) : zero2;
+          xa[s] = live ? make_float2(B2A_LD(ra), B2A_LD(ia)) : zero2;
+          xb[s] = live ? make_float2(B2A_LD(rb), B2A_LD(ib)) : zero2;
           ra += stepT; ia += stepT; rb -= stepT; ib -= stepT;
         } else {
-          xa[s] = live ? __ldg(qa) : zero2;
-          xb[s] = live ? __ldg(qb) : zero2;
+          xa[s] = live ? B2A_LD(qa) : zero2;
+          xb[s] = live ? B2A_LD(qb) : zero2;
           qa += stepT; qb -= stepT;
         }
       });
       auto load_at = [&](int64_t i) -> float2 {
         if (!live) return zero2;
-        if constexpr (PLANAR) return make_float2(__ldg(p.spec_re + i), __ldg(p.spec_im + i));
-        else return __ldg(p.spec + i);
+        if constexpr (PLANAR) return make_float2(B2A_LD(p.spec_re + i), B2A_LD(p.spec_im + i));
+        else return B2A_LD(p.spec + i);
       };
       float2 dc = make_float2(0.0f, 0.0f);
       if (u == 0) {  // Im(DC), Im(Nyquist) are ignored (irfft)
@@ -391,6 +402,357 @@ int launch_inv(b2a_plan* plan, InvFastParams& p, cudaStream_t st) {
   return B2A_OK;
 }
 
+
+// ---- fast_istft16_kernel: 16-frame tiles, two CTAs per SM, overlap carried from tile to tile -------------------------------------
+// The 32-frame kernel above holds ONE tile per SM (131 KB exchange buffer, 126 registers x 512 threads): its three phases — spectrum
+// loads, register transforms, overlap-add — run one after the other and nothing overlaps them (issue slots 36 %, DRAM 38 % busy,
+// profiles/r02_k3_1024_ncu_full.json), and every tile re-transforms the 4 halo frames it shares with its neighbour (12.5 %).
+// Here a half-warp is a group of 16 FRAMES and the two half-warps of a warp play two different column roles (units in step 1,
+// residues in step 2), so a tile is 16 frames, its exchange buffer 64 KB and a CTA 8 warps: TWO CTAs per SM whose phases interleave.
+// A CTA walks a RUN of consecutive tiles of one clip and carries the partial overlap-add sums of the next three hops from tile to
+// tile (3 x hop floats, double buffered), so only the first tile of a run re-transforms a 3-frame lead-in.  The summation order per
+// output sample is unchanged: frames in ascending order, starting from 0 (the reference's sequential scatter-add, dsp.py:193-204).
+template <int N1_, int N2_>
+struct ICfg16 {
+  static constexpr int N1 = N1_, N2 = N2_;
+  static constexpr int NC = N1 * N2, N = 2 * NC, F = NC + 1, HOP = N / 4;
+  static constexpr int ROLES = N1 / 2, WARPS = ROLES / 2, THREADS = WARPS * 32;
+  static constexpr int FT = 16, LEAD = 3;     // frames per tile; frames a run's first tile transforms ahead of its first hop
+  static constexpr int EP = NC + 1;           // row pitch in float2 (odd)
+  static_assert(N2 == ROLES, "one step-2 residue per role");
+  static_assert(N2 % 2 == 0 && N1 % 4 == 0, "even factors, two roles per warp");
+  static_assert(HOP % 2 == 0 && (HOP / 2) * 2 == THREADS, "a hop is THREADS / 2 sample pairs: two hops per overlap-add sweep");
+};
+
+struct InvRunParams {
+  int hop_first, hop_end;   // hops [hop_first, hop_end) intersect the output range
+  int run_hops;             // hops a run produces (16 * tiles - 3)
+  int runs_per_clip;
+};
+
+template <class C>
+size_t inv16_smem_bytes() {
+  return sizeof(float2) * ((size_t)C::FT * C::EP + C::ROLES * C::N2 * 3 + C::NC) + sizeof(float) * (C::N + C::HOP + 2 * 3 * C::HOP) + 16;
+}
+
+template <class C, bool POLAR, bool PLANAR>
+__global__ void __launch_bounds__(C::THREADS, 2) fast_istft16_kernel(const InvFastParams p, const InvRunParams rp) {
+  static_assert(PLANAR || !POLAR, "magnitude / phase input comes as two planes");
+  constexpr int N1 = C::N1, N2 = C::N2, NC = C::NC, HOP = C::HOP, FT = C::FT;
+  extern __shared__ float4 smem4[];
+  float2* const E = reinterpret_cast<float2*>(smem4);                   // [FT][EP]
+  float2* const s_twp_al = E + FT * C::EP;                              // [ROLES][N2] (FT * EP is even: 16-byte aligned)
+  float2* const s_tw1 = s_twp_al + C::ROLES * N2;                       // [ROLES][2][N2]
+  float2* const s_win2 = s_tw1 + C::ROLES * 2 * N2;                     // [N2][N1]
+  float* const s_wenv = reinterpret_cast<float*>(s_win2 + N2 * N1);     // [N]
+  float* const s_rden = s_wenv + C::N;                                  // [HOP]
+  float* const s_carry = s_rden + HOP;                                  // [2][3][HOP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fr = lane & 15, role = 2 * warp + (lane >> 4);
+  for (int i = threadIdx.x; i < C::ROLES * N2; i += C::THREADS) s_twp_al[i] = p.twp[i];
+  for (int i = threadIdx.x; i < C::ROLES * 2 * N2; i += C::THREADS) s_tw1[i] = p.tw1[i];
+  for (int i = threadIdx.x; i < NC; i += C::THREADS) s_win2[i] = p.win2[i];
+  for (int i = threadIdx.x; i < C::N; i += C::THREADS) s_wenv[i] = p.wenv[i];
+  for (int i = threadIdx.x; i < HOP; i += C::THREADS) s_rden[i] = p.den[i];
+
+  const int u = role;
+  const int kb_lo = u != 0 ? u : N1;                      // bin of slot s (< N2/2): kb_lo + N1*s
+  const int kb_hi = u != 0 ? u : N1 / 2 - (N2 / 2) * N1;  // bin of slot s (>= N2/2): kb_hi + N1*s
+  const int rowA = u, rowB = u != 0 ? N1 - u : N1 / 2;    // E rows (k1) of the unit's two columns
+  const int64_t T = p.T;
+  const int Ti = (int)T;
+  const int total_runs = p.batch * rp.runs_per_clip;
+
+#pragma unroll 1
+  for (int run = blockIdx.x; run < total_runs; run += gridDim.x) {
+    const int clip_i = run / rp.runs_per_clip;
+    const int h0 = rp.hop_first + (run - clip_i * rp.runs_per_clip) * rp.run_hops;
+    const int h1 = min(h0 + rp.run_hops, rp.hop_end);
+    const int nt = (h1 - h0 + C::LEAD + FT - 1) / FT;
+    __syncthreads();  // the previous run's last overlap-add has finished (E, carry)
+    for (int i = threadIdx.x; i < 3 * HOP; i += C::THREADS) s_carry[i] = 0.0f;  // buffer 0: nothing carried into the run
+#pragma unroll 1
+    for (int ti = 0; ti < nt; ++ti) {
+      const int s0 = h0 - C::LEAD + FT * ti;  // frame of lane-group position 0 == hop of tile-relative q = 0
+      const int t = s0 + fr;
+      const bool live = t >= 0 && t < Ti;
+      if (ti > 0) __syncthreads();  // previous tile's overlap-add has finished reading E
+      // Every other tile the spectrum rows of the run's NEXT TWO tiles go to L2: 32 frames = 256 contiguous bytes per bin (128 per
+      // plane), the same DRAM access size as the 32-frame kernel — a 16-frame row fetched on its own is a 128-byte access whose
+      // neighbour (the next tile's) reaches the DRAM a whole tile later, after the page has been closed.
+      if ((ti & 1) == 0 && ti + 1 < nt) {
+        int64_t tf = (int64_t)s0 + FT, tl = tf + (ti + 2 < nt ? 2 * FT : FT) - 1;
+        tf = tf < 0 ? 0 : tf;
+        tl = tl > T - 1 ? T - 1 : tl;
+        if (tl >= tf) {
+          const int64_t nb = (int64_t)clip_i * p.clip_stride;
+          for (int k = threadIdx.x; k <= NC; k += C::THREADS) {
+            const int64_t o0 = nb + (int64_t)k * T + tf, o1 = nb + (int64_t)k * T + tl;
+            if constexpr (PLANAR) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + o0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + o1));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + o0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + o1));
+            } else {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + o0));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + (o0 + o1) / 2));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + o1));
+            }
+          }
+        }
+      }
+
+      // ---- step 1: role = unit u (bin columns u and N1 - u) ----------------------------------------------
+      {
+        float2 A[N2], B[N2];
+        const int64_t stepT = (int64_t)N1 * T, jumpT = (int64_t)(kb_hi - kb_lo) * T;
+        const int64_t oa0 = (int64_t)clip_i * p.clip_stride + (live ? t : 0) + (int64_t)kb_lo * T;
+        const int64_t ob0 = (int64_t)clip_i * p.clip_stride + (live ? t : 0) + (int64_t)(NC - kb_lo) * T;
+        const float2* qa = p.spec + oa0;
+        const float2* qb = p.spec + ob0;
+        const float *ra = p.spec_re + oa0, *ia = p.spec_im + oa0;
+        const float *rb = p.spec_re + ob0, *ib = p.spec_im + ob0;
+        const float2 zero2 = make_float2(0.0f, 0.0f);
+        float2 xa[N2], xb[N2];
+        static_for<0, N2>([&](auto S_) {
+          constexpr int s = decltype(S_)::value;
+          if (s == N2 / 2) {  // unit 0 switches from column 0 to column N1/2 here (jumpT == 0 for the other units)
+            if constexpr (PLANAR) {
+              ra += jumpT; ia += jumpT; rb -= jumpT; ib -= jumpT;
+            } else {
+              qa += jumpT; qb -= jumpT;
+            }
+          }
+          if constexpr (PLANAR) {
+            xa[s] = live ? make_float2(B2A_LD(ra), B2A_LD(ia)) : zero2;
+            xb[s] = live ? make_float2(B2A_LD(rb), B2A_LD(ib)) : zero2;
+            ra += stepT; ia += stepT; rb -= stepT; ib -= stepT;
+          } else {
+            xa[s] = live ? B2A_LD(qa) : zero2;
+            xb[s] = live ? B2A_LD(qb) : zero2;
+            qa += stepT; qb -= stepT;
+          }
+        });
+        auto load_at = [&](int64_t i) -> float2 {
+          if (!live) return zero2;
+          if constexpr (PLANAR) return make_float2(B2A_LD(p.spec_re + i), B2A_LD(p.spec_im + i));
+          else return B2A_LD(p.spec + i);
+        };
+        float2 dc = make_float2(0.0f, 0.0f);
+        if (u == 0) {  // Im(DC), Im(Nyquist) are ignored (irfft)
+          const int64_t o0 = (int64_t)clip_i * p.clip_stride + t;
+          float2 x0 = load_at(o0), xn = load_at(o0 + (int64_t)NC * T);
+          if (POLAR && live) {
+            x0 = polar_to_complex(p.polar, x0);
+            xn = polar_to_complex(p.polar, xn);
+          }
+          dc = make_float2(x0.x, xn.x);
+        }
+        if (POLAR && live) {
+#pragma unroll
+          for (int s = 0; s < N2; ++s) {
+            xa[s] = polar_to_complex(p.polar, xa[s]);
+            xb[s] = polar_to_complex(p.polar, xb[s]);
+          }
+        }
+        const float4* tp4 = reinterpret_cast<const float4*>(s_twp_al + u * N2);
+        auto unpack = [&](auto U0_) {
+          constexpr bool U0 = decltype(U0_)::value;
+          static_for<0, N2 / 2>([&](auto S_) {
+            constexpr int sl0 = 2 * decltype(S_)::value;
+            const float4 w2 = tp4[sl0 / 2];  // (c, s) of slots sl0, sl0 + 1: conj(W_N^k) = (cos, sin)(2 pi k / N)
+            static_for<0, 2>([&](auto J_) {
+              constexpr int s = sl0 + decltype(J_)::value;
+              const float2 w = decltype(J_)::value == 0 ? make_float2(w2.x, w2.y) : make_float2(w2.z, w2.w);
+              const float2 a = xa[s], b = xb[s];
+              const float2 e2 = regs::pfma(b, make_float2(1.0f, -1.0f), a);   // a + conj(b)
+              const float2 d = regs::pfma(b, make_float2(-1.0f, 1.0f), a);    // a - conj(b)
+              const float2 o2 = regs::cmul(d, w);                             // (a - conj b) * conj(W_N^k)
+              const float2 zk = regs::pfma(o2, make_float2(1.0f, -1.0f), regs::pswap(e2));
+              const float2 zm = regs::pfma(regs::pswap(e2), make_float2(-1.0f, 1.0f), o2);
+              if constexpr (!U0) {
+                A[s] = zk;
+                B[N2 - 1 - s] = zm;
+              } else if constexpr (s < N2 / 2) {
+                if constexpr (s + 1 < N2 / 2) A[s + 1] = zk;
+                A[N2 - 1 - s] = zm;
+              } else {
+                B[s - N2 / 2] = zk;
+                B[3 * N2 / 2 - 1 - s] = zm;
+              }
+            });
+          });
+        };
+        if (u == 0) {  // (half-warp divergent in warp 0: its two roles are units 0 and 1)
+          unpack(std::true_type{});
+          A[0] = make_float2(dc.x - dc.y, dc.x + dc.y);  // Z[0] = (X0 + XN) + i (X0 - XN), swapped
+        } else {
+          unpack(std::false_type{});
+        }
+        Dft<N2>::run(A);
+        Dft<N2>::run(B);
+        const float4* t4a = reinterpret_cast<const float4*>(s_tw1 + (u * 2 + 0) * N2);
+        const float4* t4b = reinterpret_cast<const float4*>(s_tw1 + (u * 2 + 1) * N2);
+        float2* ea = E + fr * C::EP + rowA * N2;
+        float2* eb = E + fr * C::EP + rowB * N2;
+        static_for<0, N2 / 2>([&](auto I_) {
+          constexpr int n2 = 2 * decltype(I_)::value;
+          const float4 ta = t4a[n2 / 2], tb = t4b[n2 / 2];
+          ea[n2] = n2 == 0 ? A[0] : regs::cmul(A[n2], make_float2(ta.x, ta.y));
+          ea[n2 + 1] = regs::cmul(A[n2 + 1], make_float2(ta.z, ta.w));
+          eb[n2] = n2 == 0 ? B[0] : regs::cmul(B[n2], make_float2(tb.x, tb.y));
+          eb[n2 + 1] = regs::cmul(B[n2 + 1], make_float2(tb.z, tb.w));
+        });
+      }
+      __syncthreads();  // E[frame][k1][n2] complete
+      // ---- step 2: role = residue n2 -------------------------------------------------------------------------
+      {
+        const int n2 = role;
+        float2 v[N1];
+        float2* er = E + fr * C::EP + n2;
+        static_for<0, N1>([&](auto K_) {
+          constexpr int k1 = decltype(K_)::value;
+          v[k1] = er[k1 * N2];
+        });
+        Dft<N1>::run(v);
+        constexpr int WPD = 2;
+        const unsigned wb_sa = (unsigned)__cvta_generic_to_shared(s_win2 + n2 * N1);
+        float4 wq[N1 / 2];
+        static_for<0, WPD>([&](auto I_) { wq[decltype(I_)::value] = lds128_pinned<16 * decltype(I_)::value>(wb_sa); });
+        static_for<0, N1 / 2>([&](auto I_) {
+          constexpr int n1 = 2 * decltype(I_)::value;
+          if constexpr (n1 / 2 + WPD < N1 / 2) wq[n1 / 2 + WPD] = lds128_pinned<16 * (n1 / 2 + WPD)>(wb_sa);
+          const float4 w = wq[n1 / 2];
+          er[n1 * N2] = regs::pmul(regs::pswap(v[n1]), make_float2(w.x, w.y));
+          er[(n1 + 1) * N2] = regs::pmul(regs::pswap(v[n1 + 1]), make_float2(w.z, w.w));
+        });
+      }
+      __syncthreads();  // rows of E are now windowed frames in natural sample order
+
+      // ---- step 3: overlap-add; hop q of the tile (q = 0 .. 15) is the sum of the carried partial sum (q < 3) and the quarters
+      // 3 - j of frames q - j, j = 3 .. 0 (ascending frame order); two hops per sweep ---------------------------------------
+      {
+        const float* Yf = reinterpret_cast<const float*>(E);
+        const float* cin = s_carry + (ti & 1) * 3 * HOP;
+        float* cout = s_carry + ((ti & 1) ^ 1) * 3 * HOP;
+        const int hsel = threadIdx.x / (HOP / 2), r = 2 * (threadIdx.x - hsel * (HOP / 2));
+        float* const o = p.out + (int64_t)clip_i * p.out_clip_stride;
+        const float2 rden = *reinterpret_cast<const float2*>(s_rden + r);
+        // interior tile (CTA-uniform): every hop has its four frames, lies inside the run and the output range, the reciprocal
+        // envelope table applies and the stores are 8-byte aligned — then hops 4 .. 15 are four loads, three adds, one multiply
+        // and one store each (the general loop below spends more instructions on range tests than on the overlap-add)
+        const bool interior = ti > 0 && s0 >= 3 && s0 + FT - 1 < Ti && s0 + FT <= h1 && p.rden_ok && p.vec_ok &&
+                              (int64_t)s0 * HOP - p.out_start >= 0 && (int64_t)(s0 + FT) * HOP - p.out_start <= p.out_len;
+        if (interior) {
+          constexpr int D = 2 * C::EP - HOP;  // from quarter j of frame q - j to quarter j + 1 of frame q - j - 1
+          float* oj = o + ((int64_t)(s0 + hsel) * HOP + r - p.out_start);
+          const float* y = Yf + hsel * (2 * C::EP) + r;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {  // hops 0 .. 3: the carried partial sums, fewer in-tile frames
+            const int q = 2 * it + hsel;
+            float2 num = q < 3 ? *reinterpret_cast<const float2*>(cin + q * HOP + r) : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+              if (q - j >= 0) {
+                const float2 yv = *reinterpret_cast<const float2*>(Yf + (q - j) * (2 * C::EP) + j * HOP + r);
+                num.x += yv.x;
+                num.y += yv.y;
+              }
+            }
+            *reinterpret_cast<float2*>(oj + 2 * it * HOP) = make_float2(num.x * rden.x, num.y * rden.y);
+          }
+#pragma unroll
+          for (int it = 2; it < FT / 2; ++it) {
+            const float* yi = y + 2 * it * (2 * C::EP);
+            float2 num = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+              const float2 yv = *reinterpret_cast<const float2*>(yi - j * D);
+              num.x += yv.x;
+              num.y += yv.y;
+            }
+            *reinterpret_cast<float2*>(oj + 2 * it * HOP) = make_float2(num.x * rden.x, num.y * rden.y);
+          }
+        } else
+#pragma unroll 2
+        for (int it = 0; it < FT / 2; ++it) {
+          const int q = 2 * it + hsel, hh = s0 + q;
+          float2 num = q < 3 ? *reinterpret_cast<const float2*>(cin + q * HOP + r) : make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int j = 3; j >= 0; --j) {
+            if (q - j >= 0) {
+              const float2 yv = *reinterpret_cast<const float2*>(Yf + (q - j) * (2 * C::EP) + j * HOP + r);
+              num.x += yv.x;
+              num.y += yv.y;
+            }
+          }
+          if (hh < h0 || hh >= h1) continue;  // lead-in hops belong to the previous run, trailing ones to the next
+          float2 res;
+          if (hh - 3 >= 0 && hh < Ti && p.rden_ok) {
+            res = make_float2(num.x * rden.x, num.y * rden.y);
+          } else {
+            float2 den = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+              const int tt = hh - j;
+              if (tt >= 0 && tt < Ti) {
+                const float2 wv = *reinterpret_cast<const float2*>(s_wenv + r + j * HOP);
+                den.x += wv.x;
+                den.y += wv.y;
+              }
+            }
+            if (p.div_clamp) {
+              res.x = __fdiv_rn(num.x, fmaxf(den.x, p.div_eps));
+              res.y = __fdiv_rn(num.y, fmaxf(den.y, p.div_eps));
+            } else {
+              res.x = den.x > p.div_eps ? __fdiv_rn(num.x, den.x) : num.x;
+              res.y = den.y > p.div_eps ? __fdiv_rn(num.y, den.y) : num.y;
+            }
+          }
+          const int64_t j0 = (int64_t)hh * HOP + r - p.out_start;
+          if (p.vec_ok && j0 >= 0 && j0 + 1 < p.out_len) {
+            *reinterpret_cast<float2*>(o + j0) = res;
+          } else {
+            if (j0 >= 0 && j0 < p.out_len) o[j0] = res.x;
+            if (j0 + 1 >= 0 && j0 + 1 < p.out_len) o[j0 + 1] = res.y;
+          }
+        }
+        // partial sums of the next tile's hops 0, 1, 2: the quarters of this tile's last three frames that reach past it
+        for (int i = threadIdx.x; i < 3 * (HOP / 2); i += C::THREADS) {
+          const int qn = i / (HOP / 2), rr = 2 * (i - qn * (HOP / 2));
+          float2 sum = make_float2(0.0f, 0.0f);
+          for (int j = 3; j > qn; --j) {
+            const float2 yv = *reinterpret_cast<const float2*>(Yf + (FT + qn - j) * (2 * C::EP) + j * HOP + rr);
+            sum.x += yv.x;
+            sum.y += yv.y;
+          }
+          *reinterpret_cast<float2*>(cout + qn * HOP + rr) = sum;
+        }
+      }
+    }
+  }
+}
+
+template <class C, bool POLAR, bool PLANAR>
+int launch_inv16(b2a_plan* plan, InvFastParams& p, const InvRunParams& rp, cudaStream_t st) {
+  const size_t smem = inv16_smem_bytes<C>();
+  static SmemAttrOnce attr;
+  if (attr.need(plan->device, smem)) {
+    B2A_CUDA(cudaFuncSetAttribute(fast_istft16_kernel<C, POLAR, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need 2 x 89 KB: ask for the shared-memory configuration that holds them (the loads are streaming, L1 is idle)
+    static const int carve = getenv("B2A_X_CARVE") ? atoi(getenv("B2A_X_CARVE")) : 80;  // percent of 228 KB: rounds up to the 196 KB configuration (two CTAs)
+    if (carve >= 0)
+      B2A_CUDA(cudaFuncSetAttribute(fast_istft16_kernel<C, POLAR, PLANAR>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
+  const int64_t runs = (int64_t)p.batch * rp.runs_per_clip;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(runs, 2 * (int64_t)plan->sm_count));
+  fast_istft16_kernel<C, POLAR, PLANAR><<<grid, C::THREADS, smem, st>>>(p, rp);
+  B2A_LAUNCHED();
+  return B2A_OK;
+}
+
+using ICfg1024x16 = ICfg16<32, 16>;  // the same transform as ICfg1024, 16-frame tiles: 256 threads, 2 CTAs / SM
+
 using ICfg1024 = ICfg<32, 16>;  // Vocos / Vocos-mel heads: n_fft 1024, hop 256; 512 threads, 1 CTA / SM
 
 }  // namespace
@@ -503,6 +865,24 @@ int fast_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.wenv = fs->d_wenv;
   p.den = fs->d_den;
   p.rden_ok = fs->rden_ok;
+  static const bool use16 = getenv("B2A_X_INV16") != nullptr;  // development: the two-CTA-per-SM kernel with 16-frame tiles (not faster, see above)
+  if (use16 && (int64_t)a->batch * (a->num_frames + 3) < (int64_t)1 << 30) {
+    using C16 = ICfg1024x16;
+    InvRunParams rp;
+    rp.hop_first = (int)(start / hop);
+    rp.hop_end = (int)((start + len + hop - 1) / hop);  // hops cover OLA coordinates [start, start + len)
+    const int hops = rp.hop_end - rp.hop_first;
+    // runs: enough of them to balance two CTAs per SM (>= 4 per CTA where the batch allows), each a whole number of tiles
+    // after its 3-frame lead-in; at least one tile (13 hops)
+    const int64_t want = 4 * 2 * (int64_t)plan->sm_count;
+    int rpc = (int)std::max<int64_t>(1, (want + a->batch - 1) / a->batch);
+    int tiles = ((hops + rpc - 1) / rpc + C16::LEAD + C16::FT - 1) / C16::FT;
+    tiles = tiles < 1 ? 1 : (tiles > 64 ? 64 : tiles);
+    rp.run_hops = C16::FT * tiles - C16::LEAD;
+    rp.runs_per_clip = (hops + rp.run_hops - 1) / rp.run_hops;
+    if (p.polar.polar) return launch_inv16<C16, true, true>(plan, p, rp, st);
+    return p.spec == nullptr ? launch_inv16<C16, false, true>(plan, p, rp, st) : launch_inv16<C16, false, false>(plan, p, rp, st);
+  }
   // tiles cover OLA coordinates [0, start + len)
   p.tiles_per_clip = (int)((start + len + C::S - 1) / C::S);
   if (p.polar.polar) return launch_inv<C, true, true>(plan, p, st);
