@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
   if (!p.dump_frames) stage_twiddles(tw_s, p.tw, N);
   else __syncthreads();
   // index splits of the element-wise loops as multiply-high (operands well below 2^20 / 2^12, see fast_div)
-  const unsigned mg_N = div_magic(N), mg_FT = div_magic(FT);
+  const unsigned mg_N = div_magic(N), mg_M = div_magic(p.n_mels > 0 ? p.n_mels : F);
 
   const int64_t total_tiles = (int64_t)p.batch * p.tiles_per_clip;
   // (clip, tile) of the CTA's tiles are walked incrementally: a 64-bit division per tile and thread (two with the prefetch of
@@ -454,21 +454,26 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
     const int M = p.n_mels > 0 ? p.n_mels : F;
     float* Y = reinterpret_cast<float*>(Z);  // [FT][M]   (M <= F <= N)
     float lmax = -INFINITY, lmin = INFINITY;
-    // One item = (mel row, frame), frame fastest, owned by a QUAD of lanes: the four lanes take every fourth tap and fold with
-    // two shuffles.  The quads that share a row read the same taps (one broadcast), walk the power tile at a stride of F floats
-    // (F odd for even n_fft: conflict free), and — what matters at 8 frames per tile — every thread gets the same mix of short
-    // and long rows: with one thread per item the 640 items of an S3Gen tile left three quarters of the CTA idle while the first
-    // 128 threads walked the longest rows (60 taps) after their short ones.
-    // (large tiles of short rows — the Kaldi front-end: 64 frames x 80 rows of 3-12 taps — keep one thread per item)
-    const int items = FT * M, items_pad = (items + 7) & ~7;  // warp-uniform trip count (8 quads per warp): the shuffles need every lane
-    const bool quads = p.n_mels > 0 && items <= 4 * (int)blockDim.x;
-    const int lsh = quads ? 2 : 0, lpi = 1 << lsh;
-    const int quad = threadIdx.x >> lsh, sub = threadIdx.x & (lpi - 1);
-    for (int i = quad; i < items_pad; i += blockDim.x >> lsh) {
-      const int m = FT > 1 ? fast_div(i, FT, mg_FT) : i;
-      const int f = i < items ? i - m * FT : FT;
-      float acc = 0.0f;
-      if (f < nf) {
+    // One item = (mel row, group of 8 frames), owned by a QUAD of lanes: the four lanes take every fourth tap, each tap is
+    // loaded once and used for the 8 frames' accumulators (9 loads per 8 multiply-adds instead of 16), the quad folds with two
+    // shuffles per frame and each lane finishes two of the frames (guard, logarithm, affine).  What matters at 8 frames per tile
+    // (the 1920-point shapes): every thread gets the same mix of short and long rows — with one thread per (row, frame) item the
+    // 640 items of an S3Gen tile left three quarters of the CTA idle while 128 threads walked the 60-tap rows after their short
+    // ones — and the projection costs ~2 instructions per multiply-add instead of ~6 (ncu source page: the phase was 12 % of the
+    // kernel's time plus most of the 9 % spent at the barrier behind it).
+    const int G8 = (FT + 7) >> 3, items = M * G8, items_pad = (items + 7) & ~7;  // warp-uniform trip count: the shuffles need every lane
+    const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    for (int i = quad; i < items_pad; i += blockDim.x >> 2) {
+      const bool on = i < items;
+      const int g = on ? (M > 1 ? fast_div(i, M, mg_M) : i) : 0, m = on ? i - g * M : 0;
+      const int f0 = 8 * g;
+      float a8[8];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) a8[f] = 0.0f;
+      if (on) {
+        int fo[8];  // row offsets of the group's frames; frames past the tile repeat its last row (never stored)
+#pragma unroll
+        for (int f = 0; f < 8; ++f) fo[f] = min(f0 + f, FT - 1) * F;
         if (p.n_mels > 0) {
           int start, len, off;
           const float* w;
@@ -479,26 +484,36 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
             start = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m), off = __ldg(p.mel_off + m);
             w = p.mel_w + off;
           }
-          const float* row = P + (size_t)f * F + start;
-#pragma unroll 4
-          for (int j = sub; j < len; j += lpi) acc = fmaf(row[j], w[j], acc);
+          const float* row = P + start;
+          for (int j = sub; j < len; j += 4) {
+            const float wv = w[j];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) a8[f] = fmaf(row[fo[f] + j], wv, a8[f]);
+          }
         } else if (sub == 0) {
-          acc = P[(size_t)f * F + m];
+#pragma unroll
+          for (int f = 0; f < 8; ++f) a8[f] = P[fo[f] + m];
         }
       }
-      if (quads) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        a8[f] += __shfl_xor_sync(0xffffffffu, a8[f], 1);
+        a8[f] += __shfl_xor_sync(0xffffffffu, a8[f], 2);
       }
-      if (f >= nf || sub != 0) continue;
-      if (p.guard_kind == B2A_GUARD_MAX) acc = fmaxf(acc, p.guard_eps);
-      else if (p.guard_kind == B2A_GUARD_ADD) acc = acc + p.guard_eps;
-      if (p.log_kind == B2A_LOG_LOG10) acc = log10f(acc);
-      else if (p.log_kind == B2A_LOG_LN) acc = logf(acc);
-      lmax = fmaxf(lmax, acc);
-      lmin = fminf(lmin, acc);
-      if (p.apply_affine) acc = (acc + p.affine_add) / p.affine_div;
-      Y[f * M + m] = acc;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // lane `sub` finishes frames f0 + 2 sub + h
+        const int f = f0 + 2 * sub + h;
+        float acc = sub == 0 ? a8[h] : sub == 1 ? a8[2 + h] : sub == 2 ? a8[4 + h] : a8[6 + h];
+        if (!on || f >= nf) continue;
+        if (p.guard_kind == B2A_GUARD_MAX) acc = fmaxf(acc, p.guard_eps);
+        else if (p.guard_kind == B2A_GUARD_ADD) acc = acc + p.guard_eps;
+        if (p.log_kind == B2A_LOG_LOG10) acc = log10f(acc);
+        else if (p.log_kind == B2A_LOG_LN) acc = logf(acc);
+        lmax = fmaxf(lmax, acc);
+        lmin = fminf(lmin, acc);
+        if (p.apply_affine) acc = (acc + p.affine_add) / p.affine_div;
+        Y[f * M + m] = acc;
+      }
     }
     if (p.clip_max) {
       for (int o = 16; o > 0; o >>= 1) {
@@ -791,6 +806,7 @@ struct InvParams {
   int frames_adv;       // frames advanced per tile (tile covers frames_adv*hop output samples)
   int frames_cap;       // max frames resident per tile
   int pairs_chunk;      // pairs transformed per FFT round
+  int planes_vec2;      // both planes start on an 8-byte boundary: pairs of frames may be read with one 8-byte load
   int tiles_per_clip;
   PolarSpec polar;
   float div_eps;
@@ -898,6 +914,19 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
           for (int b = 0; b < KB; ++b) {
             const int kk = kb0 + b * blockDim.x;
             const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0 + 2 * pr0;
+            // planes: the four frames of a bin are 16 contiguous bytes per plane — two 8-byte loads per plane where the element
+            // index is even (the planes themselves are 8-byte aligned: checked by the host) instead of four 4-byte loads, each of
+            // which opens 32 sectors per warp (lanes are bins, T * 4 bytes apart): the load / store queue was the second
+            // stall reason of this phase (lg_throttle)
+            if (!p.spec && p.planes_vec2 && kk < F && 2 * pr0 + 3 < cf && ((base & 1) == 0)) {
+              const float2 r01 = *reinterpret_cast<const float2*>(p.spec_re + base), r23 = *reinterpret_cast<const float2*>(p.spec_re + base + 2);
+              const float2 i01 = *reinterpret_cast<const float2*>(p.spec_im + base), i23 = *reinterpret_cast<const float2*>(p.spec_im + base + 2);
+              x[b][0] = make_float2(r01.x, i01.x);
+              x[b][1] = make_float2(r01.y, i01.y);
+              x[b][2] = make_float2(r23.x, i23.x);
+              x[b][3] = make_float2(r23.y, i23.y);
+              continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               x[b][q] = make_float2(0.f, 0.f);
@@ -1238,6 +1267,7 @@ int generic_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.T = a->num_frames;
   p.clip_stride = a->clip_stride ? a->clip_stride : (int64_t)F * a->num_frames;
   p.batch = a->batch;
+  p.planes_vec2 = a->spec_imag && reinterpret_cast<uintptr_t>(a->spec) % 8 == 0 && reinterpret_cast<uintptr_t>(a->spec_imag) % 8 == 0;
   p.n_fft = N;
   p.hop = hop;
   p.n_freqs = F;

@@ -273,6 +273,58 @@ def test_polar_istft_1024_matches_complex_path():
     assert_wave_close(y, ref)
 
 
+@pytest.mark.parametrize("n_fft,hop", [(20, 5), (16, 4)])
+@pytest.mark.parametrize("phase_kind", ["unit", "one_outlier", "wide"])
+def test_small_polar_istft_phase_ranges(n_fft, hop, phase_kind):
+    """istft_small from magnitude / phase planes: phases inside [-1, 1] (what Kokoro's generator produces: sin(.) of a network
+    output, istftnet.py) take the reduction-free sin / cos polynomials, a warp holding ONE larger phase falls back to the
+    Cody-Waite path for all of its frames, and wide phases always do — all three against the float64-exact complex form."""
+    from mlx_audio_plus_b200.dsp import istft_polar
+
+    rng = np.random.default_rng(11)
+    F, T = n_fft // 2 + 1, 1000
+    mag = np.exp(rng.normal(0, 1.0, (3, F, T))).astype(np.float32)
+    if phase_kind == "wide":
+        ph = rng.uniform(-30, 30, mag.shape).astype(np.float32)
+    else:
+        ph = np.sin(rng.normal(0, 1.0, mag.shape)).astype(np.float32)
+        ph[0, :, :40] = np.array([1.0, -1.0] * 20, np.float32)  # the end points of the polynomial range
+        if phase_kind == "one_outlier":
+            ph[1, 3, 500] = np.float32(1.0000001)
+            ph[2, 0, 17] = np.float32(-7.5)
+    w = np.asarray(O.hanning(n_fft + 1)[:-1])
+    spec = (mag.astype(np.float64) * np.exp(1j * ph.astype(np.float64))).astype(np.complex64)
+    ref = np.stack([O.istft(spec[i], hop, n_fft, w, True, None, False) for i in range(3)])
+    y = istft_polar(dev(mag), dev(ph), n_fft, hop, w)
+    assert_wave_close(y, ref)
+
+
+@pytest.mark.parametrize("n_fft,hop,pre,offset", [(1280, 320, 0.0, 0), (1280, 320, 0.0, 1), (1920, 480, 0.97, 0), (1920, 384, 0.0, 3),
+                                                  (2048, 512, 0.97, 2), (360, 90, 0.0, 1)])
+def test_generic_forward_interior_copy_matches_oracle(n_fft, hop, pre, offset):
+    """frontend_generic_kernel stages INTERIOR tiles with a linear copy (16-byte loads when the clip's first sample is 16-byte
+    aligned, 4-byte loads otherwise, a two-load form with pre-emphasis) and only edge tiles through the per-sample padding logic:
+    several clips whose storage starts `offset` floats into an allocation, against the oracle's stft."""
+    from mlx_audio_plus_b200._arrays import Ingested
+    from mlx_audio_plus_b200.frontend import FrontendPlan
+
+    w = np.asarray(O.hanning(n_fft))
+    plan = FrontendPlan(n_fft=n_fft, hop=hop, window=w, preemph=pre)
+    assert not plan.kernel_name.startswith("fast_"), plan.kernel_name
+    B, L = 3, 40 * hop + n_fft + 37
+    xb = np.stack([synth(90 + i, L) * (0.5 + i / 3) for i in range(B)])
+    base = torch.zeros(B * L + 8, dtype=torch.float32, device="cuda")
+    base[offset:offset + B * L] = dev(xb).reshape(-1)
+    xd = base[offset:offset + B * L].view(B, L)
+    assert xd.is_contiguous() and xd.data_ptr() % 16 == (4 * offset) % 16
+    y = host(plan.run(Ingested("torch", True, xd, None, xd.device)))
+    for i in range(B):
+        xi = xb[i]
+        if pre:
+            xi = np.concatenate([xi[:1], xi[1:] - np.float32(pre) * xi[:-1]]).astype(np.float32)
+        assert_stft_close(y[i], O.stft(xi, n_fft, hop, n_fft, w))
+
+
 # ---- Kaldi-compatible features (dsp.py:439-676; SURVEY §8f row 2) -------------------------------------------------
 @pytest.mark.parametrize("where", ["cuda", "numpy"])
 def test_kaldi_fbank_and_deltas_parity(golden, where):
