@@ -68,8 +68,27 @@ __host__ __device__ inline unsigned div_magic(int d) { return d <= 1 ? 0u : 0xFF
 // memory it put an L2 round trip into every butterfly).  Ns = product of the radices already applied.  The radix-R butterfly is
 // the register codelet of fft_regs.cuh (2, 3, 4, 5 hand written; 6, 8, 10, 12, 15, 16, 20, 25, 32 composed at compile time), so a
 // 1920-point transform is three passes (16 x 8 x 15) instead of six (4 x 4 x 4 x 2 x 3 x 5), 2048 is 16 x 16 x 8.
-template <int R>
-__device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ src, float2* __restrict__ dst,
+// Where a pass reads element e of sequence `seq` from: a skewed shared-memory buffer, or — first pass of the forward kernel —
+// the staged sample span itself: two real frames, windowed and packed on the fly (FrameSrc), which removes the window / pack
+// sweep over the tile and its barrier (9 % of the S3Gen-mel kernel's time on the ncu source page).
+struct SmemSrc {
+  const float2* p;
+  int pitch;
+  __device__ __forceinline__ float2 operator()(int seq, int e) const { return p[(size_t)seq * pitch + skew(e)]; }
+};
+struct FrameSrc {
+  const float* xs;      // the tile's sample span (shared memory)
+  const float* window;  // n taps (global memory: a warp reads consecutive taps, L1-resident)
+  int hop, nf;          // frames 2 seq and 2 seq + 1 start at (2 seq) * hop, (2 seq + 1) * hop; frames >= nf are zero
+  __device__ __forceinline__ float2 operator()(int seq, int e) const {
+    const float w = __ldg(window + e);
+    const float* x = xs + 2 * seq * hop + e;
+    return make_float2(2 * seq < nf ? x[0] * w : 0.0f, 2 * seq + 1 < nf ? x[hop] * w : 0.0f);
+  }
+};
+
+template <int R, class Src>
+__device__ __forceinline__ void stockham_pass_fixed(const Src src, float2* __restrict__ dst,
                                                     const float2* __restrict__ tw, int n, int Ns, int count) {
   const int nb = n / R;            // butterflies per sequence
   const unsigned nb_magic = div_magic(nb);
@@ -79,10 +98,9 @@ __device__ __forceinline__ void stockham_pass_fixed(const float2* __restrict__ s
     const int seq = nb > 1 ? fast_div(idx, nb, nb_magic) : idx;
     const int j = idx - seq * nb;
     const int k = ns_pow2 ? (j & (Ns - 1)) : (j % Ns);
-    const float2* sp = src + (size_t)seq * seq_pitch(n);
     float2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = sp[skew(j + r * nb)];
+    for (int r = 0; r < R; ++r) v[r] = src(seq, j + r * nb);
     if (Ns > 1) {  // first pass: k == 0, every twiddle is 1
       // per-pass table [r - 1][k] = W_(Ns R)^(k r): the lanes of a warp (consecutive k) read consecutive entries.  Indexed as
       // W_n^(k tstep r) in one table of n roots, a warp's loads were strided by tstep * r entries: the twiddle loads were the
@@ -126,12 +144,14 @@ __device__ __forceinline__ void stockham_pass_any(const float2* __restrict__ src
 }
 
 // Runs all passes; returns the buffer holding the result.  All threads must call.  `tw` lives in shared memory.
-__device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2* tw, int count) {
-  int Ns = 1;
-  float2 *src = a, *dst = b;
-  for (int s = 0; s < fd.nstages; ++s) {
+// `first_pass_done`: pass 0 has already been run into `a` (fft_first_pass_from_frames).
+__device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2* tw, int count, bool first_pass_done = false) {
+  int Ns = first_pass_done ? fd.radix[0] : 1;
+  float2 *src_p = a, *dst = b;
+  for (int s = first_pass_done ? 1 : 0; s < fd.nstages; ++s) {
     const int R = fd.radix[s];
     const float2* tws = tw + (Ns - 1);  // pass tables back to back: sum over earlier passes of (R - 1) * Ns = Ns - 1
+    const SmemSrc src{src_p, seq_pitch(fd.n)};
     switch (R) {
       case 2: stockham_pass_fixed<2>(src, dst, tws, fd.n, Ns, count); break;
       case 3: stockham_pass_fixed<3>(src, dst, tws, fd.n, Ns, count); break;
@@ -146,15 +166,29 @@ __device__ float2* run_fft(const FftDesc& fd, float2* a, float2* b, const float2
       case 20: stockham_pass_fixed<20>(src, dst, tws, fd.n, Ns, count); break;
       case 25: stockham_pass_fixed<25>(src, dst, tws, fd.n, Ns, count); break;
       case 32: stockham_pass_fixed<32>(src, dst, tws, fd.n, Ns, count); break;
-      default: stockham_pass_any(src, dst, fd.tw_plain, fd.n, Ns, count, R); break;
+      default: stockham_pass_any(src_p, dst, fd.tw_plain, fd.n, Ns, count, R); break;
     }
     __syncthreads();
     Ns *= R;
-    float2* t = src;
-    src = dst;
+    float2* t = src_p;
+    src_p = dst;
     dst = t;
   }
-  return src;
+  return src_p;
+}
+
+// First pass of the forward transform straight from the sample span (power-of-two first radices 8 / 16 / 32: what `factorize`
+// puts first for every n_fft with a factor 8).  Returns false when the plan's first radix has no fused instance.
+__device__ __forceinline__ bool fft_first_pass_fusable(const FftDesc& fd) {
+  return fd.nstages >= 1 && (fd.radix[0] == 8 || fd.radix[0] == 16 || fd.radix[0] == 32);
+}
+__device__ __forceinline__ void fft_first_pass_from_frames(const FftDesc& fd, const FrameSrc& src, float2* a, int count) {
+  switch (fd.radix[0]) {
+    case 8: stockham_pass_fixed<8>(src, a, nullptr, fd.n, 1, count); break;
+    case 16: stockham_pass_fixed<16>(src, a, nullptr, fd.n, 1, count); break;
+    default: stockham_pass_fixed<32>(src, a, nullptr, fd.n, 1, count); break;
+  }
+  __syncthreads();
 }
 
 // the twiddle table into shared memory, once per CTA (n float2 behind the kernel's other buffers)
@@ -388,6 +422,10 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       __syncthreads();
       Z = run_fft(p.fft, bufB, bufA, tw_s, PAIRS);
     } else {
+      if (fft_first_pass_fusable(p.fft)) {
+        fft_first_pass_from_frames(p.fft, FrameSrc{xs, p.window, hop, nf}, bufA, PAIRS);
+        Z = run_fft(p.fft, bufA, bufB, tw_s, PAIRS, true);
+      } else {
       // a thread owns sample positions k and walks the tile's frame pairs: one window tap and one skewed offset per k
       for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const float w = __ldg(p.window + k);
@@ -400,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_generic_kernel(const Fwd
       }
       __syncthreads();
       Z = run_fft(p.fft, bufA, bufB, tw_s, PAIRS);
+      }
     }
     float2* other = (Z == bufA) ? bufB : bufA;
 
