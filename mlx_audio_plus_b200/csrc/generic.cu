@@ -925,77 +925,67 @@ __global__ void __launch_bounds__(kThreads, 1) istft_generic_kernel(const InvPar
         pf_base = (int64_t)nx_clip * p.clip_stride + nx_tlo;
         pf_n = min(2 * p.pairs_chunk, nx_nfr);
       }
-      // up to KB bins per thread and four frames (two pairs) per bin are loaded BEFORE anything is converted or stored: with one
-      // bin at a time a thread waited out one memory round trip per bin and pair group (long-scoreboard stalls were 67 % of
-      // this phase's samples, the phase 42 % of the MossFormer2 inverse)
-      constexpr int KB = 3;
-      for (int kb0 = threadIdx.x; kb0 < F; kb0 += KB * blockDim.x) {
-        if (pf_n > 0) {
-#pragma unroll
-          for (int b = 0; b < KB; ++b) {
-            const int kk = kb0 + b * blockDim.x;
-            if (kk >= F) break;
-            const int64_t b0 = pf_base + (int64_t)kk * p.T, b1 = b0 + pf_n - 1;
-            if (p.spec) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b0));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b1));
-            } else {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b0));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b1));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b0));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b1));
-            }
+      if (pf_n > 0) {
+        for (int kk = threadIdx.x; kk < F; kk += blockDim.x) {
+          const int64_t b0 = pf_base + (int64_t)kk * p.T, b1 = b0 + pf_n - 1;
+          if (p.spec) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec + b1));
+          } else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_re + b1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.spec_im + b1));
           }
         }
-        for (int pr0 = 0; pr0 < cp; pr0 += 2) {
-          float2 x[KB][4];
+      }
+      // One item = (bin, frame PAIR), pair fastest: the lanes that share a bin read ADJACENT frame pairs, so a warp's load covers
+      // 32 / cp bins with cp * 8 (planes) or cp * 16 (complex) contiguous bytes each — whole sectors when four pairs make a round.
+      // With one thread per bin every load instruction opened 32 sectors and used 4-8 bytes of each (the load / store queue was
+      // the second stall reason of this phase, which was half of the MossFormer2 inverse).  An item is exactly one packed FFT input:
+      // z = xa + i xb of frames 2 pr, 2 pr + 1.  KB items per thread are loaded before anything is converted or stored.
+      constexpr int KB = 4;
+      const int n_items = F * cp;
+      const unsigned mg_cp = div_magic(cp);
+      for (int i0 = threadIdx.x; i0 < n_items; i0 += KB * blockDim.x) {
+        float2 xa[KB], xb[KB];
 #pragma unroll
-          for (int b = 0; b < KB; ++b) {
-            const int kk = kb0 + b * blockDim.x;
-            const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0 + 2 * pr0;
-            // planes: the four frames of a bin are 16 contiguous bytes per plane — two 8-byte loads per plane where the element
-            // index is even (the planes themselves are 8-byte aligned: checked by the host) instead of four 4-byte loads, each of
-            // which opens 32 sectors per warp (lanes are bins, T * 4 bytes apart): the load / store queue was the second
-            // stall reason of this phase (lg_throttle)
-            if (!p.spec && p.planes_vec2 && kk < F && 2 * pr0 + 3 < cf && ((base & 1) == 0)) {
-              const float2 r01 = *reinterpret_cast<const float2*>(p.spec_re + base), r23 = *reinterpret_cast<const float2*>(p.spec_re + base + 2);
-              const float2 i01 = *reinterpret_cast<const float2*>(p.spec_im + base), i23 = *reinterpret_cast<const float2*>(p.spec_im + base + 2);
-              x[b][0] = make_float2(r01.x, i01.x);
-              x[b][1] = make_float2(r01.y, i01.y);
-              x[b][2] = make_float2(r23.x, i23.x);
-              x[b][3] = make_float2(r23.y, i23.y);
-              continue;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              x[b][q] = make_float2(0.f, 0.f);
-              if (kk < F && 2 * pr0 + q < cf) {
-                if (p.spec) x[b][q] = p.spec[base + q];
-                else x[b][q] = make_float2(p.spec_re[base + q], p.spec_im[base + q]);
-              }
-            }
+        for (int b = 0; b < KB; ++b) {
+          const int i = i0 + b * blockDim.x;
+          xa[b] = make_float2(0.f, 0.f);
+          xb[b] = make_float2(0.f, 0.f);
+          if (i >= n_items) continue;
+          const int kk = cp > 1 ? fast_div(i, cp, mg_cp) : i, pr = i - kk * cp;
+          const bool has_b = 2 * pr + 1 < cf;
+          const int64_t base = (int64_t)clip_i * p.clip_stride + (int64_t)kk * p.T + t_lo + c0 + 2 * pr;
+          if (p.spec) {
+            xa[b] = p.spec[base];
+            if (has_b) xb[b] = p.spec[base + 1];
+          } else if (has_b && p.planes_vec2 && (base & 1) == 0) {
+            const float2 r = *reinterpret_cast<const float2*>(p.spec_re + base), im = *reinterpret_cast<const float2*>(p.spec_im + base);
+            xa[b] = make_float2(r.x, im.x);
+            xb[b] = make_float2(r.y, im.y);
+          } else {
+            xa[b] = make_float2(p.spec_re[base], p.spec_im[base]);
+            if (has_b) xb[b] = make_float2(p.spec_re[base + 1], p.spec_im[base + 1]);
           }
+        }
 #pragma unroll
-          for (int b = 0; b < KB; ++b) {
-            const int kk = kb0 + b * blockDim.x;
-            if (kk >= F) break;
-            const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
-            const int km = real_bin ? -1 : N - kk;         // mirrored position (bins > N/2), none for DC / Nyquist
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int pr = pr0 + h;
-              if (pr >= cp) break;
-              float2 xa = x[b][2 * h], xb = x[b][2 * h + 1];
-              if (!p.spec && p.polar.polar) {
-                xa = polar_to_complex(p.polar, xa);
-                if (2 * pr + 1 < cf) xb = polar_to_complex(p.polar, xb);
-              }
-              if (real_bin) { xa.y = 0.f; xb.y = 0.f; }
-              // z = xa + i xb ; store conj(z).  Mirrored bin: conj(xa) + i conj(xb)
-              bufA[(size_t)pr * NP + skew(kk)] = make_float2(xa.x - xb.y, -(xa.y + xb.x));
-              if (km >= 0) bufA[(size_t)pr * NP + skew(km)] = make_float2(xa.x + xb.y, -(xb.x - xa.y));
-            }
+        for (int b = 0; b < KB; ++b) {
+          const int i = i0 + b * blockDim.x;
+          if (i >= n_items) break;
+          const int kk = cp > 1 ? fast_div(i, cp, mg_cp) : i, pr = i - kk * cp;
+          const bool real_bin = kk == 0 || 2 * kk == N;  // irfft ignores Im(DC) and, for even N, Im(Nyquist)
+          const int km = real_bin ? -1 : N - kk;         // mirrored position (bins > N/2), none for DC / Nyquist
+          float2 a2 = xa[b], b2 = xb[b];
+          if (!p.spec && p.polar.polar) {
+            a2 = polar_to_complex(p.polar, a2);
+            if (2 * pr + 1 < cf) b2 = polar_to_complex(p.polar, b2);
           }
+          if (real_bin) { a2.y = 0.f; b2.y = 0.f; }
+          // z = xa + i xb ; store conj(z).  Mirrored bin: conj(xa) + i conj(xb)
+          bufA[(size_t)pr * NP + skew(kk)] = make_float2(a2.x - b2.y, -(a2.y + b2.x));
+          if (km >= 0) bufA[(size_t)pr * NP + skew(km)] = make_float2(a2.x + b2.y, -(b2.x - a2.y));
         }
       }
       __syncthreads();
