@@ -11,6 +11,7 @@
 // phases of neighbouring outputs differ by `down mod up`) against an L1-resident input window.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
@@ -127,6 +128,7 @@ struct PhaseParams {
   float* out;
   int64_t n_in, n_out, in_clip_stride, out_clip_stride, pre_remove;
   int channels, up, down, J4, R, tile, ypitch, span_max;
+  int direct;  // 1: results go straight to global memory (no staging rows): two CTAs fit one SM
   const float* taps_pm;  // [up][4 * J4], zero padded
 };
 
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(512) resample_phase_kernel(const PhaseParams p
     for (int item = 2 * warp; item < items; item += 2 * nwarps) {
       const float4* w4[2];
       const float* xp[2];
-      int dst[2];
+      int dst[2], gdst[2];
       bool ok[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(512) resample_phase_kernel(const PhaseParams p
         w4[e] = reinterpret_cast<const float4*>(s_taps + ph * JP);
         xp[e] = xs + (ok[e] ? (int)bq + p.down * l : 0) + (JP - 1);  // tap j reads xp[-j]
         dst[e] = q + p.ypitch * l;
+        gdst[e] = q + p.up * l;
       }
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 2
@@ -211,8 +214,13 @@ __global__ void __launch_bounds__(512) resample_phase_kernel(const PhaseParams p
       }
 #pragma unroll
       for (int e = 0; e < 2; ++e)
-        if (ok[e]) ys[dst[e]] = (acc[e][0] + acc[e][1]) + (acc[e][2] + acc[e][3]);
+        if (ok[e]) {
+          const float r = (acc[e][0] + acc[e][1]) + (acc[e][2] + acc[e][3]);
+          if (p.direct) y[n0 + gdst[e]] = r;  // lanes are `up` outputs apart: a scattered store, but no staging rows
+          else ys[dst[e]] = r;
+        }
     }
+    if (p.direct) continue;
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const int l = i / p.up, q = i - l * p.up;
@@ -338,7 +346,14 @@ int b2a_resample(b2a_resampler* h, const b2a_resample_args* a, void* stream) {
     q.ypitch = r->up | 1;
     q.span_max = (int)(((int64_t)q.tile * r->down) / r->up + 4 * r->J4 + 2);
     q.taps_pm = r->d_taps_pm;
-    const size_t need = sizeof(float) * ((size_t)r->up * 4 * r->J4 + ((q.span_max + 3) & ~3) + (size_t)32 * q.R * q.ypitch) + 16;
+    size_t need = sizeof(float) * ((size_t)r->up * 4 * r->J4 + ((q.span_max + 3) & ~3) + (size_t)32 * q.R * q.ypitch) + 16;
+    // The kernel is bound by shared-memory latency at one 16-warp CTA per SM (44.1 -> 16 kHz: 116 KB of taps, input span and
+    // staging rows).  Without the staging rows (20 KB) two CTAs fit: the results then leave as scattered 4-byte stores, which the
+    // L2 merges — the output is a quarter of the traffic.
+    const size_t need_direct = need - sizeof(float) * (size_t)32 * q.R * q.ypitch;
+    static const int direct_mode = getenv("B2A_X_RS_DIRECT") ? atoi(getenv("B2A_X_RS_DIRECT")) : 1;  // development: 0 keeps the staging rows
+    q.direct = direct_mode && need > 113 * 1024 && need_direct <= 113 * 1024;
+    if (q.direct) need = need_direct;
     if (need <= 200 * 1024) {
       const int64_t tiles = (p.n_out + q.tile - 1) / q.tile;
       int64_t g = tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2;
