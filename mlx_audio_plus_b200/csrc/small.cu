@@ -217,13 +217,17 @@ template <int N>
 __global__ void __launch_bounds__(256) stft_small_kernel(const SmallFwdParams p) {
   constexpr int NC = N / 2, F = NC + 1;
   const int64_t lt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lt >= p.frame_count) return;
+  if (lt - (threadIdx.x & 31) >= p.frame_count) return;  // whole warp past the end (a ragged warp keeps all its lanes: see the write-out)
+  const bool dead = lt >= p.frame_count;
   const int clip_i = blockIdx.y;
   const float* clip = p.audio + (int64_t)clip_i * p.clip_stride;
   const int64_t q0 = (p.frame_begin + lt) * p.hop;
   const int64_t s0 = q0 - p.geo.pad_left;
   float x[N];
-  if (s0 >= 1 && s0 + N <= p.valid_length && s0 >= p.sample_offset + 1 && p.preemph == 0.0f) {
+  if (dead) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = 0.0f;
+  } else if (s0 >= 1 && s0 + N <= p.valid_length && s0 >= p.sample_offset + 1 && p.preemph == 0.0f) {
 #pragma unroll
     for (int k = 0; k < N; ++k) x[k] = __ldg(clip + (s0 - p.sample_offset) + k);
   } else {
@@ -245,7 +249,12 @@ __global__ void __launch_bounds__(256) stft_small_kernel(const SmallFwdParams p)
 #pragma unroll
   for (int m = 0; m < NC; ++m) z[m] = make_float2(x[2 * m] * p.w[2 * m], x[2 * m + 1] * p.w[2 * m + 1]);
   Dft<NC>::run(z);
-  float2* o = p.out + (int64_t)clip_i * p.out_clip_stride + lt * F;
+  // The 32 frames of a warp are ONE contiguous run of the (T, F) output (F complex values each): rows are parked in a per-warp
+  // staging block (pitch F: odd, conflict free) and leave as coalesced 256-byte stores — a thread storing its own row writes 8
+  // bytes at a stride of 8 F bytes, every store instruction touching all ~90 sectors of the run.
+  __shared__ float2 s_rows[8][32 * F];
+  const int lane = threadIdx.x & 31;
+  float2* const so = s_rows[threadIdx.x >> 5] + lane * F;
   static_for<0, NC / 2 + 1>([&](auto K_) {
     constexpr int k = decltype(K_)::value;
     const float2 a = z[k], b = z[(NC - k) % NC];
@@ -254,9 +263,15 @@ __global__ void __launch_bounds__(256) stft_small_kernel(const SmallFwdParams p)
     constexpr regs::cplx_d w = regs::unit_root(-k, N);  // W_N^k
     constexpr float wr = (float)w.re, wi = (float)w.im;
     const float tx = wr * ox - wi * oy, ty = wr * oy + wi * ox;
-    o[k] = make_float2(ex + tx, ey + ty);
-    o[NC - k] = make_float2(ex - tx, -(ey - ty));
+    so[k] = make_float2(ex + tx, ey + ty);
+    so[NC - k] = make_float2(ex - tx, -(ey - ty));
   });
+  __syncwarp();
+  const int64_t lt0 = lt - lane;                                      // first frame of this warp
+  const int nrows = (int)min((int64_t)32, p.frame_count - lt0);       // the clip's last warp may be ragged
+  float2* const o = p.out + (int64_t)clip_i * p.out_clip_stride + lt0 * F;
+  const float2* const sw = s_rows[threadIdx.x >> 5];
+  for (int i = lane; i < nrows * F; i += 32) o[i] = sw[i];
 }
 
 }  // namespace
