@@ -17,6 +17,9 @@ KERNELS = {
     "k1_1024_vocos100": r"fast_logmel_kernel.*Li32ELi16ELi256.*MelSpec_vocos100E",
     "k3_fast_istft": r"fast_istft_kernel.*Lb0EEE",
     "k4_istft_small_polar": r"istft_small_kernelILi20ELb1EEE",
+    "k4_stft_small_20": r"stft_small_kernelILi20EEE",
+    "k2_generic_forward": r"frontend_generic_kernel",
+    "k3b_generic_inverse": r"istft_generic_kernel",
 }
 INTEREST = ("FFMA2", "FADD2", "FMUL2", "LDTM", "STTM", "UTMASTG", "UTMALDG", "LDGSTS", "REDUX", "MUFU", "UTCBAR", "SYNCS")
 
