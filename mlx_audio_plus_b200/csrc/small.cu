@@ -29,7 +29,8 @@ struct SmallInvParams {
   int norm_sq, div_clamp;
   int64_t out_start, out_len, out_clip_stride;
   float* out;
-  float w[32];  // synthesis window (zero extended)
+  float w[32];   // synthesis window (zero extended)
+  float wn[32];  // window / n_fft: the inverse transform's 1 / N folded into the window product
   int warps_per_clip;
   PolarSpec polar;
   float div_eps;
@@ -113,22 +114,22 @@ __global__ void __launch_bounds__(256) istft_small_kernel(const SmallInvParams p
   static_for<0, NC>([&](auto K_) {
     constexpr int k = decltype(K_)::value;
     const float2 a = X[k], b = X[NC - k];
-    const float ex = a.x + b.x, ey = a.y - b.y;   // 2E
-    const float dx = a.x - b.x, dy = a.y + b.y;   // X[k] - conj X[Nc-k]
     constexpr regs::cplx_d w = regs::unit_root(k, N);  // W_N^-k = exp(+2 pi i k / N)
     constexpr float wr = (float)w.re, wi = (float)w.im;
-    const float ox = dx * wr - dy * wi, oy = dx * wi + dy * wr;  // 2O
-    // Z = E + iO = (ex - oy, ey + ox)/2 ; conj(Z) = (ex - oy, -(ey + ox))/2
-    z[k] = make_float2(ex - oy, -(ey + ox));
+    // packed f32x2 form (FFMA2 / FMUL2, as the fused kernels): 2E conjugated, X[k] - conj X[Nc-k], 2O, then
+    // conj(Z) = (ex - oy, -(ey + ox)) with Z = E + iO
+    const float2 ec = regs::pfma(a, make_float2(1.0f, -1.0f), b);   // (ex, -ey)
+    const float2 d = regs::pfma(b, make_float2(-1.0f, 1.0f), a);    // (dx, dy)
+    const float2 o = regs::cmul(d, make_float2(wr, wi));            // (ox, oy)
+    z[k] = regs::pfma(regs::pswap(o), make_float2(-1.0f, -1.0f), ec);
   });
   Dft<NC>::run(z);
   // x[2m] = Re z[m], x[2m+1] = Im z[m], z = conj(DFT(conj Z)) / Nc, and the /2 of E,O  => scale 1/N
   float y[N];
-  constexpr float inv = 1.0f / (float)N;
 #pragma unroll
-  for (int m = 0; m < NC; ++m) {
-    y[2 * m] = (z[m].x * inv) * p.w[2 * m];
-    y[2 * m + 1] = (-z[m].y * inv) * p.w[2 * m + 1];
+  for (int m = 0; m < NC; ++m) {  // p.wn = window / N (exact for n_fft 16; one rounding instead of two for n_fft 20)
+    y[2 * m] = z[m].x * p.wn[2 * m];
+    y[2 * m + 1] = -z[m].y * p.wn[2 * m + 1];
   }
 
   // ---- overlap-add by shuffles, ascending frame order: t-3, t-2, t-1, t ------------------------------------
@@ -313,6 +314,7 @@ int small_istft(b2a_plan* plan, const b2a_inverse_args* a, cudaStream_t st) {
   p.out_clip_stride = a->out_clip_stride ? a->out_clip_stride : len;
   p.out = a->out;
   for (int i = 0; i < 32; ++i) p.w[i] = i < N ? plan->h_window[i] : 0.0f;
+  for (int i = 0; i < 32; ++i) p.wn[i] = p.w[i] * (1.0f / (float)N);
   p.rden_ok = 1;
   for (int j = 0; j < d.hop; ++j) {  // ascending frame order: the oldest frame contributes tap j + 3 * hop
     float sum = 0.0f;
