@@ -107,7 +107,7 @@ __device__ __forceinline__ void stockham_pass_fixed(const Src src, float2* __res
       // bank-conflict replays of the FFT passes (23 % of the forward kernel's shared-memory wavefronts there, 58 % of the inverse's)
       const float2* t = tw + k;
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], t[(r - 1) * Ns]);
+      for (int r = 1; r < R; ++r) v[r] = regs::cmul(v[r], t[(r - 1) * Ns]);  // packed f32x2: two instructions instead of four
     }
     regs::Dft<R>::run(v);
     float2* d = dst + (size_t)seq * seq_pitch(n);
